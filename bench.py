@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- Mcells/s per solver step of the B200-native fluid step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one `lib.simulate` call (advect scalar+velocity -> BCs/forces -> divergence ->
+pressure solve -> velocity update -> BCs) on a synthetic grid of the named resolution.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+
+Timing: CUDA events on the launching stream around each step, >= 3 warm-ups, max over ranks;
+between timed steps L2 is flushed when the working set is smaller than L2 (config.l2 says which).
+`value` times the device-resident step; `e2e` times the same call with HOST (pinned) state:
+H2D of the step's inputs + step + D2H of the results inside the timed region.
+`--impl reference` times the reference's own ATen CPU path (oracle/_ref, built from
+/root/reference by oracle/build_ref.py) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "Mcells/s per solver step (advect+project+update)"
+UNIT = "Mcells/s"
+L2_BYTES = 126 * 1024 * 1024
+
+# name -> grid, pressure method, and the bounded CPU sample used for the reference arm
+WORKLOADS = {
+    # BASELINE.json configs[3]: pure stencil HBM-roofline run
+    "plume4096_jacobi100": dict(res=(1, 4096, 4096), method="jacobi", jacobi_iters=100, cpu_sample_res=512,
+                                baseline_config="4096x4096 2D plume, Jacobi 100 iter"),
+    # BASELINE.json configs[0]
+    "plume128_jacobi28": dict(res=(1, 128, 128), method="jacobi", jacobi_iters=28, cpu_sample_res=128,
+                              baseline_config="128x128 2D plume, Jacobi 28 iter"),
+    "plume1024_jacobi100": dict(res=(1, 1024, 1024), method="jacobi", jacobi_iters=100, cpu_sample_res=512,
+                                baseline_config="1024x1024 2D plume, Jacobi 100 iter"),
+    # BASELINE.json configs[4] with the Jacobi projection (3-D has no CNN in the reference)
+    "plume256cube_jacobi40": dict(res=(256, 256, 256), method="jacobi", jacobi_iters=40, cpu_sample_res=None,
+                                  baseline_config="256x256x256 3D synthetic grid, Jacobi 40 iter"),
+}
+DEFAULT_WORKLOAD = "plume4096_jacobi100"
+
+
+def plume_mconf(jacobi_iters, method):
+    """plumeConfig.yaml physics (pytorch/plumeConfig.yaml) + the solver choice of the workload."""
+    return {"dt": 0.1, "maccormackStrength": 0.6, "sampleOutsideFluid": False, "buoyancyScale": 0.25,
+            "gravityScale": 0, "viscosity": 0, "correctScalar": False, "operatingDensity": 0.0,
+            "gravityVec": {"x": 0.0, "y": -1.0, "z": 0.0}, "pTol": 0.0, "jacobiIter": jacobi_iters,
+            "simMethod": method, "injectionDensity": 0.1, "injectionVelocity": 2, "sourceRadius": 0.145}
+
+
+def synthetic_state_numpy(D, H, W, seed=0):
+    """Seeded synthetic state (SURVEY.md §8d randomised plume): U ~ N(0, 0.5^2), rho ~ U[0,1), p = 0."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    nc = 3 if D > 1 else 2
+    U = (rng.standard_normal((1, nc, D, H, W)).astype(np.float32) * np.float32(0.5))
+    rho = rng.random_sample((1, 1, D, H, W)).astype(np.float32)
+    return U, rho
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fluidnet_cxx_b200 import _native
+    from fluidnet_cxx_b200.lib import fluid
+    from fluidnet_cxx_b200.lib import simulate as sim
+
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.load()
+
+    D, H, W = wl["res"]
+    cells = D * H * W
+    mconf = plume_mconf(wl["jacobi_iters"], wl["method"])
+    nc = 3 if D > 1 else 2
+
+    # ---- synthetic state, built on the HOST (pinned) and copied in ------------------------------
+    U_np, rho_np = synthetic_state_numpy(D, H, W, seed=rank)
+    host = {"p": torch.zeros(1, 1, D, H, W).pin_memory(), "U": torch.from_numpy(U_np).pin_memory(),
+            "flags": torch.zeros(1, 1, D, H, W).pin_memory(), "density": torch.from_numpy(rho_np).pin_memory()}
+    bd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    fluid.emptyDomain(bd["flags"])
+    U0, rho0 = bd["U"], bd["density"]
+    bd["U"], bd["density"] = torch.zeros_like(U0), torch.zeros_like(rho0)
+    fluid.createPlumeBCs(bd, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
+    bd["U"], bd["density"] = U0, rho0
+    host["flags"].copy_(bd["flags"])
+    torch.cuda.synchronize()
+
+    working_set = cells * 4 * (1 + nc + 1 + 1 + 2 * nc + 2)   # state + masks
+    flush = working_set < 2 * L2_BYTES
+    flush_buf = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev) if flush else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # stage hook: CUDA events around the dominant (pressure-solve) stage inside the timed region
+    stage_events = []
+
+    def hook(name, when):
+        if name == "pressure":
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            stage_events.append(ev)
+    sim.set_stage_hook(hook)
+
+    def one_step():
+        sim.simulate(mconf, bd, None, wl["method"])
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    stage_events.clear()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.fnx_launch_count()
+    step_ms = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        if flush:
+            flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_step()
+        e1.record()
+        step_ms.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = lib.fnx_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    times = [a.elapsed_time(b) for a, b in step_ms]
+    total_ms = sum(times)
+    # dominant stage: pairs of (begin, end) events per step
+    dom_ms = sum(stage_events[2 * i].elapsed_time(stage_events[2 * i + 1]) for i in range(len(stage_events) // 2))
+    sim.set_stage_hook(None)
+
+    # ---- e2e: host (pinned) state in, results out, every step -----------------------------------
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = sum(host[k].numel() * 4 for k in ("p", "U", "flags", "density"))
+    d2h = sum(host[k].numel() * 4 for k in ("p", "U", "density"))
+    out_host = {k: torch.empty_like(host[k]).pin_memory() for k in ("p", "U", "density")}
+    masks = {k: bd[k] for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask")}
+
+    def e2e_step():
+        d = {k: host[k].to(dev, non_blocking=True) for k in ("p", "U", "flags", "density")}
+        d.update(masks)
+        sim.simulate(mconf, d, None, wl["method"])
+        for k in ("p", "U", "density"):
+            out_host[k].copy_(d[k], non_blocking=True)
+        return d
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # ---- reduce over ranks: max time ---------------------------------------------------------------
+    t = torch.tensor([total_ms, e2e_ms, dom_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, dom_ms = t.tolist()
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            with open(pk) as f:
+                peaks = json.load(f)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        total_cells = cells * world
+        value = total_cells * args.steps / (total_ms / 1e3) / 1e6
+        e2e_value = total_cells * e2e_steps / (e2e_ms / 1e3) / 1e6
+        iters = wl["jacobi_iters"]
+        # dominant kernel = temporally blocked Jacobi: 16 B/cell/iteration algorithmic (SURVEY §8d stage C)
+        algo_bytes = 16.0 * cells * iters * args.steps
+        achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
+        step_bytes = (80 if D == 1 else 104) + 16 * iters
+        out = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded N(0,0.5^2) velocity, U[0,1) density, plume inlet BCs, border obstacles)",
+            "config": {"workload": args.workload, "baseline_config": wl["baseline_config"], "grid": [D, H, W],
+                       "pressure": f"jacobi x{iters}", "cells_per_gpu": cells,
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (weak)",
+                       "l2": "flushed between timed steps" if flush else "working set larger than L2, no flush",
+                       "algorithmic_bytes_per_cell_step": step_bytes},
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_jacobi2d_blocked" if D == 1 else "k_jacobi_iter",
+                         "achieved": round(achieved, 1) if achieved else None,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4) if achieved else None,
+                         "traffic": None, "peak_source": peak_src,
+                         "stage_ms_per_step": round(dom_ms / args.steps, 4),
+                         "step_hbm_frac": round(step_bytes * cells * args.steps / (total_ms / 1e3) / 1e9 / hbm_peak, 4)},
+            "wall_s": round(t_wall, 3),
+        }
+        out["cpu_baseline"] = cpu_baseline(wl, steps=1, warmup=0) if world == 1 and not args.no_cpu_baseline else None
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def reference_step_runner(wl, res):
+    """The reference's own CPU path (oracle/_ref) on a res x res sample of the workload."""
+    import numpy as np
+    import torch
+    import ref_loader
+    if not ref_loader.available():
+        return None
+    reflib = ref_loader.load()
+    mconf = plume_mconf(wl["jacobi_iters"], wl["method"])
+    U_np, rho_np = synthetic_state_numpy(1, res, res, seed=0)
+    bd = {"p": torch.zeros(1, 1, 1, res, res), "U": torch.zeros(1, 2, 1, res, res),
+          "flags": torch.zeros(1, 1, 1, res, res), "density": torch.zeros(1, 1, 1, res, res)}
+    reflib.fluid.emptyDomain(bd["flags"])
+    reflib.fluid.createPlumeBCs(bd, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
+    bd["U"] = torch.from_numpy(U_np)
+    bd["density"] = torch.from_numpy(rho_np)
+
+    def step():
+        with torch.no_grad():
+            reflib.simulate(mconf, bd, None, wl["method"])
+    return step
+
+
+def cpu_baseline(wl, steps, warmup):
+    import torch
+    res = wl["cpu_sample_res"]
+    if res is None:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                "sample": "none: the reference asserts 3-D off (advection.py:58,108); no CPU reference exists"}
+    step = reference_step_runner(wl, res)
+    kind = "reference"
+    if step is None:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": kind, "sample": "oracle/_ref not built"}
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": round(res * res * steps / dt / 1e6, 4), "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": kind, "seconds": round(dt, 2),
+            "sample": f"{steps} step(s) of the same physics on a {res}x{res} grid (reference ATen CPU path, "
+                      f"patched build oracle/_ref, torch {torch.__version__}, {os.cpu_count()} host CPUs)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    res = wl["cpu_sample_res"]
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "the reference has no runnable 3-D path"}))
+        return
+    import torch
+    step = reference_step_runner(wl, res)
+    if step is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"}))
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = res * res * steps / dt / 1e6
+    sample = (f"{steps} timed step(s) (+{warm} warm-up) of the same physics on a {res}x{res} grid: the reference's "
+              f"ATen CPU path (oracle/_ref) needs minutes per step at the full {wl['res'][1]}x{wl['res'][2]} size")
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
+           "steps": steps, "warmup": warm, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the GPU arm)",
+           "config": {"workload": args.workload, "baseline_config": wl["baseline_config"], "grid": [1, res, res],
+                      "pressure": f"jacobi x{wl['jacobi_iters']}"},
+           "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                            "sample": sample},
+           "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+"""ctypes binding of libfluidstep_b200.so (the C-ABI declared in include/fluidstep.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or a tensor is
+not a contiguous fp32 CUDA tensor the call raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libfluidstep_b200.so")
+
+_c_void_p = ctypes.c_void_p
+_c_int = ctypes.c_int
+_c_float = ctypes.c_float
+_c_size_t = ctypes.c_size_t
+
+
+class StepParams(ctypes.Structure):
+    """struct fnx_step_params (include/fluidstep.h)."""
+    _fields_ = [("dt", _c_float), ("maccormack_strength", _c_float),
+                ("sample_outside_fluid", _c_int),
+                ("use_buoyancy", _c_int), ("use_gravity", _c_int),
+                ("buoyancy3", _c_float * 3), ("gravity3", _c_float * 3),
+                ("rho_star", _c_float), ("jacobi_iters", _c_int)]
+
+
+# name -> (restype, argtypes); every symbol include/fluidstep.h declares
+_P, _I, _F, _S = _c_void_p, _c_int, _c_float, _c_size_t
+_GRID = [_I, _I, _I, _I, _I]  # B, D, H, W, is3d
+SIGNATURES = {
+    "fnx_last_error": (ctypes.c_char_p, []),
+    "fnx_build_info": (ctypes.c_char_p, []),
+    "fnx_abi_version": (_I, []),
+    "fnx_launch_count": (ctypes.c_longlong, []),
+    "fnx_advect_scalar_workspace": (_S, [_I, _I, _I, _I]),
+    "fnx_advect_scalar": (_I, [_F, _P, _P, _P, _P] + _GRID + [_I, _I, _I, _F, _P, _S, _P]),
+    "fnx_advect_vel_workspace": (_S, [_I, _I, _I, _I, _I]),
+    "fnx_advect_vel": (_I, [_F, _P, _P, _P, _P] + _GRID + [_I, _I, _F, _P, _S, _P]),
+    "fnx_jacobi_workspace": (_S, [_I, _I, _I, _I, _I]),
+    "fnx_solve_linear_system_jacobi": (_I, [_P, _P, _P, _P] + _GRID + [_F, _I, ctypes.POINTER(_I), _P, _S, _P]),
+    "fnx_velocity_divergence": (_I, [_P, _P, _P] + _GRID + [_P]),
+    "fnx_velocity_update": (_I, [_P, _P, _P] + _GRID + [_P]),
+    "fnx_set_wall_bcs": (_I, [_P, _P] + _GRID + [_P]),
+    "fnx_add_buoyancy": (_I, [_P, _P, _P, ctypes.POINTER(_F), _F, _F] + _GRID + [_P]),
+    "fnx_add_gravity": (_I, [_P, _P, ctypes.POINTER(_F), _F] + _GRID + [_P]),
+    "fnx_flags_to_occupancy": (_I, [_P, _P, _S, _P]),
+    "fnx_set_const_vals": (_I, [_P, _P, _P, _S, _P]),
+    "fnx_empty_domain": (_I, [_P] + _GRID + [_I, _P]),
+    "fnx_get_centered": (_I, [_P, _P] + _GRID + [_P]),
+    "fnx_step_workspace": (_S, _GRID),
+    "fnx_step_advect_forces_div": (_I, [ctypes.POINTER(StepParams), _P, _P, _P, _P, _P, _P, _P, _P] + _GRID + [_P, _S, _P]),
+    "fnx_step_project_bcs": (_I, [_P, _P, _P, _P, _P] + _GRID + [_P]),
+    "fnx_step_jacobi": (_I, [ctypes.POINTER(StepParams), _P, _P, _P, _P, _P, _P, _P, _P, _P] + _GRID + [_P, _S, _P]),
+    "fnx_scale_std_workspace": (_S, [_I]),
+    "fnx_scale_std": (_I, [_P, _S, _I, _F, _P, _P, _S, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load the shared library (once).  Raises if it is missing: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is not built. Run `python -m fluidnet_cxx_b200.build` (needs nvcc); "
+                "fluidnet_cxx_b200 has no CPU/PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError = ABI mismatch, fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        for name in OPTIONAL_SIGNATURES:
+            if hasattr(lib, name):
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = OPTIONAL_SIGNATURES[name]
+        _lib = lib
+    return _lib
+
+
+OPTIONAL_SIGNATURES = {}
+
+
+def check(err, who=""):
+    if err != 0:
+        msg = load().fnx_last_error().decode("utf-8", "replace")
+        if err == -1:
+            raise RuntimeError(f"{who}: {msg}" if who else msg)
+        raise RuntimeError(f"{who}: fluidstep error {err}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("fluidnet_cxx_b200 runs on CUDA tensors only (no CPU fallback); got "
+                           f"{type(t).__name__} on {getattr(t, 'device', '?')}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"fluidnet_cxx_b200 expects float32 tensors, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError("fluidnet_cxx_b200 expects contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_of(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _Workspaces:
+    """Grow-only per-(device, tag) scratch buffers (nothing is allocated inside the C-ABI)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, device, tag, nbytes):
+        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+    def clear(self):
+        self._bufs.clear()
+
+
+workspaces = _Workspaces()
+
+
+def grid_of(flags):
+    """(B, D, H, W) of a 5-D (B, 1, D, H, W) tensor."""
+    B, _, D, H, W = flags.shape
+    return int(B), int(D), int(H), int(W)

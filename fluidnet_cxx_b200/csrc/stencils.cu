@@ -1,0 +1,713 @@
+// stencils.cu -- sm_100a kernels + C-ABI for the per-op entry points of the fluid path
+// (advection, forces, wall BCs, divergence, Jacobi, velocity update).  See include/fluidstep.h.
+// Compiled with -fmad=false (bit-exact operation order).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fluidstep.h"
+#include "advect_device.cuh"
+#include "fluid_common.cuh"
+#include "host_util.h"
+#include "stencil_device.cuh"
+
+namespace fnx {
+
+// thread -> cell mapping shared by all one-cell-per-thread kernels:
+// x = W (coalesced), y = D*H rows, z = batch
+constexpr int kBX = 64, kBY = 4;
+
+struct CellIdx {
+  int b, k, j, i;
+  long long o;  // offset inside one (D,H,W) volume
+};
+
+__device__ __forceinline__ bool cell_of(const Grid& g, CellIdx& c) {
+  c.i = blockIdx.x * blockDim.x + threadIdx.x;
+  int row = blockIdx.y * blockDim.y + threadIdx.y;
+  c.b = blockIdx.z;
+  if (c.i >= g.W || row >= g.D * g.H) return false;
+  c.k = row / g.H;
+  c.j = row - c.k * g.H;
+  c.o = (long long)row * g.W + c.i;
+  return true;
+}
+
+static inline dim3 cell_grid(const Grid& g) {
+  return dim3((g.W + kBX - 1) / kBX, (g.D * g.H + kBY - 1) / kBY, g.B);
+}
+static inline dim3 cell_block() { return dim3(kBX, kBY, 1); }
+
+// =====================================================================================
+// advectScalar (fluids_init.cpp:265-382)
+// =====================================================================================
+// pass 1 (SemiLagrangeEulerFluidNetSavePos :69-133): fwd value + the cell index of the traced
+// position (all MacCormackClampFluidNet :224-263 needs of it).
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_advect_scalar_fwd(Grid g, float mdt, const float* __restrict__ src, const float* __restrict__ U,
+                        const float* __restrict__ flags, int sample_outside, float* __restrict__ fwd,
+                        int* __restrict__ fidx) {
+  constexpr int NA = Z ? 3 : 2, NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  src += c.b * g.n; flags += c.b * g.n; U += (long long)c.b * NC * g.n;
+  fwd += c.b * g.n;
+  float val;
+  long long idx = c.o;
+  if (is_border<Z>(g, c.k, c.j, c.i)) {
+    val = 0.f;
+  } else if (__ldg(flags + c.o) != kFluid) {
+    val = __ldg(src + c.o);  // don't advect solid geometry
+  } else {
+    float pos[3] = {(float)c.i + 0.5f, (float)c.j + 0.5f, (float)c.k + 0.5f};
+    float vel[3], delta[3], back[3];
+    centered_vel<Z>(g, U, c.o, vel);
+#pragma unroll
+    for (int a = 0; a < NA; a++) delta[a] = mdt * vel[a];
+    line_trace<NA>(g, flags, pos, delta, back);
+    val = sample_outside ? sample_field<Z>(g, src, back) : sample_with_fluid<Z>(g, src, flags, back);
+    if (fidx) {
+      long long i0 = clampll(trunc_ll(back[0]), 0, g.W - 1);
+      long long j0 = clampll(trunc_ll(back[1]), 0, g.H - 1);
+      long long k0 = Z ? clampll(trunc_ll(back[2]), 0, g.D - 1) : 0;
+      idx = (k0 * g.H + j0) * g.W + i0;
+    }
+  }
+  fwd[c.o] = val;
+  if (fidx) fidx[c.b * g.n + c.o] = (int)idx;
+}
+
+// pass 2-4: backward trace on `fwd`, MacCormackCorrect :135-148, clamp :154-263
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_advect_scalar_bwd(Grid g, float dt, float half_strength, const float* __restrict__ src,
+                        const float* __restrict__ U, const float* __restrict__ flags,
+                        int sample_outside, const float* __restrict__ fwd,
+                        const int* __restrict__ fidx, float* __restrict__ dst) {
+  constexpr int NA = Z ? 3 : 2, NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  src += c.b * g.n; flags += c.b * g.n; U += (long long)c.b * NC * g.n;
+  fwd += c.b * g.n; fidx += c.b * g.n; dst += c.b * g.n;
+  const bool border = is_border<Z>(g, c.k, c.j, c.i);
+  const bool fluid = __ldg(flags + c.o) == kFluid;
+  const float fw = __ldg(fwd + c.o);
+  float v = fw;
+  if (fluid) {
+    float bwd = 0.f;  // border cells of the backward pass are zeroed (:354-363)
+    if (!border) {
+      float pos[3] = {(float)c.i + 0.5f, (float)c.j + 0.5f, (float)c.k + 0.5f};
+      float vel[3], delta[3], back[3];
+      centered_vel<Z>(g, U, c.o, vel);
+#pragma unroll
+      for (int a = 0; a < NA; a++) delta[a] = dt * vel[a];
+      line_trace<NA>(g, flags, pos, delta, back);
+      bwd = sample_outside ? sample_field<Z>(g, fwd, back) : sample_with_fluid<Z>(g, fwd, flags, back);
+    }
+    v = fw + half_strength * (__ldg(src + c.o) - bwd);
+  }
+  if (!border) {
+    // getClampBounds :154-222: 3x3(x3) neighbourhood of the forward-traced cell, fluid cells only
+    const int idx = __ldg(fidx + c.o);
+    const int k0 = Z ? (int)(idx / g.sz) : 0;
+    const int rem = (int)(idx - k0 * g.sz);
+    const int j0 = rem / g.W, i0 = rem - j0 * g.W;
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    bool any = false;
+#pragma unroll
+    for (int dk = (Z ? -1 : 0); dk <= (Z ? 1 : 0); dk++) {
+      const int kk = k0 + dk;
+      if (Z && (kk < 0 || kk >= g.D)) continue;
+#pragma unroll
+      for (int dj = -1; dj <= 1; dj++) {
+        const int jj = j0 + dj;
+        if (jj < 0 || jj >= g.H) continue;
+#pragma unroll
+        for (int di = -1; di <= 1; di++) {
+          const int ii = i0 + di;
+          if (ii < 0 || ii >= g.W) continue;
+          const long long q = ((long long)kk * g.H + jj) * g.W + ii;
+          if (sample_outside || __ldg(flags + q) == kFluid) {
+            const float s = __ldg(src + q);
+            mn = min_t(mn, s);
+            mx = max_t(mx, s);
+            any = true;
+          }
+        }
+      }
+    }
+    v = any ? max_t(mn, min_t(mx, v)) : fw;
+  }
+  dst[c.o] = v;
+}
+
+// =====================================================================================
+// advectVel (fluids_init.cpp:656-807)
+// =====================================================================================
+// SemiLagrangeEulerFluidNetMAC :388-451 (no line trace, Q2; solid-cell quirk Q1)
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_advect_vel_fwd(Grid g, float mdt, const float* __restrict__ orig, const float* __restrict__ U,
+                     const float* __restrict__ flags, float* __restrict__ fwd) {
+  constexpr int NA = Z ? 3 : 2, NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  flags += c.b * g.n; U += (long long)c.b * NC * g.n; orig += (long long)c.b * NC * g.n;
+  fwd += (long long)c.b * NC * g.n;
+  float out[3] = {0.f, 0.f, 0.f};
+  if (!is_border<Z>(g, c.k, c.j, c.i)) {
+    if (__ldg(flags + c.o) != kFluid) {
+      if (!Z) { out[0] = __ldg(orig + g.n + c.o); out[1] = 0.f; }  // Q1
+      else {
+#pragma unroll
+        for (int a = 0; a < NC; a++) out[a] = __ldg(orig + a * g.n + c.o);
+      }
+    } else {
+      const float pos[3] = {(float)c.i + 0.5f, (float)c.j + 0.5f, (float)c.k + 0.5f};
+#pragma unroll
+      for (int comp = 0; comp < NC; comp++) {
+        float v[3], p[3];
+        mac_vel<Z>(g, U, comp, c.o, v);
+#pragma unroll
+        for (int a = 0; a < NA; a++) p[a] = pos[a] + v[a] * mdt;
+        out[comp] = sample_field<Z>(g, orig + comp * g.n, p);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NC; a++) fwd[a * g.n + c.o] = out[a];
+}
+
+// backward pass on `fwd`, MacCormackCorrectMAC :453-498, MacCormackClampMAC :500-654
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_advect_vel_bwd(Grid g, float dt, float half_strength, const float* __restrict__ orig,
+                     const float* __restrict__ U, const float* __restrict__ flags,
+                     const float* __restrict__ fwd, float* __restrict__ dst) {
+  constexpr int NA = Z ? 3 : 2, NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  flags += c.b * g.n; U += (long long)c.b * NC * g.n; orig += (long long)c.b * NC * g.n;
+  fwd += (long long)c.b * NC * g.n; dst += (long long)c.b * NC * g.n;
+  if (is_border<Z>(g, c.k, c.j, c.i)) {
+#pragma unroll
+    for (int a = 0; a < NC; a++) dst[a * g.n + c.o] = 0.f;
+    return;
+  }
+  const bool solid = __ldg(flags + c.o) != kFluid;
+  const float pos[3] = {(float)c.i + 0.5f, (float)c.j + 0.5f, (float)c.k + 0.5f};
+  const float posi[3] = {(float)c.i, (float)c.j, (float)c.k};
+  const int idx[3] = {c.i, c.j, c.k};
+#pragma unroll
+  for (int comp = 0; comp < NC; comp++) {
+    float vel[3];
+    mac_vel<Z>(g, U, comp, c.o, vel);
+    const float fw = __ldg(fwd + comp * g.n + c.o);
+    // correction skipped when the cell or its lower neighbour along `comp` is not fluid
+    bool skip = solid;
+    if (!skip && idx[comp] > 0 && __ldg(flags + c.o - nb_off(g, comp)) != kFluid) skip = true;
+    float v = fw;
+    if (!skip) {
+      float p[3];
+#pragma unroll
+      for (int a = 0; a < NA; a++) p[a] = pos[a] + vel[a] * dt;
+      const float bwd = sample_field<Z>(g, fwd + comp * g.n, p);
+      v = fw + half_strength * (__ldg(orig + comp * g.n + c.o) - bwd);
+    }
+    // doClampComponentMAC: min/max of orig over the 2x2(x2) blocks at trunc(pos -/+ vel*dt), Q5
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    const float* oc = orig + comp * g.n;
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+      long long q[3] = {0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        const float va = vel[a] * dt;
+        q[a] = trunc_i32_x86(l == 0 ? posi[a] - va : posi[a] + va);
+      }
+      const long long i0 = clampll(q[0], 0, g.W - 2), j0 = clampll(q[1], 0, g.H - 2);
+      const long long k0 = Z ? clampll(q[2], 0, g.D - 2) : 0;
+      const float* b0 = oc + (k0 * g.H + j0) * g.W + i0;
+      // same visiting order as the reference: (j0,i0) (j0,i0+1) (j0+1,i0) (j0+1,i0+1)
+      float s;
+      s = __ldg(b0); mn = min_t(mn, s); mx = max_t(mx, s);
+      s = __ldg(b0 + 1); mn = min_t(mn, s); mx = max_t(mx, s);
+      s = __ldg(b0 + g.sy); mn = min_t(mn, s); mx = max_t(mx, s);
+      s = __ldg(b0 + g.sy + 1); mn = min_t(mn, s); mx = max_t(mx, s);
+      if (Z) {
+        const float* b1 = b0 + g.sz;
+        s = __ldg(b1); mn = min_t(mn, s); mx = max_t(mx, s);
+        s = __ldg(b1 + 1); mn = min_t(mn, s); mx = max_t(mx, s);
+        s = __ldg(b1 + g.sy); mn = min_t(mn, s); mx = max_t(mx, s);
+        s = __ldg(b1 + g.sy + 1); mn = min_t(mn, s); mx = max_t(mx, s);
+      }
+    }
+    dst[comp * g.n + c.o] = max_t(min_t(v, mx), mn);
+  }
+}
+
+// =====================================================================================
+// small stencils (per-op kernels of the lib.fluid surface)
+// =====================================================================================
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_add_buoyancy(Grid g, float* __restrict__ U, const float* __restrict__ flags,
+                   const float* __restrict__ density, float3 strength, float rho_star) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  if (is_border<Z>(g, c.k, c.j, c.i)) return;
+  flags += c.b * g.n; density += c.b * g.n; U += (long long)c.b * NC * g.n;
+  const float fc = __ldg(flags + c.o);
+  if (fc != kFluid) return;
+  const float rc = __ldg(density + c.o);
+  const float st[3] = {strength.x, strength.y, strength.z};
+#pragma unroll
+  for (int a = 0; a < NC; a++) {
+    const long long on = c.o - nb_off(g, a);
+    float* u = U + a * g.n + c.o;
+    *u = buoyancy_apply(*u, fc, __ldg(flags + on), rc, __ldg(density + on), st[a], rho_star);
+  }
+}
+
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_add_gravity(Grid g, float* __restrict__ U, const float* __restrict__ flags, float3 force) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  if (is_border<Z>(g, c.k, c.j, c.i)) return;
+  flags += c.b * g.n; U += (long long)c.b * NC * g.n;
+  const float fc = __ldg(flags + c.o);
+  const float fo[3] = {force.x, force.y, force.z};
+#pragma unroll
+  for (int a = 0; a < NC; a++) {
+    float* u = U + a * g.n + c.o;
+    *u = gravity_apply(*u, fc, __ldg(flags + c.o - nb_off(g, a)), fo[a]);
+  }
+}
+
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_set_wall_bcs(Grid g, float* __restrict__ U, const float* __restrict__ flags) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  flags += c.b * g.n; U += (long long)c.b * NC * g.n;
+  const float fc = __ldg(flags + c.o);
+  const int idx[3] = {c.i, c.j, c.k};
+#pragma unroll
+  for (int a = 0; a < NC; a++) {
+    const float fn = idx[a] <= 0 ? fc : __ldg(flags + c.o - nb_off(g, a));
+    float* u = U + a * g.n + c.o;
+    *u = wall_bcs_apply(*u, fc, fn);
+  }
+}
+
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_velocity_divergence(Grid g, const float* __restrict__ U, const float* __restrict__ flags,
+                          float* __restrict__ div) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  flags += c.b * g.n; U += (long long)c.b * NC * g.n; div += c.b * g.n;
+  float v = 0.f;
+  if (!is_border<Z>(g, c.k, c.j, c.i)) {
+    // (u_i - u_{i+1}) + v_j - v_{j+1} left to right (velocity_divergence.py:61-69)
+    v = __ldg(U + c.o) - __ldg(U + c.o + 1) + __ldg(U + g.n + c.o) - __ldg(U + g.n + c.o + g.sy);
+    if (Z) v = v + (__ldg(U + 2 * g.n + c.o) - __ldg(U + 2 * g.n + c.o + g.sz));
+  }
+  if (__ldg(flags + c.o) == kObstacle) v = 0.f;
+  div[c.o] = v;
+}
+
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_velocity_update(Grid g, const float* __restrict__ p, float* __restrict__ U,
+                      const float* __restrict__ flags) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  if (is_border<Z>(g, c.k, c.j, c.i)) return;
+  flags += c.b * g.n; p += c.b * g.n; U += (long long)c.b * NC * g.n;
+  const float fc = __ldg(flags + c.o), P = __ldg(p + c.o);
+#pragma unroll
+  for (int a = 0; a < NC; a++) {
+    const long long on = c.o - nb_off(g, a);
+    float* u = U + a * g.n + c.o;
+    *u = velocity_update_apply(*u, fc, __ldg(flags + on), P, __ldg(p + on));
+  }
+}
+
+__global__ void k_flags_to_occupancy(const float* __restrict__ flags, float* __restrict__ occ,
+                                     size_t count) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < count) occ[q] = occupancy_of(__ldg(flags + q));
+}
+
+__global__ void k_set_const_vals(float* __restrict__ x, const float* __restrict__ inv_mask,
+                                 const float* __restrict__ bc, size_t count) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < count) x[q] = const_vals_apply(x[q], __ldg(inv_mask + q), __ldg(bc + q));
+}
+
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY) k_empty_domain(Grid g, float* __restrict__ flags, int bnd) {
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  bool m = (c.i < bnd) | (c.i > g.W - 1 - bnd) | (c.j < bnd) | (c.j > g.H - 1 - bnd);
+  if (Z) m = m | (c.k < bnd) | (c.k > g.D - 1 - bnd);
+  flags[c.b * g.n + c.o] = m ? kObstacle : kFluid;
+}
+
+// grid.py:7-30 getCentered (output helper: last row/column/plane stay 0)
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_get_centered(Grid g, const float* __restrict__ U, float* __restrict__ out) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  U += (long long)c.b * NC * g.n; out += (long long)c.b * 3 * g.n;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (c.i < g.W - 1) x = 0.5f * (__ldg(U + c.o) + __ldg(U + c.o + 1));
+  if (c.j < g.H - 1) y = 0.5f * (__ldg(U + g.n + c.o) + __ldg(U + g.n + c.o + g.sy));
+  if (Z && c.k < g.D - 1) z = 0.5f * (__ldg(U + 2 * g.n + c.o) + __ldg(U + 2 * g.n + c.o + g.sz));
+  out[c.o] = x; out[g.n + c.o] = y; out[2 * g.n + c.o] = z;
+}
+
+// =====================================================================================
+// Jacobi (fluids_init.cpp:809-1004), one iteration per launch (generic path: p_tol > 0, 3-D, ...)
+// =====================================================================================
+struct JacobiCtrl {
+  int done;        // set when residual < p_tol
+  int iters;       // iterations executed so far
+  float residual;  // max_b ||p - p_prev||_2 of the last executed iteration
+  int pad;
+};
+
+template <bool Z, bool FIRST, bool RESID>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_jacobi_iter(Grid g, const float* __restrict__ flags, const float* __restrict__ div,
+                  const float* __restrict__ prev, float* __restrict__ cur, double* __restrict__ ssq,
+                  const JacobiCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->done) return;
+  CellIdx c;
+  const bool valid = cell_of(g, c);
+  float d2 = 0.f;
+  if (valid) {
+    flags += c.b * g.n; div += c.b * g.n; cur += c.b * g.n;
+    if (!FIRST) prev += c.b * g.n;
+    float pn = 0.f;
+    const float pC = FIRST ? 0.f : __ldg(prev + c.o);
+    if (!(is_border<Z>(g, c.k, c.j, c.i) || __ldg(flags + c.o) == kObstacle)) {
+      float s;
+      if (FIRST) {
+        s = __ldg(div + c.o);  // p0 = 0: every neighbour term is 0
+      } else {
+        // Neumann: an Obstacle neighbour contributes the centre value (:895-943)
+        const float p1 = __ldg(flags + c.o - 1) == kObstacle ? pC : __ldg(prev + c.o - 1);
+        const float p2 = __ldg(flags + c.o + 1) == kObstacle ? pC : __ldg(prev + c.o + 1);
+        const float p3 = __ldg(flags + c.o - g.sy) == kObstacle ? pC : __ldg(prev + c.o - g.sy);
+        const float p4 = __ldg(flags + c.o + g.sy) == kObstacle ? pC : __ldg(prev + c.o + g.sy);
+        s = p1 + p2 + p3 + p4;
+        if (Z) {
+          const float p5 = __ldg(flags + c.o - g.sz) == kObstacle ? pC : __ldg(prev + c.o - g.sz);
+          const float p6 = __ldg(flags + c.o + g.sz) == kObstacle ? pC : __ldg(prev + c.o + g.sz);
+          s = s + p5 + p6;
+        }
+        s = s + __ldg(div + c.o);
+      }
+      pn = Z ? s / 6.f : s * 0.25f;  // /4 is exact as *0.25
+    }
+    cur[c.o] = pn;
+    const float d = pn - pC;
+    d2 = d * d;
+  }
+  if (RESID) {
+    // block reduction of sum((p - p_prev)^2) in double, one atomic per block
+    double acc = (double)d2;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    __shared__ double wsum[kBX * kBY / 32];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if ((tid & 31) == 0) wsum[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBX * kBY / 32; w++) t += wsum[w];
+      atomicAdd(ssq + blockIdx.z, t);
+    }
+  }
+}
+
+// one thread: fold ssq[b] into the residual, test the tolerance, re-arm ssq
+__global__ void k_jacobi_ctrl(JacobiCtrl* ctrl, double* ssq, int B, float p_tol, int iter_index,
+                              float* residual_out) {
+  if (ctrl->done) return;
+  float r = 0.f;
+  for (int b = 0; b < B; b++) {
+    float rb = (float)sqrt(ssq[b]);
+    if (rb > r) r = rb;
+    ssq[b] = 0.0;
+  }
+  ctrl->residual = r;
+  ctrl->iters = iter_index + 1;
+  if (residual_out) *residual_out = r;
+  if (r < p_tol) ctrl->done = 1;
+}
+
+}  // namespace fnx
+
+// =====================================================================================
+// C-ABI
+// =====================================================================================
+using namespace fnx;
+
+static int check_grid(int B, int D, int H, int W, int is3d, const char* who) {
+  if (B < 1 || D < 1 || H < 2 || W < 2 || (is3d && D < 2) || (!is3d && D != 1)) {
+    return fnx_set_error(FNX_ERR_ARG, "%s: unsupported grid B=%d D=%d H=%d W=%d is3d=%d", who, B, D, H, W, is3d);
+  }
+  if ((long long)D * H * W >= (1LL << 31)) return fnx_set_error(FNX_ERR_ARG, "%s: grid too large for int32 cell index", who);
+  return FNX_OK;
+}
+
+#define FNX_LAUNCH_CHECK(who, nlaunch)                                              \
+  do {                                                                              \
+    fnx_count_launches(nlaunch);                                                    \
+    cudaError_t e_ = cudaGetLastError();                                            \
+    if (e_ != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define FNX_DISPATCH_3D(is3d, KERNEL, ...)            \
+  do {                                                \
+    if (is3d) KERNEL<true> __VA_ARGS__;               \
+    else KERNEL<false> __VA_ARGS__;                   \
+  } while (0)
+
+template <bool Z>
+static void launch_jacobi_iter(const Grid& g, bool first, bool resid, const float* flags, const float* div,
+                               const float* prev, float* cur, double* ssq, const JacobiCtrl* ctrl,
+                               cudaStream_t st) {
+  dim3 gr = cell_grid(g), bl = cell_block();
+  if (first) {
+    if (resid) k_jacobi_iter<Z, true, true><<<gr, bl, 0, st>>>(g, flags, div, prev, cur, ssq, ctrl);
+    else k_jacobi_iter<Z, true, false><<<gr, bl, 0, st>>>(g, flags, div, prev, cur, ssq, ctrl);
+  } else {
+    if (resid) k_jacobi_iter<Z, false, true><<<gr, bl, 0, st>>>(g, flags, div, prev, cur, ssq, ctrl);
+    else k_jacobi_iter<Z, false, false><<<gr, bl, 0, st>>>(g, flags, div, prev, cur, ssq, ctrl);
+  }
+}
+
+int fnx_jacobi_2d_blocked(const float* flags, const float* div, float* p, float* scratch, double* ssq,
+                          int B, int H, int W, int max_iter, cudaStream_t st);  // jacobi_blocked.cu
+
+
+extern "C" {
+
+size_t fnx_advect_scalar_workspace(int B, int D, int H, int W) {
+  size_t n = (size_t)B * D * H * W;
+  return n * sizeof(float) + n * sizeof(int);
+}
+
+int fnx_advect_scalar(float dt, const float* src, const float* U, const float* flags, float* dst, int B,
+                      int D, int H, int W, int is3d, int method, int boundary_width,
+                      int sample_outside_fluid, float maccormack_strength, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "advect_scalar")) return e;
+  if (boundary_width != 1) return fnx_set_error(FNX_ERR_ARG, "advect_scalar: boundary_width must be 1 (Q4)");
+  if (method != FNX_METHOD_EULER && method != FNX_METHOD_MACCORMACK)
+    return fnx_set_error(FNX_ERR_ARG, "advect_scalar: No defined method for MacCormackClamp");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = make_grid(B, D, H, W);
+  if (method == FNX_METHOD_EULER) {
+    FNX_DISPATCH_3D(is3d, k_advect_scalar_fwd, <<<cell_grid(g), cell_block(), 0, st>>>(
+        g, -dt, src, U, flags, sample_outside_fluid, dst, nullptr));
+    FNX_LAUNCH_CHECK("advect_scalar", 1);
+    return FNX_OK;
+  }
+  if (workspace_bytes < fnx_advect_scalar_workspace(B, D, H, W) || !workspace)
+    return fnx_set_error(FNX_ERR_WORKSPACE, "advect_scalar: workspace too small");
+  float* fwd = (float*)workspace;
+  int* fidx = (int*)(fwd + (size_t)B * g.n);
+  FNX_DISPATCH_3D(is3d, k_advect_scalar_fwd, <<<cell_grid(g), cell_block(), 0, st>>>(
+      g, -dt, src, U, flags, sample_outside_fluid, fwd, fidx));
+  FNX_DISPATCH_3D(is3d, k_advect_scalar_bwd, <<<cell_grid(g), cell_block(), 0, st>>>(
+      g, dt, maccormack_strength * 0.5f, src, U, flags, sample_outside_fluid, fwd, fidx, dst));
+  FNX_LAUNCH_CHECK("advect_scalar", 2);
+  return FNX_OK;
+}
+
+size_t fnx_advect_vel_workspace(int B, int D, int H, int W, int is3d) {
+  return (size_t)B * D * H * W * (is3d ? 3 : 2) * sizeof(float);
+}
+
+int fnx_advect_vel(float dt, const float* orig, const float* U, const float* flags, float* dst, int B,
+                   int D, int H, int W, int is3d, int method, int boundary_width,
+                   float maccormack_strength, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "advect_vel")) return e;
+  if (boundary_width != 1) return fnx_set_error(FNX_ERR_ARG, "advect_vel: boundary_width must be 1 (Q4)");
+  if (method != FNX_METHOD_EULER && method != FNX_METHOD_MACCORMACK)
+    return fnx_set_error(FNX_ERR_ARG, "advect_vel: No defined method for MacCormackClamp");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = make_grid(B, D, H, W);
+  if (method == FNX_METHOD_EULER) {
+    FNX_DISPATCH_3D(is3d, k_advect_vel_fwd, <<<cell_grid(g), cell_block(), 0, st>>>(g, -dt, orig, U, flags, dst));
+    FNX_LAUNCH_CHECK("advect_vel", 1);
+    return FNX_OK;
+  }
+  if (workspace_bytes < fnx_advect_vel_workspace(B, D, H, W, is3d) || !workspace)
+    return fnx_set_error(FNX_ERR_WORKSPACE, "advect_vel: workspace too small");
+  float* fwd = (float*)workspace;
+  FNX_DISPATCH_3D(is3d, k_advect_vel_fwd, <<<cell_grid(g), cell_block(), 0, st>>>(g, -dt, orig, U, flags, fwd));
+  FNX_DISPATCH_3D(is3d, k_advect_vel_bwd, <<<cell_grid(g), cell_block(), 0, st>>>(
+      g, dt, maccormack_strength * 0.5f, orig, U, flags, fwd, dst));
+  FNX_LAUNCH_CHECK("advect_vel", 2);
+  return FNX_OK;
+}
+
+int fnx_velocity_divergence(const float* U, const float* flags, float* div, int B, int D, int H, int W,
+                            int is3d, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "velocity_divergence")) return e;
+  Grid g = make_grid(B, D, H, W);
+  FNX_DISPATCH_3D(is3d, k_velocity_divergence, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, U, flags, div));
+  FNX_LAUNCH_CHECK("velocity_divergence", 1);
+  return FNX_OK;
+}
+
+int fnx_velocity_update(const float* pressure, float* U, const float* flags, int B, int D, int H, int W,
+                        int is3d, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "velocity_update")) return e;
+  Grid g = make_grid(B, D, H, W);
+  FNX_DISPATCH_3D(is3d, k_velocity_update, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, pressure, U, flags));
+  FNX_LAUNCH_CHECK("velocity_update", 1);
+  return FNX_OK;
+}
+
+int fnx_set_wall_bcs(float* U, const float* flags, int B, int D, int H, int W, int is3d, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "set_wall_bcs")) return e;
+  Grid g = make_grid(B, D, H, W);
+  FNX_DISPATCH_3D(is3d, k_set_wall_bcs, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, U, flags));
+  FNX_LAUNCH_CHECK("set_wall_bcs", 1);
+  return FNX_OK;
+}
+
+int fnx_add_buoyancy(float* U, const float* flags, const float* density, const float* gravity3,
+                     float rho_star, float dt, int B, int D, int H, int W, int is3d, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "add_buoyancy")) return e;
+  Grid g = make_grid(B, D, H, W);
+  // strength = gravity * dt as one fp32 product per component (source_terms.py:70)
+  float3 s = make_float3(gravity3[0] * dt, gravity3[1] * dt, gravity3[2] * dt);
+  FNX_DISPATCH_3D(is3d, k_add_buoyancy, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, U, flags, density, s, rho_star));
+  FNX_LAUNCH_CHECK("add_buoyancy", 1);
+  return FNX_OK;
+}
+
+int fnx_add_gravity(float* U, const float* flags, const float* gravity3, float dt, int B, int D, int H,
+                    int W, int is3d, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "add_gravity")) return e;
+  Grid g = make_grid(B, D, H, W);
+  float3 f = make_float3(gravity3[0] * dt, gravity3[1] * dt, gravity3[2] * dt);
+  FNX_DISPATCH_3D(is3d, k_add_gravity, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, U, flags, f));
+  FNX_LAUNCH_CHECK("add_gravity", 1);
+  return FNX_OK;
+}
+
+int fnx_flags_to_occupancy(const float* flags, float* occupancy, size_t count, void* stream) {
+  if (count == 0) return FNX_OK;
+  k_flags_to_occupancy<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(flags, occupancy, count);
+  FNX_LAUNCH_CHECK("flags_to_occupancy", 1);
+  return FNX_OK;
+}
+
+int fnx_set_const_vals(float* x, const float* inv_mask, const float* bc, size_t count, void* stream) {
+  if (count == 0) return FNX_OK;
+  k_set_const_vals<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, inv_mask, bc, count);
+  FNX_LAUNCH_CHECK("set_const_vals", 1);
+  return FNX_OK;
+}
+
+int fnx_empty_domain(float* flags, int B, int D, int H, int W, int is3d, int bnd, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "empty_domain")) return e;
+  if (bnd < 1) return fnx_set_error(FNX_ERR_ARG, "empty_domain: Boundary width must be greater than zero!");
+  Grid g = make_grid(B, D, H, W);
+  FNX_DISPATCH_3D(is3d, k_empty_domain, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, flags, bnd));
+  FNX_LAUNCH_CHECK("empty_domain", 1);
+  return FNX_OK;
+}
+
+int fnx_get_centered(const float* U, float* out, int B, int D, int H, int W, int is3d, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "get_centered")) return e;
+  Grid g = make_grid(B, D, H, W);
+  FNX_DISPATCH_3D(is3d, k_get_centered, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, U, out));
+  FNX_LAUNCH_CHECK("get_centered", 1);
+  return FNX_OK;
+}
+
+// ---- Jacobi ---------------------------------------------------------------------------
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t fnx_jacobi_workspace(int B, int D, int H, int W, int max_iter) {
+  (void)max_iter;
+  size_t n = (size_t)B * D * H * W;
+  return align256(n * sizeof(float)) + align256(sizeof(JacobiCtrl)) + align256((size_t)B * sizeof(double));
+}
+
+int fnx_solve_linear_system_jacobi(const float* flags, const float* div, float* p, float* residual, int B,
+                                   int D, int H, int W, int is3d, float p_tol, int max_iter, int* iters_run,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "solve_linear_system")) return e;
+  if (max_iter < 1) return fnx_set_error(FNX_ERR_ARG, "solve_linear_system: At least 1 iteration of the solver is needed.");
+  if (!workspace || workspace_bytes < fnx_jacobi_workspace(B, D, H, W, max_iter))
+    return fnx_set_error(FNX_ERR_WORKSPACE, "solve_linear_system: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = make_grid(B, D, H, W);
+  const size_t n = (size_t)B * g.n;
+  char* ws = (char*)workspace;
+  float* scratch = (float*)ws;
+  JacobiCtrl* ctrl = (JacobiCtrl*)(ws + align256(n * sizeof(float)));
+  double* ssq = (double*)((char*)ctrl + align256(sizeof(JacobiCtrl)));
+  cudaError_t ce = cudaMemsetAsync(ctrl, 0, align256(sizeof(JacobiCtrl)) + align256((size_t)B * sizeof(double)), st);
+  if (ce != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "solve_linear_system: %s", cudaGetErrorString(ce));
+
+  const bool tol = p_tol > 0.f;
+  if (!tol && !is3d) {
+    // fixed iteration count, 2-D: temporally blocked shared-memory kernel
+    int e = fnx_jacobi_2d_blocked(flags, div, p, scratch, ssq, B, H, W, max_iter, st);
+    if (e) return e;
+    k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, max_iter - 1, residual);
+    FNX_LAUNCH_CHECK("solve_linear_system", 1);
+    if (iters_run) *iters_run = max_iter;
+    return FNX_OK;
+  }
+  // buffer written by iteration `it`; the last possible iteration lands in p
+  auto wbuf = [&](int it) { return ((max_iter - 1 - it) % 2 == 0) ? p : scratch; };
+  int executed = max_iter;
+  for (int it = 0; it < max_iter; it++) {
+    const bool resid = tol || it == max_iter - 1;
+    float* cur = wbuf(it);
+    const float* prev = it == 0 ? nullptr : wbuf(it - 1);
+    if (is3d) launch_jacobi_iter<true>(g, it == 0, resid, flags, div, prev, cur, ssq, tol ? ctrl : nullptr, st);
+    else launch_jacobi_iter<false>(g, it == 0, resid, flags, div, prev, cur, ssq, tol ? ctrl : nullptr, st);
+    if (resid) k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, it, residual);
+    fnx_count_launches(resid ? 2 : 1);
+    if (tol && ((it & 7) == 7 || it == max_iter - 1)) {
+      JacobiCtrl h;
+      ce = cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "solve_linear_system: %s", cudaGetErrorString(ce));
+      if (h.done || it == max_iter - 1) { executed = h.iters; break; }
+    }
+  }
+  FNX_LAUNCH_CHECK("solve_linear_system", 0);
+  if (tol && wbuf(executed - 1) != p) {
+    ce = cudaMemcpyAsync(p, scratch, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "solve_linear_system: %s", cudaGetErrorString(ce));
+  }
+  if (iters_run) *iters_run = executed;
+  return FNX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,5 @@
+"""Reference-facing package: the names `pytorch/lib/__init__.py:1-7` exports that the
+per-timestep path uses.  Import as `fluidnet_cxx_b200.lib`, or as top-level `lib` through
+`fluidnet_cxx_b200.compat.install()` so the reference drivers run unchanged."""
+from . import fluid
+from .simulate import simulate, setConstVals

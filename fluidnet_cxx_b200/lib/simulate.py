@@ -1,0 +1,243 @@
+"""Per-timestep orchestrator: same call, same state transitions as the reference
+`lib.simulate` (pytorch/lib/simulate.py:28-171), with the standard sequence routed through the
+fused sm_100a entry points.
+
+    simulate(mconf, batch_dict, net, sim_method, output_div=False)
+
+batch_dict {'p','U','flags','density', [UBC, UBCInvMask, densityBC, densityBCInvMask]} is
+advanced in place (the dict entries are rebound to the new tensors, as in the reference).
+Sequence: advectScalar -> advectVelocity -> setConstVals -> addBuoyancy / addGravity ->
+[setWallBcs] -> setConstVals -> (Jacobi | net) -> [velocityUpdate -> setWallBcs] -> setConstVals.
+
+Also accepts the legacy 5-argument form `simulate(conf, mconf, batch_dict, net, sim_method)` that
+pytorch/rayleighTaylor.py:240 still uses (SURVEY.md hazard H3).
+"""
+import ctypes
+
+import torch
+
+from .. import _native as N
+from . import fluid
+
+
+_stage_hook = None
+
+
+def set_stage_hook(fn):
+    """fn(stage_name, 'begin'|'end') is called around the pressure stage of the fused step
+    (bench.py records CUDA events there); None restores the single-call path."""
+    global _stage_hook
+    _stage_hook = fn
+
+
+def setConstVals(batch_dict, p, U, flags, density):
+    """Apply the imposed-value masks (simulate.py:4-26): x = x*InvMask + BC, and publish clones."""
+    if ('UBCInvMask' in batch_dict) and ('UBC' in batch_dict):
+        fluid.setConstVals(U, batch_dict['UBCInvMask'], batch_dict['UBC'])
+        batch_dict['U'] = U.clone()
+    if ('densityBCInvMask' in batch_dict) and ('densityBC' in batch_dict):
+        fluid.setConstVals(density, batch_dict['densityBCInvMask'], batch_dict['densityBC'])
+        batch_dict['density'] = density.clone()
+
+
+def _gravity(mconf, scale):
+    g = mconf['gravityVec']
+    # the reference builds an fp32 tensor and multiplies it by -scale in fp32 (simulate.py:101-105)
+    t = torch.tensor([g['x'], g['y'], g['z']], dtype=torch.float32)
+    t.mul_(-scale)
+    return t
+
+
+def _periodic(mconf):
+    return 'periodic-x' in mconf and 'periodic-y' in mconf
+
+
+def _wall_bcs_with_seam(U, flags, mconf):
+    """setWallBcs plus the periodic seam copy of simulate.py:120-128."""
+    per = _periodic(mconf)
+    if per:
+        U_temp = U.clone()
+    U = fluid.setWallBcs(U, flags)
+    if per:
+        if mconf['periodic-x']:
+            U[:, 1, :, :, 1] = U_temp[:, 1, :, :, U.size(4) - 1]
+        if mconf['periodic-y']:
+            U[:, 0, :, 1] = U_temp[:, 0, :, U.size(3) - 1]
+    return U
+
+
+def _step_params(mconf, dt, jacobi_iters=0):
+    prm = N.StepParams()
+    prm.dt = dt
+    prm.maccormack_strength = float(mconf['maccormackStrength'])
+    prm.sample_outside_fluid = int(bool(mconf['sampleOutsideFluid']))
+    bs, gs = mconf['buoyancyScale'], mconf['gravityScale']
+    prm.use_buoyancy = int(bs > 0)
+    prm.use_gravity = int(gs > 0)
+    if bs > 0:
+        prm.buoyancy3 = (ctypes.c_float * 3)(*_gravity(mconf, bs).tolist())
+    if gs > 0:
+        prm.gravity3 = (ctypes.c_float * 3)(*_gravity(mconf, gs).tolist())
+    prm.rho_star = float(mconf['operatingDensity']) if bs > 0 else 0.0
+    prm.jacobi_iters = int(jacobi_iters)
+    return prm
+
+
+def _fusable(mconf, batch_dict, sim_method, output_div=False):
+    """The fused entry points cover the inviscid density-carrying step of both drivers."""
+    if 'density' not in batch_dict or 'flags_stick' in batch_dict:
+        return False
+    if mconf['viscosity'] != 0 or mconf.get('correctScalar', False):
+        return False
+    has_u = ('UBCInvMask' in batch_dict) and ('UBC' in batch_dict)
+    has_r = ('densityBCInvMask' in batch_dict) and ('densityBC' in batch_dict)
+    if has_u != has_r and (('UBC' in batch_dict) != ('UBCInvMask' in batch_dict)):
+        return False
+    if sim_method != 'jacobi' or output_div:
+        return False
+    if sim_method == 'jacobi':
+        if _periodic(mconf) and (mconf['periodic-x'] or mconf['periodic-y']):
+            return False
+        if mconf['pTol'] > 0 or mconf['jacobiIter'] < 1:
+            return False
+    return all(batch_dict[k].is_cuda and batch_dict[k].is_contiguous() and batch_dict[k].dtype == torch.float32
+               for k in ('p', 'U', 'flags', 'density'))
+
+
+def _masks(batch_dict):
+    has_u = ('UBCInvMask' in batch_dict) and ('UBC' in batch_dict)
+    has_r = ('densityBCInvMask' in batch_dict) and ('densityBC' in batch_dict)
+    return (batch_dict['UBC'] if has_u else None, batch_dict['UBCInvMask'] if has_u else None,
+            batch_dict['densityBC'] if has_r else None, batch_dict['densityBCInvMask'] if has_r else None)
+
+
+def simulate(*args, **kwargs):
+    if len(args) >= 3 and isinstance(args[2], dict) and isinstance(args[1], dict):
+        args = args[1:]           # legacy (conf, mconf, batch_dict, net, sim_method)
+    return _simulate(*args, **kwargs)
+
+
+def _simulate(mconf, batch_dict, net, sim_method, output_div=False):
+    assert sim_method == 'convnet' or sim_method == 'jacobi', \
+        'Simulation method not supported. Choose either convnet or jacobi.'
+    dt = float(mconf['dt'])
+    assert mconf['viscosity'] >= 0, 'Viscosity must be positive'
+    if _fusable(mconf, batch_dict, sim_method, output_div):
+        return _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div)
+    return _simulate_ops(mconf, batch_dict, net, sim_method, dt, output_div)
+
+
+# ---------------------------------------------------------------------------------------------
+def _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div):
+    lib = N.load()
+    flags = batch_dict['flags']
+    # new tensors for the new state (the reference never mutates the caller's old U / density)
+    U = batch_dict['U'].clone()
+    density = batch_dict['density'].clone()
+    B, D, H, W = N.grid_of(flags)
+    is3d = int(U.size(1) == 3)
+    UBC, UBCInv, rBC, rBCInv = _masks(batch_dict)
+    ws = N.workspaces.get(U.device, "step", lib.fnx_step_workspace(B, D, H, W, is3d))
+    st = N.stream_of(U)
+    prm = _step_params(mconf, dt, mconf['jacobiIter'])
+    p = torch.empty_like(flags)
+    residual = torch.empty((), dtype=torch.float32, device=U.device)
+    if _stage_hook is None:
+        # one C-ABI call for the whole step
+        N.check(lib.fnx_step_jacobi(ctypes.byref(prm), N.ptr(density), N.ptr(U), N.ptr(flags), N.ptr(p),
+                                    residual.data_ptr(), N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv),
+                                    B, D, H, W, is3d, ws.data_ptr(), ws.numel(), st), "simulate")
+    else:
+        # same kernels, issued stage by stage so a profiler hook can bracket the pressure solve
+        div = torch.empty_like(flags)
+        N.check(lib.fnx_step_advect_forces_div(ctypes.byref(prm), N.ptr(density), N.ptr(U), N.ptr(flags),
+                                               N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), N.ptr(div),
+                                               B, D, H, W, is3d, ws.data_ptr(), ws.numel(), st), "simulate")
+        wj = N.workspaces.get(U.device, "jacobi", lib.fnx_jacobi_workspace(B, D, H, W, prm.jacobi_iters))
+        _stage_hook("pressure", "begin")
+        N.check(lib.fnx_solve_linear_system_jacobi(N.ptr(flags), N.ptr(div), N.ptr(p), residual.data_ptr(), B, D, H,
+                                                   W, is3d, 0.0, prm.jacobi_iters, None, wj.data_ptr(), wj.numel(),
+                                                   st), "simulate")
+        _stage_hook("pressure", "end")
+        N.check(lib.fnx_step_project_bcs(N.ptr(p), N.ptr(U), N.ptr(flags), N.ptr(UBC), N.ptr(UBCInv), B, D, H, W,
+                                         is3d, st), "simulate")
+        if rBC is not None:
+            fluid.setConstVals(density, rBCInv, rBC)
+    batch_dict['U'], batch_dict['density'], batch_dict['p'] = U, density, p
+
+
+def _simulate_ops(mconf, batch_dict, net, sim_method, dt, output_div):
+    """Operator-by-operator sequence, line for line the order of simulate.py:28-171."""
+    maccormackStrength = mconf['maccormackStrength']
+    sampleOutsideFluid = mconf['sampleOutsideFluid']
+    buoyancyScale = mconf['buoyancyScale']
+    gravityScale = mconf['gravityScale']
+    viscosity = mconf['viscosity']
+
+    p = batch_dict['p']
+    U = batch_dict['U']
+    flags = batch_dict['flags']
+    stick = 'flags_stick' in batch_dict
+    if stick:
+        flags_stick = batch_dict['flags_stick']
+
+    if viscosity > 0:
+        orig = U.clone()
+        fluid.addViscosity(dt, orig, flags, viscosity)
+
+    if 'density' in batch_dict:
+        density = batch_dict['density']
+        density = fluid.advectScalar(dt, density, U, flags, method="maccormackFluidNet", boundary_width=1,
+                                     sample_outside_fluid=sampleOutsideFluid,
+                                     maccormack_strength=maccormackStrength)
+        if mconf.get('correctScalar', False):
+            div = fluid.velocityDivergence(U, flags)
+            fluid.correctScalar(dt, density, div, flags)
+    else:
+        density = torch.zeros_like(flags)
+
+    if viscosity == 0:
+        U = fluid.advectVelocity(dt=dt, orig=U, U=U, flags=flags, method="maccormackFluidNet",
+                                 boundary_width=1, maccormack_strength=maccormackStrength)
+    else:
+        U = fluid.advectVelocity(dt=dt, orig=orig, U=U, flags=flags, method="maccormackFluidNet",
+                                 boundary_width=1, maccormack_strength=maccormackStrength)
+
+    setConstVals(batch_dict, p, U, flags, density)
+
+    if 'density' in batch_dict:
+        if buoyancyScale > 0:
+            U = fluid.addBuoyancy(U, flags, density, _gravity(mconf, buoyancyScale), mconf['operatingDensity'], dt)
+        if gravityScale > 0:
+            U = fluid.addGravity(U, flags, _gravity(mconf, gravityScale), dt)
+
+    if output_div:
+        return
+
+    if sim_method != 'convnet':
+        U = _wall_bcs_with_seam(U, flags, mconf)
+    elif stick:
+        fluid.setWallBcsStick(U, flags, flags_stick)
+
+    setConstVals(batch_dict, p, U, flags, density)
+
+    if sim_method == 'convnet':
+        net.eval()
+        data = torch.cat((p, U, flags, density), 1)
+        p, U = net(data)
+    else:
+        div = fluid.velocityDivergence(U, flags)
+        is3D = (U.size(2) > 1)
+        p, residual = fluid.solveLinearSystemJacobi(flags=flags, div=div, is_3d=is3D, p_tol=mconf['pTol'],
+                                                    max_iter=mconf['jacobiIter'])
+        fluid.velocityUpdate(pressure=p, U=U, flags=flags)
+
+    if sim_method != 'convnet':
+        U = _wall_bcs_with_seam(U, flags, mconf)
+    elif stick:
+        fluid.setWallBcsStick(U, flags, flags_stick)
+
+    setConstVals(batch_dict, p, U, flags, density)
+    batch_dict['U'] = U
+    batch_dict['density'] = density
+    batch_dict['p'] = p

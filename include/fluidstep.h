@@ -1,0 +1,151 @@
+/*
+ * fluidstep.h -- C-ABI of the B200-native per-timestep fluid path.
+ *
+ * This is the drop-in boundary: the entry points below are what the reference's
+ * FFI for this path binds.  In jolibrain/fluidnet_cxx that FFI is the pybind
+ * module `fluidnet_cpp` (pytorch/lib/fluid/cpp/fluids_init.cpp:1009-1014) plus the
+ * pure-torch stencil functions of `lib.fluid` (pytorch/lib/fluid/__init__.py:1-14).
+ * Each function cites the reference interface it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to a contiguous fp32 tensor in the
+ *    reference layout (B, C, D, H, W); flags are fp32-encoded Manta cell types
+ *    (pytorch/lib/fluid/cell_type.py:5-14);
+ *  - `is3d` selects 2 (D must be 1) or 3 velocity channels;
+ *  - `stream` is a cudaStream_t (0 = legacy default stream); all work is
+ *    enqueued on it and the call returns without synchronising unless stated;
+ *  - nothing is allocated inside: outputs and workspaces are caller-provided
+ *    (`fnx_*_workspace` returns the byte size a call needs);
+ *  - return value 0 = ok, negative = error (see fnx_last_error()).
+ *  - in-place ops mutate `U` exactly as the reference's Python ops do.
+ *
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef FLUIDSTEP_H_
+#define FLUIDSTEP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNX_OK 0
+#define FNX_ERR_ARG (-1)   /* bad shape / unsupported argument (reference: AssertionError / AT_ERROR) */
+#define FNX_ERR_CUDA (-2)  /* CUDA runtime error, message in fnx_last_error() */
+#define FNX_ERR_WORKSPACE (-3)
+
+#define FNX_METHOD_EULER 0      /* 'eulerFluidNet'      advect_type.cpp:5-16 */
+#define FNX_METHOD_MACCORMACK 1 /* 'maccormackFluidNet' */
+
+/* library / build information */
+const char *fnx_last_error(void);
+const char *fnx_build_info(void);  /* "sm_100a ..." */
+int fnx_abi_version(void);
+/* number of kernels this library has launched so far in this process (monotonic) */
+long long fnx_launch_count(void);
+
+/* ---- advection: fluidnet_cpp.advect_scalar / advect_vel ------------------- */
+/* fluids_init.h:73-100 / fluids_init.cpp:265-382  (wrapper advection.py:14-66).
+ * dst (B,1,D,H,W) is a new tensor; src, U, flags are not modified. */
+size_t fnx_advect_scalar_workspace(int B, int D, int H, int W);
+int fnx_advect_scalar(float dt, const float *src, const float *U, const float *flags, float *dst,
+                      int B, int D, int H, int W, int is3d, int method, int boundary_width,
+                      int sample_outside_fluid, float maccormack_strength, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* fluids_init.h:102-124 / fluids_init.cpp:656-807 (wrapper advection.py:68-118).
+ * dst (B,2|3,D,H,W) is a new tensor; orig may alias U (self-advection). */
+size_t fnx_advect_vel_workspace(int B, int D, int H, int W, int is3d);
+int fnx_advect_vel(float dt, const float *orig, const float *U, const float *flags, float *dst,
+                   int B, int D, int H, int W, int is3d, int method, int boundary_width,
+                   float maccormack_strength, void *workspace, size_t workspace_bytes,
+                   void *stream);
+
+/* ---- pressure solve: fluidnet_cpp.solve_linear_system ---------------------- */
+/* fluids_init.h:126-142 / fluids_init.cpp:809-1004 (wrapper solve_linear_sys.py:4-40).
+ * p (B,1,D,H,W) out (p0 = 0 as in the reference); residual: 1 device float out.
+ * p_tol > 0 makes the call poll a device flag every few iterations (the
+ * reference syncs every iteration); p_tol <= 0 never synchronises.
+ * `iters_run` (host int, may be NULL) receives the iterations executed
+ * (only meaningful when p_tol > 0; else max_iter). */
+size_t fnx_jacobi_workspace(int B, int D, int H, int W, int max_iter);
+int fnx_solve_linear_system_jacobi(const float *flags, const float *div, float *p, float *residual,
+                                   int B, int D, int H, int W, int is3d, float p_tol,
+                                   int max_iter, int *iters_run, void *workspace,
+                                   size_t workspace_bytes, void *stream);
+
+/* ---- lib.fluid stencils ----------------------------------------------------- */
+/* velocity_divergence.py:4-74 : div (B,1,D,H,W) out */
+int fnx_velocity_divergence(const float *U, const float *flags, float *div, int B, int D, int H,
+                            int W, int is3d, void *stream);
+/* velocity_update.py:6-162 : U -= grad(p), in place */
+int fnx_velocity_update(const float *pressure, float *U, const float *flags, int B, int D, int H,
+                        int W, int is3d, void *stream);
+/* set_wall_bcs.py:4-86 : in place */
+int fnx_set_wall_bcs(float *U, const float *flags, int B, int D, int H, int W, int is3d,
+                     void *stream);
+/* source_terms.py:6-116 : in place; gravity = 3 host floats */
+int fnx_add_buoyancy(float *U, const float *flags, const float *density, const float *gravity3,
+                     float rho_star, float dt, int B, int D, int H, int W, int is3d, void *stream);
+/* source_terms.py:122-219 : in place */
+int fnx_add_gravity(float *U, const float *flags, const float *gravity3, float dt, int B, int D,
+                    int H, int W, int is3d, void *stream);
+/* flags_to_occupancy.py:6-19 */
+int fnx_flags_to_occupancy(const float *flags, float *occupancy, size_t count, void *stream);
+/* simulate.py:4-26 setConstVals : x = x*inv_mask + bc, in place */
+int fnx_set_const_vals(float *x, const float *inv_mask, const float *bc, size_t count,
+                       void *stream);
+/* util.py:5-49 emptyDomain : border ring (width bnd) = Obstacle, inside = Fluid */
+int fnx_empty_domain(float *flags, int B, int D, int H, int W, int is3d, int bnd, void *stream);
+/* grid.py:7-30 getCentered : out (B,3,D,H,W) cell-centred velocity */
+int fnx_get_centered(const float *U, float *out, int B, int D, int H, int W, int is3d,
+                     void *stream);
+
+/* ---- fused fast path behind lib.simulate (simulate.py:28-171) --------------- */
+/* One inviscid Jacobi step of the standard sequence
+ *   advectScalar -> advectVelocity -> setConstVals -> addBuoyancy/addGravity ->
+ *   setWallBcs -> setConstVals -> velocityDivergence -> Jacobi(max_iter, p_tol<=0)
+ *   -> velocityUpdate -> setWallBcs -> setConstVals
+ * with identical per-cell arithmetic to the individual entry points.  All state
+ * tensors are updated in place (density, U, p); masks may be NULL (no BCs). */
+typedef struct fnx_step_params {
+  float dt, maccormack_strength;
+  int sample_outside_fluid;
+  int use_buoyancy, use_gravity;
+  float buoyancy3[3]; /* gravityVec * (-buoyancyScale) */
+  float gravity3[3];  /* gravityVec * (-gravityScale)  */
+  float rho_star;
+  int jacobi_iters;   /* used by fnx_step_jacobi */
+} fnx_step_params;
+
+size_t fnx_step_workspace(int B, int D, int H, int W, int is3d);
+/* stage 1+2 of the step: advection + BCs + forces + wall BCs + divergence.
+ * in: density,U,flags (+masks) ; out: density,U updated in place, div written */
+int fnx_step_advect_forces_div(const fnx_step_params *prm, float *density, float *U,
+                               const float *flags, const float *UBC, const float *UBCInvMask,
+                               const float *densityBC, const float *densityBCInvMask, float *div,
+                               int B, int D, int H, int W, int is3d, void *workspace,
+                               size_t workspace_bytes, void *stream);
+/* stage 4 of the step: velocityUpdate + setWallBcs + setConstVals (in place on U) */
+int fnx_step_project_bcs(const float *pressure, float *U, const float *flags, const float *UBC,
+                         const float *UBCInvMask, int B, int D, int H, int W, int is3d,
+                         void *stream);
+/* whole Jacobi step (stages 1..4); p and residual as in fnx_solve_linear_system_jacobi */
+int fnx_step_jacobi(const fnx_step_params *prm, float *density, float *U, const float *flags,
+                    float *p, float *residual, const float *UBC, const float *UBCInvMask,
+                    const float *densityBC, const float *densityBCInvMask, int B, int D, int H,
+                    int W, int is3d, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- FluidNet / MultiScaleNet forward (model.py:76-227, multi_scale_net.py:101-127) */
+/* unbiased std over all elements of x per batch row, clamped below by `threshold`
+ * (model.py:8-23 _ScaleNet).  scale: B device floats out. */
+int fnx_scale_std(const float *x, size_t count_per_batch, int B, float threshold, float *scale,
+                  void *workspace, size_t workspace_bytes, void *stream);
+size_t fnx_scale_std_workspace(int B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUIDSTEP_H_ */

@@ -1,0 +1,102 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/fluidstep.h declares; argument validation fails loudly; no compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fluidnet_cxx_b200 import build, _native
+    build.build()
+    return _native.load()
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "fluidstep.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fnx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/fluidstep.h but not exported"
+
+
+def test_binding_covers_header(lib):
+    from fluidnet_cxx_b200 import _native
+    bound = set(_native.SIGNATURES) | set(_native.OPTIONAL_SIGNATURES)
+    assert set(declared_symbols()) <= bound
+
+
+def test_build_info(lib):
+    assert b"sm_100a" in lib.fnx_build_info()
+    assert lib.fnx_abi_version() >= 1
+
+
+def test_workspace_sizes(lib):
+    assert lib.fnx_advect_scalar_workspace(1, 1, 128, 128) == 128 * 128 * 8
+    assert lib.fnx_advect_vel_workspace(1, 1, 128, 128, 0) == 128 * 128 * 8
+    assert lib.fnx_advect_vel_workspace(1, 16, 16, 16, 1) == 16 ** 3 * 12
+    assert lib.fnx_jacobi_workspace(2, 1, 64, 64, 10) >= 2 * 64 * 64 * 4
+    assert lib.fnx_step_workspace(1, 1, 64, 64, 0) > 5 * 64 * 64 * 4
+
+
+def test_argument_errors(lib):
+    # shape validation happens before any CUDA call, so it is testable without a GPU
+    assert lib.fnx_velocity_divergence(None, None, None, 1, 4, 8, 8, 0, None) == -1   # 2-D with D > 1
+    assert b"unsupported grid" in lib.fnx_last_error()
+    assert lib.fnx_advect_scalar(0.1, None, None, None, None, 1, 1, 8, 8, 0, 7, 1, 0, 0.5, None, 0, None) == -1
+    assert lib.fnx_advect_scalar(0.1, None, None, None, None, 1, 1, 8, 8, 0, 1, 2, 0, 0.5, None, 0, None) == -1
+    it = ctypes.c_int(0)
+    assert lib.fnx_solve_linear_system_jacobi(None, None, None, None, 1, 1, 8, 8, 0, 0.0, 0, ctypes.byref(it),
+                                              None, 0, None) == -1
+    assert b"At least 1 iteration" in lib.fnx_last_error()
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected loudly (the product never routes through the oracle or torch ops)."""
+    from fluidnet_cxx_b200.lib import fluid
+    U = torch.zeros(1, 2, 1, 8, 8)
+    flags = torch.ones(1, 1, 1, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        fluid.velocityDivergence(U, flags)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        fluid.advectScalar(0.1, flags.clone(), U, flags)
+
+
+def test_reference_asserts():
+    """Same assertion behaviour as the reference wrappers (advection.py:44-62, velocity_divergence.py:18-36)."""
+    from fluidnet_cxx_b200.lib import fluid
+    U = torch.zeros(1, 2, 1, 8, 8)
+    flags = torch.ones(1, 1, 1, 8, 8)
+    with pytest.raises(AssertionError, match="Dimension mismatch"):
+        fluid.velocityDivergence(U[0], flags)
+    with pytest.raises(AssertionError, match="flags is not scalar"):
+        fluid.velocityDivergence(U, U)
+    with pytest.raises(AssertionError, match="Size mismatch"):
+        fluid.velocityDivergence(torch.zeros(1, 2, 1, 8, 9), flags)
+    with pytest.raises(AssertionError, match="Advection method not supported"):
+        fluid.advectScalar(0.1, flags.clone(), U, flags, method="rk4")
+    with pytest.raises(AssertionError, match="Input is not contiguous"):
+        fluid.setWallBcs(torch.zeros(1, 2, 1, 8, 16)[..., ::2], flags)
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under fluidnet_cxx_b200/ may import, link or execute oracle/."""
+    pkg = os.path.join(ROOT, "fluidnet_cxx_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                with open(os.path.join(root, f)) as fh:
+                    s = fh.read()
+                assert "import oracle" not in s and "oracle/" not in s and "ref_loader" not in s and \
+                    "fluid_oracle" not in s, os.path.join(root, f)

@@ -1,0 +1,323 @@
+"""GPU parity tests: the sm_100a path (called through the C-ABI via lib.fluid) against
+ (1) the committed outputs of the reference's own ATen CPU path (tests/golden/*.npz),
+ (2) the C oracle (oracle/fluid_oracle.c) on seeded inputs, 2-D and 3-D,
+ (3) size-independent properties at BASELINE.json's full sizes.
+
+Bar: fp32 bit equality (+0 == -0) for every stencil / advection / Jacobi output; 1e-5 relative
+for the Jacobi residual norm (a reduction whose summation order is unspecified)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, n_mismatch
+
+pytestmark = pytest.mark.gpu
+
+OPS = load_golden("ops_2d")
+CASES = sorted(OPS)
+
+
+@pytest.fixture(scope="module")
+def fluid():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from fluidnet_cxx_b200.lib import fluid as f
+    return f
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) golden vectors produced by the reference itself
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("method", ["maccormackFluidNet", "eulerFluidNet"])
+@pytest.mark.parametrize("so", [0, 1])
+def test_advect_scalar_golden(fluid, case, method, so):
+    g = OPS[case]
+    key = f"advectScalar_{method}_{so}"
+    if key not in g:
+        pytest.skip("reference itself raised on this input")
+    src, U, flags = cu(g["rho"]), cu(g["U"]), cu(g["flags"])
+    keep = (src.clone(), U.clone(), flags.clone())
+    out = fluid.advectScalar(float(g["dt"]), src, U, flags, method, 1, bool(so), 0.6)
+    assert n_mismatch(host(out), g[key]) == 0
+    # inputs untouched, output is a new tensor (SURVEY §8b ownership)
+    assert torch.equal(src, keep[0]) and torch.equal(U, keep[1]) and torch.equal(flags, keep[2])
+    assert out.data_ptr() != src.data_ptr()
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("method", ["maccormackFluidNet", "eulerFluidNet"])
+def test_advect_velocity_golden(fluid, case, method):
+    g = OPS[case]
+    U, flags = cu(g["U"]), cu(g["flags"])
+    out = fluid.advectVelocity(float(g["dt"]), U, U, flags, method, 1, 0.6)
+    assert n_mismatch(host(out), g[f"advectVelocity_{method}"]) == 0
+    out = fluid.advectVelocity(float(g["dt"]), cu(g["orig2"]), U, flags, "maccormackFluidNet", 1, 0.75)
+    assert n_mismatch(host(out), g["advectVelocity_orig2"]) == 0
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_small_stencils_golden(fluid, case):
+    g = OPS[case]
+    dt = float(g["dt"])
+    flags, rho, p = cu(g["flags"]), cu(g["rho"]), cu(g["p"])
+    grav = torch.from_numpy(g["gravity"])
+    U = cu(g["U"])
+    r = fluid.addBuoyancy(U, flags, rho, grav, 0.05, dt)
+    assert r is U and n_mismatch(host(U), g["addBuoyancy"]) == 0
+    U = cu(g["U"])
+    assert n_mismatch(host(fluid.addGravity(U, flags, grav, dt)), g["addGravity"]) == 0
+    U = cu(g["U"])
+    assert n_mismatch(host(fluid.setWallBcs(U, flags)), g["setWallBcs"]) == 0
+    U = cu(g["U"])
+    assert n_mismatch(host(fluid.velocityDivergence(U, flags)), g["velocityDivergence"]) == 0
+    assert fluid.velocityUpdate(pressure=p, U=U, flags=flags) is None
+    assert n_mismatch(host(U), g["velocityUpdate"]) == 0
+    assert n_mismatch(host(fluid.flagsToOccupancy(flags)), g["flagsToOccupancy"]) == 0
+    assert torch.equal(flags, cu(g["flags"]))  # flags never modified
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_jacobi_golden(fluid, case):
+    g = OPS[case]
+    flags, div = cu(g["flags"]), cu(g["velocityDivergence"])
+    for it in (4, 17):
+        p, res = fluid.solveLinearSystemJacobi(flags, div, False, 0.0, it)
+        assert n_mismatch(host(p), g[f"jacobi{it}_p"]) == 0
+        assert res.dim() == 0
+        assert abs(res.item() - g[f"jacobi{it}_res"]) <= 1e-5 * abs(g[f"jacobi{it}_res"])
+    # tolerance-terminated run (generic one-iteration-per-launch path with the device-side test)
+    p, res = fluid.solveLinearSystemJacobi(flags, div, False, float(g["jacobi_tol"]), 500)
+    assert n_mismatch(host(p), g["jacobi_tol_p"]) == 0
+    assert abs(res.item() - g["jacobi_tol_res"]) <= 1e-5 * abs(g["jacobi_tol_res"])
+    with pytest.raises(RuntimeError):
+        fluid.solveLinearSystemJacobi(flags, div, False, 0.0, 0)
+
+
+def test_plume128_jacobi28_golden(fluid):
+    """BASELINE.json configs[0]: 128x128 plume, Jacobi 28 -- the reference's own state after
+    1, 2, 8 and 24 steps; the fused step and the op-by-op sequence must both reproduce it."""
+    from fluidnet_cxx_b200.lib import simulate as sim
+    G = load_golden("plume128_jacobi28")
+    mconf = plume_mconf()
+    for mode in ("fused", "ops"):
+        bd = plume_state(fluid, 128, mconf)
+        for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask", "flags"):
+            assert n_mismatch(host(bd[k]), G["init"][k]) == 0, k
+        for it in range(1, 25):
+            if mode == "fused":
+                sim.simulate(mconf, bd, None, "jacobi")
+            else:
+                sim._simulate_ops(mconf, bd, None, "jacobi", float(mconf["dt"]), False)
+            if f"step{it}" in G:
+                for k in ("p", "U", "density"):
+                    assert n_mismatch(host(bd[k]), G[f"step{it}"][k]) == 0, (mode, it, k)
+
+
+def plume_mconf(**over):
+    m = {"dt": 0.1, "maccormackStrength": 0.6, "sampleOutsideFluid": False, "buoyancyScale": 0.25,
+         "gravityScale": 0, "viscosity": 0, "correctScalar": False, "operatingDensity": 0.0,
+         "gravityVec": {"x": 0, "y": -1, "z": 0}, "pTol": 0.0, "jacobiIter": 28, "simMethod": "jacobi",
+         "injectionDensity": 0.1, "injectionVelocity": 2, "sourceRadius": 0.145}
+    import os
+    import yaml
+    from conftest import ROOT
+    y = os.path.join(ROOT, "tests", "golden", "plumeConfig.yaml")
+    if os.path.exists(y):
+        with open(y) as f:
+            m.update(yaml.safe_load(f))
+        m.update({"sampleOutsideFluid": False, "simMethod": "jacobi", "jacobiIter": 28, "pTol": 0.0})
+    m.update(over)
+    return m
+
+
+def plume_state(fluid, res, mconf, depth=1):
+    nc = 3 if depth > 1 else 2
+    bd = {"p": torch.zeros(1, 1, depth, res, res, device="cuda"),
+          "U": torch.zeros(1, nc, depth, res, res, device="cuda"),
+          "flags": torch.zeros(1, 1, depth, res, res, device="cuda"),
+          "density": torch.zeros(1, 1, depth, res, res, device="cuda")}
+    fluid.emptyDomain(bd["flags"])
+    fluid.createPlumeBCs(bd, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
+    return bd
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) C oracle on seeded inputs (larger 2-D, and 3-D where the reference has no runnable path)
+# ---------------------------------------------------------------------------------------------
+def random_case(seed, D, H, W, border, nboxes, vscale, with_empty=False):
+    rng = np.random.RandomState(seed)
+    is3d = D > 1
+    f = np.full((1, 1, D, H, W), 1.0, np.float32)
+    if border == "obstacle":
+        f[..., 0, :] = 2; f[..., -1, :] = 2; f[..., :, 0] = 2; f[..., :, -1] = 2
+        if is3d:
+            f[:, :, 0] = 2; f[:, :, -1] = 2
+    for _ in range(nboxes):
+        h, w = rng.randint(1, 6), rng.randint(1, 6)
+        y, x = rng.randint(1, H - 1 - h), rng.randint(1, W - 1 - w)
+        if is3d:
+            d = rng.randint(1, 4); z = rng.randint(1, D - 1 - d)
+            f[0, 0, z:z + d, y:y + h, x:x + w] = 2
+        else:
+            f[0, 0, 0, y:y + h, x:x + w] = 2
+    if with_empty:
+        for _ in range(3):
+            y, x = rng.randint(1, H - 4), rng.randint(1, W - 4)
+            f[0, 0, :, y:y + 2, x:x + 3] = 4
+    nc = 3 if is3d else 2
+    U = (rng.randn(1, nc, D, H, W) * vscale).astype(np.float32)
+    rho = rng.rand(1, 1, D, H, W).astype(np.float32)
+    p = rng.randn(1, 1, D, H, W).astype(np.float32)
+    return f, U, rho, p
+
+
+ORACLE_CASES = [
+    # seed, D, H, W, border, nboxes, vscale, dt, empty
+    (10, 1, 96, 160, "obstacle", 12, 3.0, 0.3, False),
+    (11, 1, 130, 70, "fluid", 6, 9.0, 0.5, True),
+    (12, 1, 257, 131, "obstacle", 30, 1.0, 1.0, True),
+    (13, 12, 20, 28, "obstacle", 6, 2.0, 0.4, False),
+    (14, 16, 18, 14, "fluid", 4, 5.0, 0.5, True),
+    (15, 9, 33, 21, "obstacle", 10, 1.0, 1.0, False),
+]
+
+
+@pytest.mark.parametrize("case", ORACLE_CASES, ids=lambda c: f"s{c[0]}_{c[1]}x{c[2]}x{c[3]}")
+def test_ops_vs_oracle(fluid, oracle, case):
+    seed, D, H, W, border, nboxes, vscale, dt, we = case
+    f, U, rho, p = random_case(seed, D, H, W, border, nboxes, vscale, we)
+    is3d = D > 1
+    tf, tU, tr, tp = cu(f), cu(U), cu(rho), cu(p)
+    for so in (False, True):
+        for m in ("maccormackFluidNet", "eulerFluidNet"):
+            ref = oracle.advectScalar(dt, rho, U, f, m, 1, so, 0.6)
+            if oracle.advectScalar.last_errors:
+                continue   # the reference would have asserted on this input
+            got = fluid.advectScalar(dt, tr, tU, tf, m, 1, so, 0.6)
+            assert n_mismatch(host(got), ref) == 0, (m, so)
+    for m in ("maccormackFluidNet", "eulerFluidNet"):
+        assert n_mismatch(host(fluid.advectVelocity(dt, tU, tU, tf, m, 1, 0.8)),
+                          oracle.advectVelocity(dt, U, U, f, m, 1, 0.8)) == 0, m
+    grav = [0.3, -0.25, 0.15 if is3d else 0.0]
+    assert n_mismatch(host(fluid.addBuoyancy(tU.clone(), tf, tr, grav, 0.05, dt)),
+                      oracle.addBuoyancy(U, f, rho, grav, 0.05, dt)) == 0
+    assert n_mismatch(host(fluid.addGravity(tU.clone(), tf, grav, dt)), oracle.addGravity(U, f, grav, dt)) == 0
+    assert n_mismatch(host(fluid.setWallBcs(tU.clone(), tf)), oracle.setWallBcs(U, f)) == 0
+    div = oracle.velocityDivergence(U, f)
+    assert n_mismatch(host(fluid.velocityDivergence(tU, tf)), div) == 0
+    Uu = tU.clone()
+    fluid.velocityUpdate(tp, Uu, tf)
+    assert n_mismatch(host(Uu), oracle.velocityUpdate(p, U, f)) == 0
+    for iters in (1, 7, 19):
+        pr, rr = oracle.solveLinearSystemJacobi(f, div, is3d, 0.0, iters)
+        pg, rg = fluid.solveLinearSystemJacobi(tf, cu(div), is3d, 0.0, iters)
+        assert n_mismatch(host(pg), pr) == 0, iters
+        assert abs(rg.item() - rr) <= 1e-5 * abs(rr) + 1e-30
+
+
+def test_batched(fluid, oracle):
+    """B > 1 (the C++ is batch-generic)."""
+    parts = [random_case(20 + b, 1, 40, 56, "obstacle", 5, 2.0) for b in range(3)]
+    f, U, rho, p = (np.concatenate([q[i] for q in parts], 0) for i in range(4))
+    tf, tU, tr = cu(f), cu(U), cu(rho)
+    assert n_mismatch(host(fluid.advectScalar(0.3, tr, tU, tf)), oracle.advectScalar(0.3, rho, U, f)) == 0
+    assert n_mismatch(host(fluid.advectVelocity(0.3, tU, tU, tf)), oracle.advectVelocity(0.3, U, U, f)) == 0
+    div = oracle.velocityDivergence(U, f)
+    pg, rg = fluid.solveLinearSystemJacobi(tf, cu(div), False, 0.0, 11)
+    pr, rr = oracle.solveLinearSystemJacobi(f, div, False, 0.0, 11)
+    assert n_mismatch(host(pg), pr) == 0 and abs(rg.item() - rr) <= 1e-5 * rr
+
+
+def test_step3d_vs_oracle(fluid, oracle):
+    """3-D plume-like step (configs[4] semantics at a size the oracle finishes in seconds):
+    fused step == op-by-op oracle sequence."""
+    from fluidnet_cxx_b200.lib import simulate as sim
+    D = H = W = 24
+    mconf = plume_mconf(jacobiIter=9)
+    bd = plume_state(fluid, W, mconf, depth=D)
+    rng = np.random.RandomState(3)
+    bd["U"] = cu(rng.randn(1, 3, D, H, W) * 0.8)
+    bd["density"] = cu(rng.rand(1, 1, D, H, W))
+    st = {k: host(v) for k, v in bd.items()}
+    for _ in range(2):
+        sim.simulate(mconf, bd, None, "jacobi")
+        st = oracle_step(oracle, mconf, st)
+    for k in ("p", "U", "density"):
+        assert n_mismatch(host(bd[k]), st[k]) == 0, k
+
+
+def oracle_step(orc, mconf, st):
+    """simulate.py:28-171 (jacobi branch) restated on the oracle's per-op functions."""
+    dt = float(mconf["dt"])
+    f = st["flags"]
+    rho = orc.advectScalar(dt, st["density"], st["U"], f, "maccormackFluidNet", 1, mconf["sampleOutsideFluid"],
+                           mconf["maccormackStrength"])
+    U = orc.advectVelocity(dt, st["U"], st["U"], f, "maccormackFluidNet", 1, mconf["maccormackStrength"])
+
+    def cv(U, rho):
+        if "UBC" in st:
+            U = orc.setConstVals(U, st["UBCInvMask"], st["UBC"])
+            rho = orc.setConstVals(rho, st["densityBCInvMask"], st["densityBC"])
+        return U, rho
+    U, rho = cv(U, rho)
+    g = mconf["gravityVec"]
+    grav = (np.array([g["x"], g["y"], g["z"]], np.float32) * np.float32(-mconf["buoyancyScale"])).astype(np.float32)
+    U = orc.addBuoyancy(U, f, rho, grav, mconf["operatingDensity"], dt)
+    U = orc.setWallBcs(U, f)
+    U, rho = cv(U, rho)
+    div = orc.velocityDivergence(U, f)
+    p, _ = orc.solveLinearSystemJacobi(f, div, U.shape[1] == 3, 0.0, mconf["jacobiIter"])
+    U = orc.velocityUpdate(p, U, f)
+    U = orc.setWallBcs(U, f)
+    U, rho = cv(U, rho)
+    out = dict(st)
+    out.update({"p": p, "U": U, "density": rho})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# (3) properties at full size (BASELINE.json configs[3]: 4096x4096 plume, Jacobi 100)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(fluid):
+    from fluidnet_cxx_b200.lib import simulate as sim
+    res = 4096
+    mconf = plume_mconf(jacobiIter=100)
+    bd = plume_state(fluid, res, mconf)
+    torch.manual_seed(0)
+    bd["U"] = torch.randn_like(bd["U"]) * 0.5
+    bd["density"] = torch.rand_like(bd["density"])
+    flags0 = bd["flags"].clone()
+    U0 = bd["U"].clone()
+    # temporally blocked Jacobi == one-iteration-per-launch Jacobi, bit for bit
+    div = fluid.velocityDivergence(U0, flags0)
+    p_blk, r_blk = fluid.solveLinearSystemJacobi(flags0, div, False, 0.0, 100)
+    p_gen, r_gen = fluid.solveLinearSystemJacobi(flags0, div, False, 1e-30, 100)   # residual test never fires
+    assert torch.equal(p_blk, p_gen)
+    assert abs(r_blk.item() - r_gen.item()) <= 1e-5 * r_gen.item()
+    # p = 0 on the border ring; projection reduces the divergence
+    assert p_blk[..., 0, :].abs().max() == 0 and p_blk[..., :, 0].abs().max() == 0
+    assert p_blk[..., -1, :].abs().max() == 0 and p_blk[..., :, -1].abs().max() == 0
+    U1 = U0.clone()
+    fluid.velocityUpdate(p_blk, U1, flags0)
+    # border ring untouched by the update (tfluids.cpp:1055-1061)
+    assert torch.equal(U1[..., 0, :], U0[..., 0, :]) and torch.equal(U1[..., :, -1], U0[..., :, -1])
+    d0 = fluid.velocityDivergence(U0, flags0)[..., 2:-2, 2:-2].pow(2).mean()
+    d1 = fluid.velocityDivergence(U1, flags0)[..., 2:-2, 2:-2].pow(2).mean()
+    assert d1 < 0.5 * d0
+    # full fused step == op-by-op step, flags never modified, advected border = inlet BCs only
+    bd2 = {k: v.clone() for k, v in bd.items()}
+    sim.simulate(mconf, bd, None, "jacobi")
+    sim._simulate_ops(mconf, bd2, None, "jacobi", float(mconf["dt"]), False)
+    for k in ("p", "U", "density"):
+        assert torch.equal(bd[k], bd2[k]), k
+    assert torch.equal(bd["flags"], flags0)
+    assert torch.isfinite(bd["U"]).all() and torch.isfinite(bd["p"]).all()
