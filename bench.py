@@ -124,7 +124,8 @@ def run_ours(args):
     import torch.distributed as dist
     from fluidnet_cxx_b200 import _native
     from fluidnet_cxx_b200.lib import fluid
-    from fluidnet_cxx_b200.lib import simulate as sim
+    import importlib
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
 
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

@@ -24,7 +24,8 @@ class StepParams(ctypes.Structure):
                 ("sample_outside_fluid", _c_int),
                 ("use_buoyancy", _c_int), ("use_gravity", _c_int),
                 ("buoyancy3", _c_float * 3), ("gravity3", _c_float * 3),
-                ("rho_star", _c_float), ("jacobi_iters", _c_int)]
+                ("rho_star", _c_float), ("jacobi_iters", _c_int),
+                ("apply_wall_bcs", _c_int), ("density_const_passes", _c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/fluidstep.h declares
@@ -51,9 +52,10 @@ SIGNATURES = {
     "fnx_empty_domain": (_I, [_P] + _GRID + [_I, _P]),
     "fnx_get_centered": (_I, [_P, _P] + _GRID + [_P]),
     "fnx_step_workspace": (_S, _GRID),
-    "fnx_step_advect_forces_div": (_I, [ctypes.POINTER(StepParams), _P, _P, _P, _P, _P, _P, _P, _P] + _GRID + [_P, _S, _P]),
-    "fnx_step_project_bcs": (_I, [_P, _P, _P, _P, _P] + _GRID + [_P]),
-    "fnx_step_jacobi": (_I, [ctypes.POINTER(StepParams), _P, _P, _P, _P, _P, _P, _P, _P, _P] + _GRID + [_P, _S, _P]),
+    "fnx_mask_rows": (_I, [_P, _P, _P, _P, _P] + _GRID + [_P]),
+    "fnx_step_advect_forces_div": (_I, [ctypes.POINTER(StepParams)] + [_P] * 11 + _GRID + [_P, _S, _P]),
+    "fnx_step_project_bcs": (_I, [_P] * 6 + [_I] + _GRID + [_P]),
+    "fnx_step_jacobi": (_I, [ctypes.POINTER(StepParams)] + [_P] * 12 + _GRID + [_P, _S, _P]),
     "fnx_scale_std_workspace": (_S, [_I]),
     "fnx_scale_std": (_I, [_P, _S, _I, _F, _P, _P, _S, _P]),
 }

@@ -1,17 +1,25 @@
-// jacobi_blocked.cu -- temporally blocked 2-D Jacobi pressure iterations (sm_100a).
+// jacobi_blocked.cu -- temporally blocked, register-resident 2-D Jacobi pressure iterations (sm_100a).
 //
 // Reference: solveLinearSystemJacobi, pytorch/lib/fluid/cpp/fluids_init.cpp:858-1003 (Q16):
-//   p_new = ((((pL + pR) + pU) + pD) + div) / 4 on interior non-Obstacle cells, 0 elsewhere,
+//   p_new = ((((pL + pR) + pU) + pD) + div) / 4 on interior non-Obstacle cells, 0 elsewhere;
 //   an Obstacle neighbour contributes the centre value (Neumann).
 // The reference runs one whole-grid pass (≈490 ATen ops) per iteration.  Here one launch
-// advances a (TW x TH) shared-memory tile by `iters` iterations: the tile is loaded once with an
-// `iters`-cell halo, iterated in shared memory (ping-pong), and only the inner
-// (TW-2*iters) x (TH-2*iters) cells -- whose dependency cone lies inside the tile -- are written
-// back.  HBM traffic per iteration drops from 16 B/cell to ~ (12*overlap + 4)/iters B/cell.
-// Each thread owns a vertical strip of R cells for the whole launch and keeps their div values
-// and Neumann/fixed masks in registers; only p lives in shared memory.  Per-cell arithmetic and
-// summation order are exactly those of the one-iteration kernel (stencils.cu), so results are
-// bit-identical to it.  Compiled with -fmad=false.
+// advances a 128 x (8*NW) tile by up to HALO = 8 iterations:
+//   * a warp owns 8 rows x 128 columns; a lane owns 8 rows x 4 consecutive columns and keeps
+//     p (32 values), div (32 values) and the Neumann/fixed bit masks in REGISTERS for the
+//     whole launch;
+//   * left/right neighbours come from the adjacent lanes by warp shuffle, up/down neighbours
+//     inside the strip are registers; only the strip's first/last row is exchanged with the
+//     neighbouring warps through a small double-buffered shared-memory array (one
+//     __syncthreads per iteration);
+//   * the tile is loaded with an 8-cell halo and only the inner (128-16) x (8*NW-16) cells,
+//     whose dependency cone stays inside the tile, are written back (halo = exactly 2 lanes
+//     and 1 warp per side, so every store is an aligned float4);
+//   * warps whose cells touch no Obstacle/border cell run a branch-free sweep:
+//     4 FADD + 1 FMUL + 0.5 SHFL per cell-iteration.
+// HBM traffic per iteration drops from 16 B/cell to (12*overlap + 4)/8 B/cell.  The per-cell
+// arithmetic and its order are those of the one-iteration kernel (stencils.cu), so results are
+// bit-identical to it (tests/test_gpu_parity.py::test_full_size_properties).  -fmad=false.
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
@@ -21,113 +29,175 @@
 
 namespace fnx {
 
-template <int TW, int TH, int R>
-struct JacobiTile {
-  static constexpr int kThreads = TW * (TH / R);
-  static constexpr size_t kSmem = 2 * TW * TH * sizeof(float) + TW * TH;
+constexpr int JB_R = 8;      // rows per warp strip
+constexpr int JB_C = 4;      // columns per lane
+constexpr int JB_TW = 128;   // tile width  = 32 lanes * 4
+constexpr int JB_HALO = 8;   // halo cells = max iterations per launch
+
+struct Row4 {
+  float v[JB_C];
 };
 
-template <int TW, int TH, int R, bool FIRST, bool RESID>
-__global__ void __launch_bounds__(TW*(TH / R), 2)
-    k_jacobi2d_blocked(int H, int W, int iters, const float* __restrict__ flags,
+// one Jacobi sweep over the lane's 8x4 patch.  `p` holds the old values and receives the new.
+// up/dn: rows adjacent to the strip (old values).  SLOW applies the Neumann/fixed masks.
+template <bool SLOW, bool RESID>
+__device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const Row4 (&dv)[JB_R], const Row4& up,
+                                             const Row4& dn, unsigned Lb, unsigned Rb, unsigned Ub,
+                                             unsigned Db, unsigned fixedb, float& acc) {
+  Row4 prev = up;
+#pragma unroll
+  for (int rr = 0; rr < JB_R; rr++) {
+    const Row4 cur = p[rr];
+    const Row4 down = rr < JB_R - 1 ? p[rr + 1] : dn;
+    const float left = __shfl_up_sync(0xffffffffu, cur.v[JB_C - 1], 1);
+    const float right = __shfl_down_sync(0xffffffffu, cur.v[0], 1);
+    Row4 nw;
+#pragma unroll
+    for (int c = 0; c < JB_C; c++) {
+      float p1 = c == 0 ? left : cur.v[c - 1];
+      float p2 = c == JB_C - 1 ? right : cur.v[c + 1];
+      float p3 = prev.v[c];
+      float p4 = down.v[c];
+      if (SLOW) {
+        const unsigned bit = 1u << (rr * JB_C + c);
+        if (Lb & bit) p1 = cur.v[c];
+        if (Rb & bit) p2 = cur.v[c];
+        if (Ub & bit) p3 = cur.v[c];
+        if (Db & bit) p4 = cur.v[c];
+      }
+      float pn = (p1 + p2 + p3 + p4 + dv[rr].v[c]) * 0.25f;
+      if (SLOW) {
+        if (fixedb & (1u << (rr * JB_C + c))) pn = 0.f;
+      }
+      if (RESID) {
+        const float d = pn - cur.v[c];
+        acc = acc + d * d;  // per-lane fp32 partial over 32 cells, folded in double below
+      }
+      nw.v[c] = pn;
+    }
+    prev = cur;
+    p[rr] = nw;
+  }
+}
+
+template <int NW, bool FIRST, bool RESID>
+__global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 2 : 1))
+    k_jacobi2d_blocked(int H, int W, int iters, int vec_ok, const float* __restrict__ flags,
                        const float* __restrict__ div, const float* __restrict__ prev,
                        float* __restrict__ cur, double* __restrict__ ssq) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* pbuf = reinterpret_cast<float*>(smem_raw);                 // [2][TH][TW]
-  unsigned char* obst = smem_raw + 2 * TW * TH * sizeof(float);     // [TH][TW]
-  const int tid = threadIdx.x;
-  const int x = tid % TW, r0 = (tid / TW) * R;
-  const int ow = TW - 2 * iters, oh = TH - 2 * iters;
-  const int gx = blockIdx.x * ow - iters + x;
-  const int gy0 = blockIdx.y * oh - iters + r0;
+  constexpr int TH = NW * JB_R;
+  __shared__ __align__(16) float xch[2][NW][2][JB_TW];  // [parity][warp][top|bottom][column]
+  __shared__ unsigned xob[NW][32];
+  __shared__ double wsum[NW];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int OW = JB_TW - 2 * JB_HALO, OH = TH - 2 * JB_HALO;
+  const int gx0 = blockIdx.x * OW - JB_HALO + lane * JB_C;
+  const int gy0 = blockIdx.y * OH - JB_HALO + w * JB_R;
   const long long boff = (long long)blockIdx.z * H * W;
   flags += boff; div += boff; cur += boff;
   if (!FIRST) prev += boff;
 
-  float dv[R];
-  unsigned fixedb = 0, Lb = 0, Rb = 0, Ub = 0, Db = 0;
-  const bool xin = gx >= 0 && gx < W;
+  Row4 p[JB_R], dv[JB_R];
+  unsigned obw = 0, fixedb = 0;
+  const bool xvec = vec_ok && gx0 >= 0 && gx0 + JB_C <= W;
 #pragma unroll
-  for (int rr = 0; rr < R; rr++) {
+  for (int rr = 0; rr < JB_R; rr++) {
     const int gy = gy0 + rr;
-    const bool inb = xin && gy >= 0 && gy < H;
-    const long long o = (long long)gy * W + gx;
-    float f = kFluid, d = 0.f, p0 = 0.f;
-    if (inb) {
-      f = __ldg(flags + o);
-      d = __ldg(div + o);
-      if (!FIRST) p0 = __ldg(prev + o);
-    }
-    const bool ob = inb && f == kObstacle;
-    const bool border = (gx < 1) | (gx > W - 2) | (gy < 1) | (gy > H - 2);
-    if (!inb || border || ob) fixedb |= 1u << rr;
-    dv[rr] = d;
-    pbuf[(r0 + rr) * TW + x] = p0;
-    obst[(r0 + rr) * TW + x] = ob ? 1 : 0;
-  }
-  __syncthreads();
+    const bool yin = gy >= 0 && gy < H;
+    float f[JB_C];
+    if (xvec && yin) {
+      const long long o = (long long)gy * W + gx0;
+      const float4 f4 = __ldg(reinterpret_cast<const float4*>(flags + o));
+      const float4 d4 = __ldg(reinterpret_cast<const float4*>(div + o));
+      f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w;
+      dv[rr].v[0] = d4.x; dv[rr].v[1] = d4.y; dv[rr].v[2] = d4.z; dv[rr].v[3] = d4.w;
+      if (!FIRST) {
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(prev + o));
+        p[rr].v[0] = p4.x; p[rr].v[1] = p4.y; p[rr].v[2] = p4.z; p[rr].v[3] = p4.w;
+      }
+    } else {
 #pragma unroll
-  for (int rr = 0; rr < R; rr++) {
-    const int r = r0 + rr;
-    if (x > 0 && obst[r * TW + x - 1]) Lb |= 1u << rr;
-    if (x < TW - 1 && obst[r * TW + x + 1]) Rb |= 1u << rr;
-    if (r > 0 && obst[(r - 1) * TW + x]) Ub |= 1u << rr;
-    if (r < TH - 1 && obst[(r + 1) * TW + x]) Db |= 1u << rr;
+      for (int c = 0; c < JB_C; c++) {
+        const int gx = gx0 + c;
+        const bool inb = yin && gx >= 0 && gx < W;
+        const long long o = (long long)gy * W + gx;
+        f[c] = inb ? __ldg(flags + o) : -1.f;  // -1: outside the domain
+        dv[rr].v[c] = inb ? __ldg(div + o) : 0.f;
+        if (!FIRST) p[rr].v[c] = inb ? __ldg(prev + o) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < JB_C; c++) {
+      const int gx = gx0 + c;
+      if (FIRST) p[rr].v[c] = 0.f;
+      const bool ob = f[c] == kObstacle;
+      const bool border = (gx < 1) | (gx > W - 2) | (gy < 1) | (gy > H - 2);  // also covers outside
+      if (ob) obw |= 1u << (rr * JB_C + c);
+      if (ob || border) fixedb |= 1u << (rr * JB_C + c);
+    }
+  }
+  // Neumann masks: which neighbours are Obstacle cells
+  xob[w][lane] = obw;
+  __syncthreads();
+  const unsigned obl = __shfl_up_sync(0xffffffffu, obw, 1), obr = __shfl_down_sync(0xffffffffu, obw, 1);
+  const unsigned obu = w > 0 ? xob[w - 1][lane] : 0u, obd = w < NW - 1 ? xob[w + 1][lane] : 0u;
+  unsigned Lb = (obw << 1) & 0xEEEEEEEEu, Rb = (obw >> 1) & 0x77777777u;
+  if (lane > 0) Lb |= (obl >> 3) & 0x11111111u;
+  if (lane < 31) Rb |= (obr << 3) & 0x88888888u;
+  const unsigned Ub = (obw << JB_C) | (obu >> (JB_C * (JB_R - 1)));
+  const unsigned Db = (obw >> JB_C) | (obd << (JB_C * (JB_R - 1)));
+  const bool slow = __any_sync(0xffffffffu, (Lb | Rb | Ub | Db | fixedb) != 0u);
+
+  float acc = 0.f;
+  for (int t = 0; t < iters; t++) {
+    // publish the strip's first and last row (old values), fetch the neighbours'
+    float* mine = &xch[t & 1][w][0][lane * JB_C];
+    *reinterpret_cast<float4*>(mine) = make_float4(p[0].v[0], p[0].v[1], p[0].v[2], p[0].v[3]);
+    *reinterpret_cast<float4*>(mine + JB_TW) =
+        make_float4(p[JB_R - 1].v[0], p[JB_R - 1].v[1], p[JB_R - 1].v[2], p[JB_R - 1].v[3]);
+    __syncthreads();
+    Row4 up = p[0], dn = p[JB_R - 1];  // tile edge: any value (inside the discarded halo)
+    if (w > 0) {
+      const float4 u4 = *reinterpret_cast<const float4*>(&xch[t & 1][w - 1][1][lane * JB_C]);
+      up.v[0] = u4.x; up.v[1] = u4.y; up.v[2] = u4.z; up.v[3] = u4.w;
+    }
+    if (w < NW - 1) {
+      const float4 d4 = *reinterpret_cast<const float4*>(&xch[t & 1][w + 1][0][lane * JB_C]);
+      dn.v[0] = d4.x; dn.v[1] = d4.y; dn.v[2] = d4.z; dn.v[3] = d4.w;
+    }
+    if (RESID) acc = 0.f;  // only the last iteration's |p - p_prev|^2 survives
+    if (slow) jacobi_sweep<true, RESID>(p, dv, up, dn, Lb, Rb, Ub, Db, fixedb, acc);
+    else jacobi_sweep<false, RESID>(p, dv, up, dn, Lb, Rb, Ub, Db, fixedb, acc);
   }
 
-  const bool xcomp = x > 0 && x < TW - 1;
-  for (int t = 0; t < iters; t++) {
-    const float* src = pbuf + (t & 1) * TW * TH;
-    float* dst = pbuf + ((t + 1) & 1) * TW * TH;
-    float up = r0 > 0 ? src[(r0 - 1) * TW + x] : 0.f;
-    float c = src[r0 * TW + x];
+  // write back the cells whose dependency cone stayed inside the tile: warps 1..NW-2, lanes 2..29
+  const bool owner = w >= 1 && w <= NW - 2 && lane >= 2 && lane <= 29;
+  if (owner) {
 #pragma unroll
-    for (int rr = 0; rr < R; rr++) {
-      const int r = r0 + rr;
-      const float down = r < TH - 1 ? src[(r + 1) * TW + x] : 0.f;
-      if (xcomp && r > 0 && r < TH - 1) {
-        const float l = src[r * TW + x - 1], rt = src[r * TW + x + 1];
-        const float p1 = (Lb >> rr & 1u) ? c : l;
-        const float p2 = (Rb >> rr & 1u) ? c : rt;
-        const float p3 = (Ub >> rr & 1u) ? c : up;
-        const float p4 = (Db >> rr & 1u) ? c : down;
-        float pn = (p1 + p2 + p3 + p4 + dv[rr]) * 0.25f;
-        if (fixedb >> rr & 1u) pn = 0.f;
-        dst[r * TW + x] = pn;
-      }
-      up = c;
-      c = down;
-    }
-    __syncthreads();
-  }
-  // write back the cells whose dependency cone stayed inside the tile
-  const float* fin = pbuf + (iters & 1) * TW * TH;
-  const float* prv = pbuf + ((iters - 1) & 1) * TW * TH;
-  double acc = 0.0;
-  if (x >= iters && x < TW - iters && xin) {
-    const int rlo = r0 > iters ? r0 : iters;
-    int rhi = r0 + R < TH - iters ? r0 + R : TH - iters;
-    const int gybase = blockIdx.y * oh - iters;
-    if (rhi > H - gybase) rhi = H - gybase;
-    for (int r = rlo; r < rhi; r++) {
-      const float v = fin[r * TW + x];
-      cur[(long long)(gybase + r) * W + gx] = v;
-      if (RESID) {
-        const float dd = v - prv[r * TW + x];
-        acc += (double)(dd * dd);
+    for (int rr = 0; rr < JB_R; rr++) {
+      const int gy = gy0 + rr;
+      if (gy >= H) break;
+      const long long o = (long long)gy * W + gx0;
+      if (vec_ok && gx0 + JB_C <= W) {
+        *reinterpret_cast<float4*>(cur + o) = make_float4(p[rr].v[0], p[rr].v[1], p[rr].v[2], p[rr].v[3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < JB_C; c++)
+          if (gx0 + c < W) cur[o + c] = p[rr].v[c];
       }
     }
   }
   if (RESID) {
+    // the residual only counts cells this lane owns AND that exist (fixed/outside cells give 0)
+    double a = owner ? (double)acc : 0.0;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    __shared__ double wsum[TW * (TH / R) / 32];
-    if ((tid & 31) == 0) wsum[tid >> 5] = acc;
+    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+    if (lane == 0) wsum[w] = a;
     __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
       double tsum = 0.0;
 #pragma unroll
-      for (int w = 0; w < TW * (TH / R) / 32; w++) tsum += wsum[w];
+      for (int q = 0; q < NW; q++) tsum += wsum[q];
       atomicAdd(ssq + blockIdx.z, tsum);
     }
   }
@@ -137,51 +207,50 @@ __global__ void __launch_bounds__(TW*(TH / R), 2)
 
 using namespace fnx;
 
-// iterations fused per launch (halo width).  8 balances redundant halo work against HBM traffic
-// for the 128x64 tile (DESIGN.md "Jacobi"); FNX_JACOBI_T overrides for tuning.
+// iterations fused per launch: the halo is 8 cells, FNX_JACOBI_T (1..8) lowers it for tuning
 static int jacobi_block_iters() {
   static int t = 0;
   if (t == 0) {
     const char* e = getenv("FNX_JACOBI_T");
-    t = e ? atoi(e) : 8;
+    t = e ? atoi(e) : JB_HALO;
     if (t < 1) t = 1;
-    if (t > 24) t = 24;
+    if (t > JB_HALO) t = JB_HALO;
   }
   return t;
 }
 
+template <int NW>
+static void launch_blocked(bool first, bool resid, dim3 grid, cudaStream_t st, int H, int W, int iters, int vec_ok,
+                           const float* flags, const float* div, const float* prev, float* cur, double* ssq) {
+  const int threads = NW * 32;
+  if (first && resid) k_jacobi2d_blocked<NW, true, true><<<grid, threads, 0, st>>>(H, W, iters, vec_ok, flags, div, prev, cur, ssq);
+  else if (first) k_jacobi2d_blocked<NW, true, false><<<grid, threads, 0, st>>>(H, W, iters, vec_ok, flags, div, prev, cur, ssq);
+  else if (resid) k_jacobi2d_blocked<NW, false, true><<<grid, threads, 0, st>>>(H, W, iters, vec_ok, flags, div, prev, cur, ssq);
+  else k_jacobi2d_blocked<NW, false, false><<<grid, threads, 0, st>>>(H, W, iters, vec_ok, flags, div, prev, cur, ssq);
+}
+
 int fnx_jacobi_2d_blocked(const float* flags, const float* div, float* p, float* scratch, double* ssq,
                           int B, int H, int W, int max_iter, cudaStream_t st) {
-  constexpr int TW = 128, TH = 64, R = 16;
-  using Tile = JacobiTile<TW, TH, R>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaSuccess;
-    auto set = [&](const void* fn) {
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile::kSmem);
-    };
-    set((const void*)k_jacobi2d_blocked<TW, TH, R, true, true>);
-    set((const void*)k_jacobi2d_blocked<TW, TH, R, true, false>);
-    set((const void*)k_jacobi2d_blocked<TW, TH, R, false, true>);
-    set((const void*)k_jacobi2d_blocked<TW, TH, R, false, false>);
-    if (e != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "jacobi_2d_blocked: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   const int T = jacobi_block_iters();
   const int nL = (max_iter + T - 1) / T;
   auto wbuf = [&](int l) { return ((nL - 1 - l) % 2 == 0) ? p : scratch; };
+  // float4 path: rows 16-byte aligned in every buffer
+  const int vec_ok = (W % 4 == 0) && ((((uintptr_t)flags | (uintptr_t)div | (uintptr_t)p | (uintptr_t)scratch) & 15) == 0);
+  // tall tiles (16 warps) waste less halo work; short tiles keep small grids on more SMs
+  static const char* force = getenv("FNX_JACOBI_NW");
+  bool tall = (long long)H * W * B >= (1LL << 21);
+  if (force) tall = atoi(force) >= 16;
+  constexpr int OW = JB_TW - 2 * JB_HALO;
+  const int oh = (tall ? 16 : 8) * JB_R - 2 * JB_HALO;
+  dim3 grid((W + OW - 1) / OW, (H + oh - 1) / oh, B);
   int done = 0;
   for (int l = 0; l < nL; l++) {
     const int iters = (max_iter - done) < T ? (max_iter - done) : T;
-    const int ow = TW - 2 * iters, oh = TH - 2 * iters;
-    dim3 grid((W + ow - 1) / ow, (H + oh - 1) / oh, B);
     const bool first = l == 0, resid = l == nL - 1;
     const float* prev = first ? nullptr : wbuf(l - 1);
     float* cur = wbuf(l);
-    if (first && resid) k_jacobi2d_blocked<TW, TH, R, true, true><<<grid, Tile::kThreads, Tile::kSmem, st>>>(H, W, iters, flags, div, prev, cur, ssq);
-    else if (first) k_jacobi2d_blocked<TW, TH, R, true, false><<<grid, Tile::kThreads, Tile::kSmem, st>>>(H, W, iters, flags, div, prev, cur, ssq);
-    else if (resid) k_jacobi2d_blocked<TW, TH, R, false, true><<<grid, Tile::kThreads, Tile::kSmem, st>>>(H, W, iters, flags, div, prev, cur, ssq);
-    else k_jacobi2d_blocked<TW, TH, R, false, false><<<grid, Tile::kThreads, Tile::kSmem, st>>>(H, W, iters, flags, div, prev, cur, ssq);
+    if (tall) launch_blocked<16>(first, resid, grid, st, H, W, iters, vec_ok, flags, div, prev, cur, ssq);
+    else launch_blocked<8>(first, resid, grid, st, H, W, iters, vec_ok, flags, div, prev, cur, ssq);
     done += iters;
     fnx_count_launches(1);
   }

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "../../include/fluidstep.h"
+#include "advect_cells.cuh"
 #include "advect_device.cuh"
 #include "fluid_common.cuh"
 #include "host_util.h"
@@ -13,238 +14,63 @@
 
 namespace fnx {
 
-// thread -> cell mapping shared by all one-cell-per-thread kernels:
-// x = W (coalesced), y = D*H rows, z = batch
-constexpr int kBX = 64, kBY = 4;
-
-struct CellIdx {
-  int b, k, j, i;
-  long long o;  // offset inside one (D,H,W) volume
-};
-
-__device__ __forceinline__ bool cell_of(const Grid& g, CellIdx& c) {
-  c.i = blockIdx.x * blockDim.x + threadIdx.x;
-  int row = blockIdx.y * blockDim.y + threadIdx.y;
-  c.b = blockIdx.z;
-  if (c.i >= g.W || row >= g.D * g.H) return false;
-  c.k = row / g.H;
-  c.j = row - c.k * g.H;
-  c.o = (long long)row * g.W + c.i;
-  return true;
-}
-
-static inline dim3 cell_grid(const Grid& g) {
-  return dim3((g.W + kBX - 1) / kBX, (g.D * g.H + kBY - 1) / kBY, g.B);
-}
-static inline dim3 cell_block() { return dim3(kBX, kBY, 1); }
-
 // =====================================================================================
-// advectScalar (fluids_init.cpp:265-382)
+// advection kernels (per-cell bodies in advect_cells.cuh)
 // =====================================================================================
-// pass 1 (SemiLagrangeEulerFluidNetSavePos :69-133): fwd value + the cell index of the traced
-// position (all MacCormackClampFluidNet :224-263 needs of it).
 template <bool Z>
 __global__ void __launch_bounds__(kBX* kBY)
     k_advect_scalar_fwd(Grid g, float mdt, const float* __restrict__ src, const float* __restrict__ U,
                         const float* __restrict__ flags, int sample_outside, float* __restrict__ fwd,
                         int* __restrict__ fidx) {
-  constexpr int NA = Z ? 3 : 2, NC = Z ? 3 : 2;
+  constexpr int NC = Z ? 3 : 2;
   CellIdx c;
   if (!cell_of(g, c)) return;
-  src += c.b * g.n; flags += c.b * g.n; U += (long long)c.b * NC * g.n;
-  fwd += c.b * g.n;
-  float val;
-  long long idx = c.o;
-  if (is_border<Z>(g, c.k, c.j, c.i)) {
-    val = 0.f;
-  } else if (__ldg(flags + c.o) != kFluid) {
-    val = __ldg(src + c.o);  // don't advect solid geometry
-  } else {
-    float pos[3] = {(float)c.i + 0.5f, (float)c.j + 0.5f, (float)c.k + 0.5f};
-    float vel[3], delta[3], back[3];
-    centered_vel<Z>(g, U, c.o, vel);
-#pragma unroll
-    for (int a = 0; a < NA; a++) delta[a] = mdt * vel[a];
-    line_trace<NA>(g, flags, pos, delta, back);
-    val = sample_outside ? sample_field<Z>(g, src, back) : sample_with_fluid<Z>(g, src, flags, back);
-    if (fidx) {
-      long long i0 = clampll(trunc_ll(back[0]), 0, g.W - 1);
-      long long j0 = clampll(trunc_ll(back[1]), 0, g.H - 1);
-      long long k0 = Z ? clampll(trunc_ll(back[2]), 0, g.D - 1) : 0;
-      idx = (k0 * g.H + j0) * g.W + i0;
-    }
-  }
-  fwd[c.o] = val;
-  if (fidx) fidx[c.b * g.n + c.o] = (int)idx;
+  const long long bo = (long long)c.b * g.n;
+  int idx;
+  fwd[bo + c.o] = scalar_fwd_cell<Z>(g, c, mdt, src + bo, U + bo * NC, flags + bo, sample_outside, fidx != nullptr, &idx);
+  if (fidx) fidx[bo + c.o] = idx;
 }
 
-// pass 2-4: backward trace on `fwd`, MacCormackCorrect :135-148, clamp :154-263
 template <bool Z>
 __global__ void __launch_bounds__(kBX* kBY)
     k_advect_scalar_bwd(Grid g, float dt, float half_strength, const float* __restrict__ src,
-                        const float* __restrict__ U, const float* __restrict__ flags,
-                        int sample_outside, const float* __restrict__ fwd,
-                        const int* __restrict__ fidx, float* __restrict__ dst) {
-  constexpr int NA = Z ? 3 : 2, NC = Z ? 3 : 2;
+                        const float* __restrict__ U, const float* __restrict__ flags, int sample_outside,
+                        const float* __restrict__ fwd, const int* __restrict__ fidx, float* __restrict__ dst) {
+  constexpr int NC = Z ? 3 : 2;
   CellIdx c;
   if (!cell_of(g, c)) return;
-  src += c.b * g.n; flags += c.b * g.n; U += (long long)c.b * NC * g.n;
-  fwd += c.b * g.n; fidx += c.b * g.n; dst += c.b * g.n;
-  const bool border = is_border<Z>(g, c.k, c.j, c.i);
-  const bool fluid = __ldg(flags + c.o) == kFluid;
-  const float fw = __ldg(fwd + c.o);
-  float v = fw;
-  if (fluid) {
-    float bwd = 0.f;  // border cells of the backward pass are zeroed (:354-363)
-    if (!border) {
-      float pos[3] = {(float)c.i + 0.5f, (float)c.j + 0.5f, (float)c.k + 0.5f};
-      float vel[3], delta[3], back[3];
-      centered_vel<Z>(g, U, c.o, vel);
-#pragma unroll
-      for (int a = 0; a < NA; a++) delta[a] = dt * vel[a];
-      line_trace<NA>(g, flags, pos, delta, back);
-      bwd = sample_outside ? sample_field<Z>(g, fwd, back) : sample_with_fluid<Z>(g, fwd, flags, back);
-    }
-    v = fw + half_strength * (__ldg(src + c.o) - bwd);
-  }
-  if (!border) {
-    // getClampBounds :154-222: 3x3(x3) neighbourhood of the forward-traced cell, fluid cells only
-    const int idx = __ldg(fidx + c.o);
-    const int k0 = Z ? (int)(idx / g.sz) : 0;
-    const int rem = (int)(idx - k0 * g.sz);
-    const int j0 = rem / g.W, i0 = rem - j0 * g.W;
-    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-    bool any = false;
-#pragma unroll
-    for (int dk = (Z ? -1 : 0); dk <= (Z ? 1 : 0); dk++) {
-      const int kk = k0 + dk;
-      if (Z && (kk < 0 || kk >= g.D)) continue;
-#pragma unroll
-      for (int dj = -1; dj <= 1; dj++) {
-        const int jj = j0 + dj;
-        if (jj < 0 || jj >= g.H) continue;
-#pragma unroll
-        for (int di = -1; di <= 1; di++) {
-          const int ii = i0 + di;
-          if (ii < 0 || ii >= g.W) continue;
-          const long long q = ((long long)kk * g.H + jj) * g.W + ii;
-          if (sample_outside || __ldg(flags + q) == kFluid) {
-            const float s = __ldg(src + q);
-            mn = min_t(mn, s);
-            mx = max_t(mx, s);
-            any = true;
-          }
-        }
-      }
-    }
-    v = any ? max_t(mn, min_t(mx, v)) : fw;
-  }
-  dst[c.o] = v;
+  const long long bo = (long long)c.b * g.n;
+  dst[bo + c.o] = scalar_bwd_cell<Z>(g, c, dt, half_strength, src + bo, U + bo * NC, flags + bo, sample_outside,
+                                     fwd + bo, fidx + bo);
 }
 
-// =====================================================================================
-// advectVel (fluids_init.cpp:656-807)
-// =====================================================================================
-// SemiLagrangeEulerFluidNetMAC :388-451 (no line trace, Q2; solid-cell quirk Q1)
 template <bool Z>
 __global__ void __launch_bounds__(kBX* kBY)
     k_advect_vel_fwd(Grid g, float mdt, const float* __restrict__ orig, const float* __restrict__ U,
                      const float* __restrict__ flags, float* __restrict__ fwd) {
-  constexpr int NA = Z ? 3 : 2, NC = Z ? 3 : 2;
+  constexpr int NC = Z ? 3 : 2;
   CellIdx c;
   if (!cell_of(g, c)) return;
-  flags += c.b * g.n; U += (long long)c.b * NC * g.n; orig += (long long)c.b * NC * g.n;
-  fwd += (long long)c.b * NC * g.n;
-  float out[3] = {0.f, 0.f, 0.f};
-  if (!is_border<Z>(g, c.k, c.j, c.i)) {
-    if (__ldg(flags + c.o) != kFluid) {
-      if (!Z) { out[0] = __ldg(orig + g.n + c.o); out[1] = 0.f; }  // Q1
-      else {
+  const long long bo = (long long)c.b * g.n;
+  float out[3];
+  vel_fwd_cell<Z>(g, c, mdt, orig + bo * NC, U + bo * NC, flags + bo, out);
 #pragma unroll
-        for (int a = 0; a < NC; a++) out[a] = __ldg(orig + a * g.n + c.o);
-      }
-    } else {
-      const float pos[3] = {(float)c.i + 0.5f, (float)c.j + 0.5f, (float)c.k + 0.5f};
-#pragma unroll
-      for (int comp = 0; comp < NC; comp++) {
-        float v[3], p[3];
-        mac_vel<Z>(g, U, comp, c.o, v);
-#pragma unroll
-        for (int a = 0; a < NA; a++) p[a] = pos[a] + v[a] * mdt;
-        out[comp] = sample_field<Z>(g, orig + comp * g.n, p);
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < NC; a++) fwd[a * g.n + c.o] = out[a];
+  for (int a = 0; a < NC; a++) fwd[bo * NC + (long long)a * g.n + c.o] = out[a];
 }
 
-// backward pass on `fwd`, MacCormackCorrectMAC :453-498, MacCormackClampMAC :500-654
 template <bool Z>
 __global__ void __launch_bounds__(kBX* kBY)
     k_advect_vel_bwd(Grid g, float dt, float half_strength, const float* __restrict__ orig,
                      const float* __restrict__ U, const float* __restrict__ flags,
                      const float* __restrict__ fwd, float* __restrict__ dst) {
-  constexpr int NA = Z ? 3 : 2, NC = Z ? 3 : 2;
+  constexpr int NC = Z ? 3 : 2;
   CellIdx c;
   if (!cell_of(g, c)) return;
-  flags += c.b * g.n; U += (long long)c.b * NC * g.n; orig += (long long)c.b * NC * g.n;
-  fwd += (long long)c.b * NC * g.n; dst += (long long)c.b * NC * g.n;
-  if (is_border<Z>(g, c.k, c.j, c.i)) {
+  const long long bo = (long long)c.b * g.n;
+  float out[3];
+  vel_bwd_cell<Z>(g, c, dt, half_strength, orig + bo * NC, U + bo * NC, flags + bo, fwd + bo * NC, out);
 #pragma unroll
-    for (int a = 0; a < NC; a++) dst[a * g.n + c.o] = 0.f;
-    return;
-  }
-  const bool solid = __ldg(flags + c.o) != kFluid;
-  const float pos[3] = {(float)c.i + 0.5f, (float)c.j + 0.5f, (float)c.k + 0.5f};
-  const float posi[3] = {(float)c.i, (float)c.j, (float)c.k};
-  const int idx[3] = {c.i, c.j, c.k};
-#pragma unroll
-  for (int comp = 0; comp < NC; comp++) {
-    float vel[3];
-    mac_vel<Z>(g, U, comp, c.o, vel);
-    const float fw = __ldg(fwd + comp * g.n + c.o);
-    // correction skipped when the cell or its lower neighbour along `comp` is not fluid
-    bool skip = solid;
-    if (!skip && idx[comp] > 0 && __ldg(flags + c.o - nb_off(g, comp)) != kFluid) skip = true;
-    float v = fw;
-    if (!skip) {
-      float p[3];
-#pragma unroll
-      for (int a = 0; a < NA; a++) p[a] = pos[a] + vel[a] * dt;
-      const float bwd = sample_field<Z>(g, fwd + comp * g.n, p);
-      v = fw + half_strength * (__ldg(orig + comp * g.n + c.o) - bwd);
-    }
-    // doClampComponentMAC: min/max of orig over the 2x2(x2) blocks at trunc(pos -/+ vel*dt), Q5
-    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-    const float* oc = orig + comp * g.n;
-#pragma unroll
-    for (int l = 0; l < 2; l++) {
-      long long q[3] = {0, 0, 0};
-#pragma unroll
-      for (int a = 0; a < NA; a++) {
-        const float va = vel[a] * dt;
-        q[a] = trunc_i32_x86(l == 0 ? posi[a] - va : posi[a] + va);
-      }
-      const long long i0 = clampll(q[0], 0, g.W - 2), j0 = clampll(q[1], 0, g.H - 2);
-      const long long k0 = Z ? clampll(q[2], 0, g.D - 2) : 0;
-      const float* b0 = oc + (k0 * g.H + j0) * g.W + i0;
-      // same visiting order as the reference: (j0,i0) (j0,i0+1) (j0+1,i0) (j0+1,i0+1)
-      float s;
-      s = __ldg(b0); mn = min_t(mn, s); mx = max_t(mx, s);
-      s = __ldg(b0 + 1); mn = min_t(mn, s); mx = max_t(mx, s);
-      s = __ldg(b0 + g.sy); mn = min_t(mn, s); mx = max_t(mx, s);
-      s = __ldg(b0 + g.sy + 1); mn = min_t(mn, s); mx = max_t(mx, s);
-      if (Z) {
-        const float* b1 = b0 + g.sz;
-        s = __ldg(b1); mn = min_t(mn, s); mx = max_t(mx, s);
-        s = __ldg(b1 + 1); mn = min_t(mn, s); mx = max_t(mx, s);
-        s = __ldg(b1 + g.sy); mn = min_t(mn, s); mx = max_t(mx, s);
-        s = __ldg(b1 + g.sy + 1); mn = min_t(mn, s); mx = max_t(mx, s);
-      }
-    }
-    dst[comp * g.n + c.o] = max_t(min_t(v, mx), mn);
-  }
+  for (int a = 0; a < NC; a++) dst[bo * NC + (long long)a * g.n + c.o] = out[a];
 }
 
 // =====================================================================================

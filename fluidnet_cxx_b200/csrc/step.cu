@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/fluidstep.h"
+#include "advect_cells.cuh"
 #include "advect_device.cuh"
 #include "fluid_common.cuh"
 #include "host_util.h"
@@ -50,6 +51,180 @@ __global__ void k_std_finish(const double* __restrict__ ssq, size_t count, int B
   scale[b] = s < threshold ? threshold : s;  // torch.clamp(std, min=threshold); NaN stays NaN
 }
 
+// ---- fused step kernels (simulate.py:28-171) ---------------------------------------------------
+struct StepMasks {
+  const float* UBC;
+  const float* UBCInv;
+  const float* rBC;
+  const float* rBCInv;
+  const unsigned char* rows;  // per (b, d*H+row): bit0 = U masks differ from identity, bit1 = density masks
+};
+struct StepForces {
+  int use_buoyancy, use_gravity, wall_bcs, density_passes;
+  float bstrength[3], gforce[3];
+  float rho_star;
+};
+
+// one block per grid row: does this row's mask differ from (InvMask = 1, BC = 0) anywhere?
+__global__ void __launch_bounds__(128)
+    k_mask_rows(Grid g, int nc, const float* __restrict__ UBC, const float* __restrict__ UBCInv,
+                const float* __restrict__ rBC, const float* __restrict__ rBCInv, unsigned char* __restrict__ rows) {
+  const int row = blockIdx.x;  // over B*D*H
+  const int b = row / (g.D * g.H), r = row - b * (g.D * g.H);
+  int uact = 0, ract = 0;
+  for (int i = threadIdx.x; i < g.W; i += blockDim.x) {
+    if (UBC)
+      for (int c = 0; c < nc; c++) {
+        const long long o = ((long long)b * nc + c) * g.n + (long long)r * g.W + i;
+        uact |= (__ldg(UBC + o) != 0.f) | (__ldg(UBCInv + o) != 1.f);
+      }
+    if (rBC) {
+      const long long o = (long long)b * g.n + (long long)r * g.W + i;
+      ract |= (__ldg(rBC + o) != 0.f) | (__ldg(rBCInv + o) != 1.f);
+    }
+  }
+  const int any = __syncthreads_or(uact | (ract << 1));
+  const int anyu = __syncthreads_or(uact);
+  if (threadIdx.x == 0) rows[row] = (unsigned char)((anyu ? 1 : 0) | ((any & 2) ? 2 : 0));
+}
+
+// x*InvMask + BC for velocity component c / density, skipping rows whose masks are the identity.
+// NOTE: x*1 + 0 == x bit-for-bit except -0 -> +0 and NaN payloads, which compare equal.
+__device__ __forceinline__ float cv_u(const StepMasks& m, const Grid& g, int nc, int b, int row, int c,
+                                      long long o, float x) {
+  if (!m.UBC) return x;
+  if (m.rows && !(m.rows[b * g.D * g.H + row] & 1)) return x;
+  const long long q = ((long long)b * nc + c) * g.n + o;
+  return const_vals_apply(x, __ldg(m.UBCInv + q), __ldg(m.UBC + q));
+}
+__device__ __forceinline__ float cv_r(const StepMasks& m, const Grid& g, int b, int row, long long o, float x,
+                                      int passes) {
+  if (!m.rBC || passes <= 0) return x;
+  if (m.rows && !(m.rows[b * g.D * g.H + row] & 2)) return x;
+  const long long q = (long long)b * g.n + o;
+  const float inv = __ldg(m.rBCInv + q), bc = __ldg(m.rBC + q);
+  for (int t = 0; t < passes; t++) x = const_vals_apply(x, inv, bc);
+  return x;
+}
+
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_step_advect_fwd(Grid g, float mdt, const float* __restrict__ rho, const float* __restrict__ U,
+                      const float* __restrict__ flags, int sample_outside, float* __restrict__ rho_fwd,
+                      int* __restrict__ fidx, float* __restrict__ U_fwd) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  const long long bo = (long long)c.b * g.n;
+  int idx;
+  rho_fwd[bo + c.o] = scalar_fwd_cell<Z>(g, c, mdt, rho + bo, U + bo * NC, flags + bo, sample_outside, true, &idx);
+  fidx[bo + c.o] = idx;
+  float out[3];
+  vel_fwd_cell<Z>(g, c, mdt, U + bo * NC, U + bo * NC, flags + bo, out);
+#pragma unroll
+  for (int a = 0; a < NC; a++) U_fwd[bo * NC + (long long)a * g.n + c.o] = out[a];
+}
+
+// MacCormack backward pass + correction + clamp of both fields, then setConstVals (simulate.py:96)
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_step_advect_bwd(Grid g, float dt, float hs, const float* __restrict__ rho, const float* __restrict__ U,
+                      const float* __restrict__ flags, int sample_outside, const float* __restrict__ rho_fwd,
+                      const int* __restrict__ fidx, const float* __restrict__ U_fwd, StepMasks m,
+                      float* __restrict__ rho1, float* __restrict__ U1) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  const long long bo = (long long)c.b * g.n;
+  const int row = c.k * g.H + c.j;
+  float r = scalar_bwd_cell<Z>(g, c, dt, hs, rho + bo, U + bo * NC, flags + bo, sample_outside, rho_fwd + bo, fidx + bo);
+  rho1[bo + c.o] = cv_r(m, g, c.b, row, c.o, r, 1);
+  float out[3];
+  vel_bwd_cell<Z>(g, c, dt, hs, U + bo * NC, U + bo * NC, flags + bo, U_fwd + bo * NC, out);
+#pragma unroll
+  for (int a = 0; a < NC; a++) U1[bo * NC + (long long)a * g.n + c.o] = cv_u(m, g, NC, c.b, row, a, c.o, out[a]);
+}
+
+// velocity component `comp` of cell (k,j,i) after addBuoyancy -> addGravity -> [setWallBcs] -> setConstVals
+// (simulate.py:98-133), computed from the post-advection fields rho1 / U1.
+template <bool Z>
+__device__ __forceinline__ float forced_vel(const Grid& g, int b, int k, int j, int i, long long o, int comp,
+                                            const float* __restrict__ rho1, const float* __restrict__ U1,
+                                            const float* __restrict__ flags, const StepMasks& m,
+                                            const StepForces& f) {
+  constexpr int NC = Z ? 3 : 2;
+  float u = __ldg(U1 + (long long)comp * g.n + o);
+  const float fc = __ldg(flags + o);
+  const int idx = comp == 0 ? i : (comp == 1 ? j : k);
+  const long long on = o - nb_off(g, comp);
+  const float fn = idx > 0 ? __ldg(flags + on) : fc;
+  if (!is_border<Z>(g, k, j, i)) {
+    if (f.use_buoyancy) u = buoyancy_apply(u, fc, fn, __ldg(rho1 + o), __ldg(rho1 + on), f.bstrength[comp], f.rho_star);
+    if (f.use_gravity) u = gravity_apply(u, fc, fn, f.gforce[comp]);
+  }
+  if (f.wall_bcs) u = wall_bcs_apply(u, fc, fn);
+  return cv_u(m, g, NC, b, k * g.H + j, comp, o, u);
+}
+
+// forces + wall BCs + setConstVals + divergence (simulate.py:98-145) in one pass
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_step_forces_div(Grid g, const float* __restrict__ rho1, const float* __restrict__ U1,
+                      const float* __restrict__ flags, StepMasks m, StepForces f, float* __restrict__ rho_out,
+                      float* __restrict__ U_out, float* __restrict__ div) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  const long long bo = (long long)c.b * g.n;
+  rho1 += bo; flags += bo; U1 += bo * NC;
+  float u[3];
+#pragma unroll
+  for (int a = 0; a < NC; a++) {
+    u[a] = forced_vel<Z>(g, c.b, c.k, c.j, c.i, c.o, a, rho1, U1, flags, m, f);
+    U_out[bo * NC + (long long)a * g.n + c.o] = u[a];
+  }
+  rho_out[bo + c.o] = cv_r(m, g, c.b, c.k * g.H + c.j, c.o, __ldg(rho1 + c.o), f.density_passes);
+  if (div) {
+    float v = 0.f;
+    if (!is_border<Z>(g, c.k, c.j, c.i)) {
+      const float ux = forced_vel<Z>(g, c.b, c.k, c.j, c.i + 1, c.o + 1, 0, rho1, U1, flags, m, f);
+      const float uy = forced_vel<Z>(g, c.b, c.k, c.j + 1, c.i, c.o + g.sy, 1, rho1, U1, flags, m, f);
+      v = u[0] - ux + u[1] - uy;
+      if (Z) {
+        const float uz = forced_vel<Z>(g, c.b, c.k + 1, c.j, c.i, c.o + g.sz, 2, rho1, U1, flags, m, f);
+        v = v + (u[2] - uz);
+      }
+    }
+    if (__ldg(flags + c.o) == kObstacle) v = 0.f;
+    div[bo + c.o] = v;
+  }
+}
+
+// velocityUpdate -> [setWallBcs] -> setConstVals (simulate.py:154-168), in place on U
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_step_project(Grid g, const float* __restrict__ p, float* __restrict__ U, const float* __restrict__ flags,
+                   StepMasks m, int wall_bcs) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  const long long bo = (long long)c.b * g.n;
+  flags += bo; p += bo; U += bo * NC;
+  const float fc = __ldg(flags + c.o);
+  const bool interior = !is_border<Z>(g, c.k, c.j, c.i);
+  const float P = __ldg(p + c.o);
+  const int idx[3] = {c.i, c.j, c.k};
+#pragma unroll
+  for (int a = 0; a < NC; a++) {
+    const long long on = c.o - nb_off(g, a);
+    const float fn = idx[a] > 0 ? __ldg(flags + on) : fc;
+    float u = U[(long long)a * g.n + c.o];
+    if (interior) u = velocity_update_apply(u, fc, fn, P, __ldg(p + on));
+    if (wall_bcs) u = wall_bcs_apply(u, fc, fn);
+    U[(long long)a * g.n + c.o] = cv_u(m, g, NC, c.b, c.k * g.H + c.j, a, c.o, u);
+  }
+}
+
 }  // namespace fnx
 
 using namespace fnx;
@@ -90,91 +265,130 @@ int fnx_scale_std(const float* x, size_t count_per_batch, int B, float threshold
   return FNX_OK;
 }
 
-// ---- fused step (v1: the standard sequence, one entry point) --------------------------------
+// ---- fused step ------------------------------------------------------------------------------
+static inline unsigned char* ws_take(char*& ws, size_t bytes) {
+  unsigned char* p = (unsigned char*)ws;
+  ws += align256(bytes);
+  return p;
+}
+
 size_t fnx_step_workspace(int B, int D, int H, int W, int is3d) {
   const size_t n = (size_t)B * D * H * W;
   const int nc = is3d ? 3 : 2;
   size_t s = 0;
-  s += align256(n * sizeof(float));        // advected density
-  s += align256(n * nc * sizeof(float));   // advected velocity
-  s += align256(fnx_advect_scalar_workspace(B, D, H, W));
-  s += align256(fnx_advect_vel_workspace(B, D, H, W, is3d));
+  s += align256(n * sizeof(float));        // rho_fwd
+  s += align256(n * sizeof(int));          // traced cell index
+  s += align256(n * nc * sizeof(float));   // U_fwd
+  s += align256(n * sizeof(float));        // rho after advection + BCs
+  s += align256(n * nc * sizeof(float));   // U after advection + BCs
   s += align256(n * sizeof(float));        // div (fnx_step_jacobi)
   s += align256(fnx_jacobi_workspace(B, D, H, W, 1));
   return s;
 }
 
-int fnx_step_advect_forces_div(const fnx_step_params* prm, float* density, float* U, const float* flags,
-                               const float* UBC, const float* UBCInvMask, const float* densityBC,
-                               const float* densityBCInvMask, float* div, int B, int D, int H, int W, int is3d,
+int fnx_mask_rows(const float* UBC, const float* UBCInvMask, const float* densityBC, const float* densityBCInvMask,
+                  unsigned char* rows, int B, int D, int H, int W, int is3d, void* stream) {
+  if (B < 1 || D < 1 || H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "mask_rows: bad grid");
+  Grid g = make_grid(B, D, H, W);
+  const int nrows = B * D * H;
+  const bool ubc = UBC && UBCInvMask, rbc = densityBC && densityBCInvMask;
+  k_mask_rows<<<nrows, 128, 0, (cudaStream_t)stream>>>(g, is3d ? 3 : 2, ubc ? UBC : nullptr, ubc ? UBCInvMask : nullptr,
+                                                       rbc ? densityBC : nullptr, rbc ? densityBCInvMask : nullptr, rows);
+  fnx_count_launches(1);
+  FNX_CUDA_TRY("mask_rows", cudaGetLastError());
+  return FNX_OK;
+}
+
+int fnx_step_advect_forces_div(const fnx_step_params* prm, const float* density_in, const float* U_in,
+                               const float* flags, const float* UBC, const float* UBCInvMask,
+                               const float* densityBC, const float* densityBCInvMask, const unsigned char* mask_rows,
+                               float* density_out, float* U_out, float* div, int B, int D, int H, int W, int is3d,
                                void* workspace, size_t workspace_bytes, void* stream) {
   if (!prm) return fnx_set_error(FNX_ERR_ARG, "step: null params");
+  if (B < 1 || D < 1 || H < 2 || W < 2 || (is3d && D < 2) || (!is3d && D != 1) || (long long)D * H * W >= (1LL << 31))
+    return fnx_set_error(FNX_ERR_ARG, "step: unsupported grid B=%d D=%d H=%d W=%d is3d=%d", B, D, H, W, is3d);
   if (!workspace || workspace_bytes < fnx_step_workspace(B, D, H, W, is3d))
     return fnx_set_error(FNX_ERR_WORKSPACE, "step: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)B * D * H * W;
   const int nc = is3d ? 3 : 2;
   char* ws = (char*)workspace;
-  float* rho_adv = (float*)ws; ws += align256(n * sizeof(float));
-  float* U_adv = (float*)ws; ws += align256(n * nc * sizeof(float));
-  void* ws_s = ws; const size_t ws_s_bytes = align256(fnx_advect_scalar_workspace(B, D, H, W)); ws += ws_s_bytes;
-  void* ws_v = ws; const size_t ws_v_bytes = align256(fnx_advect_vel_workspace(B, D, H, W, is3d));
-
-  // simulate.py:75-94: both advections read the velocity field of the previous step
-  FNX_TRY(fnx_advect_scalar(prm->dt, density, U, flags, rho_adv, B, D, H, W, is3d, FNX_METHOD_MACCORMACK, 1,
-                            prm->sample_outside_fluid, prm->maccormack_strength, ws_s, ws_s_bytes, stream));
-  FNX_TRY(fnx_advect_vel(prm->dt, U, U, flags, U_adv, B, D, H, W, is3d, FNX_METHOD_MACCORMACK, 1,
-                         prm->maccormack_strength, ws_v, ws_v_bytes, stream));
-  FNX_CUDA_TRY("step", cudaMemcpyAsync(density, rho_adv, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  FNX_CUDA_TRY("step", cudaMemcpyAsync(U, U_adv, n * nc * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  float* rho_fwd = (float*)ws_take(ws, n * sizeof(float));
+  int* fidx = (int*)ws_take(ws, n * sizeof(int));
+  float* U_fwd = (float*)ws_take(ws, n * nc * sizeof(float));
+  float* rho1 = (float*)ws_take(ws, n * sizeof(float));
+  float* U1 = (float*)ws_take(ws, n * nc * sizeof(float));
+  Grid g = make_grid(B, D, H, W);
+  StepMasks m;
   const bool ubc = UBC && UBCInvMask, rbc = densityBC && densityBCInvMask;
-  // simulate.py:96 setConstVals
-  if (ubc) FNX_TRY(fnx_set_const_vals(U, UBCInvMask, UBC, n * nc, stream));
-  if (rbc) FNX_TRY(fnx_set_const_vals(density, densityBCInvMask, densityBC, n, stream));
-  // simulate.py:98-115 forces
-  if (prm->use_buoyancy)
-    FNX_TRY(fnx_add_buoyancy(U, flags, density, prm->buoyancy3, prm->rho_star, prm->dt, B, D, H, W, is3d, stream));
-  if (prm->use_gravity) FNX_TRY(fnx_add_gravity(U, flags, prm->gravity3, prm->dt, B, D, H, W, is3d, stream));
-  // simulate.py:120-133 wall BCs + setConstVals
-  FNX_TRY(fnx_set_wall_bcs(U, flags, B, D, H, W, is3d, stream));
-  if (ubc) FNX_TRY(fnx_set_const_vals(U, UBCInvMask, UBC, n * nc, stream));
-  if (rbc) FNX_TRY(fnx_set_const_vals(density, densityBCInvMask, densityBC, n, stream));
-  // simulate.py:145
-  if (div) FNX_TRY(fnx_velocity_divergence(U, flags, div, B, D, H, W, is3d, stream));
+  m.UBC = ubc ? UBC : nullptr; m.UBCInv = ubc ? UBCInvMask : nullptr;
+  m.rBC = rbc ? densityBC : nullptr; m.rBCInv = rbc ? densityBCInvMask : nullptr;
+  m.rows = mask_rows;
+  StepForces f;
+  f.use_buoyancy = prm->use_buoyancy; f.use_gravity = prm->use_gravity;
+  for (int a = 0; a < 3; a++) {
+    f.bstrength[a] = prm->buoyancy3[a] * prm->dt;  // gravity*dt, one fp32 product (source_terms.py:70)
+    f.gforce[a] = prm->gravity3[a] * prm->dt;
+  }
+  f.rho_star = prm->rho_star;
+  f.wall_bcs = prm->apply_wall_bcs;
+  f.density_passes = prm->density_const_passes;
+  const float hs = prm->maccormack_strength * 0.5f;
+  dim3 gr = cell_grid(g), bl = cell_block();
+  if (is3d) {
+    k_step_advect_fwd<true><<<gr, bl, 0, st>>>(g, -prm->dt, density_in, U_in, flags, prm->sample_outside_fluid, rho_fwd, fidx, U_fwd);
+    k_step_advect_bwd<true><<<gr, bl, 0, st>>>(g, prm->dt, hs, density_in, U_in, flags, prm->sample_outside_fluid, rho_fwd, fidx, U_fwd, m, rho1, U1);
+    k_step_forces_div<true><<<gr, bl, 0, st>>>(g, rho1, U1, flags, m, f, density_out, U_out, div);
+  } else {
+    k_step_advect_fwd<false><<<gr, bl, 0, st>>>(g, -prm->dt, density_in, U_in, flags, prm->sample_outside_fluid, rho_fwd, fidx, U_fwd);
+    k_step_advect_bwd<false><<<gr, bl, 0, st>>>(g, prm->dt, hs, density_in, U_in, flags, prm->sample_outside_fluid, rho_fwd, fidx, U_fwd, m, rho1, U1);
+    k_step_forces_div<false><<<gr, bl, 0, st>>>(g, rho1, U1, flags, m, f, density_out, U_out, div);
+  }
+  fnx_count_launches(3);
+  FNX_CUDA_TRY("step", cudaGetLastError());
   return FNX_OK;
 }
 
 int fnx_step_project_bcs(const float* pressure, float* U, const float* flags, const float* UBC,
-                         const float* UBCInvMask, int B, int D, int H, int W, int is3d, void* stream) {
-  const size_t n = (size_t)B * D * H * W;
-  const int nc = is3d ? 3 : 2;
-  FNX_TRY(fnx_velocity_update(pressure, U, flags, B, D, H, W, is3d, stream));  // simulate.py:154
-  FNX_TRY(fnx_set_wall_bcs(U, flags, B, D, H, W, is3d, stream));               // :159
-  if (UBC && UBCInvMask) FNX_TRY(fnx_set_const_vals(U, UBCInvMask, UBC, n * nc, stream));  // :168
+                         const float* UBCInvMask, const unsigned char* mask_rows, int apply_wall_bcs, int B, int D,
+                         int H, int W, int is3d, void* stream) {
+  if (B < 1 || D < 1 || H < 2 || W < 2 || (is3d && D < 2) || (!is3d && D != 1))
+    return fnx_set_error(FNX_ERR_ARG, "step: unsupported grid B=%d D=%d H=%d W=%d is3d=%d", B, D, H, W, is3d);
+  Grid g = make_grid(B, D, H, W);
+  StepMasks m;
+  const bool ubc = UBC && UBCInvMask;
+  m.UBC = ubc ? UBC : nullptr; m.UBCInv = ubc ? UBCInvMask : nullptr;
+  m.rBC = nullptr; m.rBCInv = nullptr; m.rows = mask_rows;
+  if (is3d) k_step_project<true><<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, pressure, U, flags, m, apply_wall_bcs);
+  else k_step_project<false><<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, pressure, U, flags, m, apply_wall_bcs);
+  fnx_count_launches(1);
+  FNX_CUDA_TRY("step", cudaGetLastError());
   return FNX_OK;
 }
 
-int fnx_step_jacobi(const fnx_step_params* prm, float* density, float* U, const float* flags, float* p,
-                    float* residual, const float* UBC, const float* UBCInvMask, const float* densityBC,
-                    const float* densityBCInvMask, int B, int D, int H, int W, int is3d, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+int fnx_step_jacobi(const fnx_step_params* prm, const float* density_in, const float* U_in, const float* flags,
+                    const float* UBC, const float* UBCInvMask, const float* densityBC, const float* densityBCInvMask,
+                    const unsigned char* mask_rows, float* density_out, float* U_out, float* p, float* residual, int B,
+                    int D, int H, int W, int is3d, void* workspace, size_t workspace_bytes, void* stream) {
   if (!prm) return fnx_set_error(FNX_ERR_ARG, "step: null params");
   if (!workspace || workspace_bytes < fnx_step_workspace(B, D, H, W, is3d))
     return fnx_set_error(FNX_ERR_WORKSPACE, "step: workspace too small");
   const size_t n = (size_t)B * D * H * W;
   const int nc = is3d ? 3 : 2;
   char* ws = (char*)workspace;
-  ws += align256(n * sizeof(float)) + align256(n * nc * sizeof(float)) +
-        align256(fnx_advect_scalar_workspace(B, D, H, W)) + align256(fnx_advect_vel_workspace(B, D, H, W, is3d));
-  float* div = (float*)ws; ws += align256(n * sizeof(float));
-  void* ws_j = ws; const size_t ws_j_bytes = align256(fnx_jacobi_workspace(B, D, H, W, 1));
-  FNX_TRY(fnx_step_advect_forces_div(prm, density, U, flags, UBC, UBCInvMask, densityBC, densityBCInvMask, div, B,
-                                     D, H, W, is3d, workspace, workspace_bytes, stream));
+  ws += 2 * align256(n * sizeof(float)) + align256(n * sizeof(int)) + 2 * align256(n * nc * sizeof(float));
+  float* div = (float*)ws_take(ws, n * sizeof(float));
+  void* ws_j = ws;
+  const size_t ws_j_bytes = align256(fnx_jacobi_workspace(B, D, H, W, 1));
+  fnx_step_params q = *prm;
+  q.apply_wall_bcs = 1;
+  q.density_const_passes = 2;  // simulate.py:133 and :168 both re-apply the density BC
+  FNX_TRY(fnx_step_advect_forces_div(&q, density_in, U_in, flags, UBC, UBCInvMask, densityBC, densityBCInvMask,
+                                     mask_rows, density_out, U_out, div, B, D, H, W, is3d, workspace, workspace_bytes,
+                                     stream));
   FNX_TRY(fnx_solve_linear_system_jacobi(flags, div, p, residual, B, D, H, W, is3d, 0.f, prm->jacobi_iters, nullptr,
                                          ws_j, ws_j_bytes, stream));
-  FNX_TRY(fnx_step_project_bcs(p, U, flags, UBC, UBCInvMask, B, D, H, W, is3d, stream));
-  // simulate.py:168: the last setConstVals also re-applies the density BC
-  if (densityBC && densityBCInvMask) FNX_TRY(fnx_set_const_vals(density, densityBCInvMask, densityBC, n, stream));
+  FNX_TRY(fnx_step_project_bcs(p, U_out, flags, UBC, UBCInvMask, mask_rows, 1, B, D, H, W, is3d, stream));
   return FNX_OK;
 }
 

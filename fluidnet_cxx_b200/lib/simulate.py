@@ -128,15 +128,40 @@ def _simulate(mconf, batch_dict, net, sim_method, output_div=False):
 
 
 # ---------------------------------------------------------------------------------------------
+_mask_rows_cache = {}
+
+
+def _mask_rows(lib, batch_dict, flags, is3d):
+    """Per-row "mask differs from identity" bytes (fnx_mask_rows), cached on the mask tensors'
+    storage + version counters so it is recomputed only when a mask is modified."""
+    UBC, UBCInv, rBC, rBCInv = _masks(batch_dict)
+    if UBC is None and rBC is None:
+        return None
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None
+                for t in (UBC, UBCInv, rBC, rBCInv))
+    hit = _mask_rows_cache.get(flags.device)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    B, D, H, W = N.grid_of(flags)
+    rows = torch.empty(B * D * H, dtype=torch.uint8, device=flags.device)
+    N.check(lib.fnx_mask_rows(N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), rows.data_ptr(), B, D, H, W,
+                              is3d, N.stream_of(flags)), "simulate")
+    _mask_rows_cache[flags.device] = (key, rows, (UBC, UBCInv, rBC, rBCInv))   # keep the tensors alive
+    return rows
+
+
 def _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div):
     lib = N.load()
     flags = batch_dict['flags']
-    # new tensors for the new state (the reference never mutates the caller's old U / density)
-    U = batch_dict['U'].clone()
-    density = batch_dict['density'].clone()
+    U_in, rho_in = batch_dict['U'], batch_dict['density']
+    # the new state goes to new tensors (the reference never mutates the caller's old U / density)
+    U = torch.empty_like(U_in)
+    density = torch.empty_like(rho_in)
     B, D, H, W = N.grid_of(flags)
     is3d = int(U.size(1) == 3)
     UBC, UBCInv, rBC, rBCInv = _masks(batch_dict)
+    rows = _mask_rows(lib, batch_dict, flags, is3d)
+    rows_ptr = rows.data_ptr() if rows is not None else None
     ws = N.workspaces.get(U.device, "step", lib.fnx_step_workspace(B, D, H, W, is3d))
     st = N.stream_of(U)
     prm = _step_params(mconf, dt, mconf['jacobiIter'])
@@ -144,25 +169,27 @@ def _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div):
     residual = torch.empty((), dtype=torch.float32, device=U.device)
     if _stage_hook is None:
         # one C-ABI call for the whole step
-        N.check(lib.fnx_step_jacobi(ctypes.byref(prm), N.ptr(density), N.ptr(U), N.ptr(flags), N.ptr(p),
-                                    residual.data_ptr(), N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv),
-                                    B, D, H, W, is3d, ws.data_ptr(), ws.numel(), st), "simulate")
+        N.check(lib.fnx_step_jacobi(ctypes.byref(prm), N.ptr(rho_in), N.ptr(U_in), N.ptr(flags), N.ptr(UBC),
+                                    N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), rows_ptr, N.ptr(density), N.ptr(U),
+                                    N.ptr(p), residual.data_ptr(), B, D, H, W, is3d, ws.data_ptr(), ws.numel(), st),
+                "simulate")
     else:
         # same kernels, issued stage by stage so a profiler hook can bracket the pressure solve
+        prm.apply_wall_bcs = 1
+        prm.density_const_passes = 2
         div = torch.empty_like(flags)
-        N.check(lib.fnx_step_advect_forces_div(ctypes.byref(prm), N.ptr(density), N.ptr(U), N.ptr(flags),
-                                               N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), N.ptr(div),
-                                               B, D, H, W, is3d, ws.data_ptr(), ws.numel(), st), "simulate")
+        N.check(lib.fnx_step_advect_forces_div(ctypes.byref(prm), N.ptr(rho_in), N.ptr(U_in), N.ptr(flags),
+                                               N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), rows_ptr,
+                                               N.ptr(density), N.ptr(U), N.ptr(div), B, D, H, W, is3d,
+                                               ws.data_ptr(), ws.numel(), st), "simulate")
         wj = N.workspaces.get(U.device, "jacobi", lib.fnx_jacobi_workspace(B, D, H, W, prm.jacobi_iters))
         _stage_hook("pressure", "begin")
         N.check(lib.fnx_solve_linear_system_jacobi(N.ptr(flags), N.ptr(div), N.ptr(p), residual.data_ptr(), B, D, H,
                                                    W, is3d, 0.0, prm.jacobi_iters, None, wj.data_ptr(), wj.numel(),
                                                    st), "simulate")
         _stage_hook("pressure", "end")
-        N.check(lib.fnx_step_project_bcs(N.ptr(p), N.ptr(U), N.ptr(flags), N.ptr(UBC), N.ptr(UBCInv), B, D, H, W,
-                                         is3d, st), "simulate")
-        if rBC is not None:
-            fluid.setConstVals(density, rBCInv, rBC)
+        N.check(lib.fnx_step_project_bcs(N.ptr(p), N.ptr(U), N.ptr(flags), N.ptr(UBC), N.ptr(UBCInv), rows_ptr, 1,
+                                         B, D, H, W, is3d, st), "simulate")
     batch_dict['U'], batch_dict['density'], batch_dict['p'] = U, density, p
 
 

@@ -104,39 +104,51 @@ int fnx_get_centered(const float *U, float *out, int B, int D, int H, int W, int
                      void *stream);
 
 /* ---- fused fast path behind lib.simulate (simulate.py:28-171) --------------- */
-/* One inviscid Jacobi step of the standard sequence
+/* The standard inviscid sequence of both reference drivers
  *   advectScalar -> advectVelocity -> setConstVals -> addBuoyancy/addGravity ->
- *   setWallBcs -> setConstVals -> velocityDivergence -> Jacobi(max_iter, p_tol<=0)
- *   -> velocityUpdate -> setWallBcs -> setConstVals
- * with identical per-cell arithmetic to the individual entry points.  All state
- * tensors are updated in place (density, U, p); masks may be NULL (no BCs). */
+ *   [setWallBcs] -> setConstVals -> velocityDivergence -> (Jacobi | CNN)
+ *   -> velocityUpdate -> [setWallBcs] -> setConstVals
+ * in four kernels + the pressure solve, with per-cell arithmetic identical to the
+ * individual entry points.  density_out / U_out may alias density_in / U_in
+ * (in place) or be new tensors; masks may be NULL (no imposed values). */
 typedef struct fnx_step_params {
   float dt, maccormack_strength;
   int sample_outside_fluid;
   int use_buoyancy, use_gravity;
-  float buoyancy3[3]; /* gravityVec * (-buoyancyScale) */
-  float gravity3[3];  /* gravityVec * (-gravityScale)  */
+  float buoyancy3[3]; /* gravityVec * (-buoyancyScale), simulate.py:101-105 */
+  float gravity3[3];  /* gravityVec * (-gravityScale),  simulate.py:109-114 */
   float rho_star;
-  int jacobi_iters;   /* used by fnx_step_jacobi */
+  int jacobi_iters;          /* fnx_step_jacobi */
+  int apply_wall_bcs;        /* simulate.py:120-123: 1 in the jacobi branch, 0 ahead of the CNN */
+  int density_const_passes;  /* further setConstVals passes folded into density_out (simulate.py:133,168) */
 } fnx_step_params;
 
 size_t fnx_step_workspace(int B, int D, int H, int W, int is3d);
-/* stage 1+2 of the step: advection + BCs + forces + wall BCs + divergence.
- * in: density,U,flags (+masks) ; out: density,U updated in place, div written */
-int fnx_step_advect_forces_div(const fnx_step_params *prm, float *density, float *U,
-                               const float *flags, const float *UBC, const float *UBCInvMask,
-                               const float *densityBC, const float *densityBCInvMask, float *div,
-                               int B, int D, int H, int W, int is3d, void *workspace,
-                               size_t workspace_bytes, void *stream);
-/* stage 4 of the step: velocityUpdate + setWallBcs + setConstVals (in place on U) */
+/* rows[b*D*H + row]: bit0 = the U masks of that grid row differ from (InvMask=1, BC=0), bit1 =
+ * the density masks do.  Lets the step kernels skip mask loads on identity rows (the plume
+ * inlet touches 4 rows).  Recompute whenever a mask tensor changes. */
+int fnx_mask_rows(const float *UBC, const float *UBCInvMask, const float *densityBC,
+                  const float *densityBCInvMask, unsigned char *rows, int B, int D, int H, int W,
+                  int is3d, void *stream);
+/* advection + BCs + forces + [wall BCs] + BCs + divergence.  div may be NULL. */
+int fnx_step_advect_forces_div(const fnx_step_params *prm, const float *density_in,
+                               const float *U_in, const float *flags, const float *UBC,
+                               const float *UBCInvMask, const float *densityBC,
+                               const float *densityBCInvMask, const unsigned char *mask_rows,
+                               float *density_out, float *U_out, float *div, int B, int D, int H,
+                               int W, int is3d, void *workspace, size_t workspace_bytes,
+                               void *stream);
+/* velocityUpdate + [setWallBcs] + setConstVals, in place on U */
 int fnx_step_project_bcs(const float *pressure, float *U, const float *flags, const float *UBC,
-                         const float *UBCInvMask, int B, int D, int H, int W, int is3d,
-                         void *stream);
-/* whole Jacobi step (stages 1..4); p and residual as in fnx_solve_linear_system_jacobi */
-int fnx_step_jacobi(const fnx_step_params *prm, float *density, float *U, const float *flags,
-                    float *p, float *residual, const float *UBC, const float *UBCInvMask,
-                    const float *densityBC, const float *densityBCInvMask, int B, int D, int H,
-                    int W, int is3d, void *workspace, size_t workspace_bytes, void *stream);
+                         const float *UBCInvMask, const unsigned char *mask_rows,
+                         int apply_wall_bcs, int B, int D, int H, int W, int is3d, void *stream);
+/* whole Jacobi step; p and residual as in fnx_solve_linear_system_jacobi (p_tol = 0) */
+int fnx_step_jacobi(const fnx_step_params *prm, const float *density_in, const float *U_in,
+                    const float *flags, const float *UBC, const float *UBCInvMask,
+                    const float *densityBC, const float *densityBCInvMask,
+                    const unsigned char *mask_rows, float *density_out, float *U_out, float *p,
+                    float *residual, int B, int D, int H, int W, int is3d, void *workspace,
+                    size_t workspace_bytes, void *stream);
 
 /* ---- FluidNet / MultiScaleNet forward (model.py:76-227, multi_scale_net.py:101-127) */
 /* unbiased std over all elements of x per batch row, clamped below by `threshold`

@@ -105,7 +105,8 @@ def test_jacobi_golden(fluid, case):
 def test_plume128_jacobi28_golden(fluid):
     """BASELINE.json configs[0]: 128x128 plume, Jacobi 28 -- the reference's own state after
     1, 2, 8 and 24 steps; the fused step and the op-by-op sequence must both reproduce it."""
-    from fluidnet_cxx_b200.lib import simulate as sim
+    import importlib
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
     G = load_golden("plume128_jacobi28")
     mconf = plume_mconf()
     for mode in ("fused", "ops"):
@@ -240,7 +241,8 @@ def test_batched(fluid, oracle):
 def test_step3d_vs_oracle(fluid, oracle):
     """3-D plume-like step (configs[4] semantics at a size the oracle finishes in seconds):
     fused step == op-by-op oracle sequence."""
-    from fluidnet_cxx_b200.lib import simulate as sim
+    import importlib
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
     D = H = W = 24
     mconf = plume_mconf(jacobiIter=9)
     bd = plume_state(fluid, W, mconf, depth=D)
@@ -288,7 +290,8 @@ def oracle_step(orc, mconf, st):
 # (3) properties at full size (BASELINE.json configs[3]: 4096x4096 plume, Jacobi 100)
 # ---------------------------------------------------------------------------------------------
 def test_full_size_properties(fluid):
-    from fluidnet_cxx_b200.lib import simulate as sim
+    import importlib
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
     res = 4096
     mconf = plume_mconf(jacobiIter=100)
     bd = plume_state(fluid, res, mconf)
