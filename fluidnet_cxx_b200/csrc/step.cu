@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(128)
       ract |= (__ldg(rBC + o) != 0.f) | (__ldg(rBCInv + o) != 1.f);
     }
   }
-  const int any = __syncthreads_or(uact | (ract << 1));
-  const int anyu = __syncthreads_or(uact);
-  if (threadIdx.x == 0) rows[row] = (unsigned char)((anyu ? 1 : 0) | ((any & 2) ? 2 : 0));
+  const int anyu = __syncthreads_or(uact);  // (returns a predicate, not a bitwise OR)
+  const int anyr = __syncthreads_or(ract);
+  if (threadIdx.x == 0) rows[row] = (unsigned char)((anyu ? 1 : 0) | (anyr ? 2 : 0));
 }
 
 // x*InvMask + BC for velocity component c / density, skipping rows whose masks are the identity.
