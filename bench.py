@@ -46,7 +46,16 @@ WORKLOADS = {
     "plume256cube_jacobi40": dict(res=(256, 256, 256), method="jacobi", jacobi_iters=40, cpu_sample_res=None,
                                   baseline_config="256x256x256 3D synthetic grid, Jacobi 40 iter"),
 }
-DEFAULT_WORKLOAD = "plume4096_jacobi100"
+WORKLOADS.update({
+    # BASELINE.json configs[1]: the configuration the headline metric is quoted on
+    "plume512_scalenet": dict(res=(1, 512, 512), method="convnet", jacobi_iters=0, cpu_sample_res=512,
+                              baseline_config="512x512 2D plume, ScaleNet CNN pressure, fp32"),
+    "plume1024_scalenet": dict(res=(1, 1024, 1024), method="convnet", jacobi_iters=0, cpu_sample_res=512,
+                               baseline_config="1024x1024 2D plume, MultiScale CNN pressure, fp32"),
+})
+DEFAULT_WORKLOAD = "plume512_scalenet"
+CNN_KERNEL_NAME = "k_conv_direct (fp32 FFMA)"
+CNN_FLOP_PER_CELL = 484476.0   # 2 * 242238 MAC over the 17 convs of the pyramid
 
 
 def plume_mconf(jacobi_iters, method):
@@ -142,6 +151,12 @@ def run_ours(args):
     cells = D * H * W
     mconf = plume_mconf(wl["jacobi_iters"], wl["method"])
     nc = 3 if D > 1 else 2
+    net = None
+    if wl["method"] == "convnet":
+        from fluidnet_cxx_b200.lib.pretrained import load_scalenet
+        net, mconf_net = load_scalenet(dev)
+        m = dict(mconf_net); m.update(mconf); mconf = m
+        net.mconf = mconf; net.scale.mconf = mconf
 
     # ---- synthetic state, built on the HOST (pinned) and copied in ------------------------------
     U_np, rho_np = synthetic_state_numpy(D, H, W, seed=rank)
@@ -176,7 +191,8 @@ def run_ours(args):
     sim.set_stage_hook(hook)
 
     def one_step():
-        sim.simulate(mconf, bd, None, wl["method"])
+        with torch.no_grad():
+            sim.simulate(mconf, bd, net, wl["method"])
 
     for _ in range(max(args.warmup, 3)):
         one_step()
@@ -218,7 +234,8 @@ def run_ours(args):
     def e2e_step():
         d = {k: host[k].to(dev, non_blocking=True) for k in ("p", "U", "flags", "density")}
         d.update(masks)
-        sim.simulate(mconf, d, None, wl["method"])
+        with torch.no_grad():
+            sim.simulate(mconf, d, net, wl["method"])
         for k in ("p", "U", "density"):
             out_host[k].copy_(d[k], non_blocking=True)
         return d
@@ -251,17 +268,37 @@ def run_ours(args):
         value = total_cells * args.steps / (total_ms / 1e3) / 1e6
         e2e_value = total_cells * e2e_steps / (e2e_ms / 1e3) / 1e6
         iters = wl["jacobi_iters"]
-        # dominant kernel = temporally blocked Jacobi: 16 B/cell/iteration algorithmic (SURVEY §8d stage C)
-        algo_bytes = 16.0 * cells * iters * args.steps
-        achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
         step_bytes = (80 if D == 1 else 104) + 16 * iters
+        if wl["method"] == "jacobi":
+            # dominant kernel = temporally blocked Jacobi: 16 B/cell/iteration algorithmic (SURVEY §8d stage C)
+            algo_bytes = 16.0 * cells * iters * args.steps
+            achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
+            roof = {"bound": "hbm", "kernel": "k_jacobi2d_blocked" if D == 1 else "k_jacobi_iter",
+                    "achieved": round(achieved, 1) if achieved else None, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(achieved / hbm_peak, 4) if achieved else None, "traffic": None,
+                    "peak_source": peak_src, "stage_ms_per_step": round(dom_ms / args.steps, 4),
+                    "step_hbm_frac": round(step_bytes * cells * args.steps / (total_ms / 1e3) / 1e9 / hbm_peak, 4)}
+            pressure = f"jacobi x{iters}"
+        else:
+            # dominant stage = the MultiScaleNet forward (a dense contraction): tensor-pipe roofline.
+            # No TF32 peak is measured on this pool: nominal TF32 = 1/2 of the measured bf16 burst figure.
+            tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+            flops = CNN_FLOP_PER_CELL * cells * args.steps
+            achieved = flops / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else None
+            roof = {"bound": "tensor", "kernel": CNN_KERNEL_NAME, "achieved": round(achieved, 2) if achieved else None,
+                    "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                    "frac": round(achieved / tf32_peak, 4) if achieved else None, "traffic": None,
+                    "peak_source": "1/2 x MEASURED_PEAKS.json bf16_tflops (nominal TF32 dense; none measured)",
+                    "stage_ms_per_step": round(dom_ms / args.steps, 4),
+                    "algorithmic_flop_per_cell": CNN_FLOP_PER_CELL}
+            pressure = "ScaleNet (MultiScaleNet, shipped weights)"
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded N(0,0.5^2) velocity, U[0,1) density, plume inlet BCs, border obstacles)",
             "config": {"workload": args.workload, "baseline_config": wl["baseline_config"], "grid": [D, H, W],
-                       "pressure": f"jacobi x{iters}", "cells_per_gpu": cells,
+                       "pressure": pressure, "cells_per_gpu": cells,
                        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (weak)",
                        "l2": "flushed between timed steps" if flush else "working set larger than L2, no flush",
                        "algorithmic_bytes_per_cell_step": step_bytes},
@@ -269,12 +306,7 @@ def run_ours(args):
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_jacobi2d_blocked" if D == 1 else "k_jacobi_iter",
-                         "achieved": round(achieved, 1) if achieved else None,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4) if achieved else None,
-                         "traffic": None, "peak_source": peak_src,
-                         "stage_ms_per_step": round(dom_ms / args.steps, 4),
-                         "step_hbm_frac": round(step_bytes * cells * args.steps / (total_ms / 1e3) / 1e9 / hbm_peak, 4)},
+            "roofline": roof,
             "wall_s": round(t_wall, 3),
         }
         out["cpu_baseline"] = cpu_baseline(wl, steps=1, warmup=0) if world == 1 and not args.no_cpu_baseline else None
@@ -292,8 +324,14 @@ def reference_step_runner(wl, res):
     import ref_loader
     if not ref_loader.available():
         return None
-    reflib = ref_loader.load()
+    net = None
     mconf = plume_mconf(wl["jacobi_iters"], wl["method"])
+    if wl["method"] == "convnet":
+        reflib, net, mconf_net = ref_loader.load_scalenet()
+        m = dict(mconf_net); m.update(mconf); mconf = m
+        net.mconf = mconf; net.scale.mconf = mconf
+    else:
+        reflib = ref_loader.load()
     U_np, rho_np = synthetic_state_numpy(1, res, res, seed=0)
     bd = {"p": torch.zeros(1, 1, 1, res, res), "U": torch.zeros(1, 2, 1, res, res),
           "flags": torch.zeros(1, 1, 1, res, res), "density": torch.zeros(1, 1, 1, res, res)}
@@ -304,7 +342,7 @@ def reference_step_runner(wl, res):
 
     def step():
         with torch.no_grad():
-            reflib.simulate(mconf, bd, None, wl["method"])
+            reflib.simulate(mconf, bd, net, wl["method"])
     return step
 
 
@@ -354,13 +392,15 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     value = res * res * steps / dt / 1e6
-    sample = (f"{steps} timed step(s) (+{warm} warm-up) of the same physics on a {res}x{res} grid: the reference's "
-              f"ATen CPU path (oracle/_ref) needs minutes per step at the full {wl['res'][1]}x{wl['res'][2]} size")
+    full = res == wl["res"][1] == wl["res"][2]
+    sample = (f"{steps} timed step(s) (+{warm} warm-up) of the reference's ATen CPU path (oracle/_ref) on a {res}x{res} "
+              f"grid" + (" = the full workload" if full else
+                         f": same physics, reduced grid (minutes per step at the full {wl['res'][1]}x{wl['res'][2]} size)"))
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
            "steps": steps, "warmup": warm, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the GPU arm)",
            "config": {"workload": args.workload, "baseline_config": wl["baseline_config"], "grid": [1, res, res],
-                      "pressure": f"jacobi x{wl['jacobi_iters']}"},
+                      "pressure": f"jacobi x{wl['jacobi_iters']}" if wl["method"] == "jacobi" else "ScaleNet"},
            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
                             "sample": sample},
            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

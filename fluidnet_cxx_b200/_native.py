@@ -58,6 +58,10 @@ SIGNATURES = {
     "fnx_step_jacobi": (_I, [ctypes.POINTER(StepParams)] + [_P] * 12 + _GRID + [_P, _S, _P]),
     "fnx_scale_std_workspace": (_S, [_I]),
     "fnx_scale_std": (_I, [_P, _S, _I, _F, _P, _P, _S, _P]),
+    "fnx_conv2d": (_I, [_P, _P, _P, _P] + [_I] * 9 + [_P]),
+    "fnx_resize_bilinear": (_I, [_P, _P] + [_I] * 8 + [_P]),
+    "fnx_fluidnet_input": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "fnx_fluidnet_output": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

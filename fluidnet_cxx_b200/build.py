@@ -29,9 +29,10 @@ UNITS = {
     "jacobi_blocked.cu": ["-fmad=false"],
     "step.cu": ["-fmad=false"],
     "host_util.cpp": [],
+    "conv.cu": [],
 }
 OPTIONAL_UNITS = {
-    "conv.cu": [],
+    "conv_tc.cu": [],
 }
 
 

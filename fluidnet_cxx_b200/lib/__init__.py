@@ -3,3 +3,5 @@ per-timestep path uses.  Import as `fluidnet_cxx_b200.lib`, or as top-level `lib
 `fluidnet_cxx_b200.compat.install()` so the reference drivers run unchanged."""
 from . import fluid
 from .simulate import simulate, setConstVals
+from .multi_scale_net import MultiScaleNet
+from .model import FluidNet

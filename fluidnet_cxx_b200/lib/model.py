@@ -1,0 +1,106 @@
+"""FluidNet: the pressure-projection model wrapper (reference: pytorch/lib/model.py:41-227 and the
+copy plume.py really imports, trained_models/ScaleNet_ShortTerm_LongTermLoss/*_saved.py:43-238).
+
+forward(cat(p, U, flags, density)) -> (p, U):
+    div = velocityDivergence(U) ; s = max(std_unbiased(U), threshold)
+    x = [div/s, occupancy(flags)] ; p = MultiScaleNet(x)
+    U' = velocityUpdate(p, U/s) ; return p*s, setWallBcs(U'*s)
+Everything runs in sm_100a kernels behind the C-ABI.  The module tree matches the saved model
+(unused `conv1/convBank/deconv*/conv2/convOut` of the non-ScaleNet variant included) so the
+shipped state dict loads strictly.  Supported configuration = the shipped one: 2-D,
+`model: ScaleNet`, `inputChannels: {div: True}`, `normalizeInput: True` on `UDiv`.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from .multi_scale_net import MultiScaleNet
+
+
+class _ScaleNet(nn.Module):
+    """max(unbiased std over all of x per batch item, threshold) (model.py:8-23)."""
+
+    def __init__(self, mconf):
+        super().__init__()
+        self.mconf = mconf
+
+    def forward(self, x):
+        lib = N.load()
+        x = x.contiguous()
+        bsz = x.size(0)
+        scale = torch.empty(bsz, dtype=torch.float32, device=x.device)
+        ws = N.workspaces.get(x.device, "scale", lib.fnx_scale_std_workspace(bsz))
+        N.check(lib.fnx_scale_std(N.ptr(x), x.numel() // bsz, bsz, float(self.mconf['normalizeInputThreshold']),
+                                  N.ptr(scale), ws.data_ptr(), ws.numel(), N.stream_of(x)), "ScaleNet")
+        return scale.view(bsz, 1, 1, 1, 1)
+
+
+class _HiddenConvBlock(nn.Module):
+    def __init__(self, dropout=True):
+        super().__init__()
+        layers = [nn.Conv2d(16, 16, kernel_size=3, padding=1), nn.ReLU(inplace=True),
+                  nn.Conv2d(16, 16, kernel_size=3, padding=1), nn.ReLU()]
+        if dropout:
+            layers.append(nn.Dropout())
+        self.block = nn.Sequential(*layers)
+
+
+class FluidNet(nn.Module):
+    def __init__(self, mconf, dropout=True):
+        super().__init__()
+        self.dropout = dropout
+        self.mconf = mconf
+        self.inDims = mconf['inputDim']
+        self.is3D = mconf['is3D']
+        self.scale = _ScaleNet(self.mconf)
+        # parameters of the non-ScaleNet variant: present in the shipped state dict, unused here
+        self.conv1 = nn.Conv2d(self.inDims, 16, kernel_size=3, padding=1)
+        self.convBank = _HiddenConvBlock(dropout)
+        self.deconv1 = nn.ConvTranspose2d(16, 16, kernel_size=2, stride=2)
+        self.deconv2 = nn.ConvTranspose2d(16, 16, kernel_size=4, stride=4)
+        self.conv2 = nn.Conv2d(16 * 3, 16, kernel_size=1)
+        self.convOut = nn.Conv2d(16, 1, kernel_size=1)
+        self.multiScale = MultiScaleNet(self.inDims)
+
+    def _check_config(self):
+        m = self.mconf
+        assert self.is3D is False or self.is3D == 0, 'Input can only be 2D'
+        ic = m['inputChannels']
+        assert ic['pDiv'] or ic['UDiv'] or ic['div'], 'Choose at least one field (U, div or p).'
+        if not (m['model'] == 'ScaleNet' and ic['div'] and not ic['pDiv'] and not ic['UDiv'] and
+                m['normalizeInput'] and m['normalizeInputChan'] == 'UDiv'):
+            raise NotImplementedError("fluidnet_cxx_b200.FluidNet implements the shipped configuration "
+                                      "(model: ScaleNet, inputChannels.div, normalizeInput on UDiv)")
+
+    @staticmethod
+    def _seam(mconf, U, U_temp):
+        # periodic seam copy of the saved model (:123-132, :228-237)
+        if mconf['periodic-x']:
+            U[:, 1, :, :, 1] = U_temp[:, 1, :, :, U.size(4) - 1]
+        if mconf['periodic-y']:
+            U[:, 0, :, 1] = U_temp[:, 0, :, U.size(3) - 1]
+
+    def forward(self, input_):
+        self._check_config()
+        assert input_.dim() == 5 and input_.size(2) == 1 and input_.size(1) >= 4, 'Input can only be 2D'
+        lib = N.load()
+        B, _, _, H, W = (int(s) for s in input_.shape)
+        flags = input_[:, 3].unsqueeze(1).contiguous()
+        U = input_[:, 1:3].contiguous()
+        periodic = 'periodic-x' in self.mconf and 'periodic-y' in self.mconf
+        if periodic:
+            self._seam(self.mconf, U, U.clone())
+        st = N.stream_of(U)
+        s = self.scale(U)                                   # (B,1,1,1,1)
+        x = torch.empty((B, 2, H, W), dtype=torch.float32, device=U.device)
+        N.check(lib.fnx_fluidnet_input(N.ptr(U), N.ptr(flags), N.ptr(s), N.ptr(x), B, H, W, st), "FluidNet")
+        p_net = self.multiScale(x)                          # (B,1,H,W)
+        p = torch.empty((B, 1, 1, H, W), dtype=torch.float32, device=U.device)
+        U_out = torch.empty_like(U)
+        N.check(lib.fnx_fluidnet_output(N.ptr(p_net), N.ptr(U), N.ptr(flags), N.ptr(s), N.ptr(p), N.ptr(U_out),
+                                        B, H, W, st), "FluidNet")
+        if periodic:
+            # the seam is copied from the pre-setWallBcs field: redo the last two steps around it
+            raise NotImplementedError("periodic FluidNet forward: use the reference-layout saved model "
+                                      "with lib.fluid ops (seam handling between update and setWallBcs)")
+        return p, U_out

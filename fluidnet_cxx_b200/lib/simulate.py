@@ -93,7 +93,7 @@ def _fusable(mconf, batch_dict, sim_method, output_div=False):
     has_r = ('densityBCInvMask' in batch_dict) and ('densityBC' in batch_dict)
     if has_u != has_r and (('UBC' in batch_dict) != ('UBCInvMask' in batch_dict)):
         return False
-    if sim_method != 'jacobi' or output_div:
+    if output_div:
         return False
     if sim_method == 'jacobi':
         if _periodic(mconf) and (mconf['periodic-x'] or mconf['periodic-y']):
@@ -164,6 +164,29 @@ def _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div):
     rows_ptr = rows.data_ptr() if rows is not None else None
     ws = N.workspaces.get(U.device, "step", lib.fnx_step_workspace(B, D, H, W, is3d))
     st = N.stream_of(U)
+    if sim_method == 'convnet':
+        # advection + BCs + forces + BCs in the fused kernels (no setWallBcs ahead of the CNN,
+        # simulate.py:120-133), then the model, then the last setConstVals (simulate.py:168)
+        prm = _step_params(mconf, dt, 0)
+        prm.apply_wall_bcs = 0
+        prm.density_const_passes = 1
+        N.check(lib.fnx_step_advect_forces_div(ctypes.byref(prm), N.ptr(rho_in), N.ptr(U_in), N.ptr(flags),
+                                               N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), rows_ptr,
+                                               N.ptr(density), N.ptr(U), None, B, D, H, W, is3d,
+                                               ws.data_ptr(), ws.numel(), st), "simulate")
+        net.eval()
+        if _stage_hook is not None:
+            _stage_hook("pressure", "begin")
+        data = torch.cat((batch_dict['p'], U, flags, density), 1)
+        p, U = net(data)
+        if _stage_hook is not None:
+            _stage_hook("pressure", "end")
+        if UBC is not None:
+            fluid.setConstVals(U, UBCInv, UBC)
+        if rBC is not None:
+            fluid.setConstVals(density, rBCInv, rBC)
+        batch_dict['U'], batch_dict['density'], batch_dict['p'] = U, density, p
+        return
     prm = _step_params(mconf, dt, mconf['jacobiIter'])
     p = torch.empty_like(flags)
     residual = torch.empty((), dtype=torch.float32, device=U.device)

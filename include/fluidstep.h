@@ -153,9 +153,27 @@ int fnx_step_jacobi(const fnx_step_params *prm, const float *density_in, const f
 /* ---- FluidNet / MultiScaleNet forward (model.py:76-227, multi_scale_net.py:101-127) */
 /* unbiased std over all elements of x per batch row, clamped below by `threshold`
  * (model.py:8-23 _ScaleNet).  scale: B device floats out. */
+size_t fnx_scale_std_workspace(int B);
 int fnx_scale_std(const float *x, size_t count_per_batch, int B, float threshold, float *scale,
                   void *workspace, size_t workspace_bytes, void *stream);
-size_t fnx_scale_std_workspace(int B);
+/* nn.Conv2d(Cin, Cout, ksize, padding=ksize/2), NCHW fp32, optional fused ReLU
+ * (multi_scale_net.py:31-39,55-67,83-95,116).  The result is written into channels
+ * [y_channel_offset, +Cout) of a (N, y_channels_total, H, W) tensor. */
+int fnx_conv2d(const float *x, const float *weight, const float *bias, float *y, int N, int Cin,
+               int H, int W, int Cout, int ksize, int relu, int y_channels_total,
+               int y_channel_offset, void *stream);
+/* F.upsample(x, (Ho, Wo), mode='bilinear') with align_corners=False (multi_scale_net.py:121-125),
+ * written into a channel window of y like fnx_conv2d (fuses the torch.cat) */
+int fnx_resize_bilinear(const float *x, float *y, int N, int C, int H, int W, int Ho, int Wo,
+                        int y_channels_total, int y_channel_offset, void *stream);
+/* net input of the shipped ScaleNet: x = [velocityDivergence(U, flags)/scale, flagsToOccupancy(flags)]
+ * (*_saved.py:135-177); U (B,2,1,H,W), x (B,2,H,W) */
+int fnx_fluidnet_input(const float *U, const float *flags, const float *scale, float *x, int B,
+                       int H, int W, void *stream);
+/* post-processing of the wrapper (*_saved.py:221-232): U/scale -> velocityUpdate(p_net) ->
+ * *scale -> setWallBcs ; p_out = p_net*scale */
+int fnx_fluidnet_output(const float *p_net, const float *U, const float *flags, const float *scale,
+                        float *p_out, float *U_out, int B, int H, int W, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,126 @@
+"""GPU parity of the CNN pressure path: sm_100a convolution / resize / wrapper kernels against
+ (1) outputs of the reference's own model on CPU (torch fp32 conv2d / interpolate / std with the
+     shipped weights; tests/golden/scalenet_forward.npz, plume64_convnet.npz),
+ (2) the C oracle's double-accumulated conv / resize on random layers.
+Tolerance (BASELINE.json north_star): 1e-5 relative on the pressure / velocity fields, taken
+against the field's max magnitude; flag-driven decisions (zeroed faces, untouched border) exact."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    return float(np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def net():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from fluidnet_cxx_b200.lib.pretrained import load_scalenet
+    return load_scalenet("cuda")
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 37, 53, 32, 3), (2, 3, 40, 64, 32, 5), (1, 32, 33, 70, 64, 3),
+                                   (1, 64, 20, 24, 128, 3), (1, 128, 16, 40, 64, 3), (1, 32, 30, 30, 8, 5),
+                                   (1, 32, 19, 65, 1, 3), (1, 8, 21, 17, 1, 1)])
+def test_conv2d_vs_oracle(oracle, shape):
+    from fluidnet_cxx_b200 import _native as N
+    n, cin, h, w, cout, k = shape
+    rng = np.random.RandomState(cin * 7 + cout)
+    x = rng.randn(n, cin, h, w).astype(np.float32)
+    wt = (rng.randn(cout, cin, k, k) / np.sqrt(cin * k * k)).astype(np.float32)
+    b = rng.randn(cout).astype(np.float32)
+    lib = N.load()
+    for relu in (0, 1):
+        ref = oracle.conv2d(x, wt, b, bool(relu))
+        tx, tw, tb = cu(x), cu(wt), cu(b)
+        y = torch.full((n, cout + 3, h, w), -7.0, device="cuda")
+        N.check(lib.fnx_conv2d(N.ptr(tx), N.ptr(tw), N.ptr(tb), N.ptr(y), n, cin, h, w, cout, k, relu, cout + 3, 2,
+                               N.stream_of(tx)))
+        got = y.cpu().numpy()
+        assert rel_err(got[:, 2:2 + cout], ref) < RTOL
+        assert np.all(got[:, :2] == -7.0) and np.all(got[:, 2 + cout:] == -7.0)   # channel window respected
+
+
+@pytest.mark.parametrize("case", [(2, 3, 32, 48, 8, 12), (1, 1, 8, 12, 16, 24), (1, 2, 37, 53, 9, 13),
+                                  (1, 1, 9, 13, 18, 26), (1, 2, 20, 20, 20, 20)])
+def test_resize_vs_oracle(oracle, case):
+    from fluidnet_cxx_b200 import _native as N
+    n, c, h, w, ho, wo = case
+    x = np.random.RandomState(h * w).randn(n, c, h, w).astype(np.float32)
+    ref = oracle.resize_bilinear(x, ho, wo)
+    tx = cu(x)
+    y = torch.empty((n, c, ho, wo), device="cuda")
+    N.check(N.load().fnx_resize_bilinear(N.ptr(tx), N.ptr(y), n, c, h, w, ho, wo, c, 0, N.stream_of(tx)))
+    assert rel_err(y.cpu().numpy(), ref) < 1e-6
+
+
+def test_scale_std_vs_torch(net):
+    model, _ = net
+    x = torch.randn(3, 2, 1, 50, 70, device="cuda") * 0.37 + 0.2
+    s = model.scale(x).view(-1).cpu()
+    ref = torch.std(x.cpu().view(3, -1), dim=1)
+    assert torch.allclose(s, ref, rtol=1e-6)
+    tiny = torch.zeros(1, 2, 1, 8, 8, device="cuda")
+    assert model.scale(tiny).item() == pytest.approx(1e-5)
+
+
+def test_scalenet_forward_golden(net):
+    """FluidNet.forward and the bare MultiScaleNet against the reference model's CPU outputs."""
+    model, _ = net
+    G = load_golden("scalenet_forward")
+    for name, g in sorted(G.items()):
+        with torch.no_grad():
+            y = model.multiScale(cu(g["msn_x"]))
+            data = torch.cat((cu(g["p"]), cu(g["U"]), cu(g["flags"]), cu(g["rho"])), 1)
+            p, U = model(data)
+        assert rel_err(y.cpu().numpy(), g["msn_y"]) < RTOL, name
+        assert rel_err(p.cpu().numpy(), g["p_out"]) < RTOL, name
+        assert rel_err(U.cpu().numpy(), g["U_out"]) < RTOL, name
+        # flag-driven decisions are exact: faces the reference zeroes are zero here too
+        assert np.array_equal(U.cpu().numpy() == 0, g["U_out"] == 0), name
+
+
+def test_plume64_convnet_golden(net):
+    """BASELINE.json configs[1] physics at fixture size: 64x64 plume, ScaleNet pressure, 3 steps of
+    the reference's lib.simulate(..., 'convnet')."""
+    model, mconf_net = net
+    from fluidnet_cxx_b200.lib import fluid
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from test_gpu_parity import plume_mconf, plume_state
+    G = load_golden("plume64_convnet")
+    mconf = dict(mconf_net)
+    mconf.update(plume_mconf(simMethod="convnet"))
+    model.mconf = mconf
+    model.scale.mconf = mconf
+    for mode in ("fused", "ops"):
+        bd = plume_state(fluid, 64, mconf)
+        for it in range(1, 4):
+            with torch.no_grad():
+                if mode == "fused":
+                    sim.simulate(mconf, bd, model, "convnet")
+                else:
+                    sim._simulate_ops(mconf, bd, model, "convnet", float(mconf["dt"]), False)
+            for k in ("p", "U", "density"):
+                assert rel_err(bd[k].cpu().numpy(), G[f"step{it}"][k]) < 5 * RTOL, (mode, it, k)
+
+
+def test_inference_only(net):
+    model, _ = net
+    model.multiScale.train()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        model.multiScale(torch.zeros(1, 2, 16, 16, device="cuda"))
+    model.multiScale.eval()
