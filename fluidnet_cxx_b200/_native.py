@@ -28,6 +28,24 @@ class StepParams(ctypes.Structure):
                 ("apply_wall_bcs", _c_int), ("density_const_passes", _c_int)]
 
 
+class ActMeta(ctypes.Structure):
+    """struct fnx_act_meta (include/fluidstep.h)."""
+    _fields_ = [("amax_bits", ctypes.c_uint), ("scale", _c_float)]
+
+
+class ConvLayer(ctypes.Structure):
+    """struct fnx_conv_layer (include/fluidstep.h)."""
+    _fields_ = [("weight", _c_void_p), ("bias", _c_void_p), ("w_tc", _c_void_p),
+                ("cin", _c_int), ("cout", _c_int), ("ksize", _c_int), ("relu", _c_int),
+                ("w_scale", _c_float), ("w_norm", _c_float), ("b_max", _c_float)]
+
+
+class MsnetPlan(ctypes.Structure):
+    """struct fnx_msnet_plan (include/fluidstep.h)."""
+    _fields_ = [("data_channels", _c_int), ("quarter", ConvLayer * 4), ("half", ConvLayer * 6),
+                ("full", ConvLayer * 6), ("final_conv", ConvLayer)]
+
+
 # name -> (restype, argtypes); every symbol include/fluidstep.h declares
 _P, _I, _F, _S = _c_void_p, _c_int, _c_float, _c_size_t
 _GRID = [_I, _I, _I, _I, _I]  # B, D, H, W, is3d
@@ -60,6 +78,16 @@ SIGNATURES = {
     "fnx_scale_std": (_I, [_P, _S, _I, _F, _P, _P, _S, _P]),
     "fnx_conv2d": (_I, [_P, _P, _P, _P] + [_I] * 9 + [_P]),
     "fnx_resize_bilinear": (_I, [_P, _P] + [_I] * 8 + [_P]),
+    "fnx_tc_act_bytes": (_S, [_I, _I, _I]),
+    "fnx_tc_weight_bytes": (_S, [_I, _I]),
+    "fnx_tc_pack_weights3x3": (_I, [_P, _I, _I, _F, _P, _P]),
+    "fnx_tc_amax": (_I, [_P, _S, _P, _P]),
+    "fnx_tc_pack_split": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "fnx_tc_unpack_split": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "fnx_conv3x3_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _I, _I, _P]),
+    "fnx_msnet_workspace": (_S, [ctypes.POINTER(MsnetPlan), _I, _I]),
+    "fnx_msnet_workspace_init": (_I, [_P, _S, _P]),
+    "fnx_msnet_forward": (_I, [ctypes.POINTER(MsnetPlan), _P, _P, _I, _I, _I, _P, _S, _P]),
     "fnx_fluidnet_input": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "fnx_fluidnet_output": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
 }

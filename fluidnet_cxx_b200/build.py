@@ -30,10 +30,9 @@ UNITS = {
     "step.cu": ["-fmad=false"],
     "host_util.cpp": [],
     "conv.cu": [],
-}
-OPTIONAL_UNITS = {
     "conv_tc.cu": [],
 }
+OPTIONAL_UNITS = {}
 
 
 def _deps():

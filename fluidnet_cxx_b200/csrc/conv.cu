@@ -13,6 +13,7 @@
 
 #include "../../include/fluidstep.h"
 #include "fluid_common.cuh"
+#include "cnn_internal.h"
 #include "host_util.h"
 #include "stencil_device.cuh"
 
@@ -29,7 +30,8 @@ constexpr int CV_TW = 64, CV_TH = 4, CV_CIC = 8;
 template <int KS, int COT>
 __global__ void __launch_bounds__(128)
     k_conv_direct(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                  float* __restrict__ y, int Cin, int Cout, int H, int W, int relu, int y_ctotal, int y_coff) {
+                  float* __restrict__ y, int Cin, int Cout, int H, int W, int relu, int y_ctotal, int y_coff,
+                  unsigned* __restrict__ amax_bits) {
   constexpr int PAD = KS / 2;
   constexpr int SW = CV_TW + KS - 1, SH = CV_TH + KS - 1;
   constexpr int CO_BLK = 4 * COT;
@@ -87,11 +89,11 @@ __global__ void __launch_bounds__(128)
     __syncthreads();
   }
   const int gy = y0 + ty;
-  if (gy >= H) return;
+  float amax = 0.f;
 #pragma unroll
   for (int c = 0; c < COT; c++) {
     const int co = co0 + tz * COT + c;
-    if (co >= Cout) continue;
+    if (co >= Cout || gy >= H) continue;
     const float b = bias ? __ldg(bias + co) : 0.f;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
@@ -99,8 +101,14 @@ __global__ void __launch_bounds__(128)
       if (gx >= W) continue;
       float v = acc[q][c] + b;
       if (relu) v = v > 0.f ? v : 0.f;
+      amax = fmaxf(amax, fabsf(v));
       y[((size_t)(y_coff + co) * H + gy) * W + gx] = v;
     }
+  }
+  if (amax_bits) {  // max |y| of the layer, consumed by the split-fp16 packer of the tensor path
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((tid & 31) == 0 && amax > 0.f) atomicMax(amax_bits, __float_as_uint(amax));
   }
 }
 
@@ -211,35 +219,41 @@ using namespace fnx;
 
 template <int KS>
 static int launch_conv(const float* x, const float* w, const float* bias, float* y, int N, int Cin, int Cout, int H,
-                       int W, int relu, int y_ctotal, int y_coff, cudaStream_t st) {
+                       int W, int relu, int y_ctotal, int y_coff, unsigned* amax, cudaStream_t st) {
   dim3 block(128);
   if (Cout >= 8) {
     constexpr int COT = 8;
     dim3 grid((W + CV_TW - 1) / CV_TW, (H + CV_TH - 1) / CV_TH, N * ((Cout + 4 * COT - 1) / (4 * COT)));
-    k_conv_direct<KS, COT><<<grid, block, 0, st>>>(x, w, bias, y, Cin, Cout, H, W, relu, y_ctotal, y_coff);
+    k_conv_direct<KS, COT><<<grid, block, 0, st>>>(x, w, bias, y, Cin, Cout, H, W, relu, y_ctotal, y_coff, amax);
   } else {
     constexpr int COT = 1;
     dim3 grid((W + CV_TW - 1) / CV_TW, (H + CV_TH - 1) / CV_TH, N * ((Cout + 4 * COT - 1) / (4 * COT)));
-    k_conv_direct<KS, COT><<<grid, block, 0, st>>>(x, w, bias, y, Cin, Cout, H, W, relu, y_ctotal, y_coff);
+    k_conv_direct<KS, COT><<<grid, block, 0, st>>>(x, w, bias, y, Cin, Cout, H, W, relu, y_ctotal, y_coff, amax);
   }
   fnx_count_launches(1);
   FNX_CUDA_TRY("conv2d", cudaGetLastError());
   return FNX_OK;
 }
 
+int fnx_conv_direct(const float* x, const float* weight, const float* bias, float* y, int N, int Cin, int H, int W,
+                    int Cout, int ksize, int relu, int y_channels_total, int y_channel_offset, unsigned* amax_bits,
+                    cudaStream_t st) {
+  if (N < 1 || Cin < 1 || Cout < 1 || H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "conv2d: bad shape");
+  if (y_channels_total < y_channel_offset + Cout) return fnx_set_error(FNX_ERR_ARG, "conv2d: output channel window out of range");
+  switch (ksize) {
+    case 1: return launch_conv<1>(x, weight, bias, y, N, Cin, Cout, H, W, relu, y_channels_total, y_channel_offset, amax_bits, st);
+    case 3: return launch_conv<3>(x, weight, bias, y, N, Cin, Cout, H, W, relu, y_channels_total, y_channel_offset, amax_bits, st);
+    case 5: return launch_conv<5>(x, weight, bias, y, N, Cin, Cout, H, W, relu, y_channels_total, y_channel_offset, amax_bits, st);
+    default: return fnx_set_error(FNX_ERR_ARG, "conv2d: kernel size %d not supported (1, 3, 5)", ksize);
+  }
+}
+
 extern "C" {
 
 int fnx_conv2d(const float* x, const float* weight, const float* bias, float* y, int N, int Cin, int H, int W,
                int Cout, int ksize, int relu, int y_channels_total, int y_channel_offset, void* stream) {
-  if (N < 1 || Cin < 1 || Cout < 1 || H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "conv2d: bad shape");
-  if (y_channels_total < y_channel_offset + Cout) return fnx_set_error(FNX_ERR_ARG, "conv2d: output channel window out of range");
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (ksize) {
-    case 1: return launch_conv<1>(x, weight, bias, y, N, Cin, Cout, H, W, relu, y_channels_total, y_channel_offset, st);
-    case 3: return launch_conv<3>(x, weight, bias, y, N, Cin, Cout, H, W, relu, y_channels_total, y_channel_offset, st);
-    case 5: return launch_conv<5>(x, weight, bias, y, N, Cin, Cout, H, W, relu, y_channels_total, y_channel_offset, st);
-    default: return fnx_set_error(FNX_ERR_ARG, "conv2d: kernel size %d not supported (1, 3, 5)", ksize);
-  }
+  return fnx_conv_direct(x, weight, bias, y, N, Cin, H, W, Cout, ksize, relu, y_channels_total, y_channel_offset,
+                         nullptr, (cudaStream_t)stream);
 }
 
 int fnx_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo, int y_channels_total,

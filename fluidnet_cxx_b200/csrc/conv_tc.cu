@@ -1,0 +1,611 @@
+// conv_tc.cu -- MultiScaleNet forward on the sm_100a tensor cores (tcgen05 + TMEM), im2col-free.
+//
+// Reference: pytorch/lib/multi_scale_net.py:101-127 (the 17 nn.Conv2d of the three-scale pyramid).
+// The wide 3x3 layers (Cin, Cout in {32, 64, 128}: 96 % of the 484 476 FLOP/cell) run here as an
+// implicit GEMM  D[pixels x Cout] += A[pixels x Cin] . W_tap[Cin x Cout]  per filter tap.
+//
+// fp32 parity through fp16 tensor cores (the parity bar is 1e-5 relative):
+// every activation a and weight w is carried as an exact two-term fp16 expansion of a power-of-two
+// scaled value,  s*a = hi + lo  (22 significant bits), and the product is formed as
+// hi*hi + hi*lo + lo*hi in three kind::f16 MMAs accumulating in fp32 TMEM (the dropped lo*lo term is
+// 2^-22 relative).  Scales are powers of two, so scaling and un-scaling are exact.  The activation
+// scale of a layer's OUTPUT is chosen before the layer runs from a rigorous bound
+// max|y| <= max|x| * max_n sum_k |w_nk| + max|b|   (max|x| is measured by the producing kernel with an
+// atomicMax), so fp16 can never overflow and the resolution floor stays > 2^-30 of the bound.
+//
+// Data layout in HBM ("split chunked"): two fp16 planes (hi, lo), each [C/8][H+2P][W+2P][8 halves]
+// with a zero border of P = 2 pixels that no kernel ever writes (it IS the convolution's zero
+// padding).  One (pixel, 8-channel chunk) = 16 bytes = one row of a K-major UMMA core matrix, so a
+// staged row of pixels is directly a no-swizzle K-major operand whose row index is affine in the
+// pixel index (SBO = 128 B): the A operand of filter tap (ky, kx) is the SAME shared-memory tile with
+// the descriptor start address advanced by (ky*row_pitch + kx)*16 bytes.  Each input row is staged
+// once per 16-channel chunk by 1-D bulk copies of the TMA engine (cp.async.bulk, UBLKCP) and reused
+// by all 9 taps and all 3 split terms.
+//
+// Kernel shape: persistent, one CTA per SM, 192 threads = producer warp (bulk copies), MMA warp (one
+// thread issues tcgen05.mma), 4 epilogue warps (tcgen05.ld -> bias/ReLU -> split -> 16-byte stores).
+// A block of work = R output rows x 128 pixels x Cout: R accumulators of 128 x Cout fp32 in TMEM
+// (R*Cout <= 512 columns) so each streamed weight slot is reused by R M-tiles.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/fluidstep.h"
+#include "cnn_internal.h"
+#include "host_util.h"
+#include "tc_ptx.cuh"
+
+namespace fnx {
+namespace tc {
+
+constexpr int PAD = FNX_TC_PAD;   // zero border of the split chunked layout
+constexpr int TW = 128;           // pixels per M tile (one row segment)
+constexpr int RP = TW + 2;        // staged row pitch in pixels (1-pixel halo each side)
+constexpr uint32_t ROWB = RP * 16;  // bytes of one staged row of one 8-channel chunk
+
+struct ActMeta {  // == fnx_act_meta
+  unsigned amax_bits;  // fp32 bit pattern of max|a| over the tensor (atomicMax target)
+  float scale;         // power of two the stored hi+lo expansion is multiplied by
+};
+
+// power of two s with bound*s <= 2^14 (fp16 max is 2^16 - 32)
+__host__ __device__ __forceinline__ float pow2_scale_for(float bound) {
+  if (!(bound > 0.f) || !isfinite(bound)) return 1.f;
+  int e;
+  frexpf(bound, &e);  // bound = f * 2^e, f in [0.5, 1)
+  int k = 14 - e;
+  k = k > 100 ? 100 : (k < -100 ? -100 : k);
+  return ldexpf(1.f, k);
+}
+
+struct ConvArgs {
+  const __half* x;     // input planes: hi at x, lo at x + x_plane
+  size_t x_plane;      // halves
+  const uint8_t* w;    // packed weights: [Cin/16][3 (ky)] slots, slot = [kx][plane][j][Cout][8 halves]
+  const float* bias;
+  void* y;             // split planes (out_mode 0) or fp32 NCHW (out_mode 1)
+  size_t y_plane;      // halves (out_mode 0)
+  const ActMeta* in_meta;
+  ActMeta* out_meta;
+  int Cin, H, W, Hp, Wp;
+  int relu, out_mode, y_ctotal, y_coff;
+  float w_scale, w_norm, b_max;
+  int tiles_x, nblocks;
+};
+
+template <int COUT, int R, int WS>
+struct Cfg {
+  static constexpr uint32_t A_J = (R + 2) * ROWB;   // stride between the two 8-channel chunks = LBO(A)
+  static constexpr uint32_t A_PLANE = 2 * A_J;
+  static constexpr uint32_t A_STAGE = 2 * A_PLANE;  // hi + lo
+  static constexpr uint32_t W_J = COUT * 16;        // LBO(B)
+  static constexpr uint32_t W_PLANE = 2 * W_J;
+  static constexpr uint32_t W_KX = 2 * W_PLANE;
+  static constexpr uint32_t W_STAGE = 3 * W_KX;     // one (16-channel chunk, ky) slot
+  static constexpr uint32_t NBAR = 4 + 2 * WS + 2;
+  static constexpr uint32_t SMEM = 2 * A_STAGE + WS * W_STAGE + NBAR * 8 + 16 + COUT * 4;
+  static constexpr uint32_t TMEM_COLS = (R * COUT <= 32) ? 32 : (R * COUT <= 64) ? 64 : (R * COUT <= 128) ? 128
+                                        : (R * COUT <= 256) ? 256 : 512;
+  static_assert(R * COUT <= 512, "accumulators exceed TMEM");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+template <int COUT, int R, int WS>
+__global__ void __launch_bounds__(192, 1) k_conv3x3_tc(const ConvArgs a) {
+  using C = Cfg<COUT, R, WS>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + 2 * C::A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + WS * C::W_STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  const uint32_t bar0 = smem_u32(bars);
+  auto A_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto W_FULL = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto W_EMPTY = [&](int s) { return bar0 + 8u * (4 + WS + s); };
+  const uint32_t ACC_FULL = bar0 + 8u * (4 + 2 * WS), ACC_EMPTY = bar0 + 8u * (5 + 2 * WS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = a.Cin >> 4;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; s++) {
+      mbar_init(A_FULL(s), 1);
+      mbar_init(A_EMPTY(s), 1);
+    }
+    for (int s = 0; s < WS; s++) {
+      mbar_init(W_FULL(s), 1);
+      mbar_init(W_EMPTY(s), 1);
+    }
+    mbar_init(ACC_FULL, 1);
+    mbar_init(ACC_EMPTY, 4);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: stage activation rows and weight slots with the TMA engine =====
+    if (lane == 0) {
+      int as = 0, aph = 0, ws = 0, wph = 0;
+      for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
+        const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * R;
+        // staged rows are padded-image rows y0+PAD-1 .. y0+PAD+R; rows past the padded image are skipped
+        int nrows = a.Hp - (y0 + PAD - 1);
+        nrows = nrows > R + 2 ? R + 2 : nrows;
+        for (int c = 0; c < nchunks; c++) {
+          mbar_wait(A_EMPTY(as), aph ^ 1);
+          mbar_expect_tx(A_FULL(as), (uint32_t)nrows * 4u * ROWB);
+          const uint32_t dst0 = smem_u32(sA + as * C::A_STAGE);
+#pragma unroll
+          for (int pl = 0; pl < 2; pl++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const __half* src = a.x + pl * a.x_plane +
+                                  (((size_t)(c * 2 + j) * a.Hp + (y0 + PAD - 1)) * a.Wp + (x0 + PAD - 1)) * 8;
+              const uint32_t dst = dst0 + pl * C::A_PLANE + j * C::A_J;
+              for (int r = 0; r < nrows; r++) bulk_g2s(dst + r * ROWB, src + (size_t)r * a.Wp * 8, ROWB, A_FULL(as));
+            }
+          for (int ky = 0; ky < 3; ky++) {
+            mbar_wait(W_EMPTY(ws), wph ^ 1);
+            mbar_expect_tx(W_FULL(ws), C::W_STAGE);
+            bulk_g2s(smem_u32(sW + ws * C::W_STAGE), a.w + (size_t)(c * 3 + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
+            if (++ws == WS) { ws = 0; wph ^= 1; }
+          }
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread =====
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16_f32acc(128, COUT);
+      int as = 0, aph = 0, ws = 0, wph = 0, it = 0;
+      for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, it++) {
+        mbar_wait(ACC_EMPTY, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < nchunks; c++) {
+          mbar_wait(A_FULL(as), aph);
+          const uint32_t a_base = smem_u32(sA + as * C::A_STAGE);
+          const uint64_t a_hi0 = smem_desc_kmajor_noswz(a_base, C::A_J, 128);
+          const uint64_t a_lo0 = smem_desc_kmajor_noswz(a_base + C::A_PLANE, C::A_J, 128);
+          for (int ky = 0; ky < 3; ky++) {
+            mbar_wait(W_FULL(ws), wph);
+            tc_fence_after();
+            const uint32_t w_base = smem_u32(sW + ws * C::W_STAGE);
+            const uint64_t w0 = smem_desc_kmajor_noswz(w_base, C::W_J, 128);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+#pragma unroll
+              for (int kx = 0; kx < 3; kx++) {
+                const uint32_t aoff = (uint32_t)(((r + ky) * RP + kx) * 16) >> 4;
+                const uint64_t w_hi = w0 + ((uint32_t)(kx * C::W_KX) >> 4);
+                const uint64_t w_lo = w_hi + (C::W_PLANE >> 4);
+                const uint32_t d = taddr + (uint32_t)(r * COUT);
+                const uint32_t first = (c | ky | kx) != 0;
+                mma_f16_ss(d, a_lo0 + aoff, w_hi, idesc, first);
+                mma_f16_ss(d, a_hi0 + aoff, w_lo, idesc, 1);
+                mma_f16_ss(d, a_hi0 + aoff, w_hi, idesc, 1);
+              }
+            }
+            mma_commit(W_EMPTY(ws));
+            if (++ws == WS) { ws = 0; wph ^= 1; }
+          }
+          mma_commit(A_EMPTY(as));
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        mma_commit(ACC_FULL);
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> bias / ReLU -> (split fp16 | fp32 NCHW) =====
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const float s_in = a.in_meta->scale;
+    const float inv = 1.f / (s_in * a.w_scale);
+    const float s_out = pow2_scale_for(__uint_as_float(a.in_meta->amax_bits) * a.w_norm + a.b_max);
+    float amax = 0.f;
+    int it = 0;
+    for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, it++) {
+      const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * R;
+      const int px = x0 + q * 32 + lane;
+      mbar_wait(ACC_FULL, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int r = 0; r < R; r++) {
+        const int y = y0 + r;
+        const bool ok = (y < a.H) && (px < a.W);
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * COUT + c0), v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            float t = fmaf(__uint_as_float(v[i]), inv, s_bias[c0 + i]);
+            if (a.relu) t = fmaxf(t, 0.f);
+            f[i] = t;
+          }
+          if (ok) {  // lanes outside the image hold garbage accumulators: never stored, never in amax
+#pragma unroll
+            for (int i = 0; i < 16; i++) amax = fmaxf(amax, fabsf(f[i]));
+            if (a.out_mode == 0) {
+              __half* yh = reinterpret_cast<__half*>(a.y);
+#pragma unroll
+              for (int g = 0; g < 2; g++) {
+                __align__(16) __half2 hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                  const float u0 = f[g * 8 + 2 * i] * s_out, u1 = f[g * 8 + 2 * i + 1] * s_out;
+                  const __half h0 = __float2half_rn(u0), h1 = __float2half_rn(u1);
+                  hi[i] = __halves2half2(h0, h1);
+                  lo[i] = __halves2half2(__float2half_rn(u0 - __half2float(h0)), __float2half_rn(u1 - __half2float(h1)));
+                }
+                const size_t off = (((size_t)((c0 >> 3) + g) * a.Hp + (y + PAD)) * a.Wp + (px + PAD)) * 8;
+                *reinterpret_cast<uint4*>(yh + off) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(yh + a.y_plane + off) = *reinterpret_cast<const uint4*>(lo);
+              }
+            } else {
+              float* yf = reinterpret_cast<float*>(a.y);
+#pragma unroll
+              for (int i = 0; i < 16; i++) yf[((size_t)(a.y_coff + c0 + i) * a.H + y) * a.W + px] = f[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ACC_EMPTY);
+    }
+    if (a.out_meta) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (lane == 0 && amax > 0.f) atomicMax(&a.out_meta->amax_bits, __float_as_uint(amax));
+      if (blockIdx.x == 0 && warp == 2 && lane == 0) a.out_meta->scale = s_out;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(taddr, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 NCHW -> split chunked planes (channels zero-padded up to Cpad), scale from the measured amax
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_pack_split(const float* __restrict__ x, int C, int Cpad, int H, int W, const ActMeta* __restrict__ in_meta,
+                 __half* __restrict__ y, size_t y_plane, ActMeta* __restrict__ out_meta) {
+  const int Hp = H + 2 * PAD, Wp = W + 2 * PAD;
+  const size_t npix = (size_t)H * W;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float s = pow2_scale_for(__uint_as_float(in_meta->amax_bits));
+  if (e == 0) {
+    out_meta->scale = s;
+    out_meta->amax_bits = in_meta->amax_bits;
+  }
+  if (e >= npix * (size_t)(Cpad >> 3)) return;
+  const size_t pix = e % npix;
+  const int j = (int)(e / npix);
+  const int py = (int)(pix / W), px = (int)(pix % W);
+  __align__(16) __half2 hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c0 = j * 8 + 2 * i;
+    const float u0 = (c0 < C ? __ldg(x + (size_t)c0 * npix + pix) : 0.f) * s;
+    const float u1 = (c0 + 1 < C ? __ldg(x + (size_t)(c0 + 1) * npix + pix) : 0.f) * s;
+    const __half h0 = __float2half_rn(u0), h1 = __float2half_rn(u1);
+    hi[i] = __halves2half2(h0, h1);
+    lo[i] = __halves2half2(__float2half_rn(u0 - __half2float(h0)), __float2half_rn(u1 - __half2float(h1)));
+  }
+  const size_t off = (((size_t)j * Hp + (py + PAD)) * Wp + (px + PAD)) * 8;
+  *reinterpret_cast<uint4*>(y + off) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(y + y_plane + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// split chunked planes -> fp32 NCHW (tests / debugging of intermediate layers)
+__global__ void __launch_bounds__(256)
+    k_unpack_split(const __half* __restrict__ x, size_t x_plane, const ActMeta* __restrict__ meta, int C, int H, int W,
+                   float* __restrict__ y) {
+  const int Hp = H + 2 * PAD, Wp = W + 2 * PAD;
+  const size_t npix = (size_t)H * W;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= npix * (size_t)C) return;
+  const size_t pix = e % npix;
+  const int c = (int)(e / npix);
+  const int py = (int)(pix / W), px = (int)(pix % W);
+  const size_t off = (((size_t)(c >> 3) * Hp + (py + PAD)) * Wp + (px + PAD)) * 8 + (c & 7);
+  y[e] = (__half2float(x[off]) + __half2float(x[x_plane + off])) / meta->scale;
+}
+
+// weight (Cout, Cin, 3, 3) fp32 -> packed split slots [Cin/16][ky][kx][plane][j][Cout][8 halves]
+__global__ void __launch_bounds__(256)
+    k_pack_weights3x3(const float* __restrict__ w, int Cin, int Cout, float w_scale, __half* __restrict__ out) {
+  const size_t total = (size_t)Cin * Cout * 9;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int t = (int)(e % 9), ci = (int)((e / 9) % Cin), n = (int)(e / (9 * (size_t)Cin));
+  const int ky = t / 3, kx = t % 3, c = ci >> 4, j = (ci >> 3) & 1, i = ci & 7;
+  const float u = w[e] * w_scale;
+  const __half h = __float2half_rn(u);
+  const __half l = __float2half_rn(u - __half2float(h));
+  const size_t slot = ((size_t)(c * 3 + ky) * 3 + kx) * 2;  // then [plane][j][n][8]
+  out[(((slot + 0) * 2 + j) * Cout + n) * 8 + i] = h;
+  out[(((slot + 1) * 2 + j) * Cout + n) * 8 + i] = l;
+}
+
+}  // namespace tc
+}  // namespace fnx
+
+// =============================================================================================
+// host side
+// =============================================================================================
+using namespace fnx::tc;
+
+#define FNX_CUDA_TRY(who, call)                                                      \
+  do {                                                                               \
+    cudaError_t e_ = (call);                                                         \
+    if (e_ != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e_)); \
+  } while (0)
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+  }
+  return n;
+}
+
+static size_t act_plane_halves(int C, int H, int W) {
+  return (size_t)(C / 8) * (H + 2 * PAD) * (W + 2 * PAD) * 8;
+}
+
+template <int COUT, int R, int WS>
+static int launch_tc(ConvArgs a, cudaStream_t st) {
+  using C = Cfg<COUT, R, WS>;
+  auto kern = k_conv3x3_tc<COUT, R, WS>;
+  FNX_CUDA_TRY("conv3x3_tc", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  a.tiles_x = (a.W + TW - 1) / TW;
+  a.nblocks = a.tiles_x * ((a.H + R - 1) / R);
+  const int grid = a.nblocks < num_sms() ? a.nblocks : num_sms();
+  kern<<<grid, 192, C::SMEM, st>>>(a);
+  fnx_count_launches(1);
+  FNX_CUDA_TRY("conv3x3_tc", cudaGetLastError());
+  return FNX_OK;
+}
+
+static bool tc_eligible(int Cin, int Cout, int ksize) {
+  return ksize == 3 && Cin >= 16 && Cin % 16 == 0 && (Cout == 32 || Cout == 64 || Cout == 128);
+}
+
+__global__ void __launch_bounds__(256) k_amax(const float* __restrict__ x, size_t n, ActMeta* meta) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&meta->amax_bits, __float_as_uint(m));
+}
+
+extern "C" {
+
+size_t fnx_tc_act_bytes(int C, int H, int W) {
+  const int Cp = (C + 15) / 16 * 16;
+  return 2 * act_plane_halves(Cp, H, W) * sizeof(__half) + 4096;
+}
+
+size_t fnx_tc_weight_bytes(int Cin, int Cout) { return (size_t)Cin * Cout * 9 * 2 * sizeof(__half); }
+
+int fnx_tc_pack_weights3x3(const float* w, int Cin, int Cout, float w_scale, void* out, void* stream) {
+  if (!tc_eligible(Cin, Cout, 3)) return fnx_set_error(FNX_ERR_ARG, "tc_pack_weights3x3: unsupported shape %d->%d", Cin, Cout);
+  const size_t total = (size_t)Cin * Cout * 9;
+  k_pack_weights3x3<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, w_scale, (__half*)out);
+  fnx_count_launches(1);
+  FNX_CUDA_TRY("tc_pack_weights3x3", cudaGetLastError());
+  return FNX_OK;
+}
+
+int fnx_tc_amax(const float* x, size_t n, fnx_act_meta* meta, void* stream) {
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  k_amax<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, (ActMeta*)meta);
+  fnx_count_launches(1);
+  FNX_CUDA_TRY("tc_amax", cudaGetLastError());
+  return FNX_OK;
+}
+
+int fnx_tc_pack_split(const float* x, int C, int H, int W, const fnx_act_meta* in_meta, void* y, fnx_act_meta* out_meta,
+                      void* stream) {
+  if (C < 1 || H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "tc_pack_split: bad shape");
+  const int Cp = (C + 15) / 16 * 16;
+  const size_t total = (size_t)H * W * (Cp / 8);
+  k_pack_split<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, C, Cp, H, W, (const ActMeta*)in_meta, (__half*)y, act_plane_halves(Cp, H, W), (ActMeta*)out_meta);
+  fnx_count_launches(1);
+  FNX_CUDA_TRY("tc_pack_split", cudaGetLastError());
+  return FNX_OK;
+}
+
+int fnx_tc_unpack_split(const void* x, const fnx_act_meta* meta, int C, int H, int W, float* y, void* stream) {
+  if (C < 1 || H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "tc_unpack_split: bad shape");
+  const int Cp = (C + 15) / 16 * 16;
+  const size_t total = (size_t)H * W * C;
+  k_unpack_split<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, act_plane_halves(Cp, H, W), (const ActMeta*)meta, C, H, W, y);
+  fnx_count_launches(1);
+  FNX_CUDA_TRY("tc_unpack_split", cudaGetLastError());
+  return FNX_OK;
+}
+
+int fnx_conv3x3_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin, int Cout,
+                   int H, int W, int relu, float w_scale, float w_norm, float b_max, int out_mode, void* y,
+                   fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset, void* stream) {
+  if (!tc_eligible(Cin, Cout, 3)) return fnx_set_error(FNX_ERR_ARG, "conv3x3_tc: unsupported shape %d->%d", Cin, Cout);
+  if (H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "conv3x3_tc: bad shape");
+  if (out_mode == 0 && !out_meta) return fnx_set_error(FNX_ERR_ARG, "conv3x3_tc: split output needs out_meta");
+  if (out_mode == 1 && y_channels_total < y_channel_offset + Cout)
+    return fnx_set_error(FNX_ERR_ARG, "conv3x3_tc: output channel window out of range");
+  ConvArgs a;
+  a.x = (const __half*)x;
+  a.x_plane = act_plane_halves(Cin, H, W);
+  a.w = (const uint8_t*)w_packed;
+  a.bias = bias;
+  a.y = y;
+  a.y_plane = act_plane_halves(Cout, H, W);
+  a.in_meta = (const ActMeta*)in_meta;
+  a.out_meta = (ActMeta*)out_meta;
+  a.Cin = Cin; a.H = H; a.W = W; a.Hp = H + 2 * PAD; a.Wp = W + 2 * PAD;
+  a.relu = relu; a.out_mode = out_mode; a.y_ctotal = y_channels_total; a.y_coff = y_channel_offset;
+  a.w_scale = w_scale; a.w_norm = w_norm; a.b_max = b_max;
+  a.tiles_x = 0; a.nblocks = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (Cout) {
+    case 128: return launch_tc<128, 4, 3>(a, st);
+    case 64: return launch_tc<64, 8, 3>(a, st);
+    default: return launch_tc<32, 8, 3>(a, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MultiScaleNet.forward (multi_scale_net.py:101-127): one call, every launch enqueued on `stream`
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  }
+};
+constexpr int MAX_META = 64;
+
+struct Runner {
+  const fnx_msnet_plan* plan;
+  Bump ws;
+  bool dry;
+  cudaStream_t st;
+  int nmeta = 0;
+  ActMeta* metas;
+  ActMeta* new_meta() { return metas ? metas + (nmeta++ % MAX_META) : (nmeta++, nullptr); }
+
+  // runs one Sequential of convs at resolution (h, w); `in` fp32 NCHW with layers[0].cin channels;
+  // the last layer's output goes to `out` (fp32 NCHW, out_ctotal channels, window at out_coff)
+  int block(const fnx_conv_layer* L, int n, const float* in, int h, int w, float* out, int out_ctotal, int out_coff) {
+    const float* cur_f32 = in;
+    const void* cur_split = nullptr;
+    ActMeta* cur_meta = nullptr;  // amax valid (and scale, when split)
+    for (int i = 0; i < n; i++) {
+      const fnx_conv_layer& l = L[i];
+      const bool last = i == n - 1;
+      const bool tc_now = l.w_tc && tc_eligible(l.cin, l.cout, l.ksize);
+      const bool tc_next = !last && L[i + 1].w_tc && tc_eligible(L[i + 1].cin, L[i + 1].cout, L[i + 1].ksize);
+      if (tc_now) {
+        if (!cur_split) {
+          if (!cur_meta) {
+            cur_meta = new_meta();
+            if (!dry) { int rc = fnx_tc_amax(cur_f32, (size_t)l.cin * h * w, (fnx_act_meta*)cur_meta, st); if (rc) return rc; }
+          }
+          void* sp = ws.take(fnx_tc_act_bytes(l.cin, h, w));
+          ActMeta* m = new_meta();
+          if (!dry) { int rc = fnx_tc_pack_split(cur_f32, l.cin, h, w, (fnx_act_meta*)cur_meta, sp, (fnx_act_meta*)m, st); if (rc) return rc; }
+          cur_split = sp; cur_meta = m;
+        }
+        if (tc_next) {
+          void* sp = ws.take(fnx_tc_act_bytes(l.cout, h, w));
+          ActMeta* m = new_meta();
+          if (!dry) {
+            int rc = fnx_conv3x3_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, h, w, l.relu, l.w_scale,
+                                    l.w_norm, l.b_max, 0, sp, (fnx_act_meta*)m, 0, 0, st);
+            if (rc) return rc;
+          }
+          cur_split = sp; cur_meta = m; cur_f32 = nullptr;
+        } else {
+          float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
+          if (!dry) {
+            int rc = fnx_conv3x3_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, h, w, l.relu, l.w_scale,
+                                    l.w_norm, l.b_max, 1, o, nullptr, last ? out_ctotal : l.cout, last ? out_coff : 0, st);
+            if (rc) return rc;
+          }
+          cur_f32 = o; cur_split = nullptr; cur_meta = nullptr;
+        }
+      } else {
+        if (!cur_f32) return fnx_set_error(FNX_ERR_ARG, "msnet: internal layout mismatch");
+        float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
+        ActMeta* m = tc_next ? new_meta() : nullptr;
+        if (!dry) {
+          int rc = fnx_conv_direct(cur_f32, l.weight, l.bias, o, 1, l.cin, h, w, l.cout, l.ksize, l.relu,
+                                   last ? out_ctotal : l.cout, last ? out_coff : 0, m ? &m->amax_bits : nullptr, st);
+          if (rc) return rc;
+        }
+        cur_f32 = o; cur_split = nullptr; cur_meta = m;
+      }
+    }
+    return FNX_OK;
+  }
+
+  int forward_one(const float* x, float* y, int H, int W) {
+    const int c = plan->data_channels;
+    const int h4 = (int)(H * 0.25), w4 = (int)(W * 0.25), h2 = (int)(H * 0.5), w2 = (int)(W * 0.5);
+    if (h4 < 1 || w4 < 1) return fnx_set_error(FNX_ERR_ARG, "msnet: grid %dx%d too small for the 1/4 scale", H, W);
+    metas = (ActMeta*)ws.take(MAX_META * sizeof(ActMeta));
+    if (!dry) FNX_CUDA_TRY("msnet", cudaMemsetAsync(metas, 0, MAX_META * sizeof(ActMeta), st));
+    float* x4 = (float*)ws.take((size_t)c * h4 * w4 * 4);
+    float* o4 = (float*)ws.take((size_t)h4 * w4 * 4);
+    float* in2 = (float*)ws.take((size_t)(c + 1) * h2 * w2 * 4);
+    float* o2 = (float*)ws.take((size_t)h2 * w2 * 4);
+    float* in1 = (float*)ws.take((size_t)(c + 1) * H * W * 4);
+    float* o1 = (float*)ws.take((size_t)plan->full[5].cout * H * W * 4);
+    int rc;
+#define RUN(expr) do { if (!dry) { rc = (expr); if (rc) return rc; } } while (0)
+    RUN(fnx_resize_bilinear(x, x4, 1, c, H, W, h4, w4, c, 0, st));
+    if ((rc = block(plan->quarter, 4, x4, h4, w4, o4, 1, 0))) return rc;
+    RUN(fnx_resize_bilinear(x, in2, 1, c, H, W, h2, w2, c + 1, 0, st));
+    RUN(fnx_resize_bilinear(o4, in2, 1, 1, h4, w4, h2, w2, c + 1, c, st));
+    if ((rc = block(plan->half, 6, in2, h2, w2, o2, 1, 0))) return rc;
+    RUN(fnx_resize_bilinear(x, in1, 1, c, H, W, H, W, c + 1, 0, st));
+    RUN(fnx_resize_bilinear(o2, in1, 1, 1, h2, w2, H, W, c + 1, c, st));
+    if ((rc = block(plan->full, 6, in1, H, W, o1, plan->full[5].cout, 0))) return rc;
+    if ((rc = block(&plan->final_conv, 1, o1, H, W, y, 1, 0))) return rc;
+#undef RUN
+    return FNX_OK;
+  }
+};
+}  // namespace
+
+size_t fnx_msnet_workspace(const fnx_msnet_plan* plan, int H, int W) {
+  Runner r{plan, Bump{nullptr}, true, nullptr};
+  if (r.forward_one(nullptr, nullptr, H, W) != FNX_OK) return 0;
+  return r.ws.off + 4096;
+}
+
+int fnx_msnet_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+  FNX_CUDA_TRY("msnet_workspace_init", cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream));
+  return FNX_OK;
+}
+
+int fnx_msnet_forward(const fnx_msnet_plan* plan, const float* x, float* y, int N, int H, int W, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!plan || N < 1 || H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "msnet_forward: bad arguments");
+  const size_t need = fnx_msnet_workspace(plan, H, W);
+  if (need == 0) return FNX_ERR_ARG;
+  if (!workspace || workspace_bytes < need)
+    return fnx_set_error(FNX_ERR_WORKSPACE, "msnet_forward: workspace %zu < %zu bytes", workspace_bytes, need);
+  const int c = plan->data_channels;
+  for (int n = 0; n < N; n++) {
+    Runner r{plan, Bump{(uint8_t*)workspace}, false, (cudaStream_t)stream};
+    int rc = r.forward_one(x + (size_t)n * c * H * W, y + (size_t)n * H * W, H, W);
+    if (rc) return rc;
+  }
+  return FNX_OK;
+}
+
+}  // extern "C"

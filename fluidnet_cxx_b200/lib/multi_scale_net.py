@@ -6,6 +6,8 @@ the Sequential indices), so the shipped `convModel_lastEpoch_best.pth` loads wit
 `load_state_dict`.  `forward` runs the hand-written sm_100a convolution / resize kernels through
 the C-ABI (inference only; there is no torch.nn fallback on the forward path).
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -45,29 +47,70 @@ class MultiScaleNet(nn.Module):
         self.convN_1 = _ConvBlock([c + 1, 32, 64, 128, 64, 32, 8], [5, 3, 3, 3, 3, 5], 4)
         self.final = nn.Conv2d(8, 1, kernel_size=1)
 
-    # -- C-ABI helpers ----------------------------------------------------------------------
-    @staticmethod
-    def _conv(lib, x, conv, relu, out=None, coff=0):
-        n, cin, h, w = x.shape
-        cout, k = conv.out_channels, conv.kernel_size[0]
-        if out is None:
-            out = torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device)
-        wt, bs = conv.weight.detach(), conv.bias.detach()
-        N.check(lib.fnx_conv2d(N.ptr(x), N.ptr(wt), N.ptr(bs), N.ptr(out), n, cin, h, w, cout, k, int(relu),
-                               out.size(1), coff, N.stream_of(x)), "MultiScaleNet.conv")
+    # -- native plan -------------------------------------------------------------------------
+    # fnx_msnet_plan (include/fluidstep.h): device pointers to the fp32 weights / biases, the
+    # split-fp16 packed weights of the tensor-core layers and their range scalars.  Built lazily on
+    # the first forward on a device and rebuilt whenever a parameter tensor changes.
+    USE_TENSOR_CORES = True   # False: every layer on the fp32 direct kernel (numerical cross-check)
+
+    def _layers(self):
+        out = []
+        for blk in (self.convN_4, self.convN_2, self.convN_1):
+            convs = blk.convs()
+            out.append([(c, i < blk.relu_count) for i, c in enumerate(convs)])
+        out.append([(self.final, False)])
         return out
 
-    @staticmethod
-    def _resize(lib, x, size, out, coff):
-        n, c, h, w = x.shape
-        N.check(lib.fnx_resize_bilinear(N.ptr(x), N.ptr(out), n, c, h, w, size[0], size[1], out.size(1), coff,
-                                        N.stream_of(x)), "MultiScaleNet.resize")
+    def _plan_key(self, device):
+        return (str(device), bool(self.USE_TENSOR_CORES)) + tuple(
+            (p.data_ptr(), p._version) for p in self.parameters())
 
-    def _run_block(self, lib, block, x):
-        convs = block.convs()
-        for i, conv in enumerate(convs):
-            x = self._conv(lib, x, conv, relu=i < block.relu_count)
-        return x
+    def _build_plan(self, device):
+        import math
+        lib = N.load()
+        st = torch.cuda.current_stream(device).cuda_stream
+        keep = []
+        plan = N.MsnetPlan()
+        plan.data_channels = self.convN_4.convs()[0].in_channels
+
+        def fill(dst, conv, relu):
+            w = conv.weight.detach().contiguous().float()
+            b = conv.bias.detach().contiguous().float()
+            keep.extend([w, b])
+            cout, cin, k, _ = w.shape
+            dst.weight, dst.bias = w.data_ptr(), b.data_ptr()
+            dst.cin, dst.cout, dst.ksize, dst.relu = cin, cout, k, int(relu)
+            dst.w_tc = None
+            dst.w_scale, dst.w_norm, dst.b_max = 1.0, 0.0, 0.0
+            if self.USE_TENSOR_CORES and k == 3 and cin % 16 == 0 and cout in (32, 64, 128):
+                wmax = float(w.abs().max())
+                # power of two with max|w| * w_scale <= 2^14 (same rule as the device side)
+                w_scale = 1.0 if not (wmax > 0 and math.isfinite(wmax)) else 2.0 ** (14 - math.frexp(wmax)[1])
+                packed = torch.empty(lib.fnx_tc_weight_bytes(cin, cout), dtype=torch.uint8, device=device)
+                N.check(lib.fnx_tc_pack_weights3x3(w.data_ptr(), cin, cout, w_scale, packed.data_ptr(), st),
+                        "MultiScaleNet.pack_weights")
+                keep.append(packed)
+                dst.w_tc = packed.data_ptr()
+                dst.w_scale = w_scale
+                dst.w_norm = float(w.abs().sum(dim=(1, 2, 3)).max())
+                dst.b_max = float(b.abs().max())
+
+        groups = self._layers()
+        for dst_arr, grp in zip((plan.quarter, plan.half, plan.full), groups[:3]):
+            for i, (conv, relu) in enumerate(grp):
+                fill(dst_arr[i], conv, relu)
+        fill(plan.final_conv, *groups[3][0])
+        return plan, keep
+
+    def _get_plan(self, device):
+        key = self._plan_key(device)
+        cache = self.__dict__.setdefault("_fnx_plan_cache", {})
+        if cache.get("key") != key:
+            cache.clear()
+            cache["plan"], cache["keep"] = self._build_plan(device)
+            cache["key"] = key
+            cache["ws"] = {}
+        return cache
 
     def forward(self, x):
         if self.training:
@@ -77,21 +120,20 @@ class MultiScaleNet(nn.Module):
         x = x.contiguous()
         lib = N.load()
         n, c, h, w = x.shape
-        quarter = (int(h * 0.25), int(w * 0.25))
-        half = (int(h * 0.5), int(w * 0.5))
-        dev = x.device
-        # quarter scale
-        x4 = torch.empty((n, c) + quarter, dtype=torch.float32, device=dev)
-        self._resize(lib, x, quarter, x4, 0)
-        o4 = self._run_block(lib, self.convN_4, x4)
-        # half scale: cat(down(x), up(o4))
-        in2 = torch.empty((n, c + 1) + half, dtype=torch.float32, device=dev)
-        self._resize(lib, x, half, in2, 0)
-        self._resize(lib, o4, half, in2, c)
-        o2 = self._run_block(lib, self.convN_2, in2)
-        # full scale: cat(x, up(o2))
-        in1 = torch.empty((n, c + 1, h, w), dtype=torch.float32, device=dev)
-        self._resize(lib, x, (h, w), in1, 0)
-        self._resize(lib, o2, (h, w), in1, c)
-        o1 = self._run_block(lib, self.convN_1, in1)
-        return self._conv(lib, o1, self.final, relu=False)
+        cache = self._get_plan(x.device)
+        plan = cache["plan"]
+        assert c == plan.data_channels, "MultiScaleNet: wrong number of input channels"
+        st = N.stream_of(x)
+        ws = cache["ws"].get((h, w))
+        if ws is None:
+            nbytes = lib.fnx_msnet_workspace(ctypes.byref(plan), h, w)
+            if nbytes == 0:
+                N.check(-1, "MultiScaleNet.workspace")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            # zero borders of the split activation buffers: written once, never touched again
+            N.check(lib.fnx_msnet_workspace_init(ws.data_ptr(), ws.numel(), st), "MultiScaleNet.workspace_init")
+            cache["ws"] = {(h, w): ws}   # one resolution at a time
+        y = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
+        N.check(lib.fnx_msnet_forward(ctypes.byref(plan), N.ptr(x), N.ptr(y), n, h, w, ws.data_ptr(), ws.numel(), st),
+                "MultiScaleNet.forward")
+        return y

@@ -124,3 +124,104 @@ def test_inference_only(net):
     with pytest.raises(RuntimeError, match="inference-only"):
         model.multiScale(torch.zeros(1, 2, 16, 16, device="cuda"))
     model.multiScale.eval()
+
+
+# ---- tensor-core path (conv_tc.cu): split-fp16 tcgen05 implicit GEMM ---------------------------
+def _tc_conv(lib, N, x, wt, b, relu, out_mode, in_split=None):
+    """x (Cin,H,W) fp32 cuda (or an already split (buf, meta) pair) -> conv3x3 on the tensor cores."""
+    import ctypes
+    import math
+    cout, cin, _, _ = wt.shape
+    st = torch.cuda.current_stream().cuda_stream
+    if in_split is None:
+        _, h, w = x.shape
+        metas = torch.zeros(8, dtype=torch.int32, device="cuda")     # 4 x fnx_act_meta
+        m_in, m_split = metas.data_ptr(), metas.data_ptr() + 8
+        N.check(lib.fnx_tc_amax(N.ptr(x), x.numel(), m_in, st))
+        xs = torch.zeros(lib.fnx_tc_act_bytes(cin, h, w), dtype=torch.uint8, device="cuda")
+        N.check(lib.fnx_tc_pack_split(N.ptr(x), cin, h, w, m_in, xs.data_ptr(), m_split, st))
+    else:
+        xs, metas, m_split, h, w = in_split
+    wmax = float(wt.abs().max())
+    w_scale = 2.0 ** (14 - math.frexp(wmax)[1])
+    wp = torch.empty(lib.fnx_tc_weight_bytes(cin, cout), dtype=torch.uint8, device="cuda")
+    N.check(lib.fnx_tc_pack_weights3x3(N.ptr(wt), cin, cout, w_scale, wp.data_ptr(), st))
+    w_norm = float(wt.abs().sum(dim=(1, 2, 3)).max())
+    b_max = float(b.abs().max())
+    if out_mode == 1:
+        y = torch.full((cout + 3, h, w), -7.0, device="cuda")
+        N.check(lib.fnx_conv3x3_tc(xs.data_ptr(), m_split, wp.data_ptr(), N.ptr(b), cin, cout, h, w, relu, w_scale,
+                                   w_norm, b_max, 1, N.ptr(y), None, cout + 3, 2, st))
+        torch.cuda.synchronize()
+        return y
+    metas2 = torch.zeros(8, dtype=torch.int32, device="cuda")
+    ys = torch.zeros(lib.fnx_tc_act_bytes(cout, h, w), dtype=torch.uint8, device="cuda")
+    N.check(lib.fnx_conv3x3_tc(xs.data_ptr(), m_split, wp.data_ptr(), N.ptr(b), cin, cout, h, w, relu, w_scale,
+                               w_norm, b_max, 0, ys.data_ptr(), metas2.data_ptr(), 0, 0, st))
+    torch.cuda.synchronize()
+    return ys, metas2, metas2.data_ptr(), h, w
+
+
+TC_SHAPES = [(32, 64, 33, 70), (64, 128, 20, 24), (128, 64, 16, 140), (64, 32, 37, 53), (32, 64, 9, 300),
+             (16, 32, 5, 7), (128, 128, 130, 129)]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv3x3_tc_vs_oracle(oracle, shape):
+    from fluidnet_cxx_b200 import _native as N
+    cin, cout, h, w = shape
+    lib = N.load()
+    rng = np.random.RandomState(cin + 3 * cout + h)
+    x = (rng.randn(cin, h, w) * rng.choice([0.01, 1.0, 30.0])).astype(np.float32)
+    wt = (rng.randn(cout, cin, 3, 3) / np.sqrt(cin * 9)).astype(np.float32)
+    b = rng.randn(cout).astype(np.float32)
+    tx, tw, tb = cu(x), cu(wt), cu(b)
+    for relu in (0, 1):
+        ref = oracle.conv2d(x[None], wt, b, bool(relu))[0]
+        y = _tc_conv(lib, N, tx, tw, tb, relu, 1).cpu().numpy()
+        assert rel_err(y[2:2 + cout], ref) < RTOL, ("nchw", relu)
+        assert np.all(y[:2] == -7.0) and np.all(y[2 + cout:] == -7.0)
+        # split output -> unpack
+        ys, metas, m, _, _ = _tc_conv(lib, N, tx, tw, tb, relu, 0)
+        got = torch.empty((cout, h, w), device="cuda")
+        N.check(lib.fnx_tc_unpack_split(ys.data_ptr(), m, cout, h, w, N.ptr(got), torch.cuda.current_stream().cuda_stream))
+        assert rel_err(got.cpu().numpy(), ref) < RTOL, ("split", relu)
+        amax = metas.view(torch.float32)[0].item()
+        assert amax == pytest.approx(float(np.abs(ref).max()), rel=1e-5)      # measured range of the layer
+        # the zero border of the split layout is never written
+        P = 2
+        planes = ys[:2 * (cout // 8) * (h + 2 * P) * (w + 2 * P) * 16].view(torch.float16).view(2, cout // 8, h + 2 * P, w + 2 * P, 8)
+        assert float(planes[:, :, :P].abs().max()) == 0 and float(planes[:, :, :, :P].abs().max()) == 0
+        assert float(planes[:, :, h + P:].abs().max()) == 0 and float(planes[:, :, :, w + P:].abs().max()) == 0
+
+
+def test_conv3x3_tc_chain(oracle):
+    """two tensor-core layers back to back through the split layout (32 -> 64 -> 32), 40 x 150."""
+    from fluidnet_cxx_b200 import _native as N
+    lib = N.load()
+    rng = np.random.RandomState(5)
+    x = rng.randn(32, 40, 150).astype(np.float32)
+    w1 = (rng.randn(64, 32, 3, 3) / np.sqrt(32 * 9)).astype(np.float32)
+    w2 = (rng.randn(32, 64, 3, 3) / np.sqrt(64 * 9)).astype(np.float32)
+    b1, b2 = rng.randn(64).astype(np.float32), rng.randn(32).astype(np.float32)
+    ref = oracle.conv2d(oracle.conv2d(x[None], w1, b1, True), w2, b2, False)[0]
+    mid = _tc_conv(lib, N, cu(x), cu(w1), cu(b1), 1, 0)
+    y = _tc_conv(lib, N, None, cu(w2), cu(b2), 0, 1, in_split=mid).cpu().numpy()
+    assert rel_err(y[2:34], ref) < RTOL
+
+
+@pytest.mark.parametrize("hw", [(128, 128), (200, 136), (64, 64)])
+def test_msnet_tensor_vs_direct(net, hw):
+    """whole MultiScaleNet: tensor-core plan against the all-fp32-direct plan on the same input."""
+    model, _ = net
+    msn = model.multiScale
+    x = torch.randn(1, 2, *hw, device="cuda")
+    x[:, 1] = (x[:, 1] > 0.8).float()
+    with torch.no_grad():
+        y_tc = msn(x).cpu().numpy()
+        try:
+            type(msn).USE_TENSOR_CORES = False
+            y_fp = msn(x).cpu().numpy()
+        finally:
+            type(msn).USE_TENSOR_CORES = True
+    assert rel_err(y_tc, y_fp) < RTOL
