@@ -79,12 +79,12 @@ SIGNATURES = {
     "fnx_conv2d": (_I, [_P, _P, _P, _P] + [_I] * 9 + [_P]),
     "fnx_resize_bilinear": (_I, [_P, _P] + [_I] * 8 + [_P]),
     "fnx_tc_act_bytes": (_S, [_I, _I, _I]),
-    "fnx_tc_weight_bytes": (_S, [_I, _I]),
-    "fnx_tc_pack_weights3x3": (_I, [_P, _I, _I, _F, _P, _P]),
+    "fnx_tc_weight_bytes": (_S, [_I, _I, _I]),
+    "fnx_tc_pack_weights": (_I, [_P, _I, _I, _I, _F, _P, _P]),
     "fnx_tc_amax": (_I, [_P, _S, _P, _P]),
     "fnx_tc_pack_split": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "fnx_tc_unpack_split": (_I, [_P, _P, _I, _I, _I, _P, _P]),
-    "fnx_conv3x3_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _I, _I, _P]),
+    "fnx_conv_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _I, _I, _P]),
     "fnx_msnet_workspace": (_S, [ctypes.POINTER(MsnetPlan), _I, _I]),
     "fnx_msnet_workspace_init": (_I, [_P, _S, _P]),
     "fnx_msnet_forward": (_I, [ctypes.POINTER(MsnetPlan), _P, _P, _I, _I, _I, _P, _S, _P]),

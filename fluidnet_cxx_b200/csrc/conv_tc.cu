@@ -1,31 +1,36 @@
 // conv_tc.cu -- MultiScaleNet forward on the sm_100a tensor cores (tcgen05 + TMEM), im2col-free.
 //
 // Reference: pytorch/lib/multi_scale_net.py:101-127 (the 17 nn.Conv2d of the three-scale pyramid).
-// The wide 3x3 layers (Cin, Cout in {32, 64, 128}: 96 % of the 484 476 FLOP/cell) run here as an
-// implicit GEMM  D[pixels x Cout] += A[pixels x Cin] . W_tap[Cin x Cout]  per filter tap.
+// Every 3x3 and 5x5 layer runs here as an implicit GEMM
+//     D[pixels x Cout] += A[pixels x Cin] . W_tap[Cin x Cout]      per filter tap
+// (channel counts are zero-padded to MMA granularity: Cin to a multiple of 16, Cout to 16/32/64/128).
 //
 // fp32 parity through fp16 tensor cores (the parity bar is 1e-5 relative):
 // every activation a and weight w is carried as an exact two-term fp16 expansion of a power-of-two
 // scaled value,  s*a = hi + lo  (22 significant bits), and the product is formed as
-// hi*hi + hi*lo + lo*hi in three kind::f16 MMAs accumulating in fp32 TMEM (the dropped lo*lo term is
-// 2^-22 relative).  Scales are powers of two, so scaling and un-scaling are exact.  The activation
-// scale of a layer's OUTPUT is chosen before the layer runs from a rigorous bound
-// max|y| <= max|x| * max_n sum_k |w_nk| + max|b|   (max|x| is measured by the producing kernel with an
-// atomicMax), so fp16 can never overflow and the resolution floor stays > 2^-30 of the bound.
+// hi*hi + hi*lo + lo*hi in three kind::f16 MMAs with fp32 TMEM accumulation (the dropped lo*lo term
+// is 2^-22 relative).  The tensor core's fp32 accumulate truncates (round toward zero), a bias of
+// half an ulp per accumulation: the two small cross terms therefore go to a SEPARATE "corr"
+// accumulator (their truncation ulps are 2^-11 smaller) and only the hi*hi term touches the main
+// one; the epilogue adds the two in round-to-nearest fp32.  Scales are powers of two, so scaling and
+// un-scaling are exact.  The activation scale of a layer's OUTPUT is chosen before the layer runs
+// from the rigorous bound  max|y| <= max|x| * max_n sum_k |w_nk| + max|b|  (max|x| is measured by the
+// producing kernel with an atomicMax), so fp16 can never overflow and the resolution floor stays
+// below 2^-30 of the bound.
 //
 // Data layout in HBM ("split chunked"): two fp16 planes (hi, lo), each [C/8][H+2P][W+2P][8 halves]
 // with a zero border of P = 2 pixels that no kernel ever writes (it IS the convolution's zero
 // padding).  One (pixel, 8-channel chunk) = 16 bytes = one row of a K-major UMMA core matrix, so a
 // staged row of pixels is directly a no-swizzle K-major operand whose row index is affine in the
 // pixel index (SBO = 128 B): the A operand of filter tap (ky, kx) is the SAME shared-memory tile with
-// the descriptor start address advanced by (ky*row_pitch + kx)*16 bytes.  Each input row is staged
-// once per 16-channel chunk by 1-D bulk copies of the TMA engine (cp.async.bulk, UBLKCP) and reused
-// by all 9 taps and all 3 split terms.
+// the descriptor start address advanced by (ky*row_pitch + kx)*16 bytes (validated on hardware by
+// tools/tc_probe.cu).  Each input row is staged once per 16-channel chunk by 1-D bulk copies of the
+// TMA engine (cp.async.bulk, SASS UBLKCP) and reused by all KS*KS taps and all 3 split terms.
 //
 // Kernel shape: persistent, one CTA per SM, 192 threads = producer warp (bulk copies), MMA warp (one
 // thread issues tcgen05.mma), 4 epilogue warps (tcgen05.ld -> bias/ReLU -> split -> 16-byte stores).
-// A block of work = R output rows x 128 pixels x Cout: R accumulators of 128 x Cout fp32 in TMEM
-// (R*Cout <= 512 columns) so each streamed weight slot is reused by R M-tiles.
+// A block of work = R output rows x 128 pixels x Cout: 2*R accumulators of 128 x Cout fp32 in TMEM
+// (2*R*Cout <= 512 columns) so each streamed weight slot is reused by R M-tiles.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -38,10 +43,8 @@
 namespace fnx {
 namespace tc {
 
-constexpr int PAD = FNX_TC_PAD;   // zero border of the split chunked layout
-constexpr int TW = 128;           // pixels per M tile (one row segment)
-constexpr int RP = TW + 2;        // staged row pitch in pixels (1-pixel halo each side)
-constexpr uint32_t ROWB = RP * 16;  // bytes of one staged row of one 8-channel chunk
+constexpr int PAD = FNX_TC_PAD;  // zero border of the split chunked layout
+constexpr int TW = 128;          // pixels per M tile (one row segment)
 
 struct ActMeta {  // == fnx_act_meta
   unsigned amax_bits;  // fp32 bit pattern of max|a| over the tensor (atomicMax target)
@@ -61,38 +64,44 @@ __host__ __device__ __forceinline__ float pow2_scale_for(float bound) {
 struct ConvArgs {
   const __half* x;     // input planes: hi at x, lo at x + x_plane
   size_t x_plane;      // halves
-  const uint8_t* w;    // packed weights: [Cin/16][3 (ky)] slots, slot = [kx][plane][j][Cout][8 halves]
-  const float* bias;
+  const uint8_t* w;    // packed weights: [Cin_pad/16][KS (ky)] slots, slot = [kx][plane][j][COUT][8 halves]
+  const float* bias;   // Cout real values
   void* y;             // split planes (out_mode 0) or fp32 NCHW (out_mode 1)
   size_t y_plane;      // halves (out_mode 0)
   const ActMeta* in_meta;
   ActMeta* out_meta;
-  int Cin, H, W, Hp, Wp;
+  int nchunks;         // Cin_pad / 16
+  int Cout;            // real output channels (<= COUT)
+  int H, W, Hp, Wp;
   int relu, out_mode, y_ctotal, y_coff;
   float w_scale, w_norm, b_max;
   int tiles_x, nblocks;
 };
 
-template <int COUT, int R, int WS>
+template <int KS, int COUT, int R, int WS>
 struct Cfg {
-  static constexpr uint32_t A_J = (R + 2) * ROWB;   // stride between the two 8-channel chunks = LBO(A)
+  static constexpr int HALO = KS / 2;
+  static constexpr int RP = TW + KS - 1;              // staged row pitch in pixels
+  static constexpr int ROWS = R + KS - 1;             // staged rows per block
+  static constexpr uint32_t ROWB = RP * 16;           // bytes of one staged row of one 8-channel chunk
+  static constexpr uint32_t A_J = ROWS * ROWB;        // stride between the two 8-channel chunks = LBO(A)
   static constexpr uint32_t A_PLANE = 2 * A_J;
-  static constexpr uint32_t A_STAGE = 2 * A_PLANE;  // hi + lo
-  static constexpr uint32_t W_J = COUT * 16;        // LBO(B)
+  static constexpr uint32_t A_STAGE = 2 * A_PLANE;    // hi + lo
+  static constexpr uint32_t W_J = COUT * 16;          // LBO(B)
   static constexpr uint32_t W_PLANE = 2 * W_J;
   static constexpr uint32_t W_KX = 2 * W_PLANE;
-  static constexpr uint32_t W_STAGE = 3 * W_KX;     // one (16-channel chunk, ky) slot
+  static constexpr uint32_t W_STAGE = KS * W_KX;      // one (16-channel chunk, ky) slot
   static constexpr uint32_t NBAR = 4 + 2 * WS + 2;
   static constexpr uint32_t SMEM = 2 * A_STAGE + WS * W_STAGE + NBAR * 8 + 16 + COUT * 4;
-  static constexpr uint32_t TMEM_COLS = (R * COUT <= 32) ? 32 : (R * COUT <= 64) ? 64 : (R * COUT <= 128) ? 128
-                                        : (R * COUT <= 256) ? 256 : 512;
-  static_assert(R * COUT <= 512, "accumulators exceed TMEM");
+  static constexpr uint32_t NCOLS = 2 * R * COUT;     // main + corr accumulators
+  static constexpr uint32_t TMEM_COLS = NCOLS <= 32 ? 32 : NCOLS <= 64 ? 64 : NCOLS <= 128 ? 128 : NCOLS <= 256 ? 256 : 512;
+  static_assert(NCOLS <= 512, "accumulators exceed TMEM");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-template <int COUT, int R, int WS>
-__global__ void __launch_bounds__(192, 1) k_conv3x3_tc(const ConvArgs a) {
-  using C = Cfg<COUT, R, WS>;
+template <int KS, int COUT, int R, int WS>
+__global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvArgs a) {
+  using C = Cfg<KS, COUT, R, WS>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + 2 * C::A_STAGE;
@@ -107,7 +116,7 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_tc(const ConvArgs a) {
   const uint32_t ACC_FULL = bar0 + 8u * (4 + 2 * WS), ACC_EMPTY = bar0 + 8u * (5 + 2 * WS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunks = a.Cin >> 4;
+  const int nchunks = a.nchunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; s++) {
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_tc(const ConvArgs a) {
     mbar_init(ACC_EMPTY, 4);
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -135,26 +144,27 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_tc(const ConvArgs a) {
       int as = 0, aph = 0, ws = 0, wph = 0;
       for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
         const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * R;
-        // staged rows are padded-image rows y0+PAD-1 .. y0+PAD+R; rows past the padded image are skipped
-        int nrows = a.Hp - (y0 + PAD - 1);
-        nrows = nrows > R + 2 ? R + 2 : nrows;
+        // staged rows = padded-image rows y0+PAD-HALO ..; rows past the padded image are skipped
+        int nrows = a.Hp - (y0 + PAD - C::HALO);
+        nrows = nrows > C::ROWS ? C::ROWS : nrows;
         for (int c = 0; c < nchunks; c++) {
           mbar_wait(A_EMPTY(as), aph ^ 1);
-          mbar_expect_tx(A_FULL(as), (uint32_t)nrows * 4u * ROWB);
+          mbar_expect_tx(A_FULL(as), (uint32_t)nrows * 4u * C::ROWB);
           const uint32_t dst0 = smem_u32(sA + as * C::A_STAGE);
 #pragma unroll
           for (int pl = 0; pl < 2; pl++)
 #pragma unroll
             for (int j = 0; j < 2; j++) {
               const __half* src = a.x + pl * a.x_plane +
-                                  (((size_t)(c * 2 + j) * a.Hp + (y0 + PAD - 1)) * a.Wp + (x0 + PAD - 1)) * 8;
+                                  (((size_t)(c * 2 + j) * a.Hp + (y0 + PAD - C::HALO)) * a.Wp + (x0 + PAD - C::HALO)) * 8;
               const uint32_t dst = dst0 + pl * C::A_PLANE + j * C::A_J;
-              for (int r = 0; r < nrows; r++) bulk_g2s(dst + r * ROWB, src + (size_t)r * a.Wp * 8, ROWB, A_FULL(as));
+              for (int r = 0; r < nrows; r++)
+                bulk_g2s(dst + r * C::ROWB, src + (size_t)r * a.Wp * 8, C::ROWB, A_FULL(as));
             }
-          for (int ky = 0; ky < 3; ky++) {
+          for (int ky = 0; ky < KS; ky++) {
             mbar_wait(W_EMPTY(ws), wph ^ 1);
             mbar_expect_tx(W_FULL(ws), C::W_STAGE);
-            bulk_g2s(smem_u32(sW + ws * C::W_STAGE), a.w + (size_t)(c * 3 + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
+            bulk_g2s(smem_u32(sW + ws * C::W_STAGE), a.w + (size_t)(c * KS + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
             if (++ws == WS) { ws = 0; wph ^= 1; }
           }
           if (++as == 2) { as = 0; aph ^= 1; }
@@ -174,23 +184,24 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_tc(const ConvArgs a) {
           const uint32_t a_base = smem_u32(sA + as * C::A_STAGE);
           const uint64_t a_hi0 = smem_desc_kmajor_noswz(a_base, C::A_J, 128);
           const uint64_t a_lo0 = smem_desc_kmajor_noswz(a_base + C::A_PLANE, C::A_J, 128);
-          for (int ky = 0; ky < 3; ky++) {
+          for (int ky = 0; ky < KS; ky++) {
             mbar_wait(W_FULL(ws), wph);
             tc_fence_after();
             const uint32_t w_base = smem_u32(sW + ws * C::W_STAGE);
             const uint64_t w0 = smem_desc_kmajor_noswz(w_base, C::W_J, 128);
+            const uint32_t nfirst = (c | ky) != 0;
 #pragma unroll
             for (int r = 0; r < R; r++) {
 #pragma unroll
-              for (int kx = 0; kx < 3; kx++) {
-                const uint32_t aoff = (uint32_t)(((r + ky) * RP + kx) * 16) >> 4;
+              for (int kx = 0; kx < KS; kx++) {
+                const uint32_t aoff = (uint32_t)(((r + ky) * C::RP + kx) * 16) >> 4;
                 const uint64_t w_hi = w0 + ((uint32_t)(kx * C::W_KX) >> 4);
                 const uint64_t w_lo = w_hi + (C::W_PLANE >> 4);
-                const uint32_t d = taddr + (uint32_t)(r * COUT);
-                const uint32_t first = (c | ky | kx) != 0;
-                mma_f16_ss(d, a_lo0 + aoff, w_hi, idesc, first);
-                mma_f16_ss(d, a_hi0 + aoff, w_lo, idesc, 1);
-                mma_f16_ss(d, a_hi0 + aoff, w_hi, idesc, 1);
+                const uint32_t d_main = taddr + (uint32_t)(r * COUT), d_corr = d_main + (uint32_t)(R * COUT);
+                const uint32_t acc = kx ? 1u : nfirst;
+                mma_f16_ss(d_corr, a_lo0 + aoff, w_hi, idesc, acc);
+                mma_f16_ss(d_corr, a_hi0 + aoff, w_lo, idesc, 1);
+                mma_f16_ss(d_main, a_hi0 + aoff, w_hi, idesc, acc);
               }
             }
             mma_commit(W_EMPTY(ws));
@@ -221,20 +232,23 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_tc(const ConvArgs a) {
         const bool ok = (y < a.H) && (px < a.W);
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * COUT + c0), v);
+          if (c0 >= a.Cout) break;  // padded output channels (warp-uniform)
+          uint32_t vm[16], vc[16];
+          const uint32_t t0 = taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * COUT + c0);
+          tmem_ld16(t0, vm);
+          tmem_ld16(t0 + (uint32_t)(R * COUT), vc);
           tmem_ld_wait();
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; i++) {
-            float t = fmaf(__uint_as_float(v[i]), inv, s_bias[c0 + i]);
+            float t = fmaf(__uint_as_float(vm[i]) + __uint_as_float(vc[i]), inv, s_bias[c0 + i]);
             if (a.relu) t = fmaxf(t, 0.f);
             f[i] = t;
           }
           if (ok) {  // lanes outside the image hold garbage accumulators: never stored, never in amax
-#pragma unroll
-            for (int i = 0; i < 16; i++) amax = fmaxf(amax, fabsf(f[i]));
             if (a.out_mode == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; i++) amax = fmaxf(amax, fabsf(f[i]));
               __half* yh = reinterpret_cast<__half*>(a.y);
 #pragma unroll
               for (int g = 0; g < 2; g++) {
@@ -253,7 +267,8 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_tc(const ConvArgs a) {
             } else {
               float* yf = reinterpret_cast<float*>(a.y);
 #pragma unroll
-              for (int i = 0; i < 16; i++) yf[((size_t)(a.y_coff + c0 + i) * a.H + y) * a.W + px] = f[i];
+              for (int i = 0; i < 16; i++)
+                if (c0 + i < a.Cout) yf[((size_t)(a.y_coff + c0 + i) * a.H + y) * a.W + px] = f[i];
             }
           }
         }
@@ -322,20 +337,23 @@ __global__ void __launch_bounds__(256)
   y[e] = (__half2float(x[off]) + __half2float(x[x_plane + off])) / meta->scale;
 }
 
-// weight (Cout, Cin, 3, 3) fp32 -> packed split slots [Cin/16][ky][kx][plane][j][Cout][8 halves]
+// weight (Cout, Cin, KS, KS) fp32 -> packed split slots [Cin_pad/16][ky][kx][plane][j][Cout_pad][8 halves]
+// (zero for the padded input / output channels)
 __global__ void __launch_bounds__(256)
-    k_pack_weights3x3(const float* __restrict__ w, int Cin, int Cout, float w_scale, __half* __restrict__ out) {
-  const size_t total = (size_t)Cin * Cout * 9;
+    k_pack_weights(const float* __restrict__ w, int Cin, int Cout, int KS, int Cin_pad, int Cout_pad, float w_scale,
+                   __half* __restrict__ out) {
+  const int taps = KS * KS;
+  const size_t total = (size_t)Cin_pad * Cout_pad * taps;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
-  const int t = (int)(e % 9), ci = (int)((e / 9) % Cin), n = (int)(e / (9 * (size_t)Cin));
-  const int ky = t / 3, kx = t % 3, c = ci >> 4, j = (ci >> 3) & 1, i = ci & 7;
-  const float u = w[e] * w_scale;
+  const int t = (int)(e % taps), ci = (int)((e / taps) % Cin_pad), n = (int)(e / ((size_t)taps * Cin_pad));
+  const int ky = t / KS, kx = t % KS, c = ci >> 4, j = (ci >> 3) & 1, i = ci & 7;
+  const float u = (ci < Cin && n < Cout) ? w[((size_t)n * Cin + ci) * taps + t] * w_scale : 0.f;
   const __half h = __float2half_rn(u);
   const __half l = __float2half_rn(u - __half2float(h));
-  const size_t slot = ((size_t)(c * 3 + ky) * 3 + kx) * 2;  // then [plane][j][n][8]
-  out[(((slot + 0) * 2 + j) * Cout + n) * 8 + i] = h;
-  out[(((slot + 1) * 2 + j) * Cout + n) * 8 + i] = l;
+  const size_t slot = ((size_t)(c * KS + ky) * KS + kx) * 2;  // then [plane][j][n][8]
+  out[(((slot + 0) * 2 + j) * Cout_pad + n) * 8 + i] = h;
+  out[(((slot + 1) * 2 + j) * Cout_pad + n) * 8 + i] = l;
 }
 
 }  // namespace tc
@@ -366,22 +384,44 @@ static size_t act_plane_halves(int C, int H, int W) {
   return (size_t)(C / 8) * (H + 2 * PAD) * (W + 2 * PAD) * 8;
 }
 
-template <int COUT, int R, int WS>
+static int pad16(int c) { return (c + 15) / 16 * 16; }
+static int cout_pad(int c) { return c <= 16 ? 16 : c <= 32 ? 32 : c <= 64 ? 64 : 128; }
+
+static bool tc_eligible(int Cin, int Cout, int ksize) {
+  return (ksize == 3 || ksize == 5) && Cin >= 1 && Cin <= 128 && Cout >= 1 && Cout <= 128 &&
+         !(ksize == 5 && Cout > 32);  // 5x5 instantiated for the narrow layers only
+}
+
+template <int KS, int COUT, int R, int WS>
 static int launch_tc(ConvArgs a, cudaStream_t st) {
-  using C = Cfg<COUT, R, WS>;
-  auto kern = k_conv3x3_tc<COUT, R, WS>;
-  FNX_CUDA_TRY("conv3x3_tc", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  using C = Cfg<KS, COUT, R, WS>;
+  auto kern = k_conv_tc<KS, COUT, R, WS>;
+  FNX_CUDA_TRY("conv_tc", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   a.tiles_x = (a.W + TW - 1) / TW;
   a.nblocks = a.tiles_x * ((a.H + R - 1) / R);
   const int grid = a.nblocks < num_sms() ? a.nblocks : num_sms();
   kern<<<grid, 192, C::SMEM, st>>>(a);
   fnx_count_launches(1);
-  FNX_CUDA_TRY("conv3x3_tc", cudaGetLastError());
+  FNX_CUDA_TRY("conv_tc", cudaGetLastError());
   return FNX_OK;
 }
 
-static bool tc_eligible(int Cin, int Cout, int ksize) {
-  return ksize == 3 && Cin >= 16 && Cin % 16 == 0 && (Cout == 32 || Cout == 64 || Cout == 128);
+// rows per block: the largest instantiated R that still gives every SM a block (small pyramid
+// levels trade weight re-use for occupancy)
+template <int KS, int COUT, int RMAX>
+static int launch_tc_rows(const ConvArgs& a, cudaStream_t st) {
+  const int tiles_x = (a.W + TW - 1) / TW;
+  auto blocks = [&](int r) { return tiles_x * ((a.H + r - 1) / r); };
+  if constexpr (RMAX >= 8) {
+    if (blocks(8) >= num_sms()) return launch_tc<KS, COUT, 8, 4>(a, st);
+  }
+  if constexpr (RMAX >= 4) {
+    if (blocks(4) >= num_sms()) return launch_tc<KS, COUT, 4, 4>(a, st);
+  }
+  if constexpr (RMAX >= 2) {
+    if (blocks(2) >= num_sms()) return launch_tc<KS, COUT, 2, 4>(a, st);
+  }
+  return launch_tc<KS, COUT, 1, 4>(a, st);
 }
 
 __global__ void __launch_bounds__(256) k_amax(const float* __restrict__ x, size_t n, ActMeta* meta) {
@@ -396,18 +436,21 @@ __global__ void __launch_bounds__(256) k_amax(const float* __restrict__ x, size_
 extern "C" {
 
 size_t fnx_tc_act_bytes(int C, int H, int W) {
-  const int Cp = (C + 15) / 16 * 16;
-  return 2 * act_plane_halves(Cp, H, W) * sizeof(__half) + 4096;
+  return 2 * act_plane_halves(pad16(C), H, W) * sizeof(__half) + 4096;
 }
 
-size_t fnx_tc_weight_bytes(int Cin, int Cout) { return (size_t)Cin * Cout * 9 * 2 * sizeof(__half); }
+size_t fnx_tc_weight_bytes(int Cin, int Cout, int ksize) {
+  return (size_t)pad16(Cin) * cout_pad(Cout) * ksize * ksize * 2 * sizeof(__half);
+}
 
-int fnx_tc_pack_weights3x3(const float* w, int Cin, int Cout, float w_scale, void* out, void* stream) {
-  if (!tc_eligible(Cin, Cout, 3)) return fnx_set_error(FNX_ERR_ARG, "tc_pack_weights3x3: unsupported shape %d->%d", Cin, Cout);
-  const size_t total = (size_t)Cin * Cout * 9;
-  k_pack_weights3x3<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, w_scale, (__half*)out);
+int fnx_tc_pack_weights(const float* w, int Cin, int Cout, int ksize, float w_scale, void* out, void* stream) {
+  if (!tc_eligible(Cin, Cout, ksize))
+    return fnx_set_error(FNX_ERR_ARG, "tc_pack_weights: unsupported layer %d->%d k%d", Cin, Cout, ksize);
+  const size_t total = (size_t)pad16(Cin) * cout_pad(Cout) * ksize * ksize;
+  k_pack_weights<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, ksize, pad16(Cin),
+                                                                                  cout_pad(Cout), w_scale, (__half*)out);
   fnx_count_launches(1);
-  FNX_CUDA_TRY("tc_pack_weights3x3", cudaGetLastError());
+  FNX_CUDA_TRY("tc_pack_weights", cudaGetLastError());
   return FNX_OK;
 }
 
@@ -424,7 +467,7 @@ int fnx_tc_amax(const float* x, size_t n, fnx_act_meta* meta, void* stream) {
 int fnx_tc_pack_split(const float* x, int C, int H, int W, const fnx_act_meta* in_meta, void* y, fnx_act_meta* out_meta,
                       void* stream) {
   if (C < 1 || H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "tc_pack_split: bad shape");
-  const int Cp = (C + 15) / 16 * 16;
+  const int Cp = pad16(C);
   const size_t total = (size_t)H * W * (Cp / 8);
   k_pack_split<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       x, C, Cp, H, W, (const ActMeta*)in_meta, (__half*)y, act_plane_halves(Cp, H, W), (ActMeta*)out_meta);
@@ -435,7 +478,7 @@ int fnx_tc_pack_split(const float* x, int C, int H, int W, const fnx_act_meta* i
 
 int fnx_tc_unpack_split(const void* x, const fnx_act_meta* meta, int C, int H, int W, float* y, void* stream) {
   if (C < 1 || H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "tc_unpack_split: bad shape");
-  const int Cp = (C + 15) / 16 * 16;
+  const int Cp = pad16(C);
   const size_t total = (size_t)H * W * C;
   k_unpack_split<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)x, act_plane_halves(Cp, H, W), (const ActMeta*)meta, C, H, W, y);
@@ -444,33 +487,41 @@ int fnx_tc_unpack_split(const void* x, const fnx_act_meta* meta, int C, int H, i
   return FNX_OK;
 }
 
-int fnx_conv3x3_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin, int Cout,
-                   int H, int W, int relu, float w_scale, float w_norm, float b_max, int out_mode, void* y,
-                   fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset, void* stream) {
-  if (!tc_eligible(Cin, Cout, 3)) return fnx_set_error(FNX_ERR_ARG, "conv3x3_tc: unsupported shape %d->%d", Cin, Cout);
-  if (H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "conv3x3_tc: bad shape");
-  if (out_mode == 0 && !out_meta) return fnx_set_error(FNX_ERR_ARG, "conv3x3_tc: split output needs out_meta");
+int fnx_conv_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin, int Cout,
+                int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max, int out_mode, void* y,
+                fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset, void* stream) {
+  if (!tc_eligible(Cin, Cout, ksize))
+    return fnx_set_error(FNX_ERR_ARG, "conv_tc: unsupported layer %d->%d k%d", Cin, Cout, ksize);
+  if (H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "conv_tc: bad shape");
+  if (out_mode == 0 && (!out_meta || Cout % 16 != 0))
+    return fnx_set_error(FNX_ERR_ARG, "conv_tc: split output needs out_meta and Cout %% 16 == 0");
   if (out_mode == 1 && y_channels_total < y_channel_offset + Cout)
-    return fnx_set_error(FNX_ERR_ARG, "conv3x3_tc: output channel window out of range");
+    return fnx_set_error(FNX_ERR_ARG, "conv_tc: output channel window out of range");
   ConvArgs a;
   a.x = (const __half*)x;
-  a.x_plane = act_plane_halves(Cin, H, W);
+  a.x_plane = act_plane_halves(pad16(Cin), H, W);
   a.w = (const uint8_t*)w_packed;
   a.bias = bias;
   a.y = y;
-  a.y_plane = act_plane_halves(Cout, H, W);
+  a.y_plane = act_plane_halves(pad16(Cout), H, W);
   a.in_meta = (const ActMeta*)in_meta;
   a.out_meta = (ActMeta*)out_meta;
-  a.Cin = Cin; a.H = H; a.W = W; a.Hp = H + 2 * PAD; a.Wp = W + 2 * PAD;
+  a.nchunks = pad16(Cin) / 16; a.Cout = Cout;
+  a.H = H; a.W = W; a.Hp = H + 2 * PAD; a.Wp = W + 2 * PAD;
   a.relu = relu; a.out_mode = out_mode; a.y_ctotal = y_channels_total; a.y_coff = y_channel_offset;
   a.w_scale = w_scale; a.w_norm = w_norm; a.b_max = b_max;
   a.tiles_x = 0; a.nblocks = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (Cout) {
-    case 128: return launch_tc<128, 4, 3>(a, st);
-    case 64: return launch_tc<64, 8, 3>(a, st);
-    default: return launch_tc<32, 8, 3>(a, st);
+  const int cp = cout_pad(Cout);
+  if (ksize == 3) {
+    switch (cp) {
+      case 128: return launch_tc_rows<3, 128, 2>(a, st);
+      case 64: return launch_tc_rows<3, 64, 4>(a, st);
+      case 32: return launch_tc_rows<3, 32, 8>(a, st);
+      default: return launch_tc_rows<3, 16, 8>(a, st);
+    }
   }
+  return cp == 32 ? launch_tc_rows<5, 32, 4>(a, st) : launch_tc_rows<5, 16, 4>(a, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -502,6 +553,7 @@ struct Runner {
   int block(const fnx_conv_layer* L, int n, const float* in, int h, int w, float* out, int out_ctotal, int out_coff) {
     const float* cur_f32 = in;
     const void* cur_split = nullptr;
+    bool is_split = false;  // which of the two holds the current tensor (pointers are null in a dry run)
     ActMeta* cur_meta = nullptr;  // amax valid (and scale, when split)
     for (int i = 0; i < n; i++) {
       const fnx_conv_layer& l = L[i];
@@ -509,7 +561,7 @@ struct Runner {
       const bool tc_now = l.w_tc && tc_eligible(l.cin, l.cout, l.ksize);
       const bool tc_next = !last && L[i + 1].w_tc && tc_eligible(L[i + 1].cin, L[i + 1].cout, L[i + 1].ksize);
       if (tc_now) {
-        if (!cur_split) {
+        if (!is_split) {
           if (!cur_meta) {
             cur_meta = new_meta();
             if (!dry) { int rc = fnx_tc_amax(cur_f32, (size_t)l.cin * h * w, (fnx_act_meta*)cur_meta, st); if (rc) return rc; }
@@ -517,28 +569,28 @@ struct Runner {
           void* sp = ws.take(fnx_tc_act_bytes(l.cin, h, w));
           ActMeta* m = new_meta();
           if (!dry) { int rc = fnx_tc_pack_split(cur_f32, l.cin, h, w, (fnx_act_meta*)cur_meta, sp, (fnx_act_meta*)m, st); if (rc) return rc; }
-          cur_split = sp; cur_meta = m;
+          cur_split = sp; cur_meta = m; is_split = true;
         }
         if (tc_next) {
           void* sp = ws.take(fnx_tc_act_bytes(l.cout, h, w));
           ActMeta* m = new_meta();
           if (!dry) {
-            int rc = fnx_conv3x3_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, h, w, l.relu, l.w_scale,
+            int rc = fnx_conv_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu, l.w_scale,
                                     l.w_norm, l.b_max, 0, sp, (fnx_act_meta*)m, 0, 0, st);
             if (rc) return rc;
           }
-          cur_split = sp; cur_meta = m; cur_f32 = nullptr;
+          cur_split = sp; cur_meta = m; cur_f32 = nullptr; is_split = true;
         } else {
           float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
           if (!dry) {
-            int rc = fnx_conv3x3_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, h, w, l.relu, l.w_scale,
+            int rc = fnx_conv_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu, l.w_scale,
                                     l.w_norm, l.b_max, 1, o, nullptr, last ? out_ctotal : l.cout, last ? out_coff : 0, st);
             if (rc) return rc;
           }
-          cur_f32 = o; cur_split = nullptr; cur_meta = nullptr;
+          cur_f32 = o; cur_split = nullptr; cur_meta = nullptr; is_split = false;
         }
       } else {
-        if (!cur_f32) return fnx_set_error(FNX_ERR_ARG, "msnet: internal layout mismatch");
+        if (is_split) return fnx_set_error(FNX_ERR_ARG, "msnet: internal layout mismatch");
         float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
         ActMeta* m = tc_next ? new_meta() : nullptr;
         if (!dry) {
@@ -546,7 +598,7 @@ struct Runner {
                                    last ? out_ctotal : l.cout, last ? out_coff : 0, m ? &m->amax_bits : nullptr, st);
           if (rc) return rc;
         }
-        cur_f32 = o; cur_split = nullptr; cur_meta = m;
+        cur_f32 = o; cur_split = nullptr; cur_meta = m; is_split = false;
       }
     }
     return FNX_OK;

@@ -82,12 +82,12 @@ class MultiScaleNet(nn.Module):
             dst.cin, dst.cout, dst.ksize, dst.relu = cin, cout, k, int(relu)
             dst.w_tc = None
             dst.w_scale, dst.w_norm, dst.b_max = 1.0, 0.0, 0.0
-            if self.USE_TENSOR_CORES and k == 3 and cin % 16 == 0 and cout in (32, 64, 128):
+            if self.USE_TENSOR_CORES and (k == 3 or (k == 5 and cout <= 32)) and cin <= 128 and cout <= 128:
                 wmax = float(w.abs().max())
                 # power of two with max|w| * w_scale <= 2^14 (same rule as the device side)
                 w_scale = 1.0 if not (wmax > 0 and math.isfinite(wmax)) else 2.0 ** (14 - math.frexp(wmax)[1])
-                packed = torch.empty(lib.fnx_tc_weight_bytes(cin, cout), dtype=torch.uint8, device=device)
-                N.check(lib.fnx_tc_pack_weights3x3(w.data_ptr(), cin, cout, w_scale, packed.data_ptr(), st),
+                packed = torch.empty(lib.fnx_tc_weight_bytes(cin, cout, k), dtype=torch.uint8, device=device)
+                N.check(lib.fnx_tc_pack_weights(w.data_ptr(), cin, cout, k, w_scale, packed.data_ptr(), st),
                         "MultiScaleNet.pack_weights")
                 keep.append(packed)
                 dst.w_tc = packed.data_ptr()
@@ -111,6 +111,11 @@ class MultiScaleNet(nn.Module):
             cache["key"] = key
             cache["ws"] = {}
         return cache
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop("_fnx_plan_cache", None)      # ctypes plan + device buffers: rebuilt on demand
+        return d
 
     def forward(self, x):
         if self.training:

@@ -167,9 +167,9 @@ int fnx_conv2d(const float *x, const float *weight, const float *bias, float *y,
 int fnx_resize_bilinear(const float *x, float *y, int N, int C, int H, int W, int Ho, int Wo,
                         int y_channels_total, int y_channel_offset, void *stream);
 /* ---- tensor-core path of the MultiScaleNet convolutions (multi_scale_net.py:101-127) ----------
- * nn.Conv2d(Cin, Cout, 3, padding=1) for Cin % 16 == 0, Cout in {32, 64, 128} as a tcgen05
- * implicit GEMM with fp32-equivalent accuracy (two-term fp16 expansion, three MMAs per K step,
- * fp32 TMEM accumulation).  Activations travel between these layers in the "split chunked"
+ * nn.Conv2d(Cin, Cout, k, padding=k/2) for k = 3 (Cin, Cout <= 128) and k = 5 (Cout <= 32) as a
+ * tcgen05 implicit GEMM with fp32-equivalent accuracy (two-term fp16 expansion, three MMAs per K
+ * step, fp32 TMEM accumulation; channels zero-padded to MMA granularity inside).  Activations travel between these layers in the "split chunked"
  * layout: two fp16 planes (hi, lo) [C/8][H+2P][W+2P][8] with a zero border of P pixels that the
  * caller zeroes ONCE (the kernels never write it) plus a device-side fnx_act_meta. */
 #define FNX_TC_PAD 2
@@ -178,21 +178,23 @@ typedef struct fnx_act_meta {
   float scale;        /* power of two the stored expansion is multiplied by */
 } fnx_act_meta;
 size_t fnx_tc_act_bytes(int C, int H, int W);
-size_t fnx_tc_weight_bytes(int Cin, int Cout);
-/* weight (Cout, Cin, 3, 3) fp32 -> packed split-fp16 slots; w_scale = power of two with max|w|*w_scale <= 2^14 */
-int fnx_tc_pack_weights3x3(const float *weight, int Cin, int Cout, float w_scale, void *out, void *stream);
+size_t fnx_tc_weight_bytes(int Cin, int Cout, int ksize);
+/* weight (Cout, Cin, k, k) fp32 -> packed split-fp16 slots; w_scale = power of two with max|w|*w_scale <= 2^14 */
+int fnx_tc_pack_weights(const float *weight, int Cin, int Cout, int ksize, float w_scale, void *out,
+                        void *stream);
 /* meta->amax_bits = max(meta->amax_bits, max|x|) */
 int fnx_tc_amax(const float *x, size_t n, fnx_act_meta *meta, void *stream);
 /* fp32 NCHW (one image) -> split chunked, scale chosen from in_meta->amax_bits */
 int fnx_tc_pack_split(const float *x, int C, int H, int W, const fnx_act_meta *in_meta, void *y,
                       fnx_act_meta *out_meta, void *stream);
 int fnx_tc_unpack_split(const void *x, const fnx_act_meta *meta, int C, int H, int W, float *y, void *stream);
-/* out_mode 0: y split chunked (out_meta required, amax_bits pre-zeroed); out_mode 1: y fp32 NCHW
- * channel window like fnx_conv2d.  w_norm = max_n sum|w[n]|, b_max = max|bias| (fp16 range bound). */
-int fnx_conv3x3_tc(const void *x, const fnx_act_meta *in_meta, const void *w_packed, const float *bias,
-                   int Cin, int Cout, int H, int W, int relu, float w_scale, float w_norm, float b_max,
-                   int out_mode, void *y, fnx_act_meta *out_meta, int y_channels_total,
-                   int y_channel_offset, void *stream);
+/* out_mode 0: y split chunked (out_meta required, amax_bits pre-zeroed, Cout % 16 == 0); out_mode 1:
+ * y fp32 NCHW channel window like fnx_conv2d.  w_norm = max_n sum|w[n]|, b_max = max|bias| (the
+ * fp16 range bound of the output). */
+int fnx_conv_tc(const void *x, const fnx_act_meta *in_meta, const void *w_packed, const float *bias,
+                int Cin, int Cout, int ksize, int H, int W, int relu, float w_scale, float w_norm,
+                float b_max, int out_mode, void *y, fnx_act_meta *out_meta, int y_channels_total,
+                int y_channel_offset, void *stream);
 
 /* MultiScaleNet.forward in one call (multi_scale_net.py:101-127): x (N, data_channels, H, W) ->
  * y (N, 1, H, W).  Layers with w_tc != NULL and a supported shape run on the tensor cores, the
@@ -201,7 +203,7 @@ int fnx_conv3x3_tc(const void *x, const fnx_act_meta *in_meta, const void *w_pac
 typedef struct fnx_conv_layer {
   const float *weight; /* (Cout, Cin, k, k) fp32 */
   const float *bias;   /* (Cout) fp32 */
-  const void *w_tc;    /* fnx_tc_pack_weights3x3 output, or NULL */
+  const void *w_tc;    /* fnx_tc_pack_weights output, or NULL */
   int cin, cout, ksize, relu;
   float w_scale, w_norm, b_max;
 } fnx_conv_layer;

@@ -100,3 +100,25 @@ def test_product_does_not_import_oracle():
                     s = fh.read()
                 assert "import oracle" not in s and "oracle/" not in s and "ref_loader" not in s and \
                     "fluid_oracle" not in s, os.path.join(root, f)
+
+
+def test_msnet_workspace_is_host_only(lib):
+    """fnx_msnet_workspace is pure host arithmetic over the plan (dry run of the forward's layer
+    schedule): usable without a GPU, grows with the grid, rejects grids with an empty 1/4 scale."""
+    from fluidnet_cxx_b200 import _native
+    plan = _native.MsnetPlan()
+    plan.data_channels = 2
+    spec = {"quarter": ([2, 32, 64, 32, 1], [3, 3, 3, 3], 2), "half": ([3, 32, 64, 128, 64, 32, 1], [5, 3, 3, 3, 3, 3], 4),
+            "full": ([3, 32, 64, 128, 64, 32, 8], [5, 3, 3, 3, 3, 5], 4)}
+    for name, (ch, ks, nrelu) in spec.items():
+        arr = getattr(plan, name)
+        for i, k in enumerate(ks):
+            arr[i].cin, arr[i].cout, arr[i].ksize, arr[i].relu = ch[i], ch[i + 1], k, int(i < nrelu)
+            arr[i].w_tc = 1 if (k == 3 and ch[i] % 16 == 0 and ch[i + 1] in (32, 64, 128)) else None
+    plan.final_conv.cin, plan.final_conv.cout, plan.final_conv.ksize = 8, 1, 1
+    small = lib.fnx_msnet_workspace(ctypes.byref(plan), 64, 64)
+    big = lib.fnx_msnet_workspace(ctypes.byref(plan), 512, 512)
+    assert 0 < small < big
+    # 512^2: split activations 32+64+128+64 channels x 4 B x (516^2) at full res dominate
+    assert big > (32 + 64 + 128 + 64) * 4 * 516 * 516
+    assert lib.fnx_msnet_workspace(ctypes.byref(plan), 3, 3) == 0
