@@ -27,10 +27,13 @@
 // tools/tc_probe.cu).  Each input row is staged once per 16-channel chunk by 1-D bulk copies of the
 // TMA engine (cp.async.bulk, SASS UBLKCP) and reused by all KS*KS taps and all 3 split terms.
 //
-// Kernel shape: persistent, one CTA per SM, 192 threads = producer warp (bulk copies), MMA warp (one
-// thread issues tcgen05.mma), 4 epilogue warps (tcgen05.ld -> bias/ReLU -> split -> 16-byte stores).
-// A block of work = R output rows x 128 pixels x Cout: 2*R accumulators of 128 x Cout fp32 in TMEM
-// (2*R*Cout <= 512 columns) so each streamed weight slot is reused by R M-tiles.
+// Kernel shape: persistent, one CTA per SM, 320 threads = producer warp (bulk copies), MMA warp (one
+// lane issues tcgen05.mma), 8 epilogue warps (tcgen05.ld -> bias/ReLU -> split -> 16-byte stores).
+// A block of work = R output rows x 128 pixels x Cout: per M tile a [main | corr] accumulator pair of
+// 128 x 2*Cout fp32 in TMEM (2*R*Cout <= 512 columns), so each streamed weight slot is reused by R M
+// tiles.  Per tap two MMAs: a_hi.[w_hi;w_lo] (N = 2*Cout, fills main and corr at once) and a_lo.w_hi.
+// The first and last 16-channel chunk of a block run tile-major with per-tile TMEM barriers so the
+// epilogue of one tile overlaps the MMAs of the next.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -64,7 +67,7 @@ __host__ __device__ __forceinline__ float pow2_scale_for(float bound) {
 struct ConvArgs {
   const __half* x;     // input planes: hi at x, lo at x + x_plane
   size_t x_plane;      // halves
-  const uint8_t* w;    // packed weights: [Cin_pad/16][KS (ky)] slots, slot = [kx][plane][j][COUT][8 halves]
+  const uint8_t* w;    // packed weights: [Cin_pad/16][KS (ky)] slots, slot = [kx][j][plane][COUT][8 halves]
   const float* bias;   // Cout real values
   void* y;             // split planes (out_mode 0) or fp32 NCHW (out_mode 1)
   size_t y_plane;      // halves (out_mode 0)
@@ -78,6 +81,9 @@ struct ConvArgs {
   int tiles_x, nblocks;
 };
 
+constexpr int NEPI = 8;                      // epilogue warps (two per TMEM lane quadrant)
+constexpr int NTHREADS = 32 * (2 + NEPI);
+
 template <int KS, int COUT, int R, int WS>
 struct Cfg {
   static constexpr int HALO = KS / 2;
@@ -87,20 +93,30 @@ struct Cfg {
   static constexpr uint32_t A_J = ROWS * ROWB;        // stride between the two 8-channel chunks = LBO(A)
   static constexpr uint32_t A_PLANE = 2 * A_J;
   static constexpr uint32_t A_STAGE = 2 * A_PLANE;    // hi + lo
-  static constexpr uint32_t W_J = COUT * 16;          // LBO(B)
-  static constexpr uint32_t W_PLANE = 2 * W_J;
-  static constexpr uint32_t W_KX = 2 * W_PLANE;
+  static constexpr uint32_t W_J = 2 * COUT * 16;      // [w_hi rows ; w_lo rows] of one 8-channel chunk = LBO(B)
+  static constexpr uint32_t W_KX = 2 * W_J;
   static constexpr uint32_t W_STAGE = KS * W_KX;      // one (16-channel chunk, ky) slot
-  static constexpr uint32_t NBAR = 4 + 2 * WS + 2;
+  static constexpr uint32_t NBAR = 4 + 2 * WS + 2 * R;
   static constexpr uint32_t SMEM = 2 * A_STAGE + WS * W_STAGE + NBAR * 8 + 16 + COUT * 4;
-  static constexpr uint32_t NCOLS = 2 * R * COUT;     // main + corr accumulators
+  static constexpr uint32_t NCOLS = 2 * R * COUT;     // per M tile: [main | corr] accumulators
   static constexpr uint32_t TMEM_COLS = NCOLS <= 32 ? 32 : NCOLS <= 64 ? 64 : NCOLS <= 128 ? 128 : NCOLS <= 256 ? 256 : 512;
   static_assert(NCOLS <= 512, "accumulators exceed TMEM");
+  static_assert(WS >= KS + 1, "the first / last chunk of a block needs all KS weight slots of the chunk resident");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
+// One filter tap of one M tile: two MMAs.
+//   [main | corr] += a_hi . [w_hi ; w_lo]^T      (N = 2*COUT: hi*hi into main, hi*lo into corr)
+//          corr   += a_lo . w_hi^T               (N = COUT)
+// The cross terms never touch the main accumulator (see the header on truncation bias).
+template <int COUT>
+__device__ __forceinline__ void mma_tap(uint32_t d_tile, uint64_t a_hi, uint64_t a_lo, uint64_t w, uint32_t accumulate) {
+  mma_f16_ss(d_tile, a_hi, w, idesc_f16_f32acc(128, 2 * COUT), accumulate);
+  mma_f16_ss(d_tile + COUT, a_lo, w, idesc_f16_f32acc(128, COUT), 1);
+}
+
 template <int KS, int COUT, int R, int WS>
-__global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
   using C = Cfg<KS, COUT, R, WS>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
@@ -113,10 +129,12 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvArgs a) {
   auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
   auto W_FULL = [&](int s) { return bar0 + 8u * (4 + s); };
   auto W_EMPTY = [&](int s) { return bar0 + 8u * (4 + WS + s); };
-  const uint32_t ACC_FULL = bar0 + 8u * (4 + 2 * WS), ACC_EMPTY = bar0 + 8u * (5 + 2 * WS);
+  auto ACC_FULL = [&](int r) { return bar0 + 8u * (4 + 2 * WS + r); };
+  auto ACC_EMPTY = [&](int r) { return bar0 + 8u * (4 + 2 * WS + R + r); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = a.nchunks;
+  const bool resident = nchunks * KS <= WS;  // all weight slots of the layer fit in the ring
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; s++) {
@@ -127,8 +145,10 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvArgs a) {
       mbar_init(W_FULL(s), 1);
       mbar_init(W_EMPTY(s), 1);
     }
-    mbar_init(ACC_FULL, 1);
-    mbar_init(ACC_EMPTY, 4);
+    for (int r = 0; r < R; r++) {
+      mbar_init(ACC_FULL(r), 1);
+      mbar_init(ACC_EMPTY(r), NEPI);
+    }
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
@@ -142,6 +162,12 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvArgs a) {
     // ===== producer: stage activation rows and weight slots with the TMA engine =====
     if (lane == 0) {
       int as = 0, aph = 0, ws = 0, wph = 0;
+      if (resident) {  // the whole layer's weights fit in the ring: load once, never release
+        for (int s = 0; s < nchunks * KS; s++) {
+          mbar_expect_tx(W_FULL(s), C::W_STAGE);
+          bulk_g2s(smem_u32(sW + s * C::W_STAGE), a.w + (size_t)s * C::W_STAGE, C::W_STAGE, W_FULL(s));
+        }
+      }
       for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
         const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * R;
         // staged rows = padded-image rows y0+PAD-HALO ..; rows past the padded image are skipped
@@ -161,82 +187,129 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvArgs a) {
               for (int r = 0; r < nrows; r++)
                 bulk_g2s(dst + r * C::ROWB, src + (size_t)r * a.Wp * 8, C::ROWB, A_FULL(as));
             }
-          for (int ky = 0; ky < KS; ky++) {
-            mbar_wait(W_EMPTY(ws), wph ^ 1);
-            mbar_expect_tx(W_FULL(ws), C::W_STAGE);
-            bulk_g2s(smem_u32(sW + ws * C::W_STAGE), a.w + (size_t)(c * KS + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
-            if (++ws == WS) { ws = 0; wph ^= 1; }
+          if (!resident) {
+            for (int ky = 0; ky < KS; ky++) {
+              mbar_wait(W_EMPTY(ws), wph ^ 1);
+              mbar_expect_tx(W_FULL(ws), C::W_STAGE);
+              bulk_g2s(smem_u32(sW + ws * C::W_STAGE), a.w + (size_t)(c * KS + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
+              if (++ws == WS) { ws = 0; wph ^= 1; }
+            }
           }
           if (++as == 2) { as = 0; aph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread =====
-    if (lane == 0) {
-      const uint32_t idesc = idesc_f16_f32acc(128, COUT);
-      int as = 0, aph = 0, ws = 0, wph = 0, it = 0;
-      for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, it++) {
-        mbar_wait(ACC_EMPTY, (it & 1) ^ 1);
-        tc_fence_after();
-        for (int c = 0; c < nchunks; c++) {
-          mbar_wait(A_FULL(as), aph);
-          const uint32_t a_base = smem_u32(sA + as * C::A_STAGE);
-          const uint64_t a_hi0 = smem_desc_kmajor_noswz(a_base, C::A_J, 128);
-          const uint64_t a_lo0 = smem_desc_kmajor_noswz(a_base + C::A_PLANE, C::A_J, 128);
+    // ===== MMA issuer: the warp stays converged, one elected lane issues =====
+    // Chunk order: tile-major when the chunk is the last of its block (tile r's accumulators are
+    // committed to the epilogue one tile at a time, so the epilogue of one tile overlaps the MMAs of
+    // the next) or when the weights are resident; otherwise ky-major, which releases weight slots
+    // progressively.  The first chunk re-acquires tile r from the epilogue just before touching it.
+    const bool leader = lane == 0;
+    int as = 0, aph = 0, ws = 0, wph = 0, it = 0;
+    for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, it++) {
+      for (int c = 0; c < nchunks; c++) {
+        const bool first = c == 0, last = c == nchunks - 1;
+        mbar_wait(A_FULL(as), aph);
+        const uint32_t a_base = smem_u32(sA + as * C::A_STAGE);
+        const uint64_t a_hi0 = smem_desc_kmajor_noswz(a_base, C::A_J, 128);
+        const uint64_t a_lo0 = smem_desc_kmajor_noswz(a_base + C::A_PLANE, C::A_J, 128);
+        if (resident || last) {
+          uint64_t wd[KS];
+          {
+            int s = resident ? c * KS : ws, ph = resident ? 0 : wph;
+#pragma unroll
+            for (int ky = 0; ky < KS; ky++) {
+              mbar_wait(W_FULL(s), ph);
+              wd[ky] = smem_desc_kmajor_noswz(smem_u32(sW + s * C::W_STAGE), C::W_J, 128);
+              if (++s == WS) { s = 0; ph ^= 1; }
+            }
+          }
+          tc_fence_after();
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            if (first) {
+              mbar_wait(ACC_EMPTY(r), (it & 1) ^ 1);
+              tc_fence_after();
+            }
+            if (leader) {
+#pragma unroll
+              for (int ky = 0; ky < KS; ky++)
+#pragma unroll
+                for (int kx = 0; kx < KS; kx++) {
+                  const uint32_t aoff = (uint32_t)(((r + ky) * C::RP + kx) * 16) >> 4;
+                  mma_tap<COUT>(taddr + (uint32_t)(r * 2 * COUT), a_hi0 + aoff, a_lo0 + aoff,
+                                wd[ky] + ((uint32_t)(kx * C::W_KX) >> 4), (first && ky == 0 && kx == 0) ? 0u : 1u);
+                }
+              if (last) mma_commit(ACC_FULL(r));
+            }
+            __syncwarp();
+          }
+          if (!resident) {
+#pragma unroll
+            for (int ky = 0; ky < KS; ky++) {
+              if (leader) mma_commit(W_EMPTY(ws));
+              if (++ws == WS) { ws = 0; wph ^= 1; }
+            }
+          }
+        } else {
           for (int ky = 0; ky < KS; ky++) {
             mbar_wait(W_FULL(ws), wph);
             tc_fence_after();
-            const uint32_t w_base = smem_u32(sW + ws * C::W_STAGE);
-            const uint64_t w0 = smem_desc_kmajor_noswz(w_base, C::W_J, 128);
-            const uint32_t nfirst = (c | ky) != 0;
+            const uint64_t w0 = smem_desc_kmajor_noswz(smem_u32(sW + ws * C::W_STAGE), C::W_J, 128);
 #pragma unroll
             for (int r = 0; r < R; r++) {
-#pragma unroll
-              for (int kx = 0; kx < KS; kx++) {
-                const uint32_t aoff = (uint32_t)(((r + ky) * C::RP + kx) * 16) >> 4;
-                const uint64_t w_hi = w0 + ((uint32_t)(kx * C::W_KX) >> 4);
-                const uint64_t w_lo = w_hi + (C::W_PLANE >> 4);
-                const uint32_t d_main = taddr + (uint32_t)(r * COUT), d_corr = d_main + (uint32_t)(R * COUT);
-                const uint32_t acc = kx ? 1u : nfirst;
-                mma_f16_ss(d_corr, a_lo0 + aoff, w_hi, idesc, acc);
-                mma_f16_ss(d_corr, a_hi0 + aoff, w_lo, idesc, 1);
-                mma_f16_ss(d_main, a_hi0 + aoff, w_hi, idesc, acc);
+              if (first && ky == 0) {
+                mbar_wait(ACC_EMPTY(r), (it & 1) ^ 1);
+                tc_fence_after();
               }
+              if (leader) {
+#pragma unroll
+                for (int kx = 0; kx < KS; kx++) {
+                  const uint32_t aoff = (uint32_t)(((r + ky) * C::RP + kx) * 16) >> 4;
+                  mma_tap<COUT>(taddr + (uint32_t)(r * 2 * COUT), a_hi0 + aoff, a_lo0 + aoff,
+                                w0 + ((uint32_t)(kx * C::W_KX) >> 4), (first && ky == 0 && kx == 0) ? 0u : 1u);
+                }
+              }
+              __syncwarp();
             }
-            mma_commit(W_EMPTY(ws));
+            if (leader) mma_commit(W_EMPTY(ws));
+            __syncwarp();
             if (++ws == WS) { ws = 0; wph ^= 1; }
           }
-          mma_commit(A_EMPTY(as));
-          if (++as == 2) { as = 0; aph ^= 1; }
         }
-        mma_commit(ACC_FULL);
+        if (leader) mma_commit(A_EMPTY(as));
+        __syncwarp();
+        if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> bias / ReLU -> (split fp16 | fp32 NCHW) =====
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int q = warp & 3;            // TMEM lane quadrant this warp may read
+    const int half_id = (warp - 2) >> 2;  // which half of the 16-column groups this warp handles
     const float s_in = a.in_meta->scale;
     const float inv = 1.f / (s_in * a.w_scale);
     const float s_out = pow2_scale_for(__uint_as_float(a.in_meta->amax_bits) * a.w_norm + a.b_max);
     float amax = 0.f;
     int it = 0;
+    constexpr int NGRP = COUT / 16;
     for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, it++) {
       const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * R;
       const int px = x0 + q * 32 + lane;
-      mbar_wait(ACC_FULL, it & 1);
-      tc_fence_after();
 #pragma unroll 1
       for (int r = 0; r < R; r++) {
         const int y = y0 + r;
         const bool ok = (y < a.H) && (px < a.W);
+        mbar_wait(ACC_FULL(r), it & 1);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < COUT; c0 += 16) {
+        for (int g = half_id; g < NGRP; g += 2) {
+          const int c0 = g * 16;
           if (c0 >= a.Cout) break;  // padded output channels (warp-uniform)
           uint32_t vm[16], vc[16];
-          const uint32_t t0 = taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * COUT + c0);
+          const uint32_t t0 = taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * 2 * COUT + c0);
           tmem_ld16(t0, vm);
-          tmem_ld16(t0 + (uint32_t)(R * COUT), vc);
+          tmem_ld16(t0 + (uint32_t)COUT, vc);
           tmem_ld_wait();
           float f[16];
 #pragma unroll
@@ -251,16 +324,16 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvArgs a) {
               for (int i = 0; i < 16; i++) amax = fmaxf(amax, fabsf(f[i]));
               __half* yh = reinterpret_cast<__half*>(a.y);
 #pragma unroll
-              for (int g = 0; g < 2; g++) {
+              for (int gg = 0; gg < 2; gg++) {
                 __align__(16) __half2 hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                  const float u0 = f[g * 8 + 2 * i] * s_out, u1 = f[g * 8 + 2 * i + 1] * s_out;
+                  const float u0 = f[gg * 8 + 2 * i] * s_out, u1 = f[gg * 8 + 2 * i + 1] * s_out;
                   const __half h0 = __float2half_rn(u0), h1 = __float2half_rn(u1);
                   hi[i] = __halves2half2(h0, h1);
                   lo[i] = __halves2half2(__float2half_rn(u0 - __half2float(h0)), __float2half_rn(u1 - __half2float(h1)));
                 }
-                const size_t off = (((size_t)((c0 >> 3) + g) * a.Hp + (y + PAD)) * a.Wp + (px + PAD)) * 8;
+                const size_t off = (((size_t)((c0 >> 3) + gg) * a.Hp + (y + PAD)) * a.Wp + (px + PAD)) * 8;
                 *reinterpret_cast<uint4*>(yh + off) = *reinterpret_cast<const uint4*>(hi);
                 *reinterpret_cast<uint4*>(yh + a.y_plane + off) = *reinterpret_cast<const uint4*>(lo);
               }
@@ -272,10 +345,10 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const ConvArgs a) {
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ACC_EMPTY(r));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ACC_EMPTY);
     }
     if (a.out_meta) {
 #pragma unroll
@@ -337,7 +410,7 @@ __global__ void __launch_bounds__(256)
   y[e] = (__half2float(x[off]) + __half2float(x[x_plane + off])) / meta->scale;
 }
 
-// weight (Cout, Cin, KS, KS) fp32 -> packed split slots [Cin_pad/16][ky][kx][plane][j][Cout_pad][8 halves]
+// weight (Cout, Cin, KS, KS) fp32 -> packed split slots [Cin_pad/16][ky][kx][j][plane][Cout_pad][8 halves]
 // (zero for the padded input / output channels)
 __global__ void __launch_bounds__(256)
     k_pack_weights(const float* __restrict__ w, int Cin, int Cout, int KS, int Cin_pad, int Cout_pad, float w_scale,
@@ -351,9 +424,9 @@ __global__ void __launch_bounds__(256)
   const float u = (ci < Cin && n < Cout) ? w[((size_t)n * Cin + ci) * taps + t] * w_scale : 0.f;
   const __half h = __float2half_rn(u);
   const __half l = __float2half_rn(u - __half2float(h));
-  const size_t slot = ((size_t)(c * KS + ky) * KS + kx) * 2;  // then [plane][j][n][8]
-  out[(((slot + 0) * 2 + j) * Cout_pad + n) * 8 + i] = h;
-  out[(((slot + 1) * 2 + j) * Cout_pad + n) * 8 + i] = l;
+  const size_t slot = ((size_t)(c * KS + ky) * KS + kx) * 2 + j;  // then [plane][n][8]: w_hi rows, then w_lo rows
+  out[((slot * 2 + 0) * Cout_pad + n) * 8 + i] = h;
+  out[((slot * 2 + 1) * Cout_pad + n) * 8 + i] = l;
 }
 
 }  // namespace tc
@@ -400,7 +473,7 @@ static int launch_tc(ConvArgs a, cudaStream_t st) {
   a.tiles_x = (a.W + TW - 1) / TW;
   a.nblocks = a.tiles_x * ((a.H + R - 1) / R);
   const int grid = a.nblocks < num_sms() ? a.nblocks : num_sms();
-  kern<<<grid, 192, C::SMEM, st>>>(a);
+  kern<<<grid, NTHREADS, C::SMEM, st>>>(a);
   fnx_count_launches(1);
   FNX_CUDA_TRY("conv_tc", cudaGetLastError());
   return FNX_OK;
@@ -408,20 +481,20 @@ static int launch_tc(ConvArgs a, cudaStream_t st) {
 
 // rows per block: the largest instantiated R that still gives every SM a block (small pyramid
 // levels trade weight re-use for occupancy)
-template <int KS, int COUT, int RMAX>
+template <int KS, int COUT, int RMAX, int WS>
 static int launch_tc_rows(const ConvArgs& a, cudaStream_t st) {
   const int tiles_x = (a.W + TW - 1) / TW;
   auto blocks = [&](int r) { return tiles_x * ((a.H + r - 1) / r); };
   if constexpr (RMAX >= 8) {
-    if (blocks(8) >= num_sms()) return launch_tc<KS, COUT, 8, 4>(a, st);
+    if (blocks(8) >= num_sms()) return launch_tc<KS, COUT, 8, WS>(a, st);
   }
   if constexpr (RMAX >= 4) {
-    if (blocks(4) >= num_sms()) return launch_tc<KS, COUT, 4, 4>(a, st);
+    if (blocks(4) >= num_sms()) return launch_tc<KS, COUT, 4, WS>(a, st);
   }
   if constexpr (RMAX >= 2) {
-    if (blocks(2) >= num_sms()) return launch_tc<KS, COUT, 2, 4>(a, st);
+    if (blocks(2) >= num_sms()) return launch_tc<KS, COUT, 2, WS>(a, st);
   }
-  return launch_tc<KS, COUT, 1, 4>(a, st);
+  return launch_tc<KS, COUT, 1, WS>(a, st);
 }
 
 __global__ void __launch_bounds__(256) k_amax(const float* __restrict__ x, size_t n, ActMeta* meta) {
@@ -515,13 +588,14 @@ int fnx_conv_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed
   const int cp = cout_pad(Cout);
   if (ksize == 3) {
     switch (cp) {
-      case 128: return launch_tc_rows<3, 128, 2>(a, st);
-      case 64: return launch_tc_rows<3, 64, 4>(a, st);
-      case 32: return launch_tc_rows<3, 32, 8>(a, st);
-      default: return launch_tc_rows<3, 16, 8>(a, st);
+      case 128: return launch_tc_rows<3, 128, 2, 6>(a, st);
+      case 64: return launch_tc_rows<3, 64, 4, 6>(a, st);
+      case 32: return launch_tc_rows<3, 32, 8, 6>(a, st);
+      default: return launch_tc_rows<3, 16, 8, 6>(a, st);
     }
   }
-  return cp == 32 ? launch_tc_rows<5, 32, 4>(a, st) : launch_tc_rows<5, 16, 4>(a, st);
+  // 5x5: weight rings sized so the net's two 5x5 layers (1 and 2 chunks) keep their weights resident
+  return cp == 32 ? launch_tc_rows<5, 32, 4, 6>(a, st) : launch_tc_rows<5, 16, 4, 10>(a, st);
 }
 
 // ---------------------------------------------------------------------------------------------
