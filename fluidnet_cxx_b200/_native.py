@@ -40,6 +40,12 @@ class ConvLayer(ctypes.Structure):
                 ("w_scale", _c_float), ("w_norm", _c_float), ("b_max", _c_float)]
 
 
+class ProfileRec(ctypes.Structure):
+    """struct fnx_profile_rec (include/fluidstep.h)."""
+    _fields_ = [("cin", _c_int), ("cout", _c_int), ("ksize", _c_int), ("h", _c_int), ("w", _c_int),
+                ("tensor", _c_int), ("ms", _c_float)]
+
+
 class MsnetPlan(ctypes.Structure):
     """struct fnx_msnet_plan (include/fluidstep.h)."""
     _fields_ = [("data_channels", _c_int), ("quarter", ConvLayer * 4), ("half", ConvLayer * 6),
@@ -88,6 +94,8 @@ SIGNATURES = {
     "fnx_msnet_workspace": (_S, [ctypes.POINTER(MsnetPlan), _I, _I]),
     "fnx_msnet_workspace_init": (_I, [_P, _S, _P]),
     "fnx_msnet_forward": (_I, [ctypes.POINTER(MsnetPlan), _P, _P, _I, _I, _I, _P, _S, _P]),
+    "fnx_profile_enable": (_I, [_I]),
+    "fnx_profile_fetch": (_I, [ctypes.POINTER(ProfileRec), _I]),
     "fnx_fluidnet_input": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "fnx_fluidnet_output": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
 }

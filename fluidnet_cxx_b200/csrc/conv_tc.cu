@@ -38,6 +38,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <mutex>
+#include <vector>
+
 #include "../../include/fluidstep.h"
 #include "cnn_internal.h"
 #include "host_util.h"
@@ -479,20 +482,32 @@ static int launch_tc(ConvArgs a, cudaStream_t st) {
   return FNX_OK;
 }
 
-// rows per block: the largest instantiated R that still gives every SM a block (small pyramid
-// levels trade weight re-use for occupancy)
+// rows per block R in {8, 4, 2, 1} (<= RMAX): one persistent CTA per SM works through
+// ceil(nblocks / SMs) blocks, so pick the R with the least idle tail; ties (within 3 %) go to the
+// larger R, which re-uses each streamed weight slot over more M tiles.
 template <int KS, int COUT, int RMAX, int WS>
 static int launch_tc_rows(const ConvArgs& a, cudaStream_t st) {
-  const int tiles_x = (a.W + TW - 1) / TW;
-  auto blocks = [&](int r) { return tiles_x * ((a.H + r - 1) / r); };
+  const int tiles_x = (a.W + TW - 1) / TW, sms = num_sms();
+  int best = 1;
+  double best_eff = -1.0;
+  for (int r = 1; r <= RMAX; r *= 2) {
+    const int nb = tiles_x * ((a.H + r - 1) / r);
+    const int rounds = (nb + sms - 1) / sms;
+    const double useful = (double)a.H / (double)(((a.H + r - 1) / r) * r);  // rows past H are wasted work
+    const double eff = useful * (double)nb / ((double)rounds * sms);
+    if (eff >= best_eff - 0.03) {
+      if (eff > best_eff) best_eff = eff;
+      best = r;
+    }
+  }
   if constexpr (RMAX >= 8) {
-    if (blocks(8) >= num_sms()) return launch_tc<KS, COUT, 8, WS>(a, st);
+    if (best == 8) return launch_tc<KS, COUT, 8, WS>(a, st);
   }
   if constexpr (RMAX >= 4) {
-    if (blocks(4) >= num_sms()) return launch_tc<KS, COUT, 4, WS>(a, st);
+    if (best == 4) return launch_tc<KS, COUT, 4, WS>(a, st);
   }
   if constexpr (RMAX >= 2) {
-    if (blocks(2) >= num_sms()) return launch_tc<KS, COUT, 2, WS>(a, st);
+    if (best == 2) return launch_tc<KS, COUT, 2, WS>(a, st);
   }
   return launch_tc<KS, COUT, 1, WS>(a, st);
 }
@@ -601,6 +616,59 @@ int fnx_conv_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed
 // ---------------------------------------------------------------------------------------------
 // MultiScaleNet.forward (multi_scale_net.py:101-127): one call, every launch enqueued on `stream`
 // ---------------------------------------------------------------------------------------------
+// ---- optional per-layer timing (bench.py roofline): CUDA events around every conv launch -------
+namespace {
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;   // pairs (begin, end)
+  std::vector<fnx_profile_rec> recs;
+  std::mutex mu;
+} g_prof;
+
+struct LayerTimer {
+  cudaStream_t st;
+  bool active = false;
+  size_t idx = 0;
+  LayerTimer(const fnx_conv_layer& l, int h, int w, int tensor, cudaStream_t s) : st(s) {
+    if (!g_prof.on) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    idx = g_prof.recs.size();
+    while (g_prof.pool.size() < 2 * (idx + 1)) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      g_prof.pool.push_back(e);
+    }
+    g_prof.recs.push_back(fnx_profile_rec{l.cin, l.cout, l.ksize, h, w, tensor, 0.f});
+    cudaEventRecord(g_prof.pool[2 * idx], st);
+    active = true;
+  }
+  ~LayerTimer() {
+    if (active) cudaEventRecord(g_prof.pool[2 * idx + 1], st);
+  }
+};
+}  // namespace
+
+int fnx_profile_enable(int enable) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.on = enable != 0;
+  g_prof.recs.clear();
+  return FNX_OK;
+}
+
+int fnx_profile_fetch(fnx_profile_rec* out, int capacity) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  const int n = (int)g_prof.recs.size();
+  for (int i = 0; i < n; i++) {
+    if (cudaEventSynchronize(g_prof.pool[2 * i + 1]) != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "profile_fetch: event sync failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]);
+    g_prof.recs[i].ms = ms;
+    if (out && i < capacity) out[i] = g_prof.recs[i];
+  }
+  g_prof.recs.clear();
+  return n;
+}
+
 namespace {
 struct Bump {
   uint8_t* base;
@@ -649,6 +717,7 @@ struct Runner {
           void* sp = ws.take(fnx_tc_act_bytes(l.cout, h, w));
           ActMeta* m = new_meta();
           if (!dry) {
+            LayerTimer lt(l, h, w, 1, st);
             int rc = fnx_conv_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu, l.w_scale,
                                     l.w_norm, l.b_max, 0, sp, (fnx_act_meta*)m, 0, 0, st);
             if (rc) return rc;
@@ -657,6 +726,7 @@ struct Runner {
         } else {
           float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
           if (!dry) {
+            LayerTimer lt(l, h, w, 1, st);
             int rc = fnx_conv_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu, l.w_scale,
                                     l.w_norm, l.b_max, 1, o, nullptr, last ? out_ctotal : l.cout, last ? out_coff : 0, st);
             if (rc) return rc;
@@ -668,6 +738,7 @@ struct Runner {
         float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
         ActMeta* m = tc_next ? new_meta() : nullptr;
         if (!dry) {
+          LayerTimer lt(l, h, w, 0, st);
           int rc = fnx_conv_direct(cur_f32, l.weight, l.bias, o, 1, l.cin, h, w, l.cout, l.ksize, l.relu,
                                    last ? out_ctotal : l.cout, last ? out_coff : 0, m ? &m->amax_bits : nullptr, st);
           if (rc) return rc;

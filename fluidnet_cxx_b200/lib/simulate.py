@@ -13,6 +13,7 @@ Also accepts the legacy 5-argument form `simulate(conf, mconf, batch_dict, net, 
 pytorch/rayleighTaylor.py:240 still uses (SURVEY.md hazard H3).
 """
 import ctypes
+import os
 
 import torch
 
@@ -123,8 +124,101 @@ def _simulate(mconf, batch_dict, net, sim_method, output_div=False):
     dt = float(mconf['dt'])
     assert mconf['viscosity'] >= 0, 'Viscosity must be positive'
     if _fusable(mconf, batch_dict, sim_method, output_div):
+        if _graphable(batch_dict, net, sim_method):
+            return _simulate_graphed(mconf, batch_dict, net, sim_method, dt)
         return _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div)
     return _simulate_ops(mconf, batch_dict, net, sim_method, dt, output_div)
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA-graph replay of the fused step.  Below a few million cells the
+# step is launch-bound (4 stencil kernels + ~50 launches of the CNN forward): the whole fixed
+# sequence is captured once per (grid, configuration, masks, weights) into a CUDA graph that works
+# on graph-owned state buffers; a step is then: copy the caller's state in, one graph launch, hand
+# out clones (the reference returns fresh tensors every step and never mutates the old ones).
+GRAPH_MAX_CELLS = 1 << 22
+_graphs = {}
+_graph_seen = {}
+
+
+def graphs_enabled():
+    return os.environ.get("FLUIDNET_B200_GRAPHS", "1") != "0"
+
+
+def clear_graph_cache():
+    _graphs.clear()
+    _graph_seen.clear()
+
+
+def _graphable(batch_dict, net, sim_method):
+    if not graphs_enabled() or _stage_hook is not None:
+        return False
+    f = batch_dict['flags']
+    if f.numel() > GRAPH_MAX_CELLS or torch.cuda.is_current_stream_capturing():
+        return False
+    if sim_method == 'convnet':
+        from .model import FluidNet
+        if not isinstance(net, FluidNet):     # a foreign nn.Module: its launches may not be capturable
+            return False
+    return True
+
+
+def _freeze(v):
+    if isinstance(v, dict):
+        return tuple(sorted((k, _freeze(x)) for k, x in v.items()))
+    if isinstance(v, (list, tuple)):
+        return tuple(_freeze(x) for x in v)
+    if isinstance(v, torch.Tensor):
+        return (v.data_ptr(), v._version)
+    return v
+
+
+# every mconf entry the fused step / the model wrapper reads
+_STEP_KEYS = ('dt', 'maccormackStrength', 'sampleOutsideFluid', 'buoyancyScale', 'gravityScale', 'gravityVec',
+              'operatingDensity', 'jacobiIter', 'pTol', 'viscosity', 'correctScalar', 'periodic-x', 'periodic-y')
+_NET_KEYS = ('normalizeInputThreshold', 'normalizeInput', 'normalizeInputChan', 'inputChannels', 'model', 'is3D',
+             'periodic-x', 'periodic-y')
+
+
+def _graph_key(mconf, batch_dict, net, sim_method):
+    state = tuple((k, tuple(batch_dict[k].shape)) for k in ('p', 'U', 'flags', 'density'))
+    masks = tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in _masks(batch_dict))
+    conf = tuple(_freeze(mconf.get(k)) for k in _STEP_KEYS)
+    netk = None
+    if sim_method == 'convnet':
+        netk = (id(net), net.multiScale._plan_key(batch_dict['U'].device),
+                tuple(_freeze(net.mconf.get(k)) for k in _NET_KEYS))
+    return (str(batch_dict['U'].device), sim_method, state, masks, conf, netk)
+
+
+def _simulate_graphed(mconf, batch_dict, net, sim_method, dt):
+    key = _graph_key(mconf, batch_dict, net, sim_method)
+    entry = _graphs.get(key)
+    if entry is None:
+        # first sighting: run eagerly (this also performs every lazy initialisation: workspaces, the
+        # CNN plan, kernel attributes); capture on the second call with the same key
+        if _graph_seen.get(key, 0) < 1:
+            if len(_graph_seen) > 64:
+                _graph_seen.clear()
+            _graph_seen[key] = 1
+            return _simulate_fused(mconf, batch_dict, net, sim_method, dt, False)
+        if len(_graphs) >= 8:
+            _graphs.clear()
+        static = {k: batch_dict[k].clone() for k in ('p', 'U', 'flags', 'density')}
+        work = dict(batch_dict)
+        work.update(static)
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph):
+            _simulate_fused(mconf, work, net, sim_method, dt, False)
+        entry = (graph, static, {k: work[k] for k in ('p', 'U', 'density')}, _masks(batch_dict))
+        _graphs[key] = entry
+    graph, static, outs, _keepalive = entry
+    for k in ('p', 'U', 'flags', 'density'):
+        static[k].copy_(batch_dict[k])
+    graph.replay()
+    for k in ('p', 'U', 'density'):
+        batch_dict[k] = outs[k].clone()
 
 
 # ---------------------------------------------------------------------------------------------

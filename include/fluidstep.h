@@ -216,6 +216,16 @@ int fnx_msnet_workspace_init(void *workspace, size_t workspace_bytes, void *stre
 int fnx_msnet_forward(const fnx_msnet_plan *plan, const float *x, float *y, int N, int H, int W,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* optional per-layer timing of fnx_msnet_forward (bench.py's roofline): while enabled, every conv
+ * launch is bracketed by CUDA events on its stream; fetch synchronises them, returns the number of
+ * records since the last fetch / enable and clears them. */
+typedef struct fnx_profile_rec {
+  int cin, cout, ksize, h, w, tensor; /* tensor: 1 = tcgen05 kernel, 0 = fp32 direct kernel */
+  float ms;
+} fnx_profile_rec;
+int fnx_profile_enable(int enable);
+int fnx_profile_fetch(fnx_profile_rec *out, int capacity);
+
 /* net input of the shipped ScaleNet: x = [velocityDivergence(U, flags)/scale, flagsToOccupancy(flags)]
  * (*_saved.py:135-177); U (B,2,1,H,W), x (B,2,H,W) */
 int fnx_fluidnet_input(const float *U, const float *flags, const float *scale, float *x, int B,
