@@ -85,12 +85,19 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []      # (arrival time, csv line)
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -99,7 +106,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -111,7 +118,15 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        # samples that arrived inside the marked timed region (nvidia-smi reports with ~20 ms period);
+        # a region shorter than one period falls back to every sample taken while this process kept
+        # the GPU under the same load (warm-up + timed + per-kernel pass), and says so
+        inside = [ln for t, ln in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e300) + 0.02]
+        window = "timed region"
+        if len(inside) < 2:
+            inside = [ln for t, ln in self.lines if self.t0 is None or t >= self.t0 - 0.5]
+            window = "warm-up + timed region + per-kernel pass (timed region shorter than the sampling period)"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -123,7 +138,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -183,17 +198,18 @@ def run_ours(args):
         with torch.no_grad():
             sim.simulate(mconf, bd, net, wl["method"])
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
 
     # ---- pass 1: the timed region of `value` (public API; CUDA-graph replay where the step is small) ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     n0 = lib.fnx_launch_count()
     step_ms = []
     barrier()
+    sampler.mark_begin()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         if flush:
@@ -205,7 +221,7 @@ def run_ours(args):
         step_ms.append((e0, e1))
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.mark_end()
     times = [a.elapsed_time(b) for a, b in step_ms]
     total_ms = sum(times)
     graphed = bool(sim.graphs_enabled() and cells <= sim.GRAPH_MAX_CELLS)
@@ -241,6 +257,7 @@ def run_ours(args):
         layer_recs = [buf[i] for i in range(max(0, min(n, 4096)))]
     dom_ms = sum(stage_events[2 * i].elapsed_time(stage_events[2 * i + 1]) for i in range(len(stage_events) // 2))
     sim.set_stage_hook(None)
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host (pinned) state in, results out, every step -----------------------------------
     e2e_steps = max(3, min(args.steps, 10))

@@ -82,6 +82,7 @@ struct ConvArgs {
   int relu, out_mode, y_ctotal, y_coff;
   float w_scale, w_norm, b_max;
   int tiles_x, nblocks;
+  int R;               // output rows per block (<= the kernel's RMAX template parameter)
 };
 
 constexpr int NEPI = 8;                      // epilogue warps (two per TMEM lane quadrant)
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = a.nchunks;
+  const int Rrt = a.R;  // rows per block at run time (R = capacity the shared/tensor memory is sized for)
   const bool resident = nchunks * KS <= WS;  // all weight slots of the layer fit in the ring
 
   if (threadIdx.x == 0) {
@@ -172,10 +174,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
         }
       }
       for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
-        const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * R;
+        const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * Rrt;
         // staged rows = padded-image rows y0+PAD-HALO ..; rows past the padded image are skipped
         int nrows = a.Hp - (y0 + PAD - C::HALO);
-        nrows = nrows > C::ROWS ? C::ROWS : nrows;
+        nrows = nrows > Rrt + KS - 1 ? Rrt + KS - 1 : nrows;
         for (int c = 0; c < nchunks; c++) {
           mbar_wait(A_EMPTY(as), aph ^ 1);
           mbar_expect_tx(A_FULL(as), (uint32_t)nrows * 4u * C::ROWB);
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
           tc_fence_after();
 #pragma unroll
           for (int r = 0; r < R; r++) {
+            if (r >= Rrt) break;
             if (first) {
               mbar_wait(ACC_EMPTY(r), (it & 1) ^ 1);
               tc_fence_after();
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
             const uint64_t w0 = smem_desc_kmajor_noswz(smem_u32(sW + ws * C::W_STAGE), C::W_J, 128);
 #pragma unroll
             for (int r = 0; r < R; r++) {
+              if (r >= Rrt) break;
               if (first && ky == 0) {
                 mbar_wait(ACC_EMPTY(r), (it & 1) ^ 1);
                 tc_fence_after();
@@ -297,10 +301,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
     int it = 0;
     constexpr int NGRP = COUT / 16;
     for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, it++) {
-      const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * R;
+      const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * Rrt;
       const int px = x0 + q * 32 + lane;
 #pragma unroll 1
-      for (int r = 0; r < R; r++) {
+      for (int r = 0; r < Rrt; r++) {
         const int y = y0 + r;
         const bool ok = (y < a.H) && (px < a.W);
         mbar_wait(ACC_FULL(r), it & 1);
@@ -468,48 +472,47 @@ static bool tc_eligible(int Cin, int Cout, int ksize) {
          !(ksize == 5 && Cout > 32);  // 5x5 instantiated for the narrow layers only
 }
 
-template <int KS, int COUT, int R, int WS>
-static int launch_tc(ConvArgs a, cudaStream_t st) {
-  using C = Cfg<KS, COUT, R, WS>;
-  auto kern = k_conv_tc<KS, COUT, R, WS>;
+// Rows per block.  One persistent CTA per SM works through ceil(nblocks / SMs) blocks; a block costs
+// max(tensor time, L2->SM fill time) (activation rows incl. halo + the streamed weight slots).  Small
+// R wastes L2 bandwidth on halo rows and weight re-streaming, large R leaves an idle tail when the
+// block count is not a multiple of the SM count: pick the R in [1, RMAX] with the least modelled time.
+template <int KS, int COUT, int RMAX, int WS>
+static int choose_rows(const ConvArgs& a) {
+  using C = Cfg<KS, COUT, RMAX, WS>;
+  const int tiles_x = (a.W + TW - 1) / TW, sms = num_sms();
+  const bool resident = a.nchunks * KS <= WS;
+  // per tap: MMA1 (N = 2*COUT) + MMA2 (N = COUT); each max(tensor floor N/2, operand read / 128 B per clk)
+  const double t_tap = fmax((double)COUT, 32.0 + COUT / 2.0) + fmax(COUT / 2.0, 32.0 + COUT / 4.0);
+  const double l2_bytes_per_clk = 24.0;
+  int best = 1;
+  double best_t = 1e300;
+  for (int r = 1; r <= RMAX; r++) {
+    const int nb = tiles_x * ((a.H + r - 1) / r);
+    const int rounds = (nb + sms - 1) / sms;
+    const double mma = (double)r * KS * KS * a.nchunks * t_tap;
+    const double bytes = (double)a.nchunks * ((double)(r + KS - 1) * 4.0 * C::ROWB + (resident ? 0.0 : (double)KS * C::W_STAGE));
+    const double t = rounds * (fmax(mma, bytes / l2_bytes_per_clk) + 600.0);
+    if (t < best_t * 0.995 || (t <= best_t * 1.005 && r > best)) {
+      best_t = t < best_t ? t : best_t;
+      best = r;
+    }
+  }
+  return best;
+}
+
+template <int KS, int COUT, int RMAX, int WS>
+static int launch_tc_rows(ConvArgs a, cudaStream_t st) {
+  using C = Cfg<KS, COUT, RMAX, WS>;
+  auto kern = k_conv_tc<KS, COUT, RMAX, WS>;
   FNX_CUDA_TRY("conv_tc", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  a.R = choose_rows<KS, COUT, RMAX, WS>(a);
   a.tiles_x = (a.W + TW - 1) / TW;
-  a.nblocks = a.tiles_x * ((a.H + R - 1) / R);
+  a.nblocks = a.tiles_x * ((a.H + a.R - 1) / a.R);
   const int grid = a.nblocks < num_sms() ? a.nblocks : num_sms();
   kern<<<grid, NTHREADS, C::SMEM, st>>>(a);
   fnx_count_launches(1);
   FNX_CUDA_TRY("conv_tc", cudaGetLastError());
   return FNX_OK;
-}
-
-// rows per block R in {8, 4, 2, 1} (<= RMAX): one persistent CTA per SM works through
-// ceil(nblocks / SMs) blocks, so pick the R with the least idle tail; ties (within 3 %) go to the
-// larger R, which re-uses each streamed weight slot over more M tiles.
-template <int KS, int COUT, int RMAX, int WS>
-static int launch_tc_rows(const ConvArgs& a, cudaStream_t st) {
-  const int tiles_x = (a.W + TW - 1) / TW, sms = num_sms();
-  int best = 1;
-  double best_eff = -1.0;
-  for (int r = 1; r <= RMAX; r *= 2) {
-    const int nb = tiles_x * ((a.H + r - 1) / r);
-    const int rounds = (nb + sms - 1) / sms;
-    const double useful = (double)a.H / (double)(((a.H + r - 1) / r) * r);  // rows past H are wasted work
-    const double eff = useful * (double)nb / ((double)rounds * sms);
-    if (eff >= best_eff - 0.03) {
-      if (eff > best_eff) best_eff = eff;
-      best = r;
-    }
-  }
-  if constexpr (RMAX >= 8) {
-    if (best == 8) return launch_tc<KS, COUT, 8, WS>(a, st);
-  }
-  if constexpr (RMAX >= 4) {
-    if (best == 4) return launch_tc<KS, COUT, 4, WS>(a, st);
-  }
-  if constexpr (RMAX >= 2) {
-    if (best == 2) return launch_tc<KS, COUT, 2, WS>(a, st);
-  }
-  return launch_tc<KS, COUT, 1, WS>(a, st);
 }
 
 __global__ void __launch_bounds__(256) k_amax(const float* __restrict__ x, size_t n, ActMeta* meta) {
@@ -598,7 +601,7 @@ int fnx_conv_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed
   a.H = H; a.W = W; a.Hp = H + 2 * PAD; a.Wp = W + 2 * PAD;
   a.relu = relu; a.out_mode = out_mode; a.y_ctotal = y_channels_total; a.y_coff = y_channel_offset;
   a.w_scale = w_scale; a.w_norm = w_norm; a.b_max = b_max;
-  a.tiles_x = 0; a.nblocks = 0;
+  a.tiles_x = 0; a.nblocks = 0; a.R = 1;
   cudaStream_t st = (cudaStream_t)stream;
   const int cp = cout_pad(Cout);
   if (ksize == 3) {
