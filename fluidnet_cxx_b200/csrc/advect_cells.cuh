@@ -19,9 +19,9 @@ struct CellIdx {
 
 __device__ __forceinline__ bool cell_of(const Grid& g, CellIdx& c) {
   c.i = blockIdx.x * blockDim.x + threadIdx.x;
-  int row = blockIdx.y * blockDim.y + threadIdx.y;
+  int row = g.row0 + blockIdx.y * blockDim.y + threadIdx.y;
   c.b = blockIdx.z;
-  if (c.i >= g.W || row >= g.D * g.H) return false;
+  if (c.i >= g.W || row >= g.row1) return false;
   c.k = row / g.H;
   c.j = row - c.k * g.H;
   c.o = (long long)row * g.W + c.i;
@@ -29,7 +29,7 @@ __device__ __forceinline__ bool cell_of(const Grid& g, CellIdx& c) {
 }
 
 static inline dim3 cell_grid(const Grid& g) {
-  return dim3((g.W + kBX - 1) / kBX, (g.D * g.H + kBY - 1) / kBY, g.B);
+  return dim3((g.W + kBX - 1) / kBX, (g.row1 - g.row0 + kBY - 1) / kBY, g.B);
 }
 static inline dim3 cell_block() { return dim3(kBX, kBY, 1); }
 

@@ -25,6 +25,8 @@ struct Grid {
   int sy;        // row stride   = W
   long long sz;  // plane stride = H*W
   long long n;   // cells per batch item = D*H*W
+  int row0, row1;  // rows of the flattened (D*H) row space the one-thread-per-cell kernels process
+                   // (whole grid by default; a slab window in the domain-decomposed step)
 };
 
 __host__ __device__ inline Grid make_grid(int B, int D, int H, int W) {
@@ -33,6 +35,7 @@ __host__ __device__ inline Grid make_grid(int B, int D, int H, int W) {
   g.sy = W;
   g.sz = (long long)H * W;
   g.n = (long long)D * H * W;
+  g.row0 = 0; g.row1 = D * H;
   return g;
 }
 

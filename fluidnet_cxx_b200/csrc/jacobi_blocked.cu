@@ -82,7 +82,7 @@ __device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const Row4 (&dv)[J
 
 template <int NW, bool FIRST, bool RESID>
 __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 2 : 1))
-    k_jacobi2d_blocked(int H, int W, int iters, int vec_ok, const float* __restrict__ flags,
+    k_jacobi2d_blocked(int H, int W, int row0, int row1, int iters, int vec_ok, const float* __restrict__ flags,
                        const float* __restrict__ div, const float* __restrict__ prev,
                        float* __restrict__ cur, double* __restrict__ ssq) {
   constexpr int TH = NW * JB_R;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 2 : 1))
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   constexpr int OW = JB_TW - 2 * JB_HALO, OH = TH - 2 * JB_HALO;
   const int gx0 = blockIdx.x * OW - JB_HALO + lane * JB_C;
-  const int gy0 = blockIdx.y * OH - JB_HALO + w * JB_R;
+  const int gy0 = row0 + blockIdx.y * OH - JB_HALO + w * JB_R;  // [row0, row1): rows this launch writes
   const long long boff = (long long)blockIdx.z * H * W;
   flags += boff; div += boff; cur += boff;
   if (!FIRST) prev += boff;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 2 : 1))
 #pragma unroll
     for (int rr = 0; rr < JB_R; rr++) {
       const int gy = gy0 + rr;
-      if (gy >= H) break;
+      if (gy >= row1) break;
       const long long o = (long long)gy * W + gx0;
       if (vec_ok && gx0 + JB_C <= W) {
         *reinterpret_cast<float4*>(cur + o) = make_float4(p[rr].v[0], p[rr].v[1], p[rr].v[2], p[rr].v[3]);
@@ -220,37 +220,40 @@ static int jacobi_block_iters() {
 }
 
 template <int NW>
-static void launch_blocked(bool first, bool resid, dim3 grid, cudaStream_t st, int H, int W, int iters, int vec_ok,
+static void launch_blocked(bool first, bool resid, dim3 grid, cudaStream_t st, int H, int W, int row0, int row1,
+                           int iters, int vec_ok,
                            const float* flags, const float* div, const float* prev, float* cur, double* ssq) {
   const int threads = NW * 32;
-  if (first && resid) k_jacobi2d_blocked<NW, true, true><<<grid, threads, 0, st>>>(H, W, iters, vec_ok, flags, div, prev, cur, ssq);
-  else if (first) k_jacobi2d_blocked<NW, true, false><<<grid, threads, 0, st>>>(H, W, iters, vec_ok, flags, div, prev, cur, ssq);
-  else if (resid) k_jacobi2d_blocked<NW, false, true><<<grid, threads, 0, st>>>(H, W, iters, vec_ok, flags, div, prev, cur, ssq);
-  else k_jacobi2d_blocked<NW, false, false><<<grid, threads, 0, st>>>(H, W, iters, vec_ok, flags, div, prev, cur, ssq);
+  if (first && resid) k_jacobi2d_blocked<NW, true, true><<<grid, threads, 0, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+  else if (first) k_jacobi2d_blocked<NW, true, false><<<grid, threads, 0, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+  else if (resid) k_jacobi2d_blocked<NW, false, true><<<grid, threads, 0, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+  else k_jacobi2d_blocked<NW, false, false><<<grid, threads, 0, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
 }
 
-int fnx_jacobi_2d_blocked(const float* flags, const float* div, float* p, float* scratch, double* ssq,
-                          int B, int H, int W, int max_iter, cudaStream_t st) {
+int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
+                          double* ssq, int B, int H, int W, int max_iter, int row0, int row1, cudaStream_t st) {
+  if (row1 <= row0) { row0 = 0; row1 = H; }
   const int T = jacobi_block_iters();
   const int nL = (max_iter + T - 1) / T;
   auto wbuf = [&](int l) { return ((nL - 1 - l) % 2 == 0) ? p : scratch; };
   // float4 path: rows 16-byte aligned in every buffer
-  const int vec_ok = (W % 4 == 0) && ((((uintptr_t)flags | (uintptr_t)div | (uintptr_t)p | (uintptr_t)scratch) & 15) == 0);
+  const int vec_ok = (W % 4 == 0) && ((((uintptr_t)flags | (uintptr_t)div | (uintptr_t)p | (uintptr_t)scratch | (uintptr_t)p_init) & 15) == 0);
   // tall tiles (16 warps) waste less halo work; short tiles keep small grids on more SMs
   static const char* force = getenv("FNX_JACOBI_NW");
   bool tall = (long long)H * W * B >= (1LL << 21);
   if (force) tall = atoi(force) >= 16;
   constexpr int OW = JB_TW - 2 * JB_HALO;
   const int oh = (tall ? 16 : 8) * JB_R - 2 * JB_HALO;
-  dim3 grid((W + OW - 1) / OW, (H + oh - 1) / oh, B);
+  dim3 grid((W + OW - 1) / OW, (row1 - row0 + oh - 1) / oh, B);
   int done = 0;
   for (int l = 0; l < nL; l++) {
     const int iters = (max_iter - done) < T ? (max_iter - done) : T;
-    const bool first = l == 0, resid = l == nL - 1;
-    const float* prev = first ? nullptr : wbuf(l - 1);
+    // p_init == nullptr: start from p = 0 (the reference); else continue from p_init (must not alias p / scratch)
+    const bool first = l == 0 && p_init == nullptr, resid = l == nL - 1 && ssq != nullptr;
+    const float* prev = l == 0 ? p_init : wbuf(l - 1);
     float* cur = wbuf(l);
-    if (tall) launch_blocked<16>(first, resid, grid, st, H, W, iters, vec_ok, flags, div, prev, cur, ssq);
-    else launch_blocked<8>(first, resid, grid, st, H, W, iters, vec_ok, flags, div, prev, cur, ssq);
+    if (tall) launch_blocked<16>(first, resid, grid, st, H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+    else launch_blocked<8>(first, resid, grid, st, H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
     done += iters;
     fnx_count_launches(1);
   }

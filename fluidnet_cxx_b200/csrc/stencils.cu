@@ -327,8 +327,9 @@ static void launch_jacobi_iter(const Grid& g, bool first, bool resid, const floa
   }
 }
 
-int fnx_jacobi_2d_blocked(const float* flags, const float* div, float* p, float* scratch, double* ssq,
-                          int B, int H, int W, int max_iter, cudaStream_t st);  // jacobi_blocked.cu
+int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
+                          double* ssq, int B, int H, int W, int max_iter, int row0, int row1,
+                          cudaStream_t st);  // jacobi_blocked.cu
 
 
 extern "C" {
@@ -501,7 +502,7 @@ int fnx_solve_linear_system_jacobi(const float* flags, const float* div, float* 
   const bool tol = p_tol > 0.f;
   if (!tol && !is3d) {
     // fixed iteration count, 2-D: temporally blocked shared-memory kernel
-    int e = fnx_jacobi_2d_blocked(flags, div, p, scratch, ssq, B, H, W, max_iter, st);
+    int e = fnx_jacobi_2d_blocked(flags, div, nullptr, p, scratch, ssq, B, H, W, max_iter, 0, 0, st);
     if (e) return e;
     k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, max_iter - 1, residual);
     FNX_LAUNCH_CHECK("solve_linear_system", 1);
@@ -533,6 +534,32 @@ int fnx_solve_linear_system_jacobi(const float* flags, const float* div, float* 
     if (ce != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "solve_linear_system: %s", cudaGetErrorString(ce));
   }
   if (iters_run) *iters_run = executed;
+  return FNX_OK;
+}
+
+int fnx_jacobi_iterate(const float* flags, const float* div, const float* p_init, float* p, int B, int D, int H, int W,
+                       int is3d, int iters, int row_begin, int row_end, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "jacobi_iterate")) return e;
+  if (iters < 1) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate: At least 1 iteration of the solver is needed.");
+  if (p_init == p) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate: p_init must not alias p");
+  if (!workspace || workspace_bytes < fnx_jacobi_workspace(B, D, H, W, iters))
+    return fnx_set_error(FNX_ERR_WORKSPACE, "jacobi_iterate: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = make_grid(B, D, H, W);
+  float* scratch = (float*)workspace;
+  if (row_end > row_begin) {
+    if (row_begin < 0 || row_end > D * H) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate: row window out of range");
+    g.row0 = row_begin; g.row1 = row_end;
+  }
+  if (!is3d) return fnx_jacobi_2d_blocked(flags, div, p_init, p, scratch, nullptr, B, H, W, iters, row_begin, row_end, st);
+  auto wbuf = [&](int it) { return ((iters - 1 - it) % 2 == 0) ? p : scratch; };
+  for (int it = 0; it < iters; it++) {
+    const float* prev = it == 0 ? p_init : wbuf(it - 1);
+    launch_jacobi_iter<true>(g, prev == nullptr, false, flags, div, prev, wbuf(it), nullptr, nullptr, st);
+    fnx_count_launches(1);
+  }
+  FNX_LAUNCH_CHECK("jacobi_iterate", 0);
   return FNX_OK;
 }
 

@@ -319,6 +319,10 @@ int fnx_step_advect_forces_div(const fnx_step_params* prm, const float* density_
   float* rho1 = (float*)ws_take(ws, n * sizeof(float));
   float* U1 = (float*)ws_take(ws, n * nc * sizeof(float));
   Grid g = make_grid(B, D, H, W);
+  if (prm->row_end > prm->row_begin) {  // slab window (domain-decomposed step): only these rows are computed
+    if (prm->row_begin < 0 || prm->row_end > D * H) return fnx_set_error(FNX_ERR_ARG, "step: row window out of range");
+    g.row0 = prm->row_begin; g.row1 = prm->row_end;
+  }
   StepMasks m;
   const bool ubc = UBC && UBCInvMask, rbc = densityBC && densityBCInvMask;
   m.UBC = ubc ? UBC : nullptr; m.UBCInv = ubc ? UBCInvMask : nullptr;
@@ -352,9 +356,20 @@ int fnx_step_advect_forces_div(const fnx_step_params* prm, const float* density_
 int fnx_step_project_bcs(const float* pressure, float* U, const float* flags, const float* UBC,
                          const float* UBCInvMask, const unsigned char* mask_rows, int apply_wall_bcs, int B, int D,
                          int H, int W, int is3d, void* stream) {
+  return fnx_step_project_bcs_rows(pressure, U, flags, UBC, UBCInvMask, mask_rows, apply_wall_bcs, B, D, H, W, is3d, 0,
+                                   0, stream);
+}
+
+int fnx_step_project_bcs_rows(const float* pressure, float* U, const float* flags, const float* UBC,
+                              const float* UBCInvMask, const unsigned char* mask_rows, int apply_wall_bcs, int B,
+                              int D, int H, int W, int is3d, int row_begin, int row_end, void* stream) {
   if (B < 1 || D < 1 || H < 2 || W < 2 || (is3d && D < 2) || (!is3d && D != 1))
     return fnx_set_error(FNX_ERR_ARG, "step: unsupported grid B=%d D=%d H=%d W=%d is3d=%d", B, D, H, W, is3d);
   Grid g = make_grid(B, D, H, W);
+  if (row_end > row_begin) {
+    if (row_begin < 0 || row_end > D * H) return fnx_set_error(FNX_ERR_ARG, "step: row window out of range");
+    g.row0 = row_begin; g.row1 = row_end;
+  }
   StepMasks m;
   const bool ubc = UBC && UBCInvMask;
   m.UBC = ubc ? UBC : nullptr; m.UBCInv = ubc ? UBCInvMask : nullptr;
@@ -381,6 +396,7 @@ int fnx_step_jacobi(const fnx_step_params* prm, const float* density_in, const f
   void* ws_j = ws;
   const size_t ws_j_bytes = align256(fnx_jacobi_workspace(B, D, H, W, 1));
   fnx_step_params q = *prm;
+  q.row_begin = q.row_end = 0;
   q.apply_wall_bcs = 1;
   q.density_const_passes = 2;  // simulate.py:133 and :168 both re-apply the density BC
   FNX_TRY(fnx_step_advect_forces_div(&q, density_in, U_in, flags, UBC, UBCInvMask, densityBC, densityBCInvMask,

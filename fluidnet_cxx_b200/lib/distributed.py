@@ -1,0 +1,306 @@
+"""Slab-decomposed fluid step: one process per GPU, halo exchange over torch.distributed
+(NCCL over NVLink on the GPU box, gloo in the CPU tests) -- SURVEY.md section 8e.
+
+The reference has no multi-device path; this is the B200 scaling layer around the same kernels.
+
+Decomposition: 1-D slabs along the outermost spatial axis (H in 2-D, D in 3-D) so a halo is a
+contiguous block of rows per channel.  Rank r owns rows [r*Hs, (r+1)*Hs) of the global grid and
+computes the WINDOW [r*Hs - ghost, (r+1)*Hs + ghost).  Every rank keeps GLOBAL-SIZED arrays and
+global coordinates (back-traced positions are rounded in the same fp32 binade as on one GPU; a
+translated local frame would not be bit-compatible) and the kernels are launched on the window's
+rows only (fnx_step_params.row_begin/row_end, fnx_jacobi_iterate, fnx_step_project_bcs_rows).
+Rows outside the window are never written: a stencil that reaches them sees stale data, and that
+error travels inward one row per stencil radius.  Every stage's dependency radius is known, so with
+enough ghost rows the OWNED rows are exactly (bit for bit) what the single-GPU step computes; ghost
+rows are refreshed from their owners before the error can reach owned rows:
+
+  exchange(density, U)                                ghost rows valid
+  advect + forces + BCs + divergence on the window    valid >= RA rows inside the window edge
+  Jacobi: chunks of k <= ghost - RA - 1 iterations    each iteration costs one more row;
+          exchange(p) between chunks                  after a chunk, valid >= RA + k - 1 < ghost rows in
+  velocityUpdate + BCs                                radius 1
+  (convnet: global std by all-reduce, then the CNN on a compact copy of the window -- convolutions
+   and x2 / x4 resizes are translation invariant --; receptive field <= 54 rows)
+
+Collectives: neighbour send/recv of halo rows (batched), one all-reduce of (sum, sum of squares)
+for the ScaleNet normalisation, one all-reduce (max) of |U| for the advection reach check.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+# rows an interior edge can contaminate in advect(MacCormack, |u| dt <= 1) + forces + BCs + divergence
+RA = 12
+# full-resolution rows the CNN stage adds on top of RA (three-scale receptive field)
+CNN_REACH = 54 - 9
+GHOST_JACOBI = 48      # k = 32 iterations between pressure exchanges
+GHOST_CONVNET = 64
+
+
+def jacobi_chunk(ghost):
+    """Jacobi iterations between two pressure halo exchanges for a ghost width: after n iterations
+    rows closer than RA + n - 1 to an interior edge are stale, and velocityUpdate reads one ghost
+    row, so n <= ghost - RA - 1; rounded down to the blocked kernel's 8 iterations per launch."""
+    k = ghost - RA - 1
+    if k < 1:
+        raise ValueError(f"ghost width {ghost} leaves no room for a Jacobi iteration (needs > {RA + 1})")
+    return (k // 8) * 8 if k >= 8 else k
+
+
+class SlabDecomposition:
+    """Row slabs of a global (B, C, D, H, W) grid over the ranks of a process group.  Tensors handled
+    by this class are GLOBAL-SIZED on every rank; only the window rows are meaningful."""
+
+    def __init__(self, global_rows, ghost, group=None, rank=None, world=None, axis=3, align=4, comm=None):
+        self.group = group
+        # comm: optional transport with exchange_rows(decomp, sends) / all_reduce(t, op) / all_gather(t)
+        # replacing torch.distributed (the single-GPU tests run several virtual ranks in one process)
+        self.comm = comm
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.axis = axis
+        self.H = int(global_rows)
+        if self.H % self.world:
+            raise ValueError(f"{self.H} rows do not split evenly over {self.world} ranks")
+        self.Hs = self.H // self.world
+        if self.world > 1 and (self.Hs % align or ghost % align):
+            raise ValueError(f"slab height {self.Hs} and ghost width {ghost} must be multiples of {align} "
+                             "(pyramid alignment of the multi-scale CNN)")
+        if self.world > 1 and ghost > self.Hs:
+            raise ValueError(f"ghost width {ghost} exceeds the slab height {self.Hs}")
+        self.ghost = int(ghost) if self.world > 1 else 0
+        self.lo = self.rank * self.Hs
+        self.hi = self.lo + self.Hs
+        self.g_top = self.ghost if self.rank > 0 else 0
+        self.g_bot = self.ghost if self.rank < self.world - 1 else 0
+        self.r0, self.r1 = self.lo - self.g_top, self.hi + self.g_bot      # the window
+        self.local_rows = self.r1 - self.r0
+
+    # -- slicing ----------------------------------------------------------------------------
+    def _sl(self, a, b):
+        idx = [slice(None)] * 5
+        idx[self.axis] = slice(a, b)
+        return tuple(idx)
+
+    def rows(self, plane_rows=1):
+        """window as a (row_begin, row_end) pair of the kernels' flattened (D*H) row space"""
+        return (self.r0 * plane_rows, self.r1 * plane_rows)
+
+    def scatter(self, full):
+        """this rank's working copy of a replicated global tensor (global-sized)"""
+        return full.clone()
+
+    def owned(self, t):
+        return t[self._sl(self.lo, self.hi)]
+
+    def window(self, t):
+        """compact contiguous copy of the window rows"""
+        return t[self._sl(self.r0, self.r1)].contiguous()
+
+    def put_window(self, full, compact):
+        full[self._sl(self.r0, self.r1)] = compact
+        return full
+
+    def gather(self, t):
+        """global tensor (on every rank) assembled from every rank's owned rows"""
+        mine = self.owned(t).contiguous()
+        if self.world == 1:
+            return mine
+        if self.comm is not None:
+            parts = self.comm.all_gather(self, mine)
+        else:
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine, group=self.group)
+        return torch.cat(parts, dim=self.axis)
+
+    # -- halo exchange ------------------------------------------------------------------------
+    def exchange(self, tensors):
+        """Refresh the ghost rows of every tensor in `tensors` (in place) from the neighbours' owned
+        rows: one packed message per neighbour and direction."""
+        if self.world == 1:
+            return
+        g = self.ghost
+        ops, unpack = [], []
+        up, down = self.rank - 1, self.rank + 1
+
+        def pack(a, b):
+            return torch.cat([t[self._sl(a, b)].reshape(-1) for t in tensors])
+
+        def unpacker(buf, a, b):
+            def run():
+                o = 0
+                for t in tensors:
+                    view = t[self._sl(a, b)]
+                    n = view.numel()
+                    view.copy_(buf[o:o + n].view(view.shape))
+                    o += n
+            return run
+
+        if self.comm is not None:
+            sends = {}
+            if up >= 0:
+                sends[up] = pack(self.lo, self.lo + g)
+            if down < self.world:
+                sends[down] = pack(self.hi - g, self.hi)
+            recvs = self.comm.exchange_rows(self, sends)
+            if up >= 0:
+                unpacker(recvs[up], self.lo - g, self.lo)()
+            if down < self.world:
+                unpacker(recvs[down], self.hi, self.hi + g)()
+            return
+        if up >= 0:
+            send = pack(self.lo, self.lo + g)                             # my top owned rows
+            recv = torch.empty_like(send)
+            ops += [dist.P2POp(dist.isend, send, self._peer(up), self.group),
+                    dist.P2POp(dist.irecv, recv, self._peer(up), self.group)]
+            unpack.append(unpacker(recv, self.lo - g, self.lo))
+        if down < self.world:
+            send = pack(self.hi - g, self.hi)                             # my bottom owned rows
+            recv = torch.empty_like(send)
+            ops += [dist.P2POp(dist.isend, send, self._peer(down), self.group),
+                    dist.P2POp(dist.irecv, recv, self._peer(down), self.group)]
+            unpack.append(unpacker(recv, self.hi, self.hi + g))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for u in unpack:
+            u()
+
+    def _peer(self, r):
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def all_reduce(self, t, op=dist.ReduceOp.SUM):
+        if self.world > 1:
+            if self.comm is not None:
+                self.comm.all_reduce(self, t, op)
+            else:
+                dist.all_reduce(t, op=op, group=self.group)
+        return t
+
+
+# ---------------------------------------------------------------------------------------------
+class CudaLocalOps:
+    """The per-window compute: the single-GPU kernels behind the C-ABI (no fallback)."""
+
+    def __init__(self):
+        from .. import _native as N
+        from . import simulate as sim
+        self.N, self.sim, self.lib = N, sim, N.load()
+
+    def advect_forces_div(self, mconf, dt, bd, want_div, wall_bcs, rows):
+        N, sim, lib = self.N, self.sim, self.lib
+        import ctypes
+        flags, U_in, rho_in = bd['flags'], bd['U'], bd['density']
+        # rows outside the window are never written: keep them finite (they are read as stale halo)
+        U, density = torch.zeros_like(U_in), torch.zeros_like(rho_in)
+        div = torch.zeros_like(flags) if want_div else None
+        B, D, H, W = N.grid_of(flags)
+        is3d = int(U.size(1) == 3)
+        UBC, UBCInv, rBC, rBCInv = sim._masks(bd)
+        mrows = sim._mask_rows(lib, bd, flags, is3d)
+        prm = sim._step_params(mconf, dt, 0)
+        prm.apply_wall_bcs = int(wall_bcs)
+        prm.density_const_passes = 2 if wall_bcs else 1
+        prm.row_begin, prm.row_end = rows
+        ws = N.workspaces.get(U.device, "step", lib.fnx_step_workspace(B, D, H, W, is3d))
+        N.check(lib.fnx_step_advect_forces_div(ctypes.byref(prm), N.ptr(rho_in), N.ptr(U_in), N.ptr(flags),
+                                               N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv),
+                                               mrows.data_ptr() if mrows is not None else None, N.ptr(density),
+                                               N.ptr(U), N.ptr(div), B, D, H, W, is3d, ws.data_ptr(), ws.numel(),
+                                               N.stream_of(U)), "simulate_distributed")
+        return density, U, div
+
+    def jacobi(self, flags, div, p_init, iters, rows):
+        N, lib = self.N, self.lib
+        B, D, H, W = N.grid_of(flags)
+        p = torch.zeros_like(flags)
+        ws = N.workspaces.get(flags.device, "jacobi", lib.fnx_jacobi_workspace(B, D, H, W, iters))
+        N.check(lib.fnx_jacobi_iterate(N.ptr(flags), N.ptr(div), N.ptr(p_init), N.ptr(p), B, D, H, W,
+                                       int(D > 1), int(iters), rows[0], rows[1], ws.data_ptr(), ws.numel(),
+                                       N.stream_of(flags)), "simulate_distributed")
+        return p
+
+    def project(self, p, U, bd, rows):
+        N, sim, lib = self.N, self.sim, self.lib
+        flags = bd['flags']
+        B, D, H, W = N.grid_of(flags)
+        is3d = int(U.size(1) == 3)
+        UBC, UBCInv, _, _ = sim._masks(bd)
+        mrows = sim._mask_rows(lib, bd, flags, is3d)
+        N.check(lib.fnx_step_project_bcs_rows(N.ptr(p), N.ptr(U), N.ptr(flags), N.ptr(UBC), N.ptr(UBCInv),
+                                              mrows.data_ptr() if mrows is not None else None, 1, B, D, H, W, is3d,
+                                              rows[0], rows[1], N.stream_of(U)), "simulate_distributed")
+        return U
+
+    def set_const(self, x, inv_mask, bc):
+        from . import fluid
+        fluid.setConstVals(x, inv_mask, bc)
+
+    def cnn(self, net, U, flags, scale):
+        return net.forward_fields(U, flags, scale=scale)
+
+
+def _global_std(decomp, U_local, threshold):
+    """max(unbiased std of the GLOBAL U, threshold) (model.py:8-23) from per-rank partial sums."""
+    own = decomp.owned(U_local).double()
+    part = torch.stack([own.sum(), (own * own).sum()])
+    decomp.all_reduce(part)
+    n = float(own.numel() * decomp.world)
+    var = (part[1] - part[0] * part[0] / n) / (n - 1.0)
+    s = torch.sqrt(torch.clamp(var, min=0.0)).float().clamp(min=float(threshold))
+    return s.view(1, 1, 1, 1, 1)
+
+
+def check_reach(decomp, U_local, dt):
+    """The ghost width assumes the back-trace moves at most one cell per step (RA): verify it.
+    One all-reduce(max) and a host read -- call it every few steps, not every step."""
+    m = decomp.owned(U_local).abs().max().reshape(1).clone()
+    decomp.all_reduce(m, op=dist.ReduceOp.MAX)
+    reach = float(m.item()) * abs(float(dt))
+    if reach > 1.0:
+        raise RuntimeError(f"slab decomposition: max|U|*dt = {reach:.3f} cells exceeds the advection reach the "
+                           f"ghost width was sized for (1 cell); use a wider ghost or a smaller dt")
+    return reach
+
+
+def simulate_distributed(mconf, bd, net, sim_method, decomp, ops=None):
+    """One solver step on this rank's window (bd holds GLOBAL-SIZED tensors; masks included).
+    Same state transitions as lib.simulate for the fused configuration (inviscid, density-carrying,
+    fixed Jacobi count or the ScaleNet model).  Only the owned rows of the returned state are
+    meaningful (decomp.owned / decomp.gather); ghost rows are refreshed by the next call.
+    Returns nothing; bd['p'], bd['U'], bd['density'] are rebound."""
+    assert sim_method in ('jacobi', 'convnet')
+    ops = ops or CudaLocalOps()
+    dt = float(mconf['dt'])
+    g = decomp.ghost
+    if decomp.world > 1:
+        need = RA + (CNN_REACH if sim_method == 'convnet' else 1)
+        if g < need:
+            raise ValueError(f"ghost width {g} < {need} rows needed by the {sim_method} step")
+    plane = bd['flags'].size(3) if decomp.axis == 2 else 1     # 3-D slabs along D: H rows per plane
+    rows = decomp.rows(plane)
+    decomp.exchange([bd['density'], bd['U']])
+    if sim_method == 'jacobi':
+        density, U, div = ops.advect_forces_div(mconf, dt, bd, True, True, rows)
+        iters = int(mconf['jacobiIter'])
+        k = jacobi_chunk(g) if decomp.world > 1 else iters
+        p, done = None, 0
+        while done < iters:
+            n = min(k, iters - done)
+            if done > 0:
+                decomp.exchange([p])
+            p = ops.jacobi(bd['flags'], div, p, n, rows)
+            done += n
+        U = ops.project(p, U, bd, rows)      # radius 1: p is valid from row ghost-1 inwards after any chunk
+    else:
+        density, U, _ = ops.advect_forces_div(mconf, dt, bd, False, False, rows)
+        scale = _global_std(decomp, U, net.mconf['normalizeInputThreshold'])
+        # the CNN runs on a compact copy of the window (translation invariant), results go back in place
+        p_w, U_w = ops.cnn(net, decomp.window(U), decomp.window(bd['flags']), scale)
+        p = decomp.put_window(torch.zeros_like(bd['flags']), p_w)
+        U = decomp.put_window(U, U_w)
+        if 'UBC' in bd and 'UBCInvMask' in bd:
+            ops.set_const(U, bd['UBCInvMask'], bd['UBC'])
+        if 'densityBC' in bd and 'densityBCInvMask' in bd:
+            ops.set_const(density, bd['densityBCInvMask'], bd['densityBC'])
+    bd['U'], bd['density'], bd['p'] = U, density, p

@@ -90,8 +90,15 @@ class FluidNet(nn.Module):
         periodic = 'periodic-x' in self.mconf and 'periodic-y' in self.mconf
         if periodic:
             self._seam(self.mconf, U, U.clone())
+        return self.forward_fields(U, flags, periodic=periodic)
+
+    def forward_fields(self, U, flags, scale=None, periodic=False):
+        """The forward pass on separate contiguous fields.  `scale` (B device floats) overrides the
+        std normalisation factor: the slab-decomposed step passes the globally reduced one."""
+        lib = N.load()
+        B, _, _, H, W = (int(s) for s in U.shape)
         st = N.stream_of(U)
-        s = self.scale(U)                                   # (B,1,1,1,1)
+        s = self.scale(U) if scale is None else scale       # (B,1,1,1,1)
         x = torch.empty((B, 2, H, W), dtype=torch.float32, device=U.device)
         N.check(lib.fnx_fluidnet_input(N.ptr(U), N.ptr(flags), N.ptr(s), N.ptr(x), B, H, W, st), "FluidNet")
         p_net = self.multiScale(x)                          # (B,1,H,W)

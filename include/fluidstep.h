@@ -76,6 +76,14 @@ int fnx_solve_linear_system_jacobi(const float *flags, const float *div, float *
                                    int max_iter, int *iters_run, void *workspace,
                                    size_t workspace_bytes, void *stream);
 
+/* `iters` Jacobi iterations of the same system continued from p_init (NULL = start from p = 0):
+ * p_init -> p, no residual.  Building block of the slab-decomposed solver (halo exchange of p
+ * between chunks of iterations); p_init must not alias p.  [row_begin, row_end) restricts the
+ * rows written (0,0 = all): rows outside are read as they are (stale halo), never written. */
+int fnx_jacobi_iterate(const float *flags, const float *div, const float *p_init, float *p, int B,
+                       int D, int H, int W, int is3d, int iters, int row_begin, int row_end,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- lib.fluid stencils ----------------------------------------------------- */
 /* velocity_divergence.py:4-74 : div (B,1,D,H,W) out */
 int fnx_velocity_divergence(const float *U, const float *flags, float *div, int B, int D, int H,
@@ -121,6 +129,10 @@ typedef struct fnx_step_params {
   int jacobi_iters;          /* fnx_step_jacobi */
   int apply_wall_bcs;        /* simulate.py:120-123: 1 in the jacobi branch, 0 ahead of the CNN */
   int density_const_passes;  /* further setConstVals passes folded into density_out (simulate.py:133,168) */
+  /* slab window of the domain-decomposed step: only rows [row_begin, row_end) of the flattened
+   * (D*H) row space are computed (arrays stay global-sized, coordinates stay global, so the rows
+   * computed are bit-identical to the single-GPU step); 0,0 = the whole grid */
+  int row_begin, row_end;
 } fnx_step_params;
 
 size_t fnx_step_workspace(int B, int D, int H, int W, int is3d);
@@ -142,6 +154,10 @@ int fnx_step_advect_forces_div(const fnx_step_params *prm, const float *density_
 int fnx_step_project_bcs(const float *pressure, float *U, const float *flags, const float *UBC,
                          const float *UBCInvMask, const unsigned char *mask_rows,
                          int apply_wall_bcs, int B, int D, int H, int W, int is3d, void *stream);
+int fnx_step_project_bcs_rows(const float *pressure, float *U, const float *flags, const float *UBC,
+                              const float *UBCInvMask, const unsigned char *mask_rows,
+                              int apply_wall_bcs, int B, int D, int H, int W, int is3d,
+                              int row_begin, int row_end, void *stream);
 /* whole Jacobi step; p and residual as in fnx_solve_linear_system_jacobi (p_tol = 0) */
 int fnx_step_jacobi(const fnx_step_params *prm, const float *density_in, const float *U_in,
                     const float *flags, const float *UBC, const float *UBCInvMask,

@@ -1,0 +1,186 @@
+"""Slab decomposition + halo exchange (fluidnet_cxx_b200.lib.distributed) on CPU: world_size 2 and 4
+over gloo, with the C oracle as the per-slab compute.  The decomposed run must reproduce the
+single-domain oracle step BIT FOR BIT on the owned rows (same per-cell arithmetic, ghost rows wide
+enough for every stage's dependency radius)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+MCONF = {"dt": 0.1, "maccormackStrength": 0.6, "sampleOutsideFluid": False, "buoyancyScale": 0.25,
+         "gravityScale": 0, "viscosity": 0, "correctScalar": False, "operatingDensity": 0.0,
+         "gravityVec": {"x": 0, "y": -1, "z": 0}, "pTol": 0.0, "jacobiIter": 20}
+GRAV = np.array([-0.0, 0.25, -0.0], np.float32)
+
+
+def jacobi_numpy(flags, div, p, iters):
+    """fluids_init.cpp:809-1004 continued from p (2-D), same fp32 operation order as the oracle."""
+    f = flags[0, 0, 0]
+    dv = div[0, 0, 0]
+    p = np.zeros_like(dv) if p is None else p[0, 0, 0].copy()
+    H, W = f.shape
+    obst = f == 2
+    interior = np.zeros_like(obst)
+    interior[1:-1, 1:-1] = True
+    act = interior & ~obst
+    for _ in range(iters):
+        pc = p
+        def nb(dy, dx):
+            sh = np.zeros_like(pc)
+            ob = np.zeros_like(obst)
+            ys, yd = (slice(1, H), slice(0, H - 1)) if dy == 1 else ((slice(0, H - 1), slice(1, H)) if dy == -1 else (slice(None), slice(None)))
+            xs, xd = (slice(1, W), slice(0, W - 1)) if dx == 1 else ((slice(0, W - 1), slice(1, W)) if dx == -1 else (slice(None), slice(None)))
+            sh[yd, xd] = pc[ys, xs]
+            ob[yd, xd] = obst[ys, xs]
+            return np.where(ob, pc, sh)
+        s = nb(0, -1) + nb(0, 1)
+        s = s + nb(-1, 0)
+        s = s + nb(1, 0)
+        s = s + np.float32(0) + np.float32(0) + dv
+        p = np.where(act, s / np.float32(4), np.float32(0)).astype(np.float32)
+    return p[None, None, None]
+
+
+class OracleOps:
+    """per-slab compute = the oracle's op-by-op restatement of simulate.py:28-171"""
+
+    def __init__(self):
+        sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+        import oracle
+        oracle.build()
+        self.o = oracle
+
+    @staticmethod
+    def _np(t):
+        return t.numpy()
+
+    def _const(self, U, rho, bd):
+        o = self.o
+        return (torch.from_numpy(o.setConstVals(U, self._np(bd["UBCInvMask"]), self._np(bd["UBC"]))),
+                torch.from_numpy(o.setConstVals(rho, self._np(bd["densityBCInvMask"]), self._np(bd["densityBC"]))))
+
+    @staticmethod
+    def _win(new, rows):
+        """the kernels write the window rows only: poison everything else (NaN would be ideal but the
+        real kernels keep outside rows finite -- zeros -- so that stale velocities cannot stretch a
+        line trace; do the same)"""
+        out = torch.zeros_like(new)
+        out[:, :, :, rows[0]:rows[1]] = new[:, :, :, rows[0]:rows[1]]
+        return out
+
+    def advect_forces_div(self, mconf, dt, bd, want_div, wall_bcs, rows):
+        o = self.o
+        f, U0, r0 = self._np(bd["flags"]), self._np(bd["U"]), self._np(bd["density"])
+        rho = o.advectScalar(dt, r0, U0, f, "maccormackFluidNet", 1, False, mconf["maccormackStrength"])
+        U = o.advectVelocity(dt, U0, U0, f, "maccormackFluidNet", 1, mconf["maccormackStrength"])
+        U, rho = self._const(U, rho, bd)
+        U = o.addBuoyancy(U.numpy(), f, rho.numpy(), GRAV, 0.0, dt)
+        if wall_bcs:
+            U = o.setWallBcs(U, f)
+        U, rho = self._const(U, rho.numpy(), bd)
+        div = torch.from_numpy(o.velocityDivergence(U.numpy(), f)) if want_div else None
+        return self._win(rho, rows), self._win(U, rows), (self._win(div, rows) if want_div else None)
+
+    def jacobi(self, flags, div, p_init, iters, rows):
+        p = torch.from_numpy(jacobi_numpy(flags.numpy(), div.numpy(), None if p_init is None else p_init.numpy(), iters))
+        return self._win(p, rows)
+
+    def project(self, p, U, bd, rows):
+        o = self.o
+        f = self._np(bd["flags"])
+        Un = o.setWallBcs(o.velocityUpdate(p.numpy(), U.numpy(), f), f)
+        return self._win(torch.from_numpy(o.setConstVals(Un, self._np(bd["UBCInvMask"]), self._np(bd["UBC"]))), rows)
+
+
+def global_state(H, W, seed):
+    rng = np.random.RandomState(seed)
+    flags = np.ones((1, 1, 1, H, W), np.float32)
+    flags[..., 0, :] = flags[..., -1, :] = flags[..., :, 0] = flags[..., :, -1] = 2
+    flags[..., H // 2 - 3:H // 2 + 4, W // 3:W // 3 + 6] = 2      # an obstacle box straddling the slab boundary
+    flags[..., 5:9, W // 2:W // 2 + 3] = 2
+    U = (rng.standard_normal((1, 2, 1, H, W)) * 0.5).astype(np.float32)
+    rho = rng.random_sample((1, 1, 1, H, W)).astype(np.float32)
+    UBC = np.zeros_like(U); UBCInv = np.ones_like(U)
+    rBC = np.zeros_like(rho); rBCInv = np.ones_like(rho)
+    UBC[:, 1, :, 0:4, W // 4:W // 2] = 2.0; UBCInv[:, :, :, 0:4, W // 4:W // 2] = 0.0
+    rBC[:, :, :, 0:4, W // 4:W // 2] = 0.1; rBCInv[:, :, :, 0:4, W // 4:W // 2] = 0.0
+    return {"p": np.zeros_like(rho), "U": U, "flags": flags, "density": rho, "UBC": UBC, "UBCInvMask": UBCInv,
+            "densityBC": rBC, "densityBCInvMask": rBCInv}
+
+
+def single_domain_steps(H, W, seed, steps):
+    ops = OracleOps()
+    bd = {k: torch.from_numpy(v.copy()) for k, v in global_state(H, W, seed).items()}
+    out = []
+    for _ in range(steps):
+        rho, U, div = ops.advect_forces_div(MCONF, MCONF["dt"], bd, True, True, (0, H))
+        p, _ = ops.o.solveLinearSystemJacobi(bd["flags"].numpy(), div.numpy(), False, 0.0, MCONF["jacobiIter"])
+        U = ops.project(torch.from_numpy(p), U, bd, (0, H))
+        bd["U"], bd["density"], bd["p"] = U, rho, torch.from_numpy(p)
+        out.append({k: bd[k].numpy().copy() for k in ("p", "U", "density")})
+    return out
+
+
+def _worker(rank, world, port, H, W, ghost, steps, seed, result_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+        from fluidnet_cxx_b200.lib.distributed import SlabDecomposition, simulate_distributed
+        dec = SlabDecomposition(H, ghost)
+        ops = OracleOps()
+        bd = {k: dec.scatter(torch.from_numpy(v)) for k, v in global_state(H, W, seed).items()}
+        results = []
+        for _ in range(steps):
+            simulate_distributed(MCONF, bd, None, "jacobi", dec, ops=ops)
+            results.append({k: dec.gather(bd[k]).numpy() for k in ("p", "U", "density")})
+        if rank == 0:
+            np.savez(result_path, **{f"{i}/{k}": v for i, r in enumerate(results) for k, v in r.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,H,ghost", [(2, 64, 24), (4, 128, 32)])
+def test_slab_decomposition_bit_exact(tmp_path, world, H, ghost):
+    W, steps, seed = 48, 2, 7
+    ref = single_domain_steps(H, W, seed, steps)
+    # the numpy Jacobi continuation used by the slab ops == the oracle's solver from p = 0
+    ops = OracleOps()
+    st = global_state(H, W, seed)
+    div = ops.o.velocityDivergence(st["U"], st["flags"])
+    p_ref, _ = ops.o.solveLinearSystemJacobi(st["flags"], div, False, 0.0, 9)
+    assert np.array_equal(jacobi_numpy(st["flags"], div, jacobi_numpy(st["flags"], div, None, 4), 5), p_ref)
+    out = str(tmp_path / "res.npz")
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, port, H, W, ghost, steps, seed, out), nprocs=world, join=True)
+    z = np.load(out)
+    for i in range(steps):
+        for k in ("p", "U", "density"):
+            got, want = z[f"{i}/{k}"], ref[i][k]
+            bad = int(np.sum(~((got == want) | (np.isnan(got) & np.isnan(want)))))
+            assert bad == 0, f"step {i} field {k}: {bad} cells differ from the single-domain step"
+
+
+def test_decomposition_geometry():
+    from fluidnet_cxx_b200.lib.distributed import SlabDecomposition, jacobi_chunk, RA
+    d = SlabDecomposition(256, 48, rank=1, world=4)
+    assert (d.lo, d.hi, d.g_top, d.g_bot, d.local_rows, d.rows()) == (64, 128, 48, 48, 160, (16, 176))
+    d0 = SlabDecomposition(256, 48, rank=0, world=4)
+    assert (d0.g_top, d0.g_bot, d0.local_rows, d0.rows()) == (0, 48, 112, (0, 112))
+    assert SlabDecomposition(100, 48, rank=0, world=1).local_rows == 100      # no ghosts on one rank
+    with pytest.raises(ValueError):
+        SlabDecomposition(130, 48, rank=0, world=4)
+    with pytest.raises(ValueError):
+        SlabDecomposition(256, 96, rank=0, world=4)                            # ghost wider than a slab
+    assert jacobi_chunk(48) == 32 and jacobi_chunk(RA + 4) == 3
+    x = torch.arange(256.).view(1, 1, 1, 256, 1).expand(1, 2, 1, 256, 3)
+    loc = d.scatter(x)
+    assert loc.shape[3] == 256 and float(d.window(loc)[0, 0, 0, 0, 0]) == 16.0 and float(d.owned(loc)[0, 0, 0, 0, 0]) == 64.0
+    assert d.window(loc).shape[3] == 160

@@ -1,0 +1,161 @@
+"""The slab-decomposed step on ONE GPU: several virtual ranks run fluidnet_cxx_b200.lib.distributed.
+simulate_distributed in threads of this process (an in-process transport stands in for NCCL), each
+launching the real row-window kernels.  Jacobi path: the gathered result equals the single-GPU fused
+step bit for bit.  ScaleNet path: within the CNN tolerance (the split-fp16 activation scales depend
+on the tensor-wide max, which differs between a window and the whole grid)."""
+import importlib
+import threading
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+
+pytestmark = pytest.mark.gpu
+
+
+class ThreadComm:
+    """exchange / all_reduce / all_gather between virtual ranks living in threads of one process"""
+
+    def __init__(self, world):
+        self.world = world
+        self.bar = threading.Barrier(world)
+        self.box = {}
+
+    def _sync(self):
+        torch.cuda.synchronize()
+        self.bar.wait()
+
+    def exchange_rows(self, dec, sends):
+        for peer, buf in sends.items():
+            self.box[(dec.rank, peer)] = buf
+        self._sync()
+        out = {peer: self.box[(peer, dec.rank)].clone() for peer in sends}
+        self._sync()
+        return out
+
+    def all_reduce(self, dec, t, op):
+        self.box[("r", dec.rank)] = t.clone()
+        self._sync()
+        parts = torch.stack([self.box[("r", r)] for r in range(self.world)])
+        t.copy_(parts.max(0).values if op == dist.ReduceOp.MAX else parts.sum(0))
+        self._sync()
+
+    def all_gather(self, dec, mine):
+        self.box[("g", dec.rank)] = mine
+        self._sync()
+        parts = [self.box[("g", r)].clone() for r in range(self.world)]
+        self._sync()
+        return parts
+
+
+def locked_ops():
+    """Virtual ranks share one process, hence one set of per-device scratch workspaces: run each
+    per-window op (its kernels + the workspace it owns) under a lock, to completion."""
+    from fluidnet_cxx_b200.lib.distributed import CudaLocalOps
+    lock = threading.Lock()
+
+    class LockedOps(CudaLocalOps):
+        pass
+
+    def wrap(name):
+        inner = getattr(CudaLocalOps, name)
+
+        def call(self, *a, **kw):
+            with lock:
+                out = inner(self, *a, **kw)
+                torch.cuda.synchronize()
+                return out
+        return call
+    for name in ("advect_forces_div", "jacobi", "project", "set_const", "cnn"):
+        setattr(LockedOps, name, wrap(name))
+    return LockedOps()
+
+
+def run_virtual(world, ghost, mconf, state, net, method, steps):
+    from fluidnet_cxx_b200.lib.distributed import SlabDecomposition, simulate_distributed
+    comm = ThreadComm(world)
+    ops = locked_ops()
+    H = state["flags"].shape[3]
+    results, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            torch.cuda.set_device(0)
+            dec = SlabDecomposition(H, ghost, rank=rank, world=world, comm=comm)
+            bd = {k: dec.scatter(v) for k, v in state.items()}
+            outs = []
+            with torch.no_grad():
+                for _ in range(steps):
+                    simulate_distributed(mconf, bd, net, method, dec, ops=ops)
+                    outs.append({k: dec.gather(bd[k]) for k in ("p", "U", "density")})
+            results[rank] = outs
+        except Exception as e:      # noqa: BLE001 - surface the failure in the main thread
+            errors.append(e)
+            comm.bar.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results[0]
+
+
+def make_state(fluid, H, W, mconf, seed=11):
+    bd = {"p": torch.zeros(1, 1, 1, H, W, device="cuda"), "U": torch.zeros(1, 2, 1, H, W, device="cuda"),
+          "flags": torch.zeros(1, 1, 1, H, W, device="cuda"), "density": torch.zeros(1, 1, 1, H, W, device="cuda")}
+    fluid.emptyDomain(bd["flags"])
+    bd["flags"][..., H // 2 - 5:H // 2 + 6, W // 3:W // 3 + 9] = 2.0       # obstacle across a slab boundary
+    fluid.createPlumeBCs(bd, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    bd["U"] = torch.randn(bd["U"].shape, device="cuda", generator=g) * 0.5
+    bd["density"] = torch.rand(bd["density"].shape, device="cuda", generator=g)
+    return bd
+
+
+@pytest.mark.parametrize("world,H,W,ghost,iters", [(2, 256, 192, 48, 100), (4, 256, 160, 24, 28)])
+def test_virtual_ranks_jacobi_bit_exact(world, H, W, ghost, iters):
+    from fluidnet_cxx_b200.lib import fluid
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from test_gpu_parity import plume_mconf
+    mconf = plume_mconf(simMethod="jacobi")
+    mconf["jacobiIter"] = iters
+    state = make_state(fluid, H, W, mconf)
+    ref_bd = {k: v.clone() for k, v in state.items()}
+    ref = []
+    for _ in range(3):
+        sim._simulate_fused(mconf, ref_bd, None, "jacobi", float(mconf["dt"]), False)
+        ref.append({k: ref_bd[k].clone() for k in ("p", "U", "density")})
+    got = run_virtual(world, ghost, mconf, state, None, "jacobi", 3)
+    for i in range(3):
+        for k in ("p", "U", "density"):
+            assert torch.equal(got[i][k], ref[i][k]), (i, k, int((got[i][k] != ref[i][k]).sum()))
+
+
+def test_virtual_ranks_convnet():
+    from fluidnet_cxx_b200.lib import fluid
+    from fluidnet_cxx_b200.lib.pretrained import load_scalenet
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from test_gpu_parity import plume_mconf
+    model, mconf_net = load_scalenet("cuda")
+    mconf = dict(mconf_net)
+    mconf.update(plume_mconf(simMethod="convnet"))
+    model.mconf = mconf
+    model.scale.mconf = mconf
+    H, W = 256, 128
+    state = make_state(fluid, H, W, mconf)
+    ref_bd = {k: v.clone() for k, v in state.items()}
+    ref = []
+    with torch.no_grad():
+        for _ in range(2):
+            sim._simulate_fused(mconf, ref_bd, model, "convnet", float(mconf["dt"]), False)
+            ref.append({k: ref_bd[k].clone() for k in ("p", "U", "density")})
+    got = run_virtual(2, 64, mconf, state, model, "convnet", 2)
+    for i in range(2):
+        assert torch.equal(got[i]["density"], ref[i]["density"]) or i > 0      # advection is bit-exact
+        for k in ("p", "U", "density"):
+            err = float((got[i][k] - ref[i][k]).abs().max() / ref[i][k].abs().max())
+            assert err < 2e-5 * (i + 1), (i, k, err)
