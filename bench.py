@@ -142,7 +142,176 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def run_ours_distributed(args):
+    """N > 1: weak scaling by slab decomposition.  The global grid is N slabs of the single-GPU
+    workload stacked along the outermost spatial axis; every rank owns one slab, computes it plus
+    ghost rows with the same kernels (row windows, global coordinates) and exchanges halos over NCCL
+    (fluidnet_cxx_b200/lib/distributed.py).  value = global cells * steps / max-over-ranks time."""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    from fluidnet_cxx_b200 import _native
+    from fluidnet_cxx_b200.lib import fluid
+    D = importlib.import_module("fluidnet_cxx_b200.lib.distributed")
+
+    wl = WORKLOADS[args.workload]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    lib = _native.load()
+    Dz, H, W = wl["res"]
+    is3d = Dz > 1
+    mconf = plume_mconf(wl["jacobi_iters"], wl["method"])
+    net = None
+    if wl["method"] == "convnet":
+        from fluidnet_cxx_b200.lib.pretrained import load_scalenet
+        net, mconf_net = load_scalenet(dev)
+        m = dict(mconf_net); m.update(mconf); mconf = m
+        net.mconf = mconf; net.scale.mconf = mconf
+    ghost = D.GHOST_CONVNET if wl["method"] == "convnet" else D.GHOST_JACOBI
+    axis = 2 if is3d else 3
+    rows_owned = Dz if is3d else H
+    ghost = min(ghost, rows_owned)
+    gD, gH = (Dz * world, H) if is3d else (1, H * world)
+    decomp = D.SlabDecomposition(rows_owned * world, ghost, axis=axis)
+    cells_global = gD * gH * W
+
+    # the same seeded global state on every rank (pinned host), window rows copied in
+    U_np, rho_np = synthetic_state_numpy(gD, gH, W, seed=0)
+    host = {"p": torch.zeros(1, 1, gD, gH, W).pin_memory(), "U": torch.from_numpy(U_np).pin_memory(),
+            "flags": torch.zeros(1, 1, gD, gH, W).pin_memory(), "density": torch.from_numpy(rho_np).pin_memory()}
+    bd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    fluid.emptyDomain(bd["flags"])
+    U0, rho0 = bd["U"], bd["density"]
+    bd["U"], bd["density"] = torch.zeros_like(U0), torch.zeros_like(rho0)
+    fluid.createPlumeBCs(bd, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
+    bd["U"], bd["density"] = U0, rho0
+    host["flags"].copy_(bd["flags"])
+    torch.cuda.synchronize()
+    D.check_reach(decomp, bd["U"], mconf["dt"])
+
+    nc = 3 if is3d else 2
+    window_cells = decomp.local_rows * (H if is3d else 1) * W
+    working_set = window_cells * 4 * (1 + nc + 1 + 1 + 2 * nc + 2)
+    flush = working_set < 2 * L2_BYTES
+    flush_buf = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev) if flush else None
+
+    class TimedOps(D.CudaLocalOps):
+        """CUDA events around the pressure stage (Jacobi chunks / CNN) for the roofline"""
+        events = []
+
+        def _timed(self, fn, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a)
+            e1.record()
+            self.events.append((e0, e1))
+            return out
+
+        def jacobi(self, *a):
+            return self._timed(super().jacobi, *a)
+
+        def cnn(self, *a):
+            return self._timed(super().cnn, *a)
+    ops = TimedOps()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        with torch.no_grad():
+            D.simulate_distributed(mconf, bd, net, wl["method"], decomp, ops=ops)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    ops.events.clear()
+    if wl["method"] == "convnet":
+        lib.fnx_profile_enable(1)
+    n0 = lib.fnx_launch_count()
+    step_ms = []
+    barrier()
+    sampler.mark_begin()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        if flush:
+            flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_step()
+        e1.record()
+        step_ms.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.mark_end()
+    launches = lib.fnx_launch_count() - n0
+    total_ms = sum(a.elapsed_time(b) for a, b in step_ms)
+    dom_ms = sum(a.elapsed_time(b) for a, b in ops.events)
+    layer_recs = []
+    if wl["method"] == "convnet":
+        buf = (_native.ProfileRec * 4096)()
+        n = lib.fnx_profile_fetch(buf, 4096)
+        lib.fnx_profile_enable(0)
+        layer_recs = [buf[i] for i in range(max(0, min(n, 4096)))]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: this rank's window rows in from pinned host memory, owned rows out, every step ----
+    e2e_steps = max(3, min(args.steps, 10))
+    win, own = decomp._sl(decomp.r0, decomp.r1), decomp._sl(decomp.lo, decomp.hi)
+    h2d = sum(host[k][win].numel() * 4 for k in ("p", "U", "flags", "density"))
+    d2h = sum(host[k][own].numel() * 4 for k in ("p", "U", "density"))
+    out_host = {k: torch.empty_like(host[k][own]).pin_memory() for k in ("p", "U", "density")}
+    masks = {k: bd[k] for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask")}
+    dev_state = {k: bd[k].clone() for k in ("p", "U", "flags", "density")}
+
+    def e2e_step():
+        for k in ("p", "U", "flags", "density"):
+            dev_state[k][win].copy_(host[k][win], non_blocking=True)
+        d = dict(dev_state)
+        d.update(masks)
+        with torch.no_grad():
+            D.simulate_distributed(mconf, d, net, wl["method"], decomp, ops=ops)
+        for k in ("p", "U", "density"):
+            out_host[k].copy_(d[k][own], non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([total_ms, e2e_ms, dom_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, dom_ms = t.tolist()
+    tb = torch.tensor([float(h2d), float(d2h), float(launches)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tb)
+    h2d_all, d2h_all, launches_all = (int(x) for x in tb.tolist())
+    if rank == 0:
+        out = make_report(args, wl, world, cells_global, window_cells, total_ms, e2e_ms, e2e_steps, dom_ms, layer_recs,
+                          h2d_all, d2h_all, launches_all, clocks, t_wall, flush, False,
+                          parallelism=(f"{world} GPUs: slab decomposition along {'D' if is3d else 'H'} "
+                                       f"({rows_owned} owned + {ghost} ghost rows per interior side), NCCL halo "
+                                       f"send/recv, global grid {gD}x{gH}x{W}"),
+                          grid=[gD, gH, W])
+        out["cpu_baseline"] = None
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_ours(args):
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_ours_distributed(args)
     import torch
     import torch.distributed as dist
     from fluidnet_cxx_b200 import _native
@@ -285,13 +454,18 @@ def run_ours(args):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
 
-    # ---- reduce over ranks: max time ---------------------------------------------------------------
-    t = torch.tensor([total_ms, e2e_ms, dom_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, dom_ms = t.tolist()
-
     if rank == 0:
+        out = make_report(args, wl, world, cells * world, cells, total_ms, e2e_ms, e2e_steps, dom_ms, layer_recs, h2d, d2h,
+                          int(launches), clocks, t_wall, flush, graphed, parallelism="1 GPU", grid=[D, H, W])
+        out["cpu_baseline"] = cpu_baseline(wl, steps=1, warmup=0) if not args.no_cpu_baseline else None
+        print(json.dumps(out), flush=True)
+
+
+def make_report(args, wl, world, total_cells, cells, total_ms, e2e_ms, e2e_steps, dom_ms, layer_recs, h2d, d2h, launches,
+                clocks, t_wall, flush, graphed, parallelism, grid):
+    """The one JSON line of the contract (rank 0).  cells = cells one GPU computes per step."""
+    D = grid[0] if world == 1 else wl["res"][0]
+    if True:
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
@@ -299,7 +473,6 @@ def run_ours(args):
                 peaks = json.load(f)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        total_cells = cells * world
         value = total_cells * args.steps / (total_ms / 1e3) / 1e6
         e2e_value = total_cells * e2e_steps / (e2e_ms / 1e3) / 1e6
         iters = wl["jacobi_iters"]
@@ -360,9 +533,9 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded N(0,0.5^2) velocity, U[0,1) density, plume inlet BCs, border obstacles)",
-            "config": {"workload": args.workload, "baseline_config": wl["baseline_config"], "grid": [D, H, W],
+            "config": {"workload": args.workload, "baseline_config": wl["baseline_config"], "grid": grid,
                        "pressure": pressure, "cells_per_gpu": cells,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (weak)",
+                       "parallelism": parallelism,
                        "l2": "flushed between timed steps" if flush else "working set larger than L2, no flush",
                        "launch": "CUDA graph replay of the fused step" if graphed else "direct kernel launches",
                        "algorithmic_bytes_per_cell_step": step_bytes},
@@ -373,11 +546,7 @@ def run_ours(args):
             "roofline": roof,
             "wall_s": round(t_wall, 3),
         }
-        out["cpu_baseline"] = cpu_baseline(wl, steps=1, warmup=0) if world == 1 and not args.no_cpu_baseline else None
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        return out
 
 
 # ---------------------------------------------------------------------------------------------

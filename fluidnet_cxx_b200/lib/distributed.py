@@ -183,8 +183,10 @@ class CudaLocalOps:
     """The per-window compute: the single-GPU kernels behind the C-ABI (no fallback)."""
 
     def __init__(self):
+        import importlib
         from .. import _native as N
-        from . import simulate as sim
+        # (the package attribute `lib.simulate` is the function; the helpers live in the module)
+        sim = importlib.import_module(__package__ + ".simulate")
         self.N, self.sim, self.lib = N, sim, N.load()
 
     def advect_forces_div(self, mconf, dt, bd, want_div, wall_bcs, rows):
