@@ -221,9 +221,17 @@ def run_ours_distributed(args):
         dist.barrier()
         torch.cuda.synchronize()
 
+    # pass 1 (value): the public stepper -- the whole step incl. NCCL halo exchange replayed as one CUDA
+    # graph when the step is launch-bound; pass 2 below re-issues it kernel by kernel for the roofline
+    use_graph = window_cells <= (1 << 22) and os.environ.get("FLUIDNET_B200_GRAPHS", "1") != "0"
+    stepper = D.GraphedDistributedStep(mconf, bd, net, wl["method"], decomp, use_graph=use_graph)
+    graphed = stepper.graphed
+    if rank == 0 and stepper.capture_error:
+        print(f"[bench] CUDA-graph capture of the distributed step failed, using direct launches: "
+              f"{stepper.capture_error}", file=sys.stderr)
+
     def one_step():
-        with torch.no_grad():
-            D.simulate_distributed(mconf, bd, net, wl["method"], decomp, ops=ops)
+        stepper.step()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -231,10 +239,6 @@ def run_ours_distributed(args):
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
-    ops.events.clear()
-    if wl["method"] == "convnet":
-        lib.fnx_profile_enable(1)
-    n0 = lib.fnx_launch_count()
     step_ms = []
     barrier()
     sampler.mark_begin()
@@ -250,8 +254,32 @@ def run_ours_distributed(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.mark_end()
-    launches = lib.fnx_launch_count() - n0
     total_ms = sum(a.elapsed_time(b) for a, b in step_ms)
+
+    # pass 2: direct launches with per-stage / per-layer events
+    bd = stepper.state
+
+    def one_step():
+        with torch.no_grad():
+            D.simulate_distributed(mconf, bd, net, wl["method"], decomp, ops=ops)
+    one_step()
+    barrier()
+    ops.events.clear()
+    if wl["method"] == "convnet":
+        lib.fnx_profile_enable(1)
+    n0 = lib.fnx_launch_count()
+    step_ms = []
+    barrier()
+    for _ in range(args.steps):
+        if flush:
+            flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_step()
+        e1.record()
+        step_ms.append((e0, e1))
+    barrier()
+    launches = lib.fnx_launch_count() - n0
     dom_ms = sum(a.elapsed_time(b) for a, b in ops.events)
     layer_recs = []
     if wl["method"] == "convnet":
@@ -267,18 +295,12 @@ def run_ours_distributed(args):
     h2d = sum(host[k][win].numel() * 4 for k in ("p", "U", "flags", "density"))
     d2h = sum(host[k][own].numel() * 4 for k in ("p", "U", "density"))
     out_host = {k: torch.empty_like(host[k][own]).pin_memory() for k in ("p", "U", "density")}
-    masks = {k: bd[k] for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask")}
-    dev_state = {k: bd[k].clone() for k in ("p", "U", "flags", "density")}
-
     def e2e_step():
         for k in ("p", "U", "flags", "density"):
-            dev_state[k][win].copy_(host[k][win], non_blocking=True)
-        d = dict(dev_state)
-        d.update(masks)
-        with torch.no_grad():
-            D.simulate_distributed(mconf, d, net, wl["method"], decomp, ops=ops)
+            stepper.state[k][win].copy_(host[k][win], non_blocking=True)
+        stepper.step()
         for k in ("p", "U", "density"):
-            out_host[k].copy_(d[k][own], non_blocking=True)
+            out_host[k].copy_(stepper.state[k][own], non_blocking=True)
 
     e2e_step()
     barrier()
@@ -298,7 +320,7 @@ def run_ours_distributed(args):
     h2d_all, d2h_all, launches_all = (int(x) for x in tb.tolist())
     if rank == 0:
         out = make_report(args, wl, world, cells_global, window_cells, total_ms, e2e_ms, e2e_steps, dom_ms, layer_recs,
-                          h2d_all, d2h_all, launches_all, clocks, t_wall, flush, False,
+                          h2d_all, d2h_all, launches_all, clocks, t_wall, flush, graphed,
                           parallelism=(f"{world} GPUs: slab decomposition along {'D' if is3d else 'H'} "
                                        f"({rows_owned} owned + {ghost} ghost rows per interior side), NCCL halo "
                                        f"send/recv, global grid {gD}x{gH}x{W}"),
