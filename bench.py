@@ -226,6 +226,7 @@ def run_ours_distributed(args):
     use_graph = window_cells <= (1 << 22) and os.environ.get("FLUIDNET_B200_GRAPHS", "1") != "0"
     stepper = D.GraphedDistributedStep(mconf, bd, net, wl["method"], decomp, use_graph=use_graph)
     graphed = stepper.graphed
+    graph_check = stepper.verify() if graphed else None     # graphs vs direct launches, owned rows
     if rank == 0 and stepper.capture_error:
         print(f"[bench] CUDA-graph capture of the distributed step failed, using direct launches: "
               f"{stepper.capture_error}", file=sys.stderr)
@@ -326,6 +327,8 @@ def run_ours_distributed(args):
                                        f"send/recv, global grid {gD}x{gH}x{W}"),
                           grid=[gD, gH, W])
         out["cpu_baseline"] = None
+        if graph_check is not None:
+            out["config"]["graph_vs_direct_max_abs_diff"] = graph_check
         print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()

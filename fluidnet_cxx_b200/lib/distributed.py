@@ -115,56 +115,64 @@ class SlabDecomposition:
         return torch.cat(parts, dim=self.axis)
 
     # -- halo exchange ------------------------------------------------------------------------
-    def exchange(self, tensors):
+    # pack (device copies) -> transfer (the only communication) -> unpack (device copies); the three
+    # are separate so the copies can live inside CUDA graphs while the NCCL calls stay outside.
+    def _halo_slices(self):
+        g, out = self.ghost, []
+        if self.rank > 0:                   # (peer, rows I send, rows I receive)
+            out.append((self.rank - 1, (self.lo, self.lo + g), (self.lo - g, self.lo)))
+        if self.rank < self.world - 1:
+            out.append((self.rank + 1, (self.hi - g, self.hi), (self.hi, self.hi + g)))
+        return out
+
+    def pack(self, tensors, bufs):
+        """copy my boundary owned rows of every tensor into one send buffer per neighbour
+        (bufs: dict reused across steps so the buffers are static)"""
+        for peer, (a, b), _ in self._halo_slices():
+            n = sum(t[self._sl(a, b)].numel() for t in tensors)
+            key = ("send", peer)
+            if key not in bufs or bufs[key].numel() != n:
+                bufs[key] = torch.empty(n, dtype=tensors[0].dtype, device=tensors[0].device)
+                bufs[("recv", peer)] = torch.empty_like(bufs[key])
+            o = 0
+            for t in tensors:
+                v = t[self._sl(a, b)]
+                bufs[key][o:o + v.numel()].view(v.shape).copy_(v)
+                o += v.numel()
+
+    def transfer(self, bufs):
+        """send buffers -> the neighbours' receive buffers (batched NCCL / gloo send+recv)"""
+        if self.world == 1:
+            return
+        if self.comm is not None:
+            recvs = self.comm.exchange_rows(self, {peer: bufs[("send", peer)] for peer, _, _ in self._halo_slices()})
+            for peer, buf in recvs.items():
+                bufs[("recv", peer)].copy_(buf)
+            return
+        ops = []
+        for peer, _, _ in self._halo_slices():
+            ops += [dist.P2POp(dist.isend, bufs[("send", peer)], self._peer(peer), self.group),
+                    dist.P2POp(dist.irecv, bufs[("recv", peer)], self._peer(peer), self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def unpack(self, tensors, bufs):
+        for peer, _, (a, b) in self._halo_slices():
+            o = 0
+            for t in tensors:
+                v = t[self._sl(a, b)]
+                v.copy_(bufs[("recv", peer)][o:o + v.numel()].view(v.shape))
+                o += v.numel()
+
+    def exchange(self, tensors, bufs=None):
         """Refresh the ghost rows of every tensor in `tensors` (in place) from the neighbours' owned
         rows: one packed message per neighbour and direction."""
         if self.world == 1:
             return
-        g = self.ghost
-        ops, unpack = [], []
-        up, down = self.rank - 1, self.rank + 1
-
-        def pack(a, b):
-            return torch.cat([t[self._sl(a, b)].reshape(-1) for t in tensors])
-
-        def unpacker(buf, a, b):
-            def run():
-                o = 0
-                for t in tensors:
-                    view = t[self._sl(a, b)]
-                    n = view.numel()
-                    view.copy_(buf[o:o + n].view(view.shape))
-                    o += n
-            return run
-
-        if self.comm is not None:
-            sends = {}
-            if up >= 0:
-                sends[up] = pack(self.lo, self.lo + g)
-            if down < self.world:
-                sends[down] = pack(self.hi - g, self.hi)
-            recvs = self.comm.exchange_rows(self, sends)
-            if up >= 0:
-                unpacker(recvs[up], self.lo - g, self.lo)()
-            if down < self.world:
-                unpacker(recvs[down], self.hi, self.hi + g)()
-            return
-        if up >= 0:
-            send = pack(self.lo, self.lo + g)                             # my top owned rows
-            recv = torch.empty_like(send)
-            ops += [dist.P2POp(dist.isend, send, self._peer(up), self.group),
-                    dist.P2POp(dist.irecv, recv, self._peer(up), self.group)]
-            unpack.append(unpacker(recv, self.lo - g, self.lo))
-        if down < self.world:
-            send = pack(self.hi - g, self.hi)                             # my bottom owned rows
-            recv = torch.empty_like(send)
-            ops += [dist.P2POp(dist.isend, send, self._peer(down), self.group),
-                    dist.P2POp(dist.irecv, recv, self._peer(down), self.group)]
-            unpack.append(unpacker(recv, self.hi, self.hi + g))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        for u in unpack:
-            u()
+        bufs = {} if bufs is None else bufs
+        self.pack(tensors, bufs)
+        self.transfer(bufs)
+        self.unpack(tensors, bufs)
 
     def _peer(self, r):
         return r if self.group is None else dist.get_global_rank(self.group, r)
@@ -242,12 +250,15 @@ class CudaLocalOps:
         return net.forward_fields(U, flags, scale=scale)
 
 
-def _global_std(decomp, U_local, threshold):
-    """max(unbiased std of the GLOBAL U, threshold) (model.py:8-23) from per-rank partial sums."""
-    own = decomp.owned(U_local).double()
-    part = torch.stack([own.sum(), (own * own).sum()])
-    decomp.all_reduce(part)
-    n = float(own.numel() * decomp.world)
+def _std_partial(decomp, U):
+    """(sum, sum of squares) of this rank's owned rows of U, fp64 (to be all-reduced)"""
+    own = decomp.owned(U).double()
+    return torch.stack([own.sum(), (own * own).sum()])
+
+
+def _std_finish(decomp, part, owned_count, threshold):
+    """max(unbiased std of the GLOBAL U, threshold) (model.py:8-23) from the reduced partial sums"""
+    n = float(owned_count * decomp.world)
     var = (part[1] - part[0] * part[0] / n) / (n - 1.0)
     s = torch.sqrt(torch.clamp(var, min=0.0)).float().clamp(min=float(threshold))
     return s.view(1, 1, 1, 1, 1)
@@ -265,38 +276,47 @@ def check_reach(decomp, U_local, dt):
     return reach
 
 
-def simulate_distributed(mconf, bd, net, sim_method, decomp, ops=None):
-    """One solver step on this rank's window (bd holds GLOBAL-SIZED tensors; masks included).
-    Same state transitions as lib.simulate for the fused configuration (inviscid, density-carrying,
-    fixed Jacobi count or the ScaleNet model).  Only the owned rows of the returned state are
-    meaningful (decomp.owned / decomp.gather); ghost rows are refreshed by the next call.
-    Returns nothing; bd['p'], bd['U'], bd['density'] are rebound."""
+def step_phases(mconf, bd, net, sim_method, decomp, ops, bufs):
+    """The slab-decomposed step as a generator: pure device work between two `yield`s, and every yield
+    hands back a zero-argument callable that performs one communication (halo transfer or the
+    all-reduce).  simulate_distributed runs it straight through; GraphedDistributedStep captures each
+    compute stretch into a CUDA graph and keeps the communication calls between the replays."""
     assert sim_method in ('jacobi', 'convnet')
-    ops = ops or CudaLocalOps()
     dt = float(mconf['dt'])
     g = decomp.ghost
-    if decomp.world > 1:
+    multi = decomp.world > 1
+    if multi:
         need = RA + (CNN_REACH if sim_method == 'convnet' else 1)
         if g < need:
             raise ValueError(f"ghost width {g} < {need} rows needed by the {sim_method} step")
     plane = bd['flags'].size(3) if decomp.axis == 2 else 1     # 3-D slabs along D: H rows per plane
     rows = decomp.rows(plane)
-    decomp.exchange([bd['density'], bd['U']])
+    sb = bufs.setdefault('state', {})
+    if multi:
+        decomp.pack([bd['density'], bd['U']], sb)
+        yield lambda: decomp.transfer(sb)
+        decomp.unpack([bd['density'], bd['U']], sb)
     if sim_method == 'jacobi':
         density, U, div = ops.advect_forces_div(mconf, dt, bd, True, True, rows)
         iters = int(mconf['jacobiIter'])
-        k = jacobi_chunk(g) if decomp.world > 1 else iters
+        k = jacobi_chunk(g) if multi else iters
         p, done = None, 0
+        pb = bufs.setdefault('p', {})
         while done < iters:
             n = min(k, iters - done)
             if done > 0:
-                decomp.exchange([p])
+                decomp.pack([p], pb)
+                yield lambda: decomp.transfer(pb)
+                decomp.unpack([p], pb)
             p = ops.jacobi(bd['flags'], div, p, n, rows)
             done += n
         U = ops.project(p, U, bd, rows)      # radius 1: p is valid from row ghost-1 inwards after any chunk
     else:
         density, U, _ = ops.advect_forces_div(mconf, dt, bd, False, False, rows)
-        scale = _global_std(decomp, U, net.mconf['normalizeInputThreshold'])
+        part = _std_partial(decomp, U)
+        if multi:
+            yield lambda: decomp.all_reduce(part)
+        scale = _std_finish(decomp, part, decomp.owned(U).numel(), net.mconf['normalizeInputThreshold'])
         # the CNN runs on a compact copy of the window (translation invariant), results go back in place
         p_w, U_w = ops.cnn(net, decomp.window(U), decomp.window(bd['flags']), scale)
         p = decomp.put_window(torch.zeros_like(bd['flags']), p_w)
@@ -308,10 +328,23 @@ def simulate_distributed(mconf, bd, net, sim_method, decomp, ops=None):
     bd['U'], bd['density'], bd['p'] = U, density, p
 
 
+def simulate_distributed(mconf, bd, net, sim_method, decomp, ops=None, bufs=None):
+    """One solver step on this rank's window (bd holds GLOBAL-SIZED tensors; masks included).
+    Same state transitions as lib.simulate for the fused configuration (inviscid, density-carrying,
+    fixed Jacobi count or the ScaleNet model).  Only the owned rows of the returned state are
+    meaningful (decomp.owned / decomp.gather); ghost rows are refreshed by the next call.
+    Returns nothing; bd['p'], bd['U'], bd['density'] are rebound."""
+    ops = ops or CudaLocalOps()
+    for comm in step_phases(mconf, bd, net, sim_method, decomp, ops, {} if bufs is None else bufs):
+        comm()
+
+
 class GraphedDistributedStep:
-    """The slab-decomposed step captured ONCE into a CUDA graph -- halo send/recv and the all-reduce
-    included (NCCL operations are capturable) -- and replayed per step: below a few million cells
-    per GPU the step is launch-bound, and a replay removes ~80 launches + the Python between them.
+    """The slab-decomposed step with every stretch of device work between two communications captured
+    ONCE into a CUDA graph and replayed per step; the NCCL calls (one batched halo send/recv per
+    exchange, one all-reduce for the ScaleNet std) are issued between the replays.  Below a few
+    million cells per GPU the step is launch-bound: a replay removes ~80 launches and the Python
+    between them.
 
         stepper = GraphedDistributedStep(mconf, bd, net, 'convnet', decomp)
         stepper.step(); ...; state = stepper.state      # global-sized tensors, owned rows valid
@@ -323,42 +356,71 @@ class GraphedDistributedStep:
         self.mconf, self.net, self.method, self.decomp = mconf, net, sim_method, decomp
         self.ops = ops or CudaLocalOps()
         self.state = {k: (v.clone() if k in ('p', 'U', 'density') else v) for k, v in bd.items()}
-        self.graph, self.graphed, self.capture_error = None, False, None
+        self.bufs = {}
+        self.schedule, self.graphed, self.capture_error = None, False, None
         self._win = decomp._sl(decomp.r0, decomp.r1)
         if not (use_graph and decomp.comm is None and self.state['flags'].is_cuda):
             return
-        # warm-up on a scratch copy: NCCL communicators, workspaces, the CNN plan, kernel attributes
+        # warm-up on a scratch copy: NCCL communicators, workspaces, halo buffers, the CNN plan
         scratch = dict(self.state)
         for k in ('p', 'U', 'density'):
             scratch[k] = self.state[k].clone()
         with torch.no_grad():
             for _ in range(max(1, warmup)):
-                simulate_distributed(mconf, scratch, net, sim_method, decomp, ops=self.ops)
+                simulate_distributed(mconf, scratch, net, sim_method, decomp, ops=self.ops, bufs=self.bufs)
         torch.cuda.synchronize()
-        if decomp.world > 1:
-            dist.barrier(group=decomp.group)
         try:
-            work = dict(self.state)
-            graph = torch.cuda.CUDAGraph()
-            with torch.no_grad(), torch.cuda.graph(graph):
-                simulate_distributed(mconf, work, net, sim_method, decomp, ops=self.ops)
-            self.graph, self.outs, self.graphed = graph, {k: work[k] for k in ('p', 'U', 'density')}, True
+            self._capture()
+            self.graphed = True
         except Exception as e:      # noqa: BLE001 - capture is an optimisation, never a requirement
             self.capture_error = repr(e)
+            self.schedule = None
             torch.cuda.synchronize()
-        # every rank must take the same path (a replay on one side and direct launches on the other
-        # would still match message for message, but keep the timing comparable)
-        if decomp.world > 1:
+        if decomp.world > 1:        # all ranks take the same path
             ok = torch.tensor([1.0 if self.graphed else 0.0], device=self.state['flags'].device)
             decomp.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() < 1.0:
-                self.graph, self.graphed = None, False
+                self.schedule, self.graphed = None, False
+
+    def _capture(self):
+        work = dict(self.state)
+        gen = step_phases(self.mconf, work, self.net, self.method, self.decomp, self.ops, self.bufs)
+        schedule, pool, done = [], None, False
+        with torch.no_grad():
+            while not done:
+                graph = torch.cuda.CUDAGraph()
+                comm = None
+                with torch.cuda.graph(graph, pool=pool):
+                    try:
+                        comm = next(gen)
+                    except StopIteration:
+                        done = True
+                pool = graph.pool()
+                schedule.append((graph, comm))
+        self.schedule = schedule
+        self.outs = {k: work[k] for k in ('p', 'U', 'density')}
+
+    def verify(self):
+        """one step through the graphs and one by direct launches from the same state: max |difference|
+        over this rank's owned rows (0.0 = bit-identical).  Leaves the state advanced by one step."""
+        start = {k: self.state[k].clone() for k in ('p', 'U', 'density')}
+        self.step()
+        got = {k: self.decomp.owned(self.state[k]).clone() for k in ('p', 'U', 'density')}
+        ref = dict(self.state)
+        ref.update(start)
+        with torch.no_grad():
+            simulate_distributed(self.mconf, ref, self.net, self.method, self.decomp, ops=self.ops, bufs={})
+        return max(float((self.decomp.owned(ref[k]) - got[k]).abs().max()) for k in got)
 
     def step(self):
         if self.graphed:
-            self.graph.replay()
+            for graph, comm in self.schedule:
+                graph.replay()
+                if comm is not None:
+                    comm()
             for k in ('p', 'U', 'density'):
                 self.state[k][self._win].copy_(self.outs[k][self._win])
         else:
             with torch.no_grad():
-                simulate_distributed(self.mconf, self.state, self.net, self.method, self.decomp, ops=self.ops)
+                simulate_distributed(self.mconf, self.state, self.net, self.method, self.decomp, ops=self.ops,
+                                     bufs=self.bufs)

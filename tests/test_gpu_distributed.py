@@ -159,3 +159,35 @@ def test_virtual_ranks_convnet():
         for k in ("p", "U", "density"):
             err = float((got[i][k] - ref[i][k]).abs().max() / ref[i][k].abs().max())
             assert err < 2e-5 * (i + 1), (i, k, err)
+
+
+@pytest.mark.parametrize("method", ["jacobi", "convnet"])
+def test_graphed_stepper_single_rank(method):
+    """GraphedDistributedStep on one rank (no communication, one graph) == the fused single-GPU step"""
+    from fluidnet_cxx_b200.lib import fluid
+    from fluidnet_cxx_b200.lib.distributed import GraphedDistributedStep, SlabDecomposition
+    from fluidnet_cxx_b200.lib.pretrained import load_scalenet
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from test_gpu_parity import plume_mconf
+    model, mconf_net = load_scalenet("cuda")
+    mconf = dict(mconf_net)
+    mconf.update(plume_mconf(simMethod=method))
+    model.mconf = mconf
+    model.scale.mconf = mconf
+    H, W = 128, 160
+    state = make_state(fluid, H, W, mconf)
+    ref_bd = {k: v.clone() for k, v in state.items()}
+    dec = SlabDecomposition(H, 0, rank=0, world=1)
+    stepper = GraphedDistributedStep(mconf, state, model, method, dec)
+    assert stepper.graphed, stepper.capture_error
+    for i in range(3):
+        with torch.no_grad():
+            sim._simulate_fused(mconf, ref_bd, model, method, float(mconf["dt"]), False)
+        stepper.step()
+        for k in ("p", "U", "density"):
+            if method == "jacobi":
+                assert torch.equal(stepper.state[k], ref_bd[k]), (i, k)
+            else:   # the std is formed from fp64 partial sums here, by the two-pass kernel there
+                err = float((stepper.state[k] - ref_bd[k]).abs().max() / ref_bd[k].abs().max())
+                assert err < 1e-5, (i, k, err)
+    assert stepper.verify() == 0.0
