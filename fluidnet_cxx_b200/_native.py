@@ -166,17 +166,21 @@ class _Workspaces:
 
     def __init__(self):
         self._bufs = {}
+        self._retired = []   # outgrown buffers stay alive: captured CUDA graphs may still point at them
 
     def get(self, device, tag, nbytes):
         key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                self._retired.append(buf)
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self._bufs[key] = buf
         return buf
 
     def clear(self):
         self._bufs.clear()
+        self._retired.clear()
 
 
 workspaces = _Workspaces()

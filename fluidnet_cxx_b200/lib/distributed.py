@@ -196,6 +196,7 @@ class CudaLocalOps:
         # (the package attribute `lib.simulate` is the function; the helpers live in the module)
         sim = importlib.import_module(__package__ + ".simulate")
         self.N, self.sim, self.lib = N, sim, N.load()
+        self._keep = {}     # per-row mask maps handed to kernels (a captured graph keeps pointing at them)
 
     def advect_forces_div(self, mconf, dt, bd, want_div, wall_bcs, rows):
         N, sim, lib = self.N, self.sim, self.lib
@@ -208,6 +209,8 @@ class CudaLocalOps:
         is3d = int(U.size(1) == 3)
         UBC, UBCInv, rBC, rBCInv = sim._masks(bd)
         mrows = sim._mask_rows(lib, bd, flags, is3d)
+        if mrows is not None:
+            self._keep[mrows.data_ptr()] = mrows
         prm = sim._step_params(mconf, dt, 0)
         prm.apply_wall_bcs = int(wall_bcs)
         prm.density_const_passes = 2 if wall_bcs else 1
@@ -237,6 +240,8 @@ class CudaLocalOps:
         is3d = int(U.size(1) == 3)
         UBC, UBCInv, _, _ = sim._masks(bd)
         mrows = sim._mask_rows(lib, bd, flags, is3d)
+        if mrows is not None:
+            self._keep[mrows.data_ptr()] = mrows
         N.check(lib.fnx_step_project_bcs_rows(N.ptr(p), N.ptr(U), N.ptr(flags), N.ptr(UBC), N.ptr(UBCInv),
                                               mrows.data_ptr() if mrows is not None else None, 1, B, D, H, W, is3d,
                                               rows[0], rows[1], N.stream_of(U)), "simulate_distributed")

@@ -137,7 +137,9 @@ class MultiScaleNet(nn.Module):
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             # zero borders of the split activation buffers: written once, never touched again
             N.check(lib.fnx_msnet_workspace_init(ws.data_ptr(), ws.numel(), st), "MultiScaleNet.workspace_init")
-            cache["ws"] = {(h, w): ws}   # one resolution at a time
+            if len(cache["ws"]) >= 4:    # a few resolutions stay resident (captured graphs point at them)
+                cache["ws"].pop(next(iter(cache["ws"])))
+            cache["ws"][(h, w)] = ws
         y = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
         N.check(lib.fnx_msnet_forward(ctypes.byref(plan), N.ptr(x), N.ptr(y), n, h, w, ws.data_ptr(), ws.numel(), st),
                 "MultiScaleNet.forward")

@@ -211,7 +211,9 @@ def _simulate_graphed(mconf, batch_dict, net, sim_method, dt):
         torch.cuda.synchronize()
         with torch.cuda.graph(graph):
             _simulate_fused(mconf, work, net, sim_method, dt, False)
-        entry = (graph, static, {k: work[k] for k in ('p', 'U', 'density')}, _masks(batch_dict))
+        is3d = int(batch_dict['U'].size(1) == 3)
+        entry = (graph, static, {k: work[k] for k in ('p', 'U', 'density')},
+                 (_masks(batch_dict), _mask_rows(N.load(), batch_dict, batch_dict['flags'], is3d)))
         _graphs[key] = entry
     graph, static, outs, _keepalive = entry
     for k in ('p', 'U', 'flags', 'density'):
@@ -233,14 +235,17 @@ def _mask_rows(lib, batch_dict, flags, is3d):
         return None
     key = tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None
                 for t in (UBC, UBCInv, rBC, rBCInv))
-    hit = _mask_rows_cache.get(flags.device)
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    dev_cache = _mask_rows_cache.setdefault(flags.device, {})
+    hit = dev_cache.get(key)
+    if hit is not None:
+        return hit[0]
     B, D, H, W = N.grid_of(flags)
     rows = torch.empty(B * D * H, dtype=torch.uint8, device=flags.device)
     N.check(lib.fnx_mask_rows(N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), rows.data_ptr(), B, D, H, W,
                               is3d, N.stream_of(flags)), "simulate")
-    _mask_rows_cache[flags.device] = (key, rows, (UBC, UBCInv, rBC, rBCInv))   # keep the tensors alive
+    if len(dev_cache) >= 16:
+        dev_cache.pop(next(iter(dev_cache)))
+    dev_cache[key] = (rows, (UBC, UBCInv, rBC, rBCInv))   # keep the mask tensors alive
     return rows
 
 
