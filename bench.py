@@ -53,6 +53,11 @@ WORKLOADS.update({
     "plume1024_scalenet": dict(res=(1, 1024, 1024), method="convnet", jacobi_iters=0, cpu_sample_res=512,
                                baseline_config="1024x1024 2D plume, MultiScale CNN pressure, fp32"),
 })
+WORKLOADS.update({
+    # BASELINE.json configs[2]: Rayleigh-Taylor (rayleighTaylorConfig.yaml physics, periodic-y seam)
+    "rt1024_scalenet": dict(res=(1, 1024, 1024), method="convnet", jacobi_iters=0, cpu_sample_res=512, case="rt",
+                            baseline_config="1024x1024 2D Rayleigh-Taylor, MultiScale CNN pressure, fp32"),
+})
 DEFAULT_WORKLOAD = "plume512_scalenet"
 CNN_FLOP_PER_CELL = 484476.0   # 2 * 242238 MAC over the 17 convs of the pyramid
 
@@ -63,6 +68,32 @@ def plume_mconf(jacobi_iters, method):
             "gravityScale": 0, "viscosity": 0, "correctScalar": False, "operatingDensity": 0.0,
             "gravityVec": {"x": 0.0, "y": -1.0, "z": 0.0}, "pTol": 0.0, "jacobiIter": jacobi_iters,
             "simMethod": method, "injectionDensity": 0.1, "injectionVelocity": 2, "sourceRadius": 0.145}
+
+
+def rt_mconf(method):
+    """rayleighTaylorConfig.yaml physics (pytorch/rayleighTaylorConfig.yaml, rayleighTaylor.py:158-159)."""
+    return {"dt": 0.5, "maccormackStrength": 0.6, "sampleOutsideFluid": False, "buoyancyScale": 1.0, "gravityScale": 0,
+            "viscosity": 0, "correctScalar": False, "operatingDensity": 0.0,
+            "gravityVec": {"x": 0.0, "y": 1.0, "z": 0.0}, "pTol": 0.0, "jacobiIter": 200, "simMethod": method,
+            "rho1": -0.01, "rho2": 0.01, "perturbThickness": 100, "perturbAmplitude": 0.01, "height": 0.5,
+            "periodic-y": True, "periodic-x": False}
+
+
+def workload_mconf(wl):
+    return rt_mconf(wl["method"]) if wl.get("case") == "rt" else plume_mconf(wl["jacobi_iters"], wl["method"])
+
+
+def init_state(fluid_mod, wl, mconf, bd, U_np, rho_np, to_tensor):
+    """emptyDomain + the driver's initial / boundary conditions on zeroed fields, then the seeded
+    synthetic velocity (plume: also density) -- same recipe for the GPU arm and the CPU reference."""
+    fluid_mod.emptyDomain(bd["flags"])
+    if wl.get("case") == "rt":
+        fluid_mod.createRayleighTaylorBCs(bd, mconf, rho1=mconf["rho1"], rho2=mconf["rho2"])
+        bd["U"] = to_tensor(U_np * 0.1)          # a small seeded perturbation on the quiescent RT state
+        return
+    fluid_mod.createPlumeBCs(bd, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
+    bd["U"] = to_tensor(U_np)
+    bd["density"] = to_tensor(rho_np)
 
 
 def synthetic_state_numpy(D, H, W, seed=0):
@@ -163,7 +194,10 @@ def run_ours_distributed(args):
     lib = _native.load()
     Dz, H, W = wl["res"]
     is3d = Dz > 1
-    mconf = plume_mconf(wl["jacobi_iters"], wl["method"])
+    mconf = workload_mconf(wl)
+    if wl.get("case") == "rt":
+        raise SystemExit("bench.py: the slab-decomposed arm covers the plume workloads (the Rayleigh-Taylor "
+                         "periodic-y seam couples the first and last slab); run rt1024_scalenet with --gpus 1")
     net = None
     if wl["method"] == "convnet":
         from fluidnet_cxx_b200.lib.pretrained import load_scalenet
@@ -182,13 +216,10 @@ def run_ours_distributed(args):
     U_np, rho_np = synthetic_state_numpy(gD, gH, W, seed=0)
     host = {"p": torch.zeros(1, 1, gD, gH, W).pin_memory(), "U": torch.from_numpy(U_np).pin_memory(),
             "flags": torch.zeros(1, 1, gD, gH, W).pin_memory(), "density": torch.from_numpy(rho_np).pin_memory()}
-    bd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-    fluid.emptyDomain(bd["flags"])
-    U0, rho0 = bd["U"], bd["density"]
-    bd["U"], bd["density"] = torch.zeros_like(U0), torch.zeros_like(rho0)
-    fluid.createPlumeBCs(bd, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
-    bd["U"], bd["density"] = U0, rho0
-    host["flags"].copy_(bd["flags"])
+    bd = {k: torch.zeros_like(v, device=dev) for k, v in host.items()}
+    init_state(fluid, wl, mconf, bd, U_np, rho_np, lambda a: torch.from_numpy(a).to(dev))
+    for k in ("flags", "U", "density"):
+        host[k].copy_(bd[k])
     torch.cuda.synchronize()
     D.check_reach(decomp, bd["U"], mconf["dt"])
 
@@ -357,7 +388,7 @@ def run_ours(args):
 
     D, H, W = wl["res"]
     cells = D * H * W
-    mconf = plume_mconf(wl["jacobi_iters"], wl["method"])
+    mconf = workload_mconf(wl)
     nc = 3 if D > 1 else 2
     net = None
     if wl["method"] == "convnet":
@@ -370,13 +401,10 @@ def run_ours(args):
     U_np, rho_np = synthetic_state_numpy(D, H, W, seed=rank)
     host = {"p": torch.zeros(1, 1, D, H, W).pin_memory(), "U": torch.from_numpy(U_np).pin_memory(),
             "flags": torch.zeros(1, 1, D, H, W).pin_memory(), "density": torch.from_numpy(rho_np).pin_memory()}
-    bd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-    fluid.emptyDomain(bd["flags"])
-    U0, rho0 = bd["U"], bd["density"]
-    bd["U"], bd["density"] = torch.zeros_like(U0), torch.zeros_like(rho0)
-    fluid.createPlumeBCs(bd, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
-    bd["U"], bd["density"] = U0, rho0
-    host["flags"].copy_(bd["flags"])
+    bd = {k: torch.zeros_like(v, device=dev) for k, v in host.items()}
+    init_state(fluid, wl, mconf, bd, U_np, rho_np, lambda a: torch.from_numpy(a).to(dev))
+    for k in ("flags", "U", "density"):
+        host[k].copy_(bd[k])
     torch.cuda.synchronize()
 
     working_set = cells * 4 * (1 + nc + 1 + 1 + 2 * nc + 2)   # state + masks
@@ -458,7 +486,7 @@ def run_ours(args):
     h2d = sum(host[k].numel() * 4 for k in ("p", "U", "flags", "density"))
     d2h = sum(host[k].numel() * 4 for k in ("p", "U", "density"))
     out_host = {k: torch.empty_like(host[k]).pin_memory() for k in ("p", "U", "density")}
-    masks = {k: bd[k] for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask")}
+    masks = {k: bd[k] for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask") if k in bd}
 
     def e2e_step():
         d = {k: host[k].to(dev, non_blocking=True) for k in ("p", "U", "flags", "density")}
@@ -583,7 +611,7 @@ def reference_step_runner(wl, res):
     if not ref_loader.available():
         return None
     net = None
-    mconf = plume_mconf(wl["jacobi_iters"], wl["method"])
+    mconf = workload_mconf(wl)
     if wl["method"] == "convnet":
         reflib, net, mconf_net = ref_loader.load_scalenet()
         m = dict(mconf_net); m.update(mconf); mconf = m
@@ -593,10 +621,7 @@ def reference_step_runner(wl, res):
     U_np, rho_np = synthetic_state_numpy(1, res, res, seed=0)
     bd = {"p": torch.zeros(1, 1, 1, res, res), "U": torch.zeros(1, 2, 1, res, res),
           "flags": torch.zeros(1, 1, 1, res, res), "density": torch.zeros(1, 1, 1, res, res)}
-    reflib.fluid.emptyDomain(bd["flags"])
-    reflib.fluid.createPlumeBCs(bd, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
-    bd["U"] = torch.from_numpy(U_np)
-    bd["density"] = torch.from_numpy(rho_np)
+    init_state(reflib.fluid, wl, mconf, bd, U_np, rho_np, torch.from_numpy)
 
     def step():
         with torch.no_grad():

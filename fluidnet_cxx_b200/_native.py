@@ -100,7 +100,7 @@ SIGNATURES = {
     "fnx_profile_enable": (_I, [_I]),
     "fnx_profile_fetch": (_I, [ctypes.POINTER(ProfileRec), _I]),
     "fnx_fluidnet_input": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
-    "fnx_fluidnet_output": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fnx_fluidnet_output": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_cnn_output(const float* __restrict__ pnet, const float* __restrict__ U, const float* __restrict__ flags,
                  const float* __restrict__ scale, float* __restrict__ p_out, float* __restrict__ U_out, int B, int H,
-                 int W) {
+                 int W, int wall_bcs) {
   const size_t n = (size_t)H * W;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (size_t)B * n) return;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256)
       v = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), 0.f);
     }
     v = __fmul_rn(v, s);
-    v = wall_bcs_apply(v, fc, fn);
+    if (wall_bcs) v = wall_bcs_apply(v, fc, fn);
     U_out[(size_t)b * 2 * n + c * n + o] = v;
   }
   p_out[(size_t)b * n + o] = __fmul_rn(P, s);
@@ -279,11 +279,11 @@ int fnx_fluidnet_input(const float* U, const float* flags, const float* scale, f
 }
 
 int fnx_fluidnet_output(const float* p_net, const float* U, const float* flags, const float* scale, float* p_out,
-                        float* U_out, int B, int H, int W, void* stream) {
+                        float* U_out, int B, int H, int W, int apply_wall_bcs, void* stream) {
   if (B < 1 || H < 2 || W < 2) return fnx_set_error(FNX_ERR_ARG, "fluidnet_output: bad shape");
   const size_t total = (size_t)B * H * W;
   k_cnn_output<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p_net, U, flags, scale, p_out, U_out,
-                                                                                 B, H, W);
+                                                                                 B, H, W, apply_wall_bcs);
   fnx_count_launches(1);
   FNX_CUDA_TRY("fluidnet_output", cudaGetLastError());
   return FNX_OK;

@@ -105,9 +105,12 @@ class FluidNet(nn.Module):
         p = torch.empty((B, 1, 1, H, W), dtype=torch.float32, device=U.device)
         U_out = torch.empty_like(U)
         N.check(lib.fnx_fluidnet_output(N.ptr(p_net), N.ptr(U), N.ptr(flags), N.ptr(s), N.ptr(p), N.ptr(U_out),
-                                        B, H, W, st), "FluidNet")
-        if periodic:
-            # the seam is copied from the pre-setWallBcs field: redo the last two steps around it
-            raise NotImplementedError("periodic FluidNet forward: use the reference-layout saved model "
-                                      "with lib.fluid ops (seam handling between update and setWallBcs)")
+                                        B, H, W, 1, st), "FluidNet")
+        if periodic and (self.mconf['periodic-x'] or self.mconf['periodic-y']):
+            # the seam is copied from the field BEFORE setWallBcs (*_saved.py:228-237): same kernel
+            # without the wall pass, only its seam line is used
+            U_temp = torch.empty_like(U)
+            N.check(lib.fnx_fluidnet_output(N.ptr(p_net), N.ptr(U), N.ptr(flags), N.ptr(s), N.ptr(p),
+                                            N.ptr(U_temp), B, H, W, 0, st), "FluidNet")
+            self._seam(self.mconf, U_out, U_temp)
         return p, U_out

@@ -247,9 +247,11 @@ int fnx_profile_fetch(fnx_profile_rec *out, int capacity);
 int fnx_fluidnet_input(const float *U, const float *flags, const float *scale, float *x, int B,
                        int H, int W, void *stream);
 /* post-processing of the wrapper (*_saved.py:221-232): U/scale -> velocityUpdate(p_net) ->
- * *scale -> setWallBcs ; p_out = p_net*scale */
+ * *scale -> [setWallBcs] ; p_out = p_net*scale.  apply_wall_bcs = 0 gives the field the periodic
+ * seam copy of *_saved.py:228-237 reads (the velocity before setWallBcs). */
 int fnx_fluidnet_output(const float *p_net, const float *U, const float *flags, const float *scale,
-                        float *p_out, float *U_out, int B, int H, int W, void *stream);
+                        float *p_out, float *U_out, int B, int H, int W, int apply_wall_bcs,
+                        void *stream);
 
 #ifdef __cplusplus
 }

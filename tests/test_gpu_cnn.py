@@ -273,3 +273,52 @@ def test_graph_replay_equals_direct_launches(net, method):
             sim.simulate(mconf, bd, model, method)
     assert len(sim._graphs) == 1
     sim.clear_graph_cache()
+
+
+@pytest.mark.parametrize("method", ["convnet", "jacobi"])
+def test_rt64_periodic_golden(net, method):
+    """BASELINE.json configs[2] physics at fixture size: Rayleigh-Taylor state (rayleighTaylor.py:140-167,
+    periodic-y seam), 3 steps of the reference's lib.simulate with the ScaleNet / the Jacobi solver
+    (tests/golden/rt64_periodic.npz, written by tests/golden/make_golden_rt.py from oracle/_ref)."""
+    model, mconf_net = net
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from conftest import GOLDEN
+    import os
+    z = np.load(os.path.join(GOLDEN, "rt64_periodic.npz"))
+    mconf = dict(mconf_net)
+    mconf.update({"dt": 0.5, "maccormackStrength": 0.6, "sampleOutsideFluid": False, "buoyancyScale": 1.0,
+                  "gravityScale": 0, "viscosity": 0, "correctScalar": False, "operatingDensity": 0.0,
+                  "gravityVec": {"x": 0.0, "y": 1.0, "z": 0.0}, "pTol": 0.0, "jacobiIter": 34,
+                  "periodic-y": True, "periodic-x": False, "simMethod": method})
+    model.mconf = mconf
+    model.scale.mconf = mconf
+    try:
+        for use_graph in (False, True):
+            sim.clear_graph_cache()
+            bd = {"p": torch.zeros(1, 1, 1, 64, 48, device="cuda"), "U": cu(z[f"{method}/U0"]),
+                  "flags": cu(z[f"{method}/flags"]), "density": cu(z[f"{method}/density0"])}
+            for it in range(1, 4):
+                with torch.no_grad():
+                    if use_graph:
+                        sim.simulate(mconf, bd, model, method)
+                    else:
+                        os.environ["FLUIDNET_B200_GRAPHS"] = "0"
+                        try:
+                            sim.simulate(mconf, bd, model, method)
+                        finally:
+                            os.environ.pop("FLUIDNET_B200_GRAPHS")
+                for k in ("p", "U", "density"):
+                    want = z[f"{method}/step{it}_{k}"]
+                    got = bd[k].cpu().numpy()
+                    if method == "jacobi":
+                        assert np.array_equal(got, want) or n_bad(got, want) == 0, (use_graph, it, k, n_bad(got, want))
+                    else:
+                        assert rel_err(got, want) < 5 * RTOL, (use_graph, it, k, rel_err(got, want))
+    finally:
+        sim.clear_graph_cache()
+        model.mconf = mconf_net
+        model.scale.mconf = mconf_net
+
+
+def n_bad(a, b):
+    return int(np.sum(~((a == b) | (np.isnan(a) & np.isnan(b)))))
