@@ -514,6 +514,16 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
 
 
+def ncu_traffic(kernel_key):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_traffic.json), or None when that kernel / size has not been captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except OSError:
+        return None
+
+
 def make_report(args, wl, world, total_cells, cells, total_ms, e2e_ms, e2e_steps, dom_ms, layer_recs, h2d, d2h, launches,
                 clocks, t_wall, flush, graphed, parallelism, grid):
     """The one JSON line of the contract (rank 0).  cells = cells one GPU computes per step."""
@@ -536,7 +546,9 @@ def make_report(args, wl, world, total_cells, cells, total_ms, e2e_ms, e2e_steps
             achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
             roof = {"bound": "hbm", "kernel": "k_jacobi2d_blocked" if D == 1 else "k_jacobi_iter",
                     "achieved": round(achieved, 1) if achieved else None, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(achieved / hbm_peak, 4) if achieved else None, "traffic": None,
+                    "frac": round(achieved / hbm_peak, 4) if achieved else None,
+                    "traffic": ncu_traffic(f"k_jacobi2d_blocked @{wl['res'][1]}x{wl['res'][2]}") if D == 1 else None,
+                    "algorithmic_bytes_per_launch": 16.0 * cells * 8,
                     "peak_source": peak_src, "stage_ms_per_step": round(dom_ms / args.steps, 4),
                     "step_hbm_frac": round(step_bytes * cells * args.steps / (total_ms / 1e3) / 1e9 / hbm_peak, 4)}
             pressure = f"jacobi x{iters}"
@@ -567,7 +579,8 @@ def make_report(args, wl, world, total_cells, cells, total_ms, e2e_ms, e2e_steps
                 achieved = fl / (ms / n / 1e3) / 1e12
                 roof = {"bound": "tensor", "kernel": f"k_conv_tc (tcgen05 split-fp16 implicit GEMM) {cin}->{cout} k{k} @{h}x{w}",
                         "achieved": round(achieved, 2), "peak": round(tc_peak, 1), "unit": "TFLOP/s",
-                        "frac": round(achieved / tc_peak, 4), "traffic": None, "peak_source": peak_src_tc,
+                        "frac": round(achieved / tc_peak, 4),
+                        "traffic": ncu_traffic(f"k_conv_tc {cin}->{cout} k{k} @{h}x{w}"), "peak_source": peak_src_tc,
                         "launch_ms": round(ms / n, 4), "launches_timed": n, "algorithmic_flop_per_launch": fl,
                         "executed_tensor_tflops": round(3 * achieved, 2),
                         "executed_tensor_frac": round(3 * achieved / tc_peak, 4),
