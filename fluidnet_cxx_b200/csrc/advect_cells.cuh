@@ -9,7 +9,9 @@
 namespace fnx {
 
 // thread -> cell mapping shared by all one-cell-per-thread kernels:
-// x = W (coalesced), y = D*H rows, z = batch
+// threadIdx.x = W (coalesced), threadIdx.y = row; blockIdx.x = linear tile index, column tiles
+// fastest (consecutive blocks touch consecutive memory; D*H row blocks can exceed the 65535 limit
+// of gridDim.y, so rows are not a grid dimension of their own), blockIdx.z = batch
 constexpr int kBX = 64, kBY = 4;
 
 struct CellIdx {
@@ -18,8 +20,10 @@ struct CellIdx {
 };
 
 __device__ __forceinline__ bool cell_of(const Grid& g, CellIdx& c) {
-  c.i = blockIdx.x * blockDim.x + threadIdx.x;
-  int row = g.row0 + blockIdx.y * blockDim.y + threadIdx.y;
+  const unsigned wtiles = (unsigned)(g.W + kBX - 1) / kBX;
+  const unsigned rb = blockIdx.x / wtiles, wt = blockIdx.x - rb * wtiles;
+  c.i = wt * blockDim.x + threadIdx.x;
+  int row = g.row0 + rb * blockDim.y + threadIdx.y;
   c.b = blockIdx.z;
   if (c.i >= g.W || row >= g.row1) return false;
   c.k = row / g.H;
@@ -29,7 +33,7 @@ __device__ __forceinline__ bool cell_of(const Grid& g, CellIdx& c) {
 }
 
 static inline dim3 cell_grid(const Grid& g) {
-  return dim3((g.W + kBX - 1) / kBX, (g.row1 - g.row0 + kBY - 1) / kBY, g.B);
+  return dim3(((g.row1 - g.row0 + kBY - 1) / kBY) * ((g.W + kBX - 1) / kBX), 1, g.B);
 }
 static inline dim3 cell_block() { return dim3(kBX, kBY, 1); }
 
