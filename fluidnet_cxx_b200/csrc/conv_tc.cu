@@ -83,6 +83,10 @@ struct ConvArgs {
   float w_scale, w_norm, b_max;
   int tiles_x, nblocks;
   int R;               // output rows per block (<= the kernel's RMAX template parameter)
+  // out_mode 2: fused 1x1 head (multi_scale_net.py:116 `final`): y[pixel] = sum_c head_w[c]*out[c] + head_b,
+  // one fp32 channel, for layers with Cout <= 16 (the 32->8 5x5 layer feeding the 8->1 conv)
+  const float* head_w;
+  const float* head_b;
 };
 
 constexpr int NEPI = 8;                      // epilogue warps (two per TMEM lane quadrant)
@@ -344,11 +348,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
                 *reinterpret_cast<uint4*>(yh + off) = *reinterpret_cast<const uint4*>(hi);
                 *reinterpret_cast<uint4*>(yh + a.y_plane + off) = *reinterpret_cast<const uint4*>(lo);
               }
-            } else {
+            } else if (a.out_mode == 1) {
               float* yf = reinterpret_cast<float*>(a.y);
 #pragma unroll
               for (int i = 0; i < 16; i++)
-                if (c0 + i < a.Cout) yf[((size_t)(a.y_coff + c0 + i) * a.H + y) * a.W + px] = f[i];
+                if (c0 + i < a.Cout) {
+                  yf[((size_t)(a.y_coff + c0 + i) * a.H + y) * a.W + px] = f[i];
+                  amax = fmaxf(amax, fabsf(f[i]));
+                }
+            } else {  // fused 1x1 head over the (<= 16) channels of this single column group
+              float hsum = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; i++)
+                if (i < a.Cout) hsum = fmaf(__ldg(a.head_w + i), f[i], hsum);
+              hsum += __ldg(a.head_b);
+              reinterpret_cast<float*>(a.y)[(size_t)y * a.W + px] = hsum;
+              amax = fmaxf(amax, fabsf(hsum));
             }
           }
         }
@@ -361,7 +376,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
       if (lane == 0 && amax > 0.f) atomicMax(&a.out_meta->amax_bits, __float_as_uint(amax));
-      if (blockIdx.x == 0 && warp == 2 && lane == 0) a.out_meta->scale = s_out;
+      if (a.out_mode == 0 && blockIdx.x == 0 && warp == 2 && lane == 0) a.out_meta->scale = s_out;
     }
   }
   tc_fence_before();
@@ -398,6 +413,61 @@ __global__ void __launch_bounds__(256)
     lo[i] = __halves2half2(__float2half_rn(u0 - __half2float(h0)), __float2half_rn(u1 - __half2float(h1)));
   }
   const size_t off = (((size_t)j * Hp + (py + PAD)) * Wp + (px + PAD)) * 8;
+  *reinterpret_cast<uint4*>(y + off) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(y + y_plane + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// bilinear sample of F.interpolate(align_corners=False) -- the arithmetic of k_resize_bilinear (conv.cu)
+__device__ __forceinline__ float bilinear_at(const float* __restrict__ p, int H, int W, int Ho, int Wo, int j, int i) {
+  if (Ho == H && Wo == W) return __ldg(p + (size_t)j * W + i);
+  const float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
+  float fy = sh * ((float)j + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  float fx = sw * ((float)i + 0.5f) - 0.5f;
+  fx = fx < 0.f ? 0.f : fx;
+  const int yl = (int)fy, xl = (int)fx;
+  const int yh = yl + (yl < H - 1 ? 1 : 0), xh = xl + (xl < W - 1 ? 1 : 0);
+  const float ly = fy - (float)yl, lx = fx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * __ldg(p + (size_t)yl * W + xl) + lx * __ldg(p + (size_t)yl * W + xh)) +
+         ly * (hx * __ldg(p + (size_t)yh * W + xl) + lx * __ldg(p + (size_t)yh * W + xh));
+}
+
+// Input of one pyramid level, straight into the split chunked layout (16 channels, the unused ones 0):
+//   channels [0, C) = resize(x (C, H, W) -> (h, w)),  channel C = resize(o (1, hc, wc) -> (h, w)) if o
+// (multi_scale_net.py:113,117-125: F.upsample + torch.cat).  Replaces 2 resizes + amax + pack.  The
+// scale comes from max(amax x, amax o): bilinear interpolation never exceeds the range of its source.
+__global__ void __launch_bounds__(256)
+    k_pyramid_input(const float* __restrict__ x, int C, int H, int W, const ActMeta* __restrict__ x_meta,
+                    const float* __restrict__ o, int hc, int wc, const ActMeta* __restrict__ o_meta, int h, int w,
+                    __half* __restrict__ y, size_t y_plane, ActMeta* __restrict__ out_meta) {
+  const int Hp = h + 2 * PAD, Wp = w + 2 * PAD;
+  const size_t npix = (size_t)h * w;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float bound = __uint_as_float(x_meta->amax_bits);
+  if (o) bound = fmaxf(bound, __uint_as_float(o_meta->amax_bits));
+  const float s = pow2_scale_for(bound);
+  if (e == 0) {
+    out_meta->scale = s;
+    out_meta->amax_bits = __float_as_uint(bound);
+  }
+  if (e >= npix) return;
+  const int py = (int)(e / w), px = (int)(e % w);
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    v[c] = 0.f;
+    if (c < C) v[c] = bilinear_at(x + (size_t)c * H * W, H, W, h, w, py, px);
+    else if (c == C && o) v[c] = bilinear_at(o, hc, wc, h, w, py, px);
+  }
+  __align__(16) __half2 hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float u0 = v[2 * i] * s, u1 = v[2 * i + 1] * s;
+    const __half h0 = __float2half_rn(u0), h1 = __float2half_rn(u1);
+    hi[i] = __halves2half2(h0, h1);
+    lo[i] = __halves2half2(__float2half_rn(u0 - __half2float(h0)), __float2half_rn(u1 - __half2float(h1)));
+  }
+  const size_t off = (((size_t)0 * Hp + (py + PAD)) * Wp + (px + PAD)) * 8;   // chunk 0; chunk 1 stays zero
   *reinterpret_cast<uint4*>(y + off) = *reinterpret_cast<const uint4*>(hi);
   *reinterpret_cast<uint4*>(y + y_plane + off) = *reinterpret_cast<const uint4*>(lo);
 }
@@ -578,9 +648,23 @@ int fnx_tc_unpack_split(const void* x, const fnx_act_meta* meta, int C, int H, i
   return FNX_OK;
 }
 
+static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin,
+                          int Cout, int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max,
+                          int out_mode, void* y, fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset,
+                          const float* head_w, const float* head_b, void* stream);
+
 int fnx_conv_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin, int Cout,
                 int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max, int out_mode, void* y,
                 fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset, void* stream) {
+  if (out_mode != 0 && out_mode != 1) return fnx_set_error(FNX_ERR_ARG, "conv_tc: out_mode must be 0 or 1");
+  return conv_tc_launch(x, in_meta, w_packed, bias, Cin, Cout, ksize, H, W, relu, w_scale, w_norm, b_max, out_mode, y,
+                        out_meta, y_channels_total, y_channel_offset, nullptr, nullptr, stream);
+}
+
+static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin,
+                          int Cout, int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max,
+                          int out_mode, void* y, fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset,
+                          const float* head_w, const float* head_b, void* stream) {
   if (!tc_eligible(Cin, Cout, ksize))
     return fnx_set_error(FNX_ERR_ARG, "conv_tc: unsupported layer %d->%d k%d", Cin, Cout, ksize);
   if (H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "conv_tc: bad shape");
@@ -588,7 +672,10 @@ int fnx_conv_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed
     return fnx_set_error(FNX_ERR_ARG, "conv_tc: split output needs out_meta and Cout %% 16 == 0");
   if (out_mode == 1 && y_channels_total < y_channel_offset + Cout)
     return fnx_set_error(FNX_ERR_ARG, "conv_tc: output channel window out of range");
+  if (out_mode == 2 && (Cout > 16 || !head_w || !head_b))
+    return fnx_set_error(FNX_ERR_ARG, "conv_tc: the fused 1x1 head needs Cout <= 16 and its weights");
   ConvArgs a;
+  a.head_w = head_w; a.head_b = head_b;
   a.x = (const __half*)x;
   a.x_plane = act_plane_halves(pad16(Cin), H, W);
   a.w = (const uint8_t*)w_packed;
@@ -693,18 +780,24 @@ struct Runner {
   ActMeta* metas;
   ActMeta* new_meta() { return metas ? metas + (nmeta++ % MAX_META) : (nmeta++, nullptr); }
 
-  // runs one Sequential of convs at resolution (h, w); `in` fp32 NCHW with layers[0].cin channels;
-  // the last layer's output goes to `out` (fp32 NCHW, out_ctotal channels, window at out_coff)
-  int block(const fnx_conv_layer* L, int n, const float* in, int h, int w, float* out, int out_ctotal, int out_coff) {
+  static bool is_tc(const fnx_conv_layer& l) { return l.w_tc && tc_eligible(l.cin, l.cout, l.ksize); }
+
+  // runs one Sequential of convs at resolution (h, w).  Input: `in` fp32 NCHW with layers[0].cin channels,
+  // or (in_split, in_meta) already in the split chunked layout.  The last layer's output goes to `out`
+  // (fp32 NCHW, out_ctotal channels, window at out_coff); `last_meta` (optional) receives its max|.|;
+  // `head` (optional) = a 1x1 conv fused into the last layer's epilogue, `out` is then its 1-channel result.
+  int block(const fnx_conv_layer* L, int n, const float* in, const void* in_split, ActMeta* in_meta, bool split_in,
+            int h, int w, float* out, int out_ctotal, int out_coff, ActMeta* last_meta = nullptr,
+            const fnx_conv_layer* head = nullptr) {
     const float* cur_f32 = in;
-    const void* cur_split = nullptr;
-    bool is_split = false;  // which of the two holds the current tensor (pointers are null in a dry run)
-    ActMeta* cur_meta = nullptr;  // amax valid (and scale, when split)
+    const void* cur_split = in_split;
+    bool is_split = split_in;  // which of the two holds the current tensor (pointers are null in a dry run)
+    ActMeta* cur_meta = in_meta;         // amax valid (and scale, when split)
     for (int i = 0; i < n; i++) {
       const fnx_conv_layer& l = L[i];
       const bool last = i == n - 1;
-      const bool tc_now = l.w_tc && tc_eligible(l.cin, l.cout, l.ksize);
-      const bool tc_next = !last && L[i + 1].w_tc && tc_eligible(L[i + 1].cin, L[i + 1].cout, L[i + 1].ksize);
+      const bool tc_now = is_tc(l);
+      const bool tc_next = !last && is_tc(L[i + 1]);
       if (tc_now) {
         if (!is_split) {
           if (!cur_meta) {
@@ -727,11 +820,15 @@ struct Runner {
           }
           cur_split = sp; cur_meta = m; cur_f32 = nullptr; is_split = true;
         } else {
+          const bool fuse_head = last && head != nullptr;
           float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
           if (!dry) {
             LayerTimer lt(l, h, w, 1, st);
-            int rc = fnx_conv_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu, l.w_scale,
-                                    l.w_norm, l.b_max, 1, o, nullptr, last ? out_ctotal : l.cout, last ? out_coff : 0, st);
+            int rc = conv_tc_launch(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu,
+                                    l.w_scale, l.w_norm, l.b_max, fuse_head ? 2 : 1, o,
+                                    (fnx_act_meta*)(last ? last_meta : nullptr), last ? out_ctotal : l.cout,
+                                    last ? out_coff : 0, fuse_head ? head->weight : nullptr,
+                                    fuse_head ? head->bias : nullptr, st);
             if (rc) return rc;
           }
           cur_f32 = o; cur_split = nullptr; cur_meta = nullptr; is_split = false;
@@ -739,16 +836,32 @@ struct Runner {
       } else {
         if (is_split) return fnx_set_error(FNX_ERR_ARG, "msnet: internal layout mismatch");
         float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
-        ActMeta* m = tc_next ? new_meta() : nullptr;
+        ActMeta* m = tc_next ? new_meta() : (last ? last_meta : nullptr);
         if (!dry) {
           LayerTimer lt(l, h, w, 0, st);
           int rc = fnx_conv_direct(cur_f32, l.weight, l.bias, o, 1, l.cin, h, w, l.cout, l.ksize, l.relu,
                                    last ? out_ctotal : l.cout, last ? out_coff : 0, m ? &m->amax_bits : nullptr, st);
           if (rc) return rc;
         }
-        cur_f32 = o; cur_split = nullptr; cur_meta = m; is_split = false;
+        cur_f32 = o; cur_split = nullptr; cur_meta = tc_next ? m : nullptr; is_split = false;
       }
     }
+    return FNX_OK;
+  }
+
+  // input of one pyramid level in the split chunked layout (k_pyramid_input)
+  int pyramid_input(const float* x, int c, int H, int W, ActMeta* x_meta, const float* o, int hc, int wc, ActMeta* o_meta,
+                    int h, int w, void** split_out, ActMeta** meta_out) {
+    void* sp = ws.take(fnx_tc_act_bytes(16, h, w));
+    ActMeta* m = new_meta();
+    if (!dry) {
+      const size_t npix = (size_t)h * w;
+      k_pyramid_input<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(x, c, H, W, x_meta, o, hc, wc, o_meta, h, w, (__half*)sp,
+                                                                     act_plane_halves(16, h, w), m);
+      fnx_count_launches(1);
+      FNX_CUDA_TRY("msnet", cudaGetLastError());
+    }
+    *split_out = sp; *meta_out = m;
     return FNX_OK;
   }
 
@@ -758,25 +871,45 @@ struct Runner {
     if (h4 < 1 || w4 < 1) return fnx_set_error(FNX_ERR_ARG, "msnet: grid %dx%d too small for the 1/4 scale", H, W);
     metas = (ActMeta*)ws.take(MAX_META * sizeof(ActMeta));
     if (!dry) FNX_CUDA_TRY("msnet", cudaMemsetAsync(metas, 0, MAX_META * sizeof(ActMeta), st));
-    float* x4 = (float*)ws.take((size_t)c * h4 * w4 * 4);
-    float* o4 = (float*)ws.take((size_t)h4 * w4 * 4);
-    float* in2 = (float*)ws.take((size_t)(c + 1) * h2 * w2 * 4);
-    float* o2 = (float*)ws.take((size_t)h2 * w2 * 4);
-    float* in1 = (float*)ws.take((size_t)(c + 1) * H * W * 4);
-    float* o1 = (float*)ws.take((size_t)plan->full[5].cout * H * W * 4);
     int rc;
+    // the 1x1 `final` conv rides in the epilogue of the last full-resolution layer when that one is a
+    // tensor-core layer with <= 16 output channels
+    const fnx_conv_layer& lastf = plan->full[5];
+    const fnx_conv_layer& fin = plan->final_conv;
+    const bool fuse_head = is_tc(lastf) && lastf.cout <= 16 && fin.ksize == 1 && fin.cin == lastf.cout && fin.cout == 1 &&
+                           !fin.relu;
+    float* o4 = (float*)ws.take((size_t)h4 * w4 * 4);
+    float* o2 = (float*)ws.take((size_t)h2 * w2 * 4);
+    float* o1 = fuse_head ? nullptr : (float*)ws.take((size_t)lastf.cout * H * W * 4);
+    if (is_tc(plan->quarter[0]) && is_tc(plan->half[0]) && is_tc(plan->full[0]) && c + 1 <= 8) {
+      // tensor-core plan: every level's input goes straight into the split layout
+      ActMeta *mx = new_meta(), *mo4 = new_meta(), *mo2 = new_meta(), *m;
+      void* sp;
+      if (!dry && (rc = fnx_tc_amax(x, (size_t)c * H * W, (fnx_act_meta*)mx, st))) return rc;
+      if ((rc = pyramid_input(x, c, H, W, mx, nullptr, 0, 0, nullptr, h4, w4, &sp, &m))) return rc;
+      if ((rc = block(plan->quarter, 4, nullptr, sp, m, true, h4, w4, o4, 1, 0, mo4))) return rc;
+      if ((rc = pyramid_input(x, c, H, W, mx, o4, h4, w4, mo4, h2, w2, &sp, &m))) return rc;
+      if ((rc = block(plan->half, 6, nullptr, sp, m, true, h2, w2, o2, 1, 0, mo2))) return rc;
+      if ((rc = pyramid_input(x, c, H, W, mx, o2, h2, w2, mo2, H, W, &sp, &m))) return rc;
+      if (fuse_head) return block(plan->full, 6, nullptr, sp, m, true, H, W, y, 1, 0, nullptr, &fin);
+      if ((rc = block(plan->full, 6, nullptr, sp, m, true, H, W, o1, lastf.cout, 0))) return rc;
+      return block(&fin, 1, o1, nullptr, nullptr, false, H, W, y, 1, 0);
+    }
+    float* x4 = (float*)ws.take((size_t)c * h4 * w4 * 4);
+    float* in2 = (float*)ws.take((size_t)(c + 1) * h2 * w2 * 4);
+    float* in1 = (float*)ws.take((size_t)(c + 1) * H * W * 4);
 #define RUN(expr) do { if (!dry) { rc = (expr); if (rc) return rc; } } while (0)
     RUN(fnx_resize_bilinear(x, x4, 1, c, H, W, h4, w4, c, 0, st));
-    if ((rc = block(plan->quarter, 4, x4, h4, w4, o4, 1, 0))) return rc;
+    if ((rc = block(plan->quarter, 4, x4, nullptr, nullptr, false, h4, w4, o4, 1, 0))) return rc;
     RUN(fnx_resize_bilinear(x, in2, 1, c, H, W, h2, w2, c + 1, 0, st));
     RUN(fnx_resize_bilinear(o4, in2, 1, 1, h4, w4, h2, w2, c + 1, c, st));
-    if ((rc = block(plan->half, 6, in2, h2, w2, o2, 1, 0))) return rc;
+    if ((rc = block(plan->half, 6, in2, nullptr, nullptr, false, h2, w2, o2, 1, 0))) return rc;
     RUN(fnx_resize_bilinear(x, in1, 1, c, H, W, H, W, c + 1, 0, st));
     RUN(fnx_resize_bilinear(o2, in1, 1, 1, h2, w2, H, W, c + 1, c, st));
-    if ((rc = block(plan->full, 6, in1, H, W, o1, plan->full[5].cout, 0))) return rc;
-    if ((rc = block(&plan->final_conv, 1, o1, H, W, y, 1, 0))) return rc;
 #undef RUN
-    return FNX_OK;
+    if (fuse_head) return block(plan->full, 6, in1, nullptr, nullptr, false, H, W, y, 1, 0, nullptr, &fin);
+    if ((rc = block(plan->full, 6, in1, nullptr, nullptr, false, H, W, o1, lastf.cout, 0))) return rc;
+    return block(&fin, 1, o1, nullptr, nullptr, false, H, W, y, 1, 0);
   }
 };
 }  // namespace
