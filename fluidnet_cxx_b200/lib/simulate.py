@@ -200,7 +200,7 @@ def _simulate_graphed(mconf, batch_dict, net, sim_method, dt):
         if _graph_seen.get(key, 0) < 1:
             if len(_graph_seen) > 64:
                 _graph_seen.clear()
-            _graph_seen[key] = 1
+            _graph_seen[key] = _graph_seen.get(key, 0) + 1
             return _simulate_fused(mconf, batch_dict, net, sim_method, dt, False)
         if len(_graphs) >= 8:
             _graphs.clear()
@@ -209,8 +209,13 @@ def _simulate_graphed(mconf, batch_dict, net, sim_method, dt):
         work.update(static)
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(graph):
-            _simulate_fused(mconf, work, net, sim_method, dt, False)
+        try:
+            with torch.cuda.graph(graph):
+                _simulate_fused(mconf, work, net, sim_method, dt, False)
+        except Exception:      # noqa: BLE001 - capture is an optimisation: fall back to direct launches
+            torch.cuda.synchronize()
+            _graph_seen[key] = -(1 << 30)          # do not try again for this configuration
+            return _simulate_fused(mconf, batch_dict, net, sim_method, dt, False)
         is3d = int(batch_dict['U'].size(1) == 3)
         entry = (graph, static, {k: work[k] for k in ('p', 'U', 'density')},
                  (_masks(batch_dict), _mask_rows(N.load(), batch_dict, batch_dict['flags'], is3d)))
