@@ -197,14 +197,31 @@ class CudaLocalOps:
         sim = importlib.import_module(__package__ + ".simulate")
         self.N, self.sim, self.lib = N, sim, N.load()
         self._keep = {}     # per-row mask maps handed to kernels (a captured graph keeps pointing at them)
+        self._pool = {}     # persistent zero-initialised output buffers (see _out)
+
+    def _out(self, name, like, avoid=()):
+        """A global-sized output buffer for `name`.  The kernels write the window rows only and the
+        rows outside must stay finite (they are read as stale halo), so outputs are taken from a small
+        pool of persistent buffers zeroed ONCE, instead of a fresh memset of the whole global array per
+        step (at 8 ranks that memset cost more than the halo exchange).  Never returns a buffer that
+        aliases one of `avoid` (the step's inputs / the previous Jacobi chunk)."""
+        key = (name, tuple(like.shape), like.device)
+        bufs = self._pool.setdefault(key, [])
+        busy = {t.data_ptr() for t in avoid if t is not None}
+        for b in bufs:
+            if b.data_ptr() not in busy:
+                return b
+        b = torch.zeros_like(like)
+        bufs.append(b)
+        return b
 
     def advect_forces_div(self, mconf, dt, bd, want_div, wall_bcs, rows):
         N, sim, lib = self.N, self.sim, self.lib
         import ctypes
         flags, U_in, rho_in = bd['flags'], bd['U'], bd['density']
-        # rows outside the window are never written: keep them finite (they are read as stale halo)
-        U, density = torch.zeros_like(U_in), torch.zeros_like(rho_in)
-        div = torch.zeros_like(flags) if want_div else None
+        # rows outside the window are never written: they stay at the pool's initial zeros
+        U, density = self._out("U", U_in, (U_in,)), self._out("density", rho_in, (rho_in,))
+        div = self._out("div", flags) if want_div else None
         B, D, H, W = N.grid_of(flags)
         is3d = int(U.size(1) == 3)
         UBC, UBCInv, rBC, rBCInv = sim._masks(bd)
@@ -226,7 +243,7 @@ class CudaLocalOps:
     def jacobi(self, flags, div, p_init, iters, rows):
         N, lib = self.N, self.lib
         B, D, H, W = N.grid_of(flags)
-        p = torch.zeros_like(flags)
+        p = self._out("p", flags, (p_init,))
         ws = N.workspaces.get(flags.device, "jacobi", lib.fnx_jacobi_workspace(B, D, H, W, iters))
         N.check(lib.fnx_jacobi_iterate(N.ptr(flags), N.ptr(div), N.ptr(p_init), N.ptr(p), B, D, H, W,
                                        int(D > 1), int(iters), rows[0], rows[1], ws.data_ptr(), ws.numel(),
@@ -246,6 +263,9 @@ class CudaLocalOps:
                                               mrows.data_ptr() if mrows is not None else None, 1, B, D, H, W, is3d,
                                               rows[0], rows[1], N.stream_of(U)), "simulate_distributed")
         return U
+
+    def p_buffer(self, like, current_p):
+        return self._out("p", like, (current_p,))
 
     def set_const(self, x, inv_mask, bc):
         from . import fluid
@@ -324,7 +344,7 @@ def step_phases(mconf, bd, net, sim_method, decomp, ops, bufs):
         scale = _std_finish(decomp, part, decomp.owned(U).numel(), net.mconf['normalizeInputThreshold'])
         # the CNN runs on a compact copy of the window (translation invariant), results go back in place
         p_w, U_w = ops.cnn(net, decomp.window(U), decomp.window(bd['flags']), scale)
-        p = decomp.put_window(torch.zeros_like(bd['flags']), p_w)
+        p = decomp.put_window(ops.p_buffer(bd['flags'], bd.get('p')), p_w)
         U = decomp.put_window(U, U_w)
         if 'UBC' in bd and 'UBCInvMask' in bd:
             ops.set_const(U, bd['UBCInvMask'], bd['UBC'])
@@ -338,7 +358,9 @@ def simulate_distributed(mconf, bd, net, sim_method, decomp, ops=None, bufs=None
     Same state transitions as lib.simulate for the fused configuration (inviscid, density-carrying,
     fixed Jacobi count or the ScaleNet model).  Only the owned rows of the returned state are
     meaningful (decomp.owned / decomp.gather); ghost rows are refreshed by the next call.
-    Returns nothing; bd['p'], bd['U'], bd['density'] are rebound."""
+    Returns nothing; bd['p'], bd['U'], bd['density'] are rebound -- to buffers of `ops`' output pool,
+    which are recycled two steps later: clone what must outlive the next calls (pass the same `ops`
+    every step; a fresh one allocates a fresh pool)."""
     ops = ops or CudaLocalOps()
     for comm in step_phases(mconf, bd, net, sim_method, decomp, ops, {} if bufs is None else bufs):
         comm()

@@ -74,6 +74,9 @@ class OracleOps:
         out[:, :, :, rows[0]:rows[1]] = new[:, :, :, rows[0]:rows[1]]
         return out
 
+    def p_buffer(self, like, current_p):
+        return torch.zeros_like(like)
+
     def advect_forces_div(self, mconf, dt, bd, want_div, wall_bcs, rows):
         o = self.o
         f, U0, r0 = self._np(bd["flags"]), self._np(bd["U"]), self._np(bd["density"])

@@ -69,13 +69,13 @@ def locked_ops():
         return call
     for name in ("advect_forces_div", "jacobi", "project", "set_const", "cnn"):
         setattr(LockedOps, name, wrap(name))
-    return LockedOps()
+    return LockedOps      # one instance per virtual rank: each rank owns its pool of output buffers
 
 
 def run_virtual(world, ghost, mconf, state, net, method, steps):
     from fluidnet_cxx_b200.lib.distributed import SlabDecomposition, simulate_distributed
     comm = ThreadComm(world)
-    ops = locked_ops()
+    ops_cls = locked_ops()
     H = state["flags"].shape[3]
     results, errors = [None] * world, []
 
@@ -83,6 +83,7 @@ def run_virtual(world, ghost, mconf, state, net, method, steps):
         try:
             torch.cuda.set_device(0)
             dec = SlabDecomposition(H, ghost, rank=rank, world=world, comm=comm)
+            ops = ops_cls()
             bd = {k: dec.scatter(v) for k, v in state.items()}
             outs = []
             with torch.no_grad():
