@@ -207,8 +207,12 @@ def run_ours_distributed(args):
     ghost = D.GHOST_CONVNET if wl["method"] == "convnet" else D.GHOST_JACOBI
     axis = 2 if is3d else 3
     rows_owned = Dz if is3d else H
-    ghost = min(ghost, rows_owned)
-    gD, gH = (Dz * world, H) if is3d else (1, H * world)
+    if args.scaling == "strong":
+        if rows_owned % world:
+            raise SystemExit(f"bench.py: {rows_owned} rows do not split over {world} GPUs")
+        rows_owned //= world
+    ghost = min(ghost, rows_owned // 4 * 4)
+    gD, gH = (rows_owned * world, H) if is3d else (1, rows_owned * world)
     decomp = D.SlabDecomposition(rows_owned * world, ghost, axis=axis)
     cells_global = gD * gH * W
 
@@ -358,6 +362,7 @@ def run_ours_distributed(args):
                                        f"send/recv, global grid {gD}x{gH}x{W}"),
                           grid=[gD, gH, W])
         out["cpu_baseline"] = None
+        out["scaling"] = args.scaling
         if graph_check is not None:
             out["config"]["graph_vs_direct_max_abs_diff"] = graph_check
         print(json.dumps(out), flush=True)
@@ -711,6 +716,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N slabs of the workload grid stacked along H/D (default); "
+                         "strong = the workload grid itself split into N slabs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
