@@ -561,6 +561,10 @@ static int choose_rows(const ConvArgs& a) {
   // per tap: MMA1 (N = 2*COUT) + MMA2 (N = COUT); each max(tensor floor N/2, operand read / 128 B per clk)
   const double t_tap = fmax((double)COUT, 32.0 + COUT / 2.0) + fmax(COUT / 2.0, 32.0 + COUT / 4.0);
   const double l2_bytes_per_clk = 24.0;
+  if (const char* e = getenv("FNX_TC_ROWS")) {  // tuning override: force R (clamped to the kernel's capacity)
+    const int r = atoi(e);
+    if (r >= 1) return r < RMAX ? r : RMAX;
+  }
   int best = 1;
   double best_t = 1e300;
   for (int r = 1; r <= RMAX; r++) {
