@@ -220,7 +220,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
     // committed to the epilogue one tile at a time, so the epilogue of one tile overlaps the MMAs of
     // the next) or when the weights are resident; otherwise ky-major, which releases weight slots
     // progressively.  The first chunk re-acquires tile r from the epilogue just before touching it.
-    const bool leader = lane == 0;
     int as = 0, aph = 0, ws = 0, wph = 0, it = 0;
     for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, it++) {
       for (int c = 0; c < nchunks; c++) {
@@ -248,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
               mbar_wait(ACC_EMPTY(r), (it & 1) ^ 1);
               tc_fence_after();
             }
-            if (leader) {
+            if (elect_one()) {
 #pragma unroll
               for (int ky = 0; ky < KS; ky++)
 #pragma unroll
@@ -264,7 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
           if (!resident) {
 #pragma unroll
             for (int ky = 0; ky < KS; ky++) {
-              if (leader) mma_commit(W_EMPTY(ws));
+              if (elect_one()) mma_commit(W_EMPTY(ws));
               if (++ws == WS) { ws = 0; wph ^= 1; }
             }
           }
@@ -280,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
                 mbar_wait(ACC_EMPTY(r), (it & 1) ^ 1);
                 tc_fence_after();
               }
-              if (leader) {
+              if (elect_one()) {
 #pragma unroll
                 for (int kx = 0; kx < KS; kx++) {
                   const uint32_t aoff = (uint32_t)(((r + ky) * C::RP + kx) * 16) >> 4;
@@ -290,12 +289,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
               }
               __syncwarp();
             }
-            if (leader) mma_commit(W_EMPTY(ws));
+            if (elect_one()) mma_commit(W_EMPTY(ws));
             __syncwarp();
             if (++ws == WS) { ws = 0; wph ^= 1; }
           }
         }
-        if (leader) mma_commit(A_EMPTY(as));
+        if (elect_one()) mma_commit(A_EMPTY(as));
         __syncwarp();
         if (++as == 2) { as = 0; aph ^= 1; }
       }

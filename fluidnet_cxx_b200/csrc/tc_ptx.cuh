@@ -13,6 +13,18 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp (elect.sync): the form the compiler recognises as "exactly one thread",
+// so tcgen05 instructions under it are issued from uniform registers without a per-lane loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------
 // wait: block until every grid this one depends on has completed and its writes are visible (a no-op
 // when the kernel was launched without the programmatic attribute); launch_dependents: let the
