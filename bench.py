@@ -215,6 +215,27 @@ def run_ours_distributed(args):
     gD, gH = (rows_owned * world, H) if is3d else (1, rows_owned * world)
     decomp = D.SlabDecomposition(rows_owned * world, ghost, axis=axis)
     cells_global = gD * gH * W
+    transport = "nccl"
+    if args.transport in ("auto", "peer"):
+        # probe the peer-memory path on every rank (symmetric allocation + rendezvous); all ranks agree
+        ok = 1.0
+        try:
+            decomp.transport = "peer"
+            decomp.peer = D.PeerMemoryTransport(decomp)
+            decomp.peer.region("probe", 64, torch.float32, dev)
+            torch.cuda.synchronize()
+        except Exception as e:      # noqa: BLE001
+            ok = 0.0
+            if rank == 0:
+                print(f"[bench] peer-memory transport unavailable ({e!r}); using NCCL send/recv", file=sys.stderr)
+        t_ok = torch.tensor([ok], device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if t_ok.item() >= 1.0:
+            transport = "peer"
+        else:
+            decomp.transport, decomp.peer = "nccl", None
+            if args.transport == "peer":
+                raise SystemExit("bench.py: --transport peer requested but peer memory could not be set up")
 
     # the same seeded global state on every rank (pinned host), window rows copied in
     U_np, rho_np = synthetic_state_numpy(gD, gH, W, seed=0)
@@ -358,8 +379,10 @@ def run_ours_distributed(args):
         out = make_report(args, wl, world, cells_global, window_cells, total_ms, e2e_ms, e2e_steps, dom_ms, layer_recs,
                           h2d_all, d2h_all, launches_all, clocks, t_wall, flush, graphed,
                           parallelism=(f"{world} GPUs: slab decomposition along {'D' if is3d else 'H'} "
-                                       f"({rows_owned} owned + {ghost} ghost rows per interior side), NCCL halo "
-                                       f"send/recv, global grid {gD}x{gH}x{W}"),
+                                       f"({rows_owned} owned + {ghost} ghost rows per interior side), halo exchange by "
+                                       + ("stores into the neighbours' inboxes over NVLink peer memory"
+                                          if transport == "peer" else "NCCL send/recv")
+                                       + f", global grid {gD}x{gH}x{W}"),
                           grid=[gD, gH, W])
         out["cpu_baseline"] = None
         out["scaling"] = args.scaling
@@ -716,6 +739,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1 halo exchange: peer = stores into the neighbour's inbox over NVLink peer memory "
+                         "(whole step in one CUDA graph), nccl = batched send/recv; auto = peer when it can be set up")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N slabs of the workload grid stacked along H/D (default); "
                          "strong = the workload grid itself split into N slabs")
