@@ -74,6 +74,8 @@ SIGNATURES = {
     "fnx_set_wall_bcs": (_I, [_P, _P] + _GRID + [_P]),
     "fnx_add_buoyancy": (_I, [_P, _P, _P, ctypes.POINTER(_F), _F, _F] + _GRID + [_P]),
     "fnx_add_gravity": (_I, [_P, _P, ctypes.POINTER(_F), _F] + _GRID + [_P]),
+    "fnx_add_viscosity": (_I, [_P, _P, ctypes.c_double, ctypes.c_double, _I, _I, _I, _P, _S, _P]),
+    "fnx_correct_scalar": (_I, [_P, _P, _P, ctypes.c_double, _S, _P]),
     "fnx_flags_to_occupancy": (_I, [_P, _P, _S, _P]),
     "fnx_set_const_vals": (_I, [_P, _P, _P, _S, _P]),
     "fnx_empty_domain": (_I, [_P] + _GRID + [_I, _P]),

@@ -114,6 +114,44 @@ __global__ void __launch_bounds__(kBX* kBY)
   }
 }
 
+// viscosity.py:7-70 addViscosity (2-D; the reference's 3-D branch uses an undefined mask): interior
+// component c = mask_c * (u + s*((((u_E + u_N) + u_W) + u_SW) - 4u)), mask_c = cell and its lower
+// neighbour along c are Fluid; u_SW = U(i-1, j-1) as written at :68.  Reads `Uin`, writes `Uout`
+// (the reference evaluates the whole right-hand side before assigning).
+__global__ void __launch_bounds__(kBX* kBY)
+    k_add_viscosity(Grid g, const float* __restrict__ Uin, float* __restrict__ Uout, const float* __restrict__ flags,
+                    float s) {
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  flags += c.b * g.n; Uin += (long long)c.b * 2 * g.n; Uout += (long long)c.b * 2 * g.n;
+  if (is_border<false>(g, c.k, c.j, c.i)) {
+#pragma unroll
+    for (int a = 0; a < 2; a++) Uout[a * g.n + c.o] = __ldg(Uin + a * g.n + c.o);
+    return;
+  }
+  const bool fl = __ldg(flags + c.o) == kFluid;
+  const float m[2] = {(fl && __ldg(flags + c.o - 1) == kFluid) ? 1.f : 0.f,
+                      (fl && __ldg(flags + c.o - g.sy) == kFluid) ? 1.f : 0.f};
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    const float* q = Uin + a * g.n + c.o;
+    const float lap = (((__ldg(q + 1) + __ldg(q + g.sy)) + __ldg(q - 1)) + __ldg(q - g.sy - 1)) - (4.f * __ldg(q));
+    Uout[a * g.n + c.o] = m[a] * (__ldg(q) + s * lap);
+  }
+}
+
+// advection.py:9-12 correctScalar: src += (t*src)*div on Fluid cells, t = (float)(dt*0.5)
+__global__ void __launch_bounds__(256)
+    k_correct_scalar(float* __restrict__ src, const float* __restrict__ div, const float* __restrict__ flags, float t,
+                     size_t count) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  if (__ldg(flags + q) == kFluid) {
+    const float v = src[q];
+    src[q] = v + (t * v) * __ldg(div + q);
+  }
+}
+
 template <bool Z>
 __global__ void __launch_bounds__(kBX* kBY)
     k_set_wall_bcs(Grid g, float* __restrict__ U, const float* __restrict__ flags) {
@@ -439,6 +477,29 @@ int fnx_add_gravity(float* U, const float* flags, const float* gravity3, float d
   float3 f = make_float3(gravity3[0] * dt, gravity3[1] * dt, gravity3[2] * dt);
   FNX_DISPATCH_3D(is3d, k_add_gravity, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, U, flags, f));
   FNX_LAUNCH_CHECK("add_gravity", 1);
+  return FNX_OK;
+}
+
+int fnx_add_viscosity(float* U, const float* flags, double dt, double viscosity, int B, int H, int W, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (int e = check_grid(B, 1, H, W, 0, "add_viscosity")) return e;
+  const size_t bytes = (size_t)B * 2 * H * W * sizeof(float);
+  if (!workspace || workspace_bytes < bytes) return fnx_set_error(FNX_ERR_WORKSPACE, "add_viscosity: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  // out of place into the workspace (every term is the pre-update field), then back
+  Grid g = make_grid(B, 1, H, W);
+  k_add_viscosity<<<cell_grid(g), cell_block(), 0, st>>>(g, U, (float*)workspace, flags, (float)(dt * viscosity));
+  FNX_LAUNCH_CHECK("add_viscosity", 1);
+  cudaError_t ce = cudaMemcpyAsync(U, workspace, bytes, cudaMemcpyDeviceToDevice, st);
+  if (ce != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "add_viscosity: %s", cudaGetErrorString(ce));
+  return FNX_OK;
+}
+
+int fnx_correct_scalar(float* src, const float* div, const float* flags, double dt, size_t count, void* stream) {
+  if (count == 0) return FNX_OK;
+  k_correct_scalar<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, div, flags, (float)(dt * 0.5),
+                                                                                   count);
+  FNX_LAUNCH_CHECK("correct_scalar", 1);
   return FNX_OK;
 }
 

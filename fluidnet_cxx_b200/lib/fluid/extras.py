@@ -1,8 +1,8 @@
 """Members of the reference surface that are OFF the plume / Rayleigh-Taylor path
 (`viscosity: 0`, no `flags_stick`; partly broken upstream).  They are kept
 importable because `lib.fluid` exports them (pytorch/lib/fluid/__init__.py:4,9,10); the
-geometry helpers are setup-time torch code, the two solver variants are explicit
-"not on the B200 path yet" errors rather than silent fallbacks."""
+geometry helpers are setup-time torch code; setWallBcsStick is an explicit "not on the B200 path"
+error rather than a silent fallback (the reference version cannot run either)."""
 import torch
 
 from .cell_type import CellType
@@ -11,10 +11,6 @@ from .cell_type import CellType
 def setWallBcsStick(U, flags, flags_stick):
     raise NotImplementedError("setWallBcsStick (set_wall_bcs_stick.py) is outside the B200 hot path "
                               "(the reference version raises NameError at :62)")
-
-
-def addViscosity(dt, orig, flags, viscosity):
-    raise NotImplementedError("addViscosity (viscosity.py:7-70) is outside the B200 hot path; run with viscosity: 0")
 
 
 def createCylinder(batch_dict, centerX, centerY, radius):

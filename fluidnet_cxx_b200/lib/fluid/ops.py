@@ -141,9 +141,29 @@ def _check_advection_method(method):
 
 
 def correctScalar(dt, src, div, flags):
-    """src += dt*0.5*src*div on fluid cells (advection.py:9-12); rarely used (mconf['correctScalar'])."""
-    maskFluid = flags.eq(1)
-    src.copy_(torch.where(maskFluid, src + dt * 0.5 * src * div, src))
+    """src += dt*0.5*src*div on fluid cells, in place (advection.py:9-12; mconf['correctScalar'])."""
+    assert src.is_same_size(div) and src.is_same_size(flags), "Size mismatch"
+    N.check(N.load().fnx_correct_scalar(N.ptr(src), N.ptr(div), N.ptr(flags), float(dt), src.numel(), N.stream_of(src)),
+            "correctScalar")
+
+
+def addViscosity(dt, U, flags, viscosity):
+    """Explicit viscous update of the velocity, in place (viscosity.py:7-70; 2-D, as the reference)."""
+    assert U.dim() == 5 and flags.dim() == 5, "Dimension mismatch"
+    assert flags.size(1) == 1, "flags is not scalar"
+    b, d, h, w = (int(flags.size(i)) for i in (0, 2, 3, 4))
+    is3D = (U.size(1) == 3)
+    if not is3D:
+        assert d == 1, "d > 1 for a 2D domain"
+        assert U.size(4) == w, "2D velocity field must have only 2 channels"
+    assert U.size(0) == b and U.size(2) == d and U.size(3) == h and U.size(4) == w, "size mismatch"
+    assert U.is_contiguous() and flags.is_contiguous(), "Input is not contiguous"
+    if is3D:
+        raise NameError("name 'mask_fluid_k' is not defined")      # viscosity.py:50: the 3-D branch never ran
+    lib = N.load()
+    ws = N.workspaces.get(U.device, "viscosity", U.numel() * 4)
+    N.check(lib.fnx_add_viscosity(N.ptr(U), N.ptr(flags), float(dt), float(viscosity), b, h, w, ws.data_ptr(),
+                                  ws.numel(), N.stream_of(U)), "addViscosity")
 
 
 def advectScalar(dt, src, U, flags, method='maccormackFluidNet', boundary_width=1,

@@ -100,6 +100,13 @@ int fnx_add_buoyancy(float *U, const float *flags, const float *density, const f
 /* source_terms.py:122-219 : in place */
 int fnx_add_gravity(float *U, const float *flags, const float *gravity3, float dt, int B, int D,
                     int H, int W, int is3d, void *stream);
+/* viscosity.py:7-70 addViscosity (2-D): in place on U (B,2,1,H,W); workspace >= B*2*H*W floats.
+ * dt and viscosity are the Python floats of the call: their product is formed in double, as there. */
+int fnx_add_viscosity(float *U, const float *flags, double dt, double viscosity, int B, int H, int W,
+                      void *workspace, size_t workspace_bytes, void *stream);
+/* advection.py:9-12 correctScalar: src += dt*0.5*src*div on Fluid cells, in place */
+int fnx_correct_scalar(float *src, const float *div, const float *flags, double dt, size_t count,
+                       void *stream);
 /* flags_to_occupancy.py:6-19 */
 int fnx_flags_to_occupancy(const float *flags, float *occupancy, size_t count, void *stream);
 /* simulate.py:4-26 setConstVals : x = x*inv_mask + bc, in place */

@@ -567,6 +567,43 @@ void orc_add_gravity(float *U, const float *flags, const float gravity[3], float
   }
 }
 
+/* viscosity.py:7-70 addViscosity (2-D only; the 3-D branch of the reference references an undefined
+   mask).  In place on the interior; every right-hand side term is read from the field BEFORE the
+   update (the reference evaluates the whole expression, then assigns).  Component c is kept only
+   where the cell and its lower neighbour along c are both Fluid, else it becomes 0.  The fourth
+   neighbour term is U(i-1, j-1) as written at :68 (not U(i, j-1)).  s = (float)(dt * viscosity) with
+   the product formed in double (two Python floats). */
+void orc_add_viscosity(float *U, const float *flags, double dt, double viscosity, int B, int H, int W) {
+  size_t n = (size_t)H * W;
+  float s = (float)(dt * viscosity);
+  float *old = (float *)malloc(2 * n * sizeof(float));
+  for (int b = 0; b < B; b++) {
+    float *u = U + (size_t)b * 2 * n;
+    const float *f = flags + (size_t)b * n;
+    memcpy(old, u, 2 * n * sizeof(float));
+    for (int j = 1; j < H - 1; j++)
+      for (int i = 1; i < W - 1; i++) {
+        size_t o = (size_t)j * W + i;
+        int fl = f[o] == TYPE_FLUID;
+        float m[2] = {(fl && f[o - 1] == TYPE_FLUID) ? 1.f : 0.f, (fl && f[o - W] == TYPE_FLUID) ? 1.f : 0.f};
+        for (int c = 0; c < 2; c++) {
+          const float *q = old + c * n;
+          float lap = (((q[o + 1] + q[o + W]) + q[o - 1]) + q[o - W - 1]) - (4.f * q[o]);
+          u[c * n + o] = m[c] * (q[o] + s * lap);
+        }
+      }
+  }
+  free(old);
+}
+
+/* advection.py:9-12 correctScalar: src += dt*0.5*src*div on Fluid cells, in place;
+   t = (float)(dt*0.5) (double product), then ((t*src)*div) in fp32 */
+void orc_correct_scalar(float *src, const float *div, const float *flags, double dt, size_t count) {
+  float t = (float)(dt * 0.5);
+  for (size_t q = 0; q < count; q++)
+    if (flags[q] == TYPE_FLUID) src[q] = src[q] + (t * src[q]) * div[q];
+}
+
 /* set_wall_bcs.py:4-86 (Q13) */
 void orc_set_wall_bcs(float *U, const float *flags, int B, int D, int H, int W, int is3d) {
   grid_t g = {B, D, H, W, is3d};

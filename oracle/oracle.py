@@ -104,6 +104,25 @@ def addGravity(U, flags, gravity, dt):
     return U
 
 
+def addViscosity(dt, U, flags, viscosity):
+    """viscosity.py:7-70 (2-D); returns the updated copy (the reference works in place)."""
+    B, D, H, W = _dims(flags)
+    assert D == 1 and U.shape[1] == 2, "addViscosity: the reference only works in 2-D"
+    U = np.array(U, dtype=np.float32, order="C", copy=True)
+    flags, pf = _c(flags)
+    lib().orc_add_viscosity(U.ctypes.data_as(_f32p), pf, ctypes.c_double(dt), ctypes.c_double(viscosity), B, H, W)
+    return U
+
+
+def correctScalar(dt, src, div, flags):
+    """advection.py:9-12; returns the updated copy (the reference works in place)."""
+    src = np.array(src, dtype=np.float32, order="C", copy=True)
+    div, pd = _c(div)
+    flags, pf = _c(flags)
+    lib().orc_correct_scalar(src.ctypes.data_as(_f32p), pd, pf, ctypes.c_double(dt), ctypes.c_size_t(src.size))
+    return src
+
+
 def setWallBcs(U, flags):
     B, D, H, W = _dims(flags)
     is3d = int(U.shape[1] == 3)

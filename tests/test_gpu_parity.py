@@ -324,3 +324,29 @@ def test_full_size_properties(fluid):
         assert torch.equal(bd[k], bd2[k]), k
     assert torch.equal(bd["flags"], flags0)
     assert torch.isfinite(bd["U"]).all() and torch.isfinite(bd["p"]).all()
+
+
+def test_viscosity_and_correct_scalar_golden():
+    """fnx_add_viscosity / fnx_correct_scalar and the viscous, scalar-corrected branch of lib.simulate
+    (simulate.py:67-69,79-81) against the reference's outputs, bit for bit."""
+    import os
+    from conftest import GOLDEN
+    from fluidnet_cxx_b200.lib import fluid, simulate
+    z = np.load(os.path.join(GOLDEN, "extras_2d.npz"))
+    for name in ("a", "b"):
+        f, U, rho = cu(z[f"{name}/flags"]), z[f"{name}/U"], z[f"{name}/rho"]
+        for visc in (0.05, 1.3):
+            Uv = cu(U)
+            fluid.addViscosity(0.1, Uv, f, visc)
+            assert n_mismatch(Uv.cpu().numpy(), z[f"{name}/visc_{visc}"]) == 0, (name, visc)
+        r = cu(rho)
+        fluid.correctScalar(0.1, r, cu(z[f"{name}/div"]), f)
+        assert n_mismatch(r.cpu().numpy(), z[f"{name}/corrected"]) == 0, name
+    mconf = plume_mconf(simMethod="jacobi", jacobiIter=12, viscosity=0.2, correctScalar=True)
+    bd = {"p": torch.zeros(1, 1, 1, 48, 48, device="cuda")}
+    for k in ("U", "density", "flags", "UBC", "UBCInvMask", "densityBC", "densityBCInvMask"):
+        bd[k] = cu(z[f"sim/{k}0"])
+    for it in range(1, 3):
+        simulate(mconf, bd, None, "jacobi")
+        for k in ("p", "U", "density"):
+            assert n_mismatch(bd[k].cpu().numpy(), z[f"sim/step{it}_{k}"]) == 0, (it, k)
