@@ -122,3 +122,34 @@ def test_msnet_workspace_is_host_only(lib):
     # 512^2: split activations 32+64+128+64 channels x 4 B x (516^2) at full res dominate
     assert big > (32 + 64 + 128 + 64) * 4 * 516 * 516
     assert lib.fnx_msnet_workspace(ctypes.byref(plan), 3, 3) == 0
+
+
+def test_manta_file_roundtrip_and_reference_reader(tmp_path):
+    """lib.load_manta_data.loadMantaFile reads the Mantaflow .bin layout exactly like the reference's
+    struct.unpack reader (pytorch/lib/load_manta_data.py:4-41, re-stated here byte by byte)."""
+    import struct
+    import numpy as np
+    from fluidnet_cxx_b200.lib.load_manta_data import loadMantaFile, saveMantaFile
+    for is3d, (nz, ny, nx) in ((False, (1, 7, 5)), (True, (3, 4, 6))):
+        rng = np.random.RandomState(nz)
+        n = nz * ny * nx
+        p = torch.from_numpy(rng.randn(1, 1, nz, ny, nx).astype(np.float32))
+        U = torch.from_numpy(rng.randn(1, 3 if is3d else 2, nz, ny, nx).astype(np.float32))
+        flags = torch.from_numpy(rng.choice([1, 2, 4], size=(1, 1, nz, ny, nx)).astype(np.float32))
+        rho = torch.from_numpy(rng.rand(1, 1, nz, ny, nx).astype(np.float32))
+        path = str(tmp_path / f"f{int(is3d)}.bin")
+        saveMantaFile(path, p, U, flags, rho)
+        # the reference reader, field by field
+        with open(path, "rb") as f:
+            head = struct.unpack("i" * 5, f.read(20))
+            assert head[1:] == (nx, ny, nz, int(is3d))
+            arr = struct.unpack("f" * 3 * n, f.read(12 * n))
+            assert np.array_equal(np.float32(arr[:n]), U[0, 0].numpy().ravel())
+            assert np.array_equal(np.float32(arr[2 * n:]), p.numpy().ravel())
+        p2, U2, f2, r2, is3d2 = loadMantaFile(path)
+        assert is3d2 == is3d and U2.shape == U.shape and f2.dtype == torch.float32
+        assert torch.equal(p2, p) and torch.equal(U2, U) and torch.equal(f2, flags) and torch.equal(r2, rho)
+    with open(str(tmp_path / "bad.bin"), "wb") as f:
+        f.write(struct.pack("i" * 5, 0, 4, 4, 1, 0) + b"\0" * 10)
+    with pytest.raises(AssertionError):
+        loadMantaFile(str(tmp_path / "bad.bin"))
