@@ -214,7 +214,7 @@ def test_conv_tc_chain(oracle):
     assert rel_err(y[2:34], ref) < RTOL
 
 
-@pytest.mark.parametrize("hw", [(128, 128), (200, 136), (64, 64)])
+@pytest.mark.parametrize("hw", [(128, 128), (200, 136), (64, 64), (512, 512)])
 def test_msnet_tensor_vs_direct(net, hw):
     """whole MultiScaleNet: tensor-core plan against the all-fp32-direct plan on the same input."""
     model, _ = net
@@ -322,3 +322,24 @@ def test_rt64_periodic_golden(net, method):
 
 def n_bad(a, b):
     return int(np.sum(~((a == b) | (np.isnan(a) & np.isnan(b)))))
+
+
+def test_conv_tc_power_of_two_scaling_is_exact():
+    """Full-size property of the split-fp16 scheme (BASELINE configs[1] layer shape, 64->128 at 512x512):
+    scaling the input by 2^k moves the measured max, hence the activation scale, by exactly 2^k, so every
+    fp16 mantissa, every MMA product and every accumulation is the same: conv(2^k x) == 2^k conv(x) bit
+    for bit (zero bias), for k up and down the exponent range -- the range management never rounds."""
+    from fluidnet_cxx_b200 import _native as N
+    lib = N.load()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(64, 512, 512, device="cuda", generator=g)
+    w = torch.randn(128, 64, 3, 3, device="cuda", generator=g) / 24.0
+    b = torch.zeros(128, device="cuda")
+    base = _tc_conv(lib, N, x, w, b, 0, 1)[2:130]
+    assert float(base.abs().max()) > 0
+    for k in (-20, -3, 7, 30):
+        y = _tc_conv(lib, N, x * (2.0 ** k), w, b, 0, 1)[2:130]
+        assert torch.equal(y, base * (2.0 ** k)), k
+    # and the result is invariant to where the tile grid falls: a shifted crop gives the same pixels
+    crop = _tc_conv(lib, N, x[:, 100:360, 37:300].contiguous(), w, b, 0, 1)[2:130]
+    assert torch.equal(crop[:, 1:-1, 1:-1], base[:, 101:359, 38:299])
