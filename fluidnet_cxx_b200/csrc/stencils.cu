@@ -307,6 +307,110 @@ __global__ void __launch_bounds__(kBX* kBY)
   }
 }
 
+// ---- 3-D fixed-count path: neighbour masks precomputed once per solve, 4 cells per thread --------
+// The flags never change during a solve: one byte per cell replaces the 7 fp32 flag loads of every
+// iteration.  bit0 = p is pinned to 0 (border ring or Obstacle), bits 1..6 = the -x, +x, -y, +y, -z,
+// +z neighbour is an Obstacle (Neumann: it contributes the centre value, fluids_init.cpp:895-943).
+__global__ void __launch_bounds__(256)
+    k_jacobi3d_mask(Grid g, const float* __restrict__ flags, unsigned char* __restrict__ mask) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)g.B * g.n) return;
+  const long long o = q % g.n;
+  const int i = (int)(o % g.W), j = (int)((o / g.W) % g.H), k = (int)(o / g.sz);
+  const float* f = flags + (q - o);
+  unsigned m = 0;
+  if (is_border<true>(g, k, j, i) || __ldg(f + o) == kObstacle) {
+    m = 1;
+  } else {
+    m |= (__ldg(f + o - 1) == kObstacle) << 1;
+    m |= (__ldg(f + o + 1) == kObstacle) << 2;
+    m |= (__ldg(f + o - g.sy) == kObstacle) << 3;
+    m |= (__ldg(f + o + g.sy) == kObstacle) << 4;
+    m |= (__ldg(f + o - g.sz) == kObstacle) << 5;
+    m |= (__ldg(f + o + g.sz) == kObstacle) << 6;
+  }
+  mask[q] = (unsigned char)m;
+}
+
+// one iteration, a thread owns 4 consecutive x cells (W % 4 == 0): float4 loads of the centre row and of
+// the four y / z neighbour rows, two scalar loads for the x neighbours of the group's ends.  Per-cell
+// arithmetic = k_jacobi_iter<true>: ((((p1+p2)+p3)+p4)+p5)+p6, + div, / 6.
+template <bool FIRST, bool RESID>
+__global__ void __launch_bounds__(256)
+    k_jacobi3d_vec(Grid g, const unsigned char* __restrict__ mask, const float* __restrict__ div,
+                   const float* __restrict__ prev, float* __restrict__ cur, double* __restrict__ ssq) {
+  const int w4 = g.W >> 2;
+  const long long groups_per_batch = (long long)(g.row1 - g.row0) * w4;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  float d2 = 0.f;
+  if (t < groups_per_batch) {
+    const int row = g.row0 + (int)(t / w4), i0 = (int)(t % w4) * 4;
+    const long long o = (long long)row * g.W + i0;
+    mask += (long long)b * g.n; div += (long long)b * g.n; cur += (long long)b * g.n;
+    if (!FIRST) prev += (long long)b * g.n;
+    const uchar4 m4 = *reinterpret_cast<const uchar4*>(mask + o);
+    const unsigned mm[4] = {m4.x, m4.y, m4.z, m4.w};
+    float pc[4] = {0.f, 0.f, 0.f, 0.f}, pn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!FIRST) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(prev + o));
+      pc[0] = c4.x; pc[1] = c4.y; pc[2] = c4.z; pc[3] = c4.w;
+    }
+    if (!(mm[0] & mm[1] & mm[2] & mm[3] & 1u)) {  // at least one free cell: an interior row and plane
+      const float4 d4 = __ldg(reinterpret_cast<const float4*>(div + o));
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      if (FIRST) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) pn[c] = (mm[c] & 1u) ? 0.f : dv[c] / 6.f;  // p0 = 0: only div remains
+      } else {
+        const float4 u4 = __ldg(reinterpret_cast<const float4*>(prev + o - g.sy));
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(prev + o + g.sy));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(prev + o - g.sz));
+        const float4 f4 = __ldg(reinterpret_cast<const float4*>(prev + o + g.sz));
+        const float pl = i0 > 0 ? __ldg(prev + o - 1) : 0.f, pr = i0 + 4 < g.W ? __ldg(prev + o + 4) : 0.f;
+        const float xm[4] = {pl, pc[0], pc[1], pc[2]}, xp[4] = {pc[1], pc[2], pc[3], pr};
+        const float ym[4] = {u4.x, u4.y, u4.z, u4.w}, yp[4] = {s4.x, s4.y, s4.z, s4.w};
+        const float zm[4] = {b4.x, b4.y, b4.z, b4.w}, zp[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const unsigned m = mm[c];
+          if (m & 1u) continue;
+          const float pC = pc[c];
+          const float p1 = (m & 2u) ? pC : xm[c], p2 = (m & 4u) ? pC : xp[c];
+          const float p3 = (m & 8u) ? pC : ym[c], p4 = (m & 16u) ? pC : yp[c];
+          const float p5 = (m & 32u) ? pC : zm[c], p6 = (m & 64u) ? pC : zp[c];
+          float sum = p1 + p2 + p3 + p4;
+          sum = sum + p5 + p6;
+          sum = sum + dv[c];
+          pn[c] = sum / 6.f;
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(cur + o) = make_float4(pn[0], pn[1], pn[2], pn[3]);
+    if (RESID) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const float d = pn[c] - pc[c];
+        d2 += d * d;  // (the scalar kernel sums one square per thread; the total is formed in double below)
+      }
+    }
+  }
+  if (RESID) {
+    double acc = (double)d2;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    __shared__ double wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tt = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) tt += wsum[w];
+      atomicAdd(ssq + b, tt);
+    }
+  }
+}
+
 // one thread: fold ssq[b] into the residual, test the tolerance, re-arm ssq
 __global__ void k_jacobi_ctrl(JacobiCtrl* ctrl, double* ssq, int B, float p_tol, int iter_index,
                               float* residual_out) {
@@ -369,6 +473,33 @@ int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_i
                           double* ssq, int B, int H, int W, int max_iter, int row0, int row1,
                           cudaStream_t st);  // jacobi_blocked.cu
 
+
+// 3-D fixed iteration count: mask once, then the 4-cells-per-thread kernel (needs W % 4 == 0 and 16-byte
+// aligned fields; otherwise the caller falls back to k_jacobi_iter).  p_init == nullptr: start from 0.
+static bool jacobi3d_vec_ok(const Grid& g, const float* a, const float* b, const float* c, const float* d) {
+  return (g.W % 4 == 0) && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0);
+}
+
+static int jacobi3d_vec_run(const Grid& g, const float* flags, const float* div, const float* p_init, float* p,
+                            float* scratch, unsigned char* mask, double* ssq, int iters, cudaStream_t st) {
+  const long long total = (long long)g.B * g.n;
+  k_jacobi3d_mask<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, flags, mask);
+  const long long groups = (long long)(g.row1 - g.row0) * (g.W >> 2);
+  dim3 grid((unsigned)((groups + 255) / 256), g.B);
+  auto wbuf = [&](int it) { return ((iters - 1 - it) % 2 == 0) ? p : scratch; };
+  for (int it = 0; it < iters; it++) {
+    const float* prev = it == 0 ? p_init : wbuf(it - 1);
+    const bool first = prev == nullptr, resid = ssq != nullptr && it == iters - 1;
+    if (first && resid) k_jacobi3d_vec<true, true><<<grid, 256, 0, st>>>(g, mask, div, prev, wbuf(it), ssq);
+    else if (first) k_jacobi3d_vec<true, false><<<grid, 256, 0, st>>>(g, mask, div, prev, wbuf(it), ssq);
+    else if (resid) k_jacobi3d_vec<false, true><<<grid, 256, 0, st>>>(g, mask, div, prev, wbuf(it), ssq);
+    else k_jacobi3d_vec<false, false><<<grid, 256, 0, st>>>(g, mask, div, prev, wbuf(it), ssq);
+  }
+  fnx_count_launches(iters + 1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "jacobi3d: %s", cudaGetErrorString(e));
+  return FNX_OK;
+}
 
 extern "C" {
 
@@ -540,7 +671,8 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t fnx_jacobi_workspace(int B, int D, int H, int W, int max_iter) {
   (void)max_iter;
   size_t n = (size_t)B * D * H * W;
-  return align256(n * sizeof(float)) + align256(sizeof(JacobiCtrl)) + align256((size_t)B * sizeof(double));
+  return align256(n * sizeof(float)) + align256(sizeof(JacobiCtrl)) + align256((size_t)B * sizeof(double)) +
+         (D > 1 ? align256(n) : 0);  // 3-D: one neighbour-mask byte per cell
 }
 
 int fnx_solve_linear_system_jacobi(const float* flags, const float* div, float* p, float* residual, int B,
@@ -564,6 +696,16 @@ int fnx_solve_linear_system_jacobi(const float* flags, const float* div, float* 
   if (!tol && !is3d) {
     // fixed iteration count, 2-D: temporally blocked shared-memory kernel
     int e = fnx_jacobi_2d_blocked(flags, div, nullptr, p, scratch, ssq, B, H, W, max_iter, 0, 0, st);
+    if (e) return e;
+    k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, max_iter - 1, residual);
+    FNX_LAUNCH_CHECK("solve_linear_system", 1);
+    if (iters_run) *iters_run = max_iter;
+    return FNX_OK;
+  }
+  if (!tol && is3d && jacobi3d_vec_ok(g, flags, div, p, scratch)) {
+    // fixed iteration count, 3-D: precomputed neighbour masks + 4 cells per thread
+    unsigned char* mask = (unsigned char*)((char*)ssq + align256((size_t)B * sizeof(double)));
+    int e = jacobi3d_vec_run(g, flags, div, nullptr, p, scratch, mask, ssq, max_iter, st);
     if (e) return e;
     k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, max_iter - 1, residual);
     FNX_LAUNCH_CHECK("solve_linear_system", 1);
@@ -614,6 +756,12 @@ int fnx_jacobi_iterate(const float* flags, const float* div, const float* p_init
     g.row0 = row_begin; g.row1 = row_end;
   }
   if (!is3d) return fnx_jacobi_2d_blocked(flags, div, p_init, p, scratch, nullptr, B, H, W, iters, row_begin, row_end, st);
+  if (jacobi3d_vec_ok(g, flags, div, p, scratch) && (((uintptr_t)p_init) & 15) == 0) {
+    const size_t n = (size_t)B * g.n;
+    unsigned char* mask = (unsigned char*)workspace + align256(n * sizeof(float)) + align256(sizeof(JacobiCtrl)) +
+                          align256((size_t)B * sizeof(double));
+    return jacobi3d_vec_run(g, flags, div, p_init, p, scratch, mask, nullptr, iters, st);
+  }
   auto wbuf = [&](int it) { return ((iters - 1 - it) % 2 == 0) ? p : scratch; };
   for (int it = 0; it < iters; it++) {
     const float* prev = it == 0 ? p_init : wbuf(it - 1);
