@@ -572,11 +572,12 @@ def make_report(args, wl, world, total_cells, cells, total_ms, e2e_ms, e2e_steps
             # dominant kernel = temporally blocked Jacobi: 16 B/cell/iteration algorithmic (SURVEY §8d stage C)
             algo_bytes = 16.0 * cells * iters * args.steps
             achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
-            roof = {"bound": "hbm", "kernel": "k_jacobi2d_blocked" if D == 1 else "k_jacobi_iter",
+            roof = {"bound": "hbm", "kernel": "k_jacobi2d_blocked (8 iterations per launch)" if D == 1
+                    else "k_jacobi3d_vec (1 iteration per launch)",
                     "achieved": round(achieved, 1) if achieved else None, "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(achieved / hbm_peak, 4) if achieved else None,
                     "traffic": ncu_traffic(f"k_jacobi2d_blocked @{wl['res'][1]}x{wl['res'][2]}") if D == 1 else None,
-                    "algorithmic_bytes_per_launch": 16.0 * cells * 8,
+                    "algorithmic_bytes_per_launch": 16.0 * cells * (8 if D == 1 else 1),
                     "peak_source": peak_src, "stage_ms_per_step": round(dom_ms / args.steps, 4),
                     "step_hbm_frac": round(step_bytes * cells * args.steps / (total_ms / 1e3) / 1e9 / hbm_peak, 4)}
             pressure = f"jacobi x{iters}"
