@@ -65,9 +65,9 @@ __device__ __forceinline__ float scalar_fwd_cell(const Grid& g, const CellIdx& c
     line_trace<NA>(g, flags, pos, delta, back);
     val = sample_outside ? sample_field<Z>(g, src, back) : sample_with_fluid<Z>(g, src, flags, back);
     if (want_idx) {
-      long long i0 = clampll(trunc_ll(back[0]), 0, g.W - 1);
-      long long j0 = clampll(trunc_ll(back[1]), 0, g.H - 1);
-      long long k0 = Z ? clampll(trunc_ll(back[2]), 0, g.D - 1) : 0;
+      const int i0 = trunc_clamp0(back[0], g.W - 1);
+      const int j0 = trunc_clamp0(back[1], g.H - 1);
+      const int k0 = Z ? trunc_clamp0(back[2], g.D - 1) : 0;
       idx = (k0 * g.H + j0) * g.W + i0;
     }
   }
@@ -119,7 +119,7 @@ __device__ __forceinline__ float scalar_bwd_cell(const Grid& g, const CellIdx& c
         for (int di = -1; di <= 1; di++) {
           const int ii = i0 + di;
           if (ii < 0 || ii >= g.W) continue;
-          const long long q = ((long long)kk * g.H + jj) * g.W + ii;
+          const int q = (kk * g.H + jj) * g.W + ii;
           if (sample_outside || __ldg(flags + q) == kFluid) {
             const float s = __ldg(src + q);
             mn = min_t(mn, s);
@@ -199,15 +199,14 @@ __device__ __forceinline__ void vel_bwd_cell(const Grid& g, const CellIdx& c, fl
     const float* oc = orig + comp * g.n;
 #pragma unroll
     for (int l = 0; l < 2; l++) {
-      long long q[3] = {0, 0, 0};
+      const int hi[3] = {g.W - 2, g.H - 2, g.D - 2};
+      int q[3] = {0, 0, 0};
 #pragma unroll
       for (int a = 0; a < NA; a++) {
         const float va = vel[a] * dt;
-        q[a] = trunc_i32_x86(l == 0 ? posi[a] - va : posi[a] + va);
+        q[a] = trunc_x86_clamp0(l == 0 ? posi[a] - va : posi[a] + va, hi[a]);
       }
-      const long long i0 = clampll(q[0], 0, g.W - 2), j0 = clampll(q[1], 0, g.H - 2);
-      const long long k0 = Z ? clampll(q[2], 0, g.D - 2) : 0;
-      const float* b0 = oc + (k0 * g.H + j0) * g.W + i0;
+      const float* b0 = oc + (q[2] * g.H + q[1]) * g.W + q[0];
       // same visiting order as the reference: (j0,i0) (j0,i0+1) (j0+1,i0) (j0+1,i0+1)
       float s;
       s = __ldg(b0); mn = min_t(mn, s); mx = max_t(mx, s);

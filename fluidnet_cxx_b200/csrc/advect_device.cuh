@@ -23,6 +23,31 @@ template <bool Z>
 __device__ __forceinline__ Taps<Z> make_taps(const Grid& g, const float* pos) {
   Taps<Z> t;
   float px = pos[0] - 0.5f, py = pos[1] - 0.5f;
+  // every position that can index a real grid takes the 32-bit path; the int64 code below it is the
+  // same arithmetic for the (garbage-velocity) positions beyond 1e9 and for NaN
+  bool small = (fabsf(px) < 1.0e9f) & (fabsf(py) < 1.0e9f);
+  if (Z) small = small & (fabsf(pos[2] - 0.5f) < 1.0e9f);
+  if (small) {
+    const int ix = __float2int_rz(px), iy = __float2int_rz(py);
+    const float s1 = px - (float)ix, t1 = py - (float)iy;
+    const float s0 = 1.f - s1, t0 = 1.f - t1;
+    int x0 = ix < 0 ? 0 : ix, y0 = iy < 0 ? 0 : iy, z0 = 0;
+    x0 = x0 > g.W - 2 ? g.W - 2 : x0;
+    y0 = y0 > g.H - 2 ? g.H - 2 : y0;
+    t.s1 = clamp01(s1); t.t1 = clamp01(t1);
+    t.s0 = clamp01(s0); t.t0 = clamp01(t0);
+    t.f0 = 1.f; t.f1 = 0.f;
+    if (Z) {
+      const float pz = pos[2] - 0.5f;
+      const int iz = __float2int_rz(pz);
+      const float f1 = pz - (float)iz, f0 = 1.f - f1;
+      z0 = iz < 0 ? 0 : iz;
+      z0 = z0 > g.D - 2 ? g.D - 2 : z0;
+      t.f1 = clamp01(f1); t.f0 = clamp01(f0);
+    }
+    t.o = (z0 * g.H + y0) * g.W + x0;  // < 2^31 cells per batch item (checked at the entry points)
+    return t;
+  }
   long long ix = trunc_ll(px), iy = trunc_ll(py);
   float s1 = px - (float)ix, t1 = py - (float)iy;
   float s0 = 1.f - s1, t0 = 1.f - t1;

@@ -67,6 +67,22 @@ __device__ __forceinline__ long long trunc_i32_x86(float x) {
   return (long long)__float2int_rz(x);
 }
 
+// clampll(trunc_ll(x), 0, hi) for EVERY float x, in 32-bit arithmetic: cvt.rzi.s32.f32 saturates
+// (NaN -> 0, +-big -> INT_MAX / INT_MIN) and each saturated value lands on the same side of [0, hi]
+// as the 64-bit truncation (NaN -> LLONG_MIN -> 0) does.
+__device__ __forceinline__ int trunc_clamp0(float x, int hi) {
+  int r = __float2int_rz(x);
+  r = r < 0 ? 0 : r;
+  return r > hi ? hi : r;
+}
+// clampll(trunc_i32_x86(x), 0, hi): the x86 conversion gives INT_MIN outside int32 and for NaN -> 0
+__device__ __forceinline__ int trunc_x86_clamp0(float x, int hi) {
+  if (!(x > -2147483904.0f && x < 2147483648.0f)) return hi < 0 ? hi : 0;
+  int r = __float2int_rz(x);
+  r = r < 0 ? 0 : r;
+  return r > hi ? hi : r;
+}
+
 // at::min / at::max semantics of the oracle (strict compare, first operand kept on ties/NaN)
 __device__ __forceinline__ float min_t(float a, float b) { return (b < a) ? b : a; }
 __device__ __forceinline__ float max_t(float a, float b) { return (b > a) ? b : a; }
