@@ -673,6 +673,10 @@ def reference_step_runner(wl, res):
 
 def cpu_baseline(wl, steps, warmup):
     import torch
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     res = wl["cpu_sample_res"]
     if res is None:
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
@@ -704,6 +708,12 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "the reference has no runnable 3-D path"}))
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm is the only work on this box while
+    # it runs, give it every host thread
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     step = reference_step_runner(wl, res)
     if step is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"}))
