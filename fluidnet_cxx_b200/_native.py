@@ -38,7 +38,7 @@ class ConvLayer(ctypes.Structure):
     """struct fnx_conv_layer (include/fluidstep.h)."""
     _fields_ = [("weight", _c_void_p), ("bias", _c_void_p), ("w_tc", _c_void_p),
                 ("cin", _c_int), ("cout", _c_int), ("ksize", _c_int), ("relu", _c_int),
-                ("w_scale", _c_float), ("w_norm", _c_float), ("b_max", _c_float)]
+                ("w_scale", _c_float), ("w_norm", _c_float), ("b_max", _c_float), ("w_replicas", _c_int)]
 
 
 class ProfileRec(ctypes.Structure):

@@ -88,6 +88,10 @@ struct ConvArgs {
   // one fp32 channel, for layers with Cout <= 16 (the 32->8 5x5 layer feeding the 8->1 conv)
   const float* head_w;
   const float* head_b;
+  // the packed weights may be replicated `w_nrep` times, `w_rep_stride` bytes apart: CTA b streams copy
+  // b % w_nrep, which spreads the (identical, simultaneous) weight fills of all SMs over more L2 lines
+  int w_nrep;
+  size_t w_rep_stride;
 };
 
 constexpr int NEPI = 8;                      // epilogue warps (two per TMEM lane quadrant)
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = a.nchunks;
+  const uint8_t* const wsrc = a.w + (a.w_nrep > 1 ? (size_t)(blockIdx.x % a.w_nrep) * a.w_rep_stride : 0);
   const int Rrt = a.R;  // rows per block at run time (R = capacity the shared/tensor memory is sized for)
   const bool resident = nchunks * KS <= WS;  // all weight slots of the layer fit in the ring
 
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
       if (resident) {  // the whole layer's weights fit in the ring: load once, never release
         for (int s = 0; s < nchunks * KS; s++) {
           mbar_expect_tx(W_FULL(s), C::W_STAGE);
-          bulk_g2s(smem_u32(sW + s * C::W_STAGE), a.w + (size_t)s * C::W_STAGE, C::W_STAGE, W_FULL(s));
+          bulk_g2s(smem_u32(sW + s * C::W_STAGE), wsrc + (size_t)s * C::W_STAGE, C::W_STAGE, W_FULL(s));
         }
       }
       pdl_wait();
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
             for (int ky = 0; ky < KS; ky++) {
               mbar_wait(W_EMPTY(ws), wph ^ 1);
               mbar_expect_tx(W_FULL(ws), C::W_STAGE);
-              bulk_g2s(smem_u32(sW + ws * C::W_STAGE), a.w + (size_t)(c * KS + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
+              bulk_g2s(smem_u32(sW + ws * C::W_STAGE), wsrc + (size_t)(c * KS + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
               if (++ws == WS) { ws = 0; wph ^= 1; }
             }
           }
@@ -673,20 +678,20 @@ int fnx_tc_unpack_split(const void* x, const fnx_act_meta* meta, int C, int H, i
 static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin,
                           int Cout, int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max,
                           int out_mode, void* y, fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset,
-                          const float* head_w, const float* head_b, void* stream);
+                          const float* head_w, const float* head_b, int w_nrep, void* stream);
 
 int fnx_conv_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin, int Cout,
                 int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max, int out_mode, void* y,
                 fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset, void* stream) {
   if (out_mode != 0 && out_mode != 1) return fnx_set_error(FNX_ERR_ARG, "conv_tc: out_mode must be 0 or 1");
   return conv_tc_launch(x, in_meta, w_packed, bias, Cin, Cout, ksize, H, W, relu, w_scale, w_norm, b_max, out_mode, y,
-                        out_meta, y_channels_total, y_channel_offset, nullptr, nullptr, stream);
+                        out_meta, y_channels_total, y_channel_offset, nullptr, nullptr, 1, stream);
 }
 
 static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin,
                           int Cout, int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max,
                           int out_mode, void* y, fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset,
-                          const float* head_w, const float* head_b, void* stream) {
+                          const float* head_w, const float* head_b, int w_nrep, void* stream) {
   if (!tc_eligible(Cin, Cout, ksize))
     return fnx_set_error(FNX_ERR_ARG, "conv_tc: unsupported layer %d->%d k%d", Cin, Cout, ksize);
   if (H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "conv_tc: bad shape");
@@ -698,6 +703,8 @@ static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void
     return fnx_set_error(FNX_ERR_ARG, "conv_tc: the fused 1x1 head needs Cout <= 16 and its weights");
   ConvArgs a;
   a.head_w = head_w; a.head_b = head_b;
+  a.w_nrep = w_nrep > 1 ? w_nrep : 1;
+  a.w_rep_stride = fnx_tc_weight_bytes(Cin, Cout, ksize);
   a.x = (const __half*)x;
   a.x_plane = act_plane_halves(pad16(Cin), H, W);
   a.w = (const uint8_t*)w_packed;
@@ -836,8 +843,9 @@ struct Runner {
           ActMeta* m = new_meta();
           if (!dry) {
             LayerTimer lt(l, h, w, 1, st);
-            int rc = fnx_conv_tc(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu, l.w_scale,
-                                    l.w_norm, l.b_max, 0, sp, (fnx_act_meta*)m, 0, 0, st);
+            int rc = conv_tc_launch(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu,
+                                    l.w_scale, l.w_norm, l.b_max, 0, sp, (fnx_act_meta*)m, 0, 0, nullptr, nullptr,
+                                    l.w_replicas, st);
             if (rc) return rc;
           }
           cur_split = sp; cur_meta = m; cur_f32 = nullptr; is_split = true;
@@ -850,7 +858,7 @@ struct Runner {
                                     l.w_scale, l.w_norm, l.b_max, fuse_head ? 2 : 1, o,
                                     (fnx_act_meta*)(last ? last_meta : nullptr), last ? out_ctotal : l.cout,
                                     last ? out_coff : 0, fuse_head ? head->weight : nullptr,
-                                    fuse_head ? head->bias : nullptr, st);
+                                    fuse_head ? head->bias : nullptr, l.w_replicas, st);
             if (rc) return rc;
           }
           cur_f32 = o; cur_split = nullptr; cur_meta = nullptr; is_split = false;

@@ -7,6 +7,7 @@ the Sequential indices), so the shipped `convModel_lastEpoch_best.pth` loads wit
 the C-ABI (inference only; there is no torch.nn fallback on the forward path).
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -52,6 +53,7 @@ class MultiScaleNet(nn.Module):
     # split-fp16 packed weights of the tensor-core layers and their range scalars.  Built lazily on
     # the first forward on a device and rebuilt whenever a parameter tensor changes.
     USE_TENSOR_CORES = True   # False: every layer on the fp32 direct kernel (numerical cross-check)
+    WEIGHT_REPLICAS = int(os.environ.get("FNX_TC_WEIGHT_REPLICAS", "1"))
 
     def _layers(self):
         out = []
@@ -62,7 +64,7 @@ class MultiScaleNet(nn.Module):
         return out
 
     def _plan_key(self, device):
-        return (str(device), bool(self.USE_TENSOR_CORES)) + tuple(
+        return (str(device), bool(self.USE_TENSOR_CORES), int(self.WEIGHT_REPLICAS)) + tuple(
             (p.data_ptr(), p._version) for p in self.parameters())
 
     def _build_plan(self, device):
@@ -81,14 +83,20 @@ class MultiScaleNet(nn.Module):
             dst.weight, dst.bias = w.data_ptr(), b.data_ptr()
             dst.cin, dst.cout, dst.ksize, dst.relu = cin, cout, k, int(relu)
             dst.w_tc = None
+            dst.w_replicas = 1
             dst.w_scale, dst.w_norm, dst.b_max = 1.0, 0.0, 0.0
             if self.USE_TENSOR_CORES and (k == 3 or (k == 5 and cout <= 32)) and cin <= 128 and cout <= 128:
                 wmax = float(w.abs().max())
                 # power of two with max|w| * w_scale <= 2^14 (same rule as the device side)
                 w_scale = 1.0 if not (wmax > 0 and math.isfinite(wmax)) else 2.0 ** (14 - math.frexp(wmax)[1])
-                packed = torch.empty(lib.fnx_tc_weight_bytes(cin, cout, k), dtype=torch.uint8, device=device)
+                nbytes = lib.fnx_tc_weight_bytes(cin, cout, k)
+                nrep = self.WEIGHT_REPLICAS
+                packed = torch.empty(nrep * nbytes, dtype=torch.uint8, device=device)
                 N.check(lib.fnx_tc_pack_weights(w.data_ptr(), cin, cout, k, w_scale, packed.data_ptr(), st),
                         "MultiScaleNet.pack_weights")
+                for r in range(1, nrep):      # identical copies: every SM streams the same slots at the same time
+                    packed[r * nbytes:(r + 1) * nbytes].copy_(packed[:nbytes])
+                dst.w_replicas = nrep
                 keep.append(packed)
                 dst.w_tc = packed.data_ptr()
                 dst.w_scale = w_scale

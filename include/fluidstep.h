@@ -229,6 +229,7 @@ typedef struct fnx_conv_layer {
   const void *w_tc;    /* fnx_tc_pack_weights output, or NULL */
   int cin, cout, ksize, relu;
   float w_scale, w_norm, b_max;
+  int w_replicas;      /* w_tc holds this many identical copies, fnx_tc_weight_bytes apart (0/1 = one) */
 } fnx_conv_layer;
 typedef struct fnx_msnet_plan {
   int data_channels;
