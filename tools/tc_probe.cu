@@ -64,6 +64,44 @@ __global__ void __launch_bounds__(128) k_probe(const uint8_t* imgA, const uint8_
   if (warp == 0) tmem_dealloc(taddr, ncols);
 }
 
+// ---- throughput probe: `reps` back-to-back MMAs of one shape from no-swizzle K-major operands ----
+// distinct A tiles per MMA (start address advanced like a convolution tap) so nothing is collector-cached
+__global__ void __launch_bounds__(128) k_mma_rate(int N, int reps, int a_step_bytes, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = tmem_base;
+  if (warp == 1) {
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      const uint32_t idesc = idesc_f16_f32acc(128, N);
+      const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 96 * 1024);
+      t0 = clock64();
+      for (int r = 0; r < reps; r++) {
+        const uint64_t da = smem_desc_kmajor_noswz(a0 + (uint32_t)((r & 31) * a_step_bytes), 6 * 2080, 128);
+        const uint64_t db = smem_desc_kmajor_noswz(b0, (uint32_t)N * 16, 128);
+        mma_f16_ss(taddr + (uint32_t)((r & 1) * 256), da, db, idesc, 1);
+      }
+      mma_commit(smem_u32(&bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    t1 = clock64();
+    if ((threadIdx.x & 31) == 0) cycles[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(taddr, 512);
+}
+
 static float h2f(const uint8_t* img, size_t byte_off) {
   __half h;
   memcpy(&h, img + byte_off, 2);
@@ -84,6 +122,25 @@ int main(int argc, char** argv) {
       {"a_sbo=160 (8-wide 2D tile)", 0, 24 * 160, 160, 0, 64 * 16, 128, 64, 1, 0, 0, 0, 0},
       {"a_lbo=16 (chunk1 = next pixel)", 0, 16, 128, 0, 64 * 16, 128, 64, 1, 0, 0, 0, 0},
   };
+  if (argc > 1 && !strcmp(argv[1], "rate")) {
+    long long* dc;
+    cudaMalloc(&dc, 8);
+    cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int shapes[] = {16, 32, 64, 128, 256};
+    for (int N : shapes)
+      for (int step : {0, 16, 2080}) {
+        long long hc = 0;
+        const int reps = 2048;
+        k_mma_rate<<<1, 128, 200 * 1024>>>(N, reps, step, dc);
+        k_mma_rate<<<1, 128, 200 * 1024>>>(N, reps, step, dc);
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) { printf("CUDA ERROR %s\n", cudaGetErrorString(err)); return 2; }
+        cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+        printf("M=128 N=%3d K=16 no-swizzle, A start step %4d B: %7.1f clk/MMA  (tensor floor %d, operand bytes %d -> %d clk at 128 B/clk)\n",
+               N, step, (double)hc / reps, N / 2, 4096 + N * 32, (4096 + N * 32) / 128);
+      }
+    return 0;
+  }
   int only = argc > 1 ? atoi(argv[1]) : -1;
   srand(1);
   int fails = 0;
