@@ -6,9 +6,9 @@
 //
 // This translation unit is compiled WITH FMA contraction (it is a dense contraction whose
 // reference arithmetic lives in PyTorch's conv kernels; parity bar 1e-5 relative).
-// The tcgen05 implicit-GEMM path for the wide layers lives in conv_tc.cu; this file serves
-// the narrow layers (Cin 2/3, Cout 1/8), every kernel size, and is the numerical cross-check
-// of the tensor-core path.
+// The tcgen05 implicit-GEMM path of every 3x3 / 5x5 layer lives in conv_tc.cu; this file is the fp32
+// direct convolution (any kernel size; the numerical cross-check of the tensor-core path and the
+// `USE_TENSOR_CORES = False` plan), the standalone resize and the FluidNet wrapper stencils.
 #include <cuda_runtime.h>
 
 #include "../../include/fluidstep.h"
