@@ -179,44 +179,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
 
   if (warp == 0) {
     // ===== producer: stage activation rows and weight slots with the TMA engine =====
-    if (lane == 0) {
-      int as = 0, aph = 0, ws = 0, wph = 0;
-      if (resident) {  // the whole layer's weights fit in the ring: load once, never release
-        for (int s = 0; s < nchunks * KS; s++) {
-          mbar_expect_tx(W_FULL(s), C::W_STAGE);
-          bulk_g2s(smem_u32(sW + s * C::W_STAGE), wsrc + (size_t)s * C::W_STAGE, C::W_STAGE, W_FULL(s));
-        }
+    // Lane 0 owns the barrier protocol (waits, expect_tx); the bulk copies of a stage -- one per
+    // (plane, 8-channel chunk, row), 2 KB each -- are issued by all 32 lanes in parallel: issued from a
+    // single thread they cost more than the copies themselves on the narrow layers.
+    int as = 0, aph = 0, ws = 0, wph = 0;
+    if (resident && lane == 0) {  // the whole layer's weights fit in the ring: load once, never release
+      for (int s = 0; s < nchunks * KS; s++) {
+        mbar_expect_tx(W_FULL(s), C::W_STAGE);
+        bulk_g2s(smem_u32(sW + s * C::W_STAGE), wsrc + (size_t)s * C::W_STAGE, C::W_STAGE, W_FULL(s));
       }
-      pdl_wait();
-      for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
-        const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * Rrt;
-        // staged rows = padded-image rows y0+PAD-HALO ..; rows past the padded image are skipped
-        int nrows = a.Hp - (y0 + PAD - C::HALO);
-        nrows = nrows > Rrt + KS - 1 ? Rrt + KS - 1 : nrows;
-        for (int c = 0; c < nchunks; c++) {
+    }
+    pdl_wait();
+    for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
+      const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * Rrt;
+      // staged rows = padded-image rows y0+PAD-HALO ..; rows past the padded image are skipped
+      int nrows = a.Hp - (y0 + PAD - C::HALO);
+      nrows = nrows > Rrt + KS - 1 ? Rrt + KS - 1 : nrows;
+      for (int c = 0; c < nchunks; c++) {
+        if (lane == 0) {
           mbar_wait(A_EMPTY(as), aph ^ 1);
           mbar_expect_tx(A_FULL(as), (uint32_t)nrows * 4u * C::ROWB);
-          const uint32_t dst0 = smem_u32(sA + as * C::A_STAGE);
-#pragma unroll
-          for (int pl = 0; pl < 2; pl++)
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-              const __half* src = a.x + pl * a.x_plane +
-                                  (((size_t)(c * 2 + j) * a.Hp + (y0 + PAD - C::HALO)) * a.Wp + (x0 + PAD - C::HALO)) * 8;
-              const uint32_t dst = dst0 + pl * C::A_PLANE + j * C::A_J;
-              for (int r = 0; r < nrows; r++)
-                bulk_g2s(dst + r * C::ROWB, src + (size_t)r * a.Wp * 8, C::ROWB, A_FULL(as));
-            }
-          if (!resident) {
-            for (int ky = 0; ky < KS; ky++) {
-              mbar_wait(W_EMPTY(ws), wph ^ 1);
-              mbar_expect_tx(W_FULL(ws), C::W_STAGE);
-              bulk_g2s(smem_u32(sW + ws * C::W_STAGE), wsrc + (size_t)(c * KS + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
-              if (++ws == WS) { ws = 0; wph ^= 1; }
-            }
-          }
-          if (++as == 2) { as = 0; aph ^= 1; }
         }
+        __syncwarp();
+        const uint32_t dst0 = smem_u32(sA + as * C::A_STAGE);
+        for (int e = lane; e < 4 * nrows; e += 32) {
+          const int pj = e / nrows, r = e - pj * nrows;  // pj = plane * 2 + j
+          const int pl = pj >> 1, j = pj & 1;
+          const __half* src = a.x + pl * a.x_plane +
+                              (((size_t)(c * 2 + j) * a.Hp + (y0 + PAD - C::HALO + r)) * a.Wp + (x0 + PAD - C::HALO)) * 8;
+          bulk_g2s(dst0 + pl * C::A_PLANE + j * C::A_J + r * C::ROWB, src, C::ROWB, A_FULL(as));
+        }
+        if (!resident && lane == 0) {
+          for (int ky = 0; ky < KS; ky++) {
+            mbar_wait(W_EMPTY(ws), wph ^ 1);
+            mbar_expect_tx(W_FULL(ws), C::W_STAGE);
+            bulk_g2s(smem_u32(sW + ws * C::W_STAGE), wsrc + (size_t)(c * KS + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
+            if (++ws == WS) { ws = 0; wph ^= 1; }
+          }
+        }
+        __syncwarp();
+        if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp == 1) {
