@@ -109,8 +109,12 @@ struct Cfg {
   static constexpr uint32_t W_J = 2 * COUT * 16;      // [w_hi rows ; w_lo rows] of one 8-channel chunk = LBO(B)
   static constexpr uint32_t W_KX = 2 * W_J;
   static constexpr uint32_t W_STAGE = KS * W_KX;      // one (16-channel chunk, ky) slot
-  static constexpr uint32_t NBAR = 4 + 2 * WS + 2 * R;
-  static constexpr uint32_t SMEM = 2 * A_STAGE + WS * W_STAGE + NBAR * 8 + 16 + COUT * 4;
+  // activation stages: a stage can only be refilled once every MMA that read it has completed, so a
+  // third stage lets the fill of chunk c+2 start while chunk c is still running (when it fits)
+  static constexpr uint32_t FIXED = WS * W_STAGE + (6 + 2 * WS + 2 * R) * 8 + 16 + COUT * 4;
+  static constexpr int AS = (3 * A_STAGE + FIXED <= 227 * 1024) ? 3 : 2;
+  static constexpr uint32_t NBAR = 2 * AS + 2 * WS + 2 * R;
+  static constexpr uint32_t SMEM = AS * A_STAGE + WS * W_STAGE + NBAR * 8 + 16 + COUT * 4;
   static constexpr uint32_t NCOLS = 2 * R * COUT;     // per M tile: [main | corr] accumulators
   static constexpr uint32_t TMEM_COLS = NCOLS <= 32 ? 32 : NCOLS <= 64 ? 64 : NCOLS <= 128 ? 128 : NCOLS <= 256 ? 256 : 512;
   static_assert(NCOLS <= 512, "accumulators exceed TMEM");
@@ -133,17 +137,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
   using C = Cfg<KS, COUT, R, WS>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sW = smem + 2 * C::A_STAGE;
+  constexpr int AS = C::AS;
+  uint8_t* sW = smem + AS * C::A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + WS * C::W_STAGE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
   const uint32_t bar0 = smem_u32(bars);
   auto A_FULL = [&](int s) { return bar0 + 8u * s; };
-  auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto W_FULL = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto W_EMPTY = [&](int s) { return bar0 + 8u * (4 + WS + s); };
-  auto ACC_FULL = [&](int r) { return bar0 + 8u * (4 + 2 * WS + r); };
-  auto ACC_EMPTY = [&](int r) { return bar0 + 8u * (4 + 2 * WS + R + r); };
+  auto A_EMPTY = [&](int s) { return bar0 + 8u * (AS + s); };
+  auto W_FULL = [&](int s) { return bar0 + 8u * (2 * AS + s); };
+  auto W_EMPTY = [&](int s) { return bar0 + 8u * (2 * AS + WS + s); };
+  auto ACC_FULL = [&](int r) { return bar0 + 8u * (2 * AS + 2 * WS + r); };
+  auto ACC_EMPTY = [&](int r) { return bar0 + 8u * (2 * AS + 2 * WS + R + r); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = a.nchunks;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
   const bool resident = nchunks * KS <= WS;  // all weight slots of the layer fit in the ring
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < AS; s++) {
       mbar_init(A_FULL(s), 1);
       mbar_init(A_EMPTY(s), 1);
     }
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
           }
         }
         __syncwarp();
-        if (++as == 2) { as = 0; aph ^= 1; }
+        if (++as == AS) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
         }
         if (elect_one()) mma_commit(A_EMPTY(as));
         __syncwarp();
-        if (++as == 2) { as = 0; aph ^= 1; }
+        if (++as == AS) { as = 0; aph ^= 1; }
       }
     }
   } else {
@@ -724,7 +729,7 @@ static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void
   const int cp = cout_pad(Cout);
   if (ksize == 3) {
     switch (cp) {
-      case 128: return launch_tc_rows<3, 128, 2, 6>(a, st);
+      case 128: return launch_tc_rows<3, 128, 2, 5>(a, st);  // 5 weight slots leave room for a 3rd activation stage
       case 64: return launch_tc_rows<3, 64, 4, 6>(a, st);
       case 32: return launch_tc_rows<3, 32, 8, 6>(a, st);
       default: return launch_tc_rows<3, 16, 8, 6>(a, st);
