@@ -84,6 +84,7 @@ struct ConvArgs {
   float w_scale, w_norm, b_max;
   int tiles_x, nblocks;
   int R;               // output rows per block (<= the kernel's RMAX template parameter)
+  int iters;           // blocks per CTA in cluster mode (same for every CTA)
   // out_mode 2: fused 1x1 head (multi_scale_net.py:116 `final`): y[pixel] = sum_c head_w[c]*out[c] + head_b,
   // one fp32 channel, for layers with Cout <= 16 (the 32->8 5x5 layer feeding the 8->1 conv)
   const float* head_w;
@@ -132,9 +133,17 @@ __device__ __forceinline__ void mma_tap(uint32_t d_tile, uint64_t a_hi, uint64_t
   mma_f16_ss(d_tile + COUT, a_lo, w, idesc_f16_f32acc(128, COUT), 1);
 }
 
-template <int KS, int COUT, int R, int WS>
+// CL = CTAs per cluster.  CL = 2 (opt-in, FNX_TC_CLUSTER=1): the two CTAs of a cluster work on different
+// blocks but consume the same weight slots in lockstep, so rank 0 loads every slot ONCE with a multicast
+// bulk copy into both CTAs' rings; a slot is refilled when both MMA issuers have committed it (multicast
+// arrive on both W_EMPTY barriers, count 2).  Halves the L2->SM weight fills (DESIGN.md "Fill budget").
+template <int KS, int COUT, int R, int WS, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
   using C = Cfg<KS, COUT, R, WS>;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  // every CTA of a cluster runs the same number of blocks (a CTA past the end re-runs the last block
+  // without storing anything) so the weight-slot sequence stays in lockstep
+  const int my_iters = CL > 1 ? a.iters : (a.nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   constexpr int AS = C::AS;
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
     }
     for (int s = 0; s < WS; s++) {
       mbar_init(W_FULL(s), 1);
-      mbar_init(W_EMPTY(s), 1);
+      mbar_init(W_EMPTY(s), CL);
     }
     for (int r = 0; r < R; r++) {
       mbar_init(ACC_FULL(r), 1);
@@ -176,6 +185,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers exist before any multicast copy / arrive targets them
   const uint32_t taddr = *tmem_slot;
   // Programmatic dependent launch: everything above (and the weight prefetch below) touches only
   // static data and this CTA's own shared / tensor memory, so it may overlap the tail of the previous
@@ -188,14 +198,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
     // (plane, 8-channel chunk, row), 2 KB each -- are issued by all 32 lanes in parallel: issued from a
     // single thread they cost more than the copies themselves on the narrow layers.
     int as = 0, aph = 0, ws = 0, wph = 0;
+    auto load_w = [&](int slot_smem, int slot_gmem) {  // arm my barrier; one copy per CTA, or one per cluster
+      mbar_expect_tx(W_FULL(slot_smem), C::W_STAGE);
+      const uint8_t* src = wsrc + (size_t)slot_gmem * C::W_STAGE;
+      if (CL == 1) bulk_g2s(smem_u32(sW + slot_smem * C::W_STAGE), src, C::W_STAGE, W_FULL(slot_smem));
+      else if (crank == 0)
+        bulk_g2s_multicast(smem_u32(sW + slot_smem * C::W_STAGE), src, C::W_STAGE, W_FULL(slot_smem), (uint16_t)((1u << CL) - 1));
+    };
     if (resident && lane == 0) {  // the whole layer's weights fit in the ring: load once, never release
-      for (int s = 0; s < nchunks * KS; s++) {
-        mbar_expect_tx(W_FULL(s), C::W_STAGE);
-        bulk_g2s(smem_u32(sW + s * C::W_STAGE), wsrc + (size_t)s * C::W_STAGE, C::W_STAGE, W_FULL(s));
-      }
+      for (int s = 0; s < nchunks * KS; s++) load_w(s, s);
     }
     pdl_wait();
-    for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
+    for (int it = 0; it < my_iters; it++) {
+      int blk = (int)blockIdx.x + it * (int)gridDim.x;
+      blk = blk < a.nblocks ? blk : a.nblocks - 1;
       const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * Rrt;
       // staged rows = padded-image rows y0+PAD-HALO ..; rows past the padded image are skipped
       int nrows = a.Hp - (y0 + PAD - C::HALO);
@@ -216,9 +232,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
         }
         if (!resident && lane == 0) {
           for (int ky = 0; ky < KS; ky++) {
-            mbar_wait(W_EMPTY(ws), wph ^ 1);
-            mbar_expect_tx(W_FULL(ws), C::W_STAGE);
-            bulk_g2s(smem_u32(sW + ws * C::W_STAGE), wsrc + (size_t)(c * KS + ky) * C::W_STAGE, C::W_STAGE, W_FULL(ws));
+            mbar_wait(W_EMPTY(ws), wph ^ 1);  // every CTA of the cluster has consumed this slot
+            load_w(ws, c * KS + ky);
             if (++ws == WS) { ws = 0; wph ^= 1; }
           }
         }
@@ -232,8 +247,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
     // committed to the epilogue one tile at a time, so the epilogue of one tile overlaps the MMAs of
     // the next) or when the weights are resident; otherwise ky-major, which releases weight slots
     // progressively.  The first chunk re-acquires tile r from the epilogue just before touching it.
-    int as = 0, aph = 0, ws = 0, wph = 0, it = 0;
-    for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, it++) {
+    int as = 0, aph = 0, ws = 0, wph = 0;
+    auto release_w = [&](int slot) {
+      if (CL == 1) mma_commit(W_EMPTY(slot));
+      else mma_commit_multicast(W_EMPTY(slot), (uint16_t)((1u << CL) - 1));
+    };
+    for (int it = 0; it < my_iters; it++) {
       for (int c = 0; c < nchunks; c++) {
         const bool first = c == 0, last = c == nchunks - 1;
         mbar_wait(A_FULL(as), aph);
@@ -275,7 +294,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
           if (!resident) {
 #pragma unroll
             for (int ky = 0; ky < KS; ky++) {
-              if (elect_one()) mma_commit(W_EMPTY(ws));
+              if (elect_one()) release_w(ws);
               if (++ws == WS) { ws = 0; wph ^= 1; }
             }
           }
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
               }
               __syncwarp();
             }
-            if (elect_one()) mma_commit(W_EMPTY(ws));
+            if (elect_one()) release_w(ws);
             __syncwarp();
             if (++ws == WS) { ws = 0; wph ^= 1; }
           }
@@ -320,15 +339,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
     const float inv = 1.f / (s_in * a.w_scale);
     const float s_out = pow2_scale_for(__uint_as_float(a.in_meta->amax_bits) * a.w_norm + a.b_max);
     float amax = 0.f;
-    int it = 0;
     constexpr int NGRP = COUT / 16;
-    for (int blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, it++) {
+    for (int it = 0; it < my_iters; it++) {
+      const int blk = (int)blockIdx.x + it * (int)gridDim.x;
+      const bool live = blk < a.nblocks;  // a lockstep filler iteration computes but never stores
       const int x0 = (blk % a.tiles_x) * TW, y0 = (blk / a.tiles_x) * Rrt;
       const int px = x0 + q * 32 + lane;
 #pragma unroll 1
       for (int r = 0; r < Rrt; r++) {
         const int y = y0 + r;
-        const bool ok = (y < a.H) && (px < a.W);
+        const bool ok = live && (y < a.H) && (px < a.W);
         mbar_wait(ACC_FULL(r), it & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -399,6 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on it
   if (warp == 1) tmem_dealloc(taddr, C::TMEM_COLS);
 }
 
@@ -595,26 +616,47 @@ static int choose_rows(const ConvArgs& a) {
 template <int KS, int COUT, int RMAX, int WS>
 static int launch_tc_rows(ConvArgs a, cudaStream_t st) {
   using C = Cfg<KS, COUT, RMAX, WS>;
-  auto kern = k_conv_tc<KS, COUT, RMAX, WS>;
-  FNX_CUDA_TRY("conv_tc", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   a.R = choose_rows<KS, COUT, RMAX, WS>(a);
   a.tiles_x = (a.W + TW - 1) / TW;
   a.nblocks = a.tiles_x * ((a.H + a.R - 1) / a.R);
-  const int grid = a.nblocks < num_sms() ? a.nblocks : num_sms();
+  // opt-in (FNX_TC_CLUSTER=1): 2-CTA clusters with multicast weight slots for the layers that stream weights
+  static const bool want_cluster = []() { const char* e = getenv("FNX_TC_CLUSTER"); return e && e[0] == '1'; }();
+  const bool cluster = want_cluster && a.nchunks * KS > WS && a.nblocks >= 2;
+  int grid = a.nblocks < num_sms() ? a.nblocks : num_sms();
+  if (cluster) grid = (grid + 1) & ~1;
+  if (cluster && grid > num_sms()) grid -= 2;
+  a.iters = (a.nblocks + grid - 1) / grid;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = C::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  // opt-in (FNX_PDL=1): measured on B200 it does not pay -- the next conv CTA cannot co-reside with a
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  // PDL is opt-in (FNX_PDL=1): measured on B200 it does not pay -- the next conv CTA cannot co-reside with a
   // running one (shared memory, TMEM), and early-launched grids cost 1-3 % (512^2: 0.633 vs 0.623 ms/step)
   static const bool pdl = []() { const char* e = getenv("FNX_PDL"); return e && e[0] == '1'; }();
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
+  if (cluster) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    na++;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  FNX_CUDA_TRY("conv_tc", cudaLaunchKernelEx(&cfg, kern, a));
+  cfg.numAttrs = na;
+  if (cluster) {
+    auto kern = k_conv_tc<KS, COUT, RMAX, WS, 2>;
+    FNX_CUDA_TRY("conv_tc", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    FNX_CUDA_TRY("conv_tc", cudaLaunchKernelEx(&cfg, kern, a));
+  } else {
+    auto kern = k_conv_tc<KS, COUT, RMAX, WS, 1>;
+    FNX_CUDA_TRY("conv_tc", cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    FNX_CUDA_TRY("conv_tc", cudaLaunchKernelEx(&cfg, kern, a));
+  }
   fnx_count_launches(1);
   return FNX_OK;
 }
@@ -724,7 +766,7 @@ static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void
   a.H = H; a.W = W; a.Hp = H + 2 * PAD; a.Wp = W + 2 * PAD;
   a.relu = relu; a.out_mode = out_mode; a.y_ctotal = y_channels_total; a.y_coff = y_channel_offset;
   a.w_scale = w_scale; a.w_norm = w_norm; a.b_max = b_max;
-  a.tiles_x = 0; a.nblocks = 0; a.R = 1;
+  a.tiles_x = 0; a.nblocks = 0; a.R = 1; a.iters = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int cp = cout_pad(Cout);
   if (ksize == 3) {
