@@ -92,6 +92,7 @@ SIGNATURES = {
     "fnx_tc_act_bytes": (_S, [_I, _I, _I]),
     "fnx_tc_weight_bytes": (_S, [_I, _I, _I]),
     "fnx_tc_pack_weights": (_I, [_P, _I, _I, _I, _F, _P, _P]),
+    "fnx_tc_set_debug": (_I, [_P]),
     "fnx_tc_amax": (_I, [_P, _S, _P, _P]),
     "fnx_tc_pack_split": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "fnx_tc_unpack_split": (_I, [_P, _P, _I, _I, _I, _P, _P]),

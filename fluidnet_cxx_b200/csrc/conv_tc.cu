@@ -85,6 +85,8 @@ struct ConvArgs {
   int tiles_x, nblocks;
   int R;               // output rows per block (<= the kernel's RMAX template parameter)
   int iters;           // blocks per CTA in cluster mode (same for every CTA)
+  long long* dbg;      // optional (fnx_tc_set_debug): per CTA {A_FULL wait, W_FULL wait, ACC_EMPTY wait, total} clocks
+                       // of the MMA warp
   // out_mode 2: fused 1x1 head (multi_scale_net.py:116 `final`): y[pixel] = sum_c head_w[c]*out[c] + head_b,
   // one fp32 channel, for layers with Cout <= 16 (the 32->8 5x5 layer feeding the 8->1 conv)
   const float* head_w;
@@ -248,6 +250,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
     // the next) or when the weights are resident; otherwise ky-major, which releases weight slots
     // progressively.  The first chunk re-acquires tile r from the epilogue just before touching it.
     int as = 0, aph = 0, ws = 0, wph = 0;
+    long long t_a = 0, t_w = 0, t_acc = 0;
+    const long long t_begin = a.dbg ? clock64() : 0;
+    auto timed_wait = [&](uint32_t bar, uint32_t parity, long long& acc) {
+      if (a.dbg) {
+        const long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += clock64() - t0;
+      } else {
+        mbar_wait(bar, parity);
+      }
+    };
     auto release_w = [&](int slot) {
       if (CL == 1) mma_commit(W_EMPTY(slot));
       else mma_commit_multicast(W_EMPTY(slot), (uint16_t)((1u << CL) - 1));
@@ -255,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
     for (int it = 0; it < my_iters; it++) {
       for (int c = 0; c < nchunks; c++) {
         const bool first = c == 0, last = c == nchunks - 1;
-        mbar_wait(A_FULL(as), aph);
+        timed_wait(A_FULL(as), aph, t_a);
         const uint32_t a_base = smem_u32(sA + as * C::A_STAGE);
         const uint64_t a_hi0 = smem_desc_kmajor_noswz(a_base, C::A_J, 128);
         const uint64_t a_lo0 = smem_desc_kmajor_noswz(a_base + C::A_PLANE, C::A_J, 128);
@@ -265,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
             int s = resident ? c * KS : ws, ph = resident ? 0 : wph;
 #pragma unroll
             for (int ky = 0; ky < KS; ky++) {
-              mbar_wait(W_FULL(s), ph);
+              timed_wait(W_FULL(s), ph, t_w);
               wd[ky] = smem_desc_kmajor_noswz(smem_u32(sW + s * C::W_STAGE), C::W_J, 128);
               if (++s == WS) { s = 0; ph ^= 1; }
             }
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
           for (int r = 0; r < R; r++) {
             if (r >= Rrt) break;
             if (first) {
-              mbar_wait(ACC_EMPTY(r), (it & 1) ^ 1);
+              timed_wait(ACC_EMPTY(r), (it & 1) ^ 1, t_acc);
               tc_fence_after();
             }
             if (elect_one()) {
@@ -300,14 +313,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
           }
         } else {
           for (int ky = 0; ky < KS; ky++) {
-            mbar_wait(W_FULL(ws), wph);
+            timed_wait(W_FULL(ws), wph, t_w);
             tc_fence_after();
             const uint64_t w0 = smem_desc_kmajor_noswz(smem_u32(sW + ws * C::W_STAGE), C::W_J, 128);
 #pragma unroll
             for (int r = 0; r < R; r++) {
               if (r >= Rrt) break;
               if (first && ky == 0) {
-                mbar_wait(ACC_EMPTY(r), (it & 1) ^ 1);
+                timed_wait(ACC_EMPTY(r), (it & 1) ^ 1, t_acc);
                 tc_fence_after();
               }
               if (elect_one()) {
@@ -329,6 +342,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
         __syncwarp();
         if (++as == AS) { as = 0; aph ^= 1; }
       }
+    }
+    if (a.dbg && lane == 0) {
+      long long* d = a.dbg + 4 * (size_t)blockIdx.x;
+      d[0] = t_a; d[1] = t_w; d[2] = t_acc; d[3] = clock64() - t_begin;
     }
   } else {
     // ===== epilogue: TMEM -> registers -> bias / ReLU -> (split fp16 | fp32 NCHW) =====
@@ -573,6 +590,8 @@ static size_t act_plane_halves(int C, int H, int W) {
   return (size_t)(C / 8) * (H + 2 * PAD) * (W + 2 * PAD) * 8;
 }
 
+static long long* g_tc_debug = nullptr;  // fnx_tc_set_debug
+
 static int pad16(int c) { return (c + 15) / 16 * 16; }
 static int cout_pad(int c) { return c <= 16 ? 16 : c <= 32 ? 32 : c <= 64 ? 64 : 128; }
 
@@ -626,6 +645,7 @@ static int launch_tc_rows(ConvArgs a, cudaStream_t st) {
   if (cluster) grid = (grid + 1) & ~1;
   if (cluster && grid > num_sms()) grid -= 2;
   a.iters = (a.nblocks + grid - 1) / grid;
+  a.dbg = g_tc_debug;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NTHREADS);
@@ -688,6 +708,11 @@ int fnx_tc_pack_weights(const float* w, int Cin, int Cout, int ksize, float w_sc
                                                                                   cout_pad(Cout), w_scale, (__half*)out);
   fnx_count_launches(1);
   FNX_CUDA_TRY("tc_pack_weights", cudaGetLastError());
+  return FNX_OK;
+}
+
+int fnx_tc_set_debug(long long* buf) {
+  g_tc_debug = buf;  // device buffer of >= 4 * SM-count int64, or NULL to switch the instrumentation off
   return FNX_OK;
 }
 
@@ -766,7 +791,7 @@ static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void
   a.H = H; a.W = W; a.Hp = H + 2 * PAD; a.Wp = W + 2 * PAD;
   a.relu = relu; a.out_mode = out_mode; a.y_ctotal = y_channels_total; a.y_coff = y_channel_offset;
   a.w_scale = w_scale; a.w_norm = w_norm; a.b_max = b_max;
-  a.tiles_x = 0; a.nblocks = 0; a.R = 1; a.iters = 0;
+  a.tiles_x = 0; a.nblocks = 0; a.R = 1; a.iters = 0; a.dbg = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   const int cp = cout_pad(Cout);
   if (ksize == 3) {

@@ -205,6 +205,9 @@ size_t fnx_tc_weight_bytes(int Cin, int Cout, int ksize);
 /* weight (Cout, Cin, k, k) fp32 -> packed split-fp16 slots; w_scale = power of two with max|w|*w_scale <= 2^14 */
 int fnx_tc_pack_weights(const float *weight, int Cin, int Cout, int ksize, float w_scale, void *out,
                         void *stream);
+/* tuning aid: while buf != NULL every fnx_conv_tc launch writes, per CTA b, buf[4b..4b+3] = clocks its MMA warp
+ * spent waiting for {activation stages, weight slots, accumulators handed back by the epilogue} and its total */
+int fnx_tc_set_debug(long long *buf);
 /* meta->amax_bits = max(meta->amax_bits, max|x|) */
 int fnx_tc_amax(const float *x, size_t n, fnx_act_meta *meta, void *stream);
 /* fp32 NCHW (one image) -> split chunked, scale chosen from in_meta->amax_bits */
