@@ -633,6 +633,11 @@ def make_report(args, wl, world, total_cells, cells, total_ms, e2e_ms, e2e_steps
                        "parallelism": parallelism,
                        "l2": "flushed between timed steps" if flush else "working set larger than L2, no flush",
                        "launch": "CUDA graph replay of the fused step" if graphed else "direct kernel launches",
+                       "arithmetic": ("fp32 stencils (bit-exact vs the reference's ATen CPU path)"
+                                      + ("; CNN convs fp32-equivalent on tcgen05: two-term fp16 expansion (hi+lo, 22 "
+                                         "significant bits) of activations and weights, 3 MMA terms, fp32 TMEM "
+                                         "accumulation -- 1e-5 parity vs torch fp32 (tests/test_gpu_cnn.py)"
+                                         if wl["method"] == "convnet" else "")),
                        "algorithmic_bytes_per_cell_step": step_bytes},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
