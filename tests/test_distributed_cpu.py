@@ -187,3 +187,47 @@ def test_decomposition_geometry():
     loc = d.scatter(x)
     assert loc.shape[3] == 256 and float(d.window(loc)[0, 0, 0, 0, 0]) == 16.0 and float(d.owned(loc)[0, 0, 0, 0, 0]) == 64.0
     assert d.window(loc).shape[3] == 160
+
+
+def test_pack_transfer_unpack_roundtrip_in_process():
+    """SlabDecomposition.pack / transfer / unpack with an in-process transport (three virtual ranks, no
+    process group): after an exchange every ghost row holds its owner's value, owned rows are untouched,
+    and the packed message is one contiguous buffer per neighbour and direction."""
+    from fluidnet_cxx_b200.lib.distributed import SlabDecomposition
+
+    class Mailbox:
+        def __init__(self):
+            self.box = {}
+
+        def exchange_rows(self, dec, sends):          # called rank by rank: two passes (post, then collect)
+            for peer, buf in sends.items():
+                self.box[(dec.rank, peer)] = buf.clone()
+            return {peer: self.box.get((peer, dec.rank), torch.zeros_like(buf)) for peer, buf in sends.items()}
+
+    H, W, g, world = 48, 5, 4, 3
+    comm = Mailbox()
+    decs = [SlabDecomposition(H, g, rank=r, world=world, comm=comm) for r in range(world)]
+    full = torch.arange(H, dtype=torch.float32).view(1, 1, 1, H, 1).expand(1, 2, 1, H, W).contiguous()
+    locs = []
+    for d in decs:
+        t = torch.full_like(full, -1.0)
+        t[:, :, :, d.lo:d.hi] = full[:, :, :, d.lo:d.hi] + 1000 * d.rank       # owned rows tagged with the owner
+        locs.append(t)
+    bufs = [{} for _ in decs]
+    for _ in range(2):                                   # pass 1 posts every message, pass 2 delivers them
+        for d, t, b in zip(decs, locs, bufs):
+            d.pack([t], b)
+            d.transfer(b)
+            d.unpack([t], b)
+    for d, t in zip(decs, locs):
+        rows = t[0, 0, 0, :, 0]
+        assert torch.equal(rows[d.lo:d.hi], full[0, 0, 0, d.lo:d.hi, 0] + 1000 * d.rank)
+        if d.rank > 0:
+            assert torch.equal(rows[d.lo - g:d.lo], full[0, 0, 0, d.lo - g:d.lo, 0] + 1000 * (d.rank - 1))
+        if d.rank < world - 1:
+            assert torch.equal(rows[d.hi:d.hi + g], full[0, 0, 0, d.hi:d.hi + g, 0] + 1000 * (d.rank + 1))
+        outside = torch.cat([rows[:max(d.r0, 0)], rows[d.r1:]])
+        assert bool((outside == -1).all())               # nothing outside the window is ever written
+        n_neigh = (d.rank > 0) + (d.rank < world - 1)
+        assert sum(1 for k in bufs[d.rank] if k[0] == "send") == n_neigh
+        assert all(v.numel() == 2 * g * W for k, v in bufs[d.rank].items() if k[0] == "send")
