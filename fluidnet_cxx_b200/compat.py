@@ -8,7 +8,8 @@ import sys
 def install():
     import fluidnet_cxx_b200.lib as L
     sys.modules["lib"] = L
-    for sub in ("fluid", "simulate", "multi_scale_net", "model"):
+    for sub in ("fluid", "simulate", "multi_scale_net", "model", "dataset_load", "util_print", "plot_field",
+                "argument_parser", "load_manta_data"):
         sys.modules["lib." + sub] = importlib.import_module("fluidnet_cxx_b200.lib." + sub)
     sys.modules["lib.fluid.cell_type"] = importlib.import_module("fluidnet_cxx_b200.lib.fluid.cell_type")
     sys.modules["fluidnet_cpp"] = importlib.import_module("fluidnet_cxx_b200.fluidnet_cpp")
