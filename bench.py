@@ -7,14 +7,23 @@ One "step" = one `lib.simulate` call (advect scalar+velocity -> BCs/forces -> di
 pressure solve -> velocity update -> BCs) on a synthetic grid of the named resolution.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 
+Default line: BASELINE.json configs[3], the largest single-GPU configuration (4096^2 plume,
+Jacobi-100: 16.8 M cells); the CNN configurations (configs[2] 1024^2 Rayleigh-Taylor ScaleNet,
+configs[1] 512^2 plume ScaleNet) are measured in the same run and reported as sub-records under
+"also", each with its own roofline / e2e / cpu_baseline.  `--workload NAME` runs one only.
+N > 1 (torchrun): the default line is STRONG scaling (the same global grid cut into N slabs,
+`--scaling weak` stacks N copies instead); a weak-scaling record rides under "also".
+
 Timing: CUDA events on the launching stream around each step, >= 3 warm-ups, max over ranks;
 between timed steps L2 is flushed when the working set is smaller than L2 (config.l2 says which).
 `value` times the device-resident step; `e2e` times the same call with HOST (pinned) state:
 H2D of the step's inputs + step + D2H of the results inside the timed region.
 `--impl reference` times the reference's own ATen CPU path (oracle/_ref, built from
 /root/reference by oracle/build_ref.py) on a bounded sample of the same workload.
+A wall-clock guard (--hang-timeout) ends a stuck run with the stalled phase and Python stacks.
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -34,32 +43,34 @@ L2_BYTES = 126 * 1024 * 1024
 
 # name -> grid, pressure method, and the bounded CPU sample used for the reference arm
 WORKLOADS = {
-    # BASELINE.json configs[3]: pure stencil HBM-roofline run
+    # BASELINE.json configs[3]: pure stencil HBM-roofline run -- the largest single-GPU configuration
     "plume4096_jacobi100": dict(res=(1, 4096, 4096), method="jacobi", jacobi_iters=100, cpu_sample_res=512,
-                                baseline_config="4096x4096 2D plume, Jacobi 100 iter"),
+                                cpu_steps=(1, 2), baseline_config="4096x4096 2D plume, Jacobi 100 iter"),
     # BASELINE.json configs[0]
     "plume128_jacobi28": dict(res=(1, 128, 128), method="jacobi", jacobi_iters=28, cpu_sample_res=128,
-                              baseline_config="128x128 2D plume, Jacobi 28 iter"),
+                              cpu_steps=(1, 10), baseline_config="128x128 2D plume, Jacobi 28 iter"),
     "plume1024_jacobi100": dict(res=(1, 1024, 1024), method="jacobi", jacobi_iters=100, cpu_sample_res=512,
-                                baseline_config="1024x1024 2D plume, Jacobi 100 iter"),
-    # BASELINE.json configs[4] with the Jacobi projection (3-D has no CNN in the reference)
+                                cpu_steps=(1, 2), baseline_config="1024x1024 2D plume, Jacobi 100 iter"),
+    # BASELINE.json configs[4] with the Jacobi projection
     "plume256cube_jacobi40": dict(res=(256, 256, 256), method="jacobi", jacobi_iters=40, cpu_sample_res=None,
-                                  baseline_config="256x256x256 3D synthetic grid, Jacobi 40 iter"),
-}
-WORKLOADS.update({
-    # BASELINE.json configs[1]: the configuration the headline metric is quoted on
+                                  cpu_steps=(0, 0), baseline_config="256x256x256 3D synthetic grid, Jacobi 40 iter"),
+    # BASELINE.json configs[1]
     "plume512_scalenet": dict(res=(1, 512, 512), method="convnet", jacobi_iters=0, cpu_sample_res=512,
-                              baseline_config="512x512 2D plume, ScaleNet CNN pressure, fp32"),
-    "plume1024_scalenet": dict(res=(1, 1024, 1024), method="convnet", jacobi_iters=0, cpu_sample_res=512,
-                               baseline_config="1024x1024 2D plume, MultiScale CNN pressure, fp32"),
-})
-WORKLOADS.update({
+                              cpu_steps=(1, 5), baseline_config="512x512 2D plume, ScaleNet CNN pressure, fp32"),
+    "plume1024_scalenet": dict(res=(1, 1024, 1024), method="convnet", jacobi_iters=0, cpu_sample_res=1024,
+                               cpu_steps=(1, 2), baseline_config="1024x1024 2D plume, MultiScale CNN pressure, fp32"),
     # BASELINE.json configs[2]: Rayleigh-Taylor (rayleighTaylorConfig.yaml physics, periodic-y seam)
-    "rt1024_scalenet": dict(res=(1, 1024, 1024), method="convnet", jacobi_iters=0, cpu_sample_res=512, case="rt",
+    "rt1024_scalenet": dict(res=(1, 1024, 1024), method="convnet", jacobi_iters=0, cpu_sample_res=1024, case="rt",
+                            cpu_steps=(1, 2),
                             baseline_config="1024x1024 2D Rayleigh-Taylor, MultiScale CNN pressure, fp32"),
-})
-DEFAULT_WORKLOAD = "plume512_scalenet"
+}
+# The N=1 line of the contract = the largest single-GPU configuration of BASELINE.json.configs (its
+# metric names no configuration): configs[3], 16.8 M cells.  The CNN configurations follow in "also".
+DEFAULT_WORKLOAD = "plume4096_jacobi100"
+ALSO_SINGLE = ("rt1024_scalenet", "plume512_scalenet")
 CNN_FLOP_PER_CELL = 484476.0   # 2 * 242238 MAC over the 17 convs of the pyramid
+CONFIG_KEYS = ("workload", "baseline_config", "grid", "measured_grid", "pressure", "cells_per_gpu", "parallelism",
+               "l2", "launch", "arithmetic", "algorithmic_bytes_per_cell_step")
 
 
 def plume_mconf(jacobi_iters, method):
@@ -106,6 +117,24 @@ def synthetic_state_numpy(D, H, W, seed=0):
     return U, rho
 
 
+def pressure_name(wl):
+    return f"jacobi x{wl['jacobi_iters']}" if wl["method"] == "jacobi" else "ScaleNet (MultiScaleNet, shipped weights)"
+
+
+def step_bytes_per_cell(wl):
+    """80 + 16 N_iter B/cell (2-D), 104 + 16 N_iter (3-D); the CNN step moves the 80 / 104
+    B/cell of stages A, B, D plus the CNN's own I/O"""
+    return (80 if wl["res"][0] == 1 else 104) + 16 * wl["jacobi_iters"]
+
+
+def load_peaks():
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            return json.load(f)
+    return {}
+
+
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
@@ -150,7 +179,7 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         # samples that arrived inside the marked timed region (nvidia-smi reports with ~20 ms period);
-        # a region shorter than one period falls back to every sample taken while this process kept
+        # a region shorter than two periods falls back to every sample taken while this process kept
         # the GPU under the same load (warm-up + timed + per-kernel pass), and says so
         inside = [ln for t, ln in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e300) + 0.02]
         window = "timed region"
@@ -172,12 +201,285 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
+def ncu_traffic(kernel_key):
+    """dram bytes per launch of a kernel from this round's ncu --set full capture
+    (profiles/r2_traffic.json; falls back to the round-1 file, labelled), or (None, None)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                v = json.load(f).get(kernel_key)
+            if v is not None:
+                return v, f"profiles/{name} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)"
+        except OSError:
+            pass
+    return None, None
+
+
 # ---------------------------------------------------------------------------------------------
-def run_ours_distributed(args):
-    """N > 1: weak scaling by slab decomposition.  The global grid is N slabs of the single-GPU
-    workload stacked along the outermost spatial axis; every rank owns one slab, computes it plus
-    ghost rows with the same kernels (row windows, global coordinates) and exchanges halos over NCCL
-    (fluidnet_cxx_b200/lib/distributed.py).  value = global cells * steps / max-over-ranks time."""
+def build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs, jacobi_launch_iters=8):
+    """The roofline object of one record.  stage_ms = {"advect_forces", "pressure", "project"} totals
+    (ms over `steps` steps of the per-kernel pass)."""
+    peaks = load_peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    D = wl["res"][0]
+    iters = wl["jacobi_iters"]
+    dom_ms = stage_ms.get("pressure", 0.0)
+    # the stencil group the north star names (fused advect + forces/BCs/divergence + update): stages A+B+D
+    grp_ms = stage_ms.get("advect_forces", 0.0) + stage_ms.get("project", 0.0)
+    grp_bytes = (80.0 if D == 1 else 104.0) * cells * steps
+    group = None
+    if wl["method"] == "jacobi" and grp_ms > 0:
+        gbs = grp_bytes / (grp_ms / 1e3) / 1e9
+        group = {"kernels": "k_step_advect_fwd + k_step_advect_bwd + k_step_forces_div + k_step_project",
+                 "algorithmic_bytes_per_cell": 80 if D == 1 else 104, "ms_per_step": round(grp_ms / steps, 4),
+                 "achieved": round(gbs, 1), "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
+                 "advect_forces_ms_per_step": round(stage_ms.get("advect_forces", 0.0) / steps, 4),
+                 "project_ms_per_step": round(stage_ms.get("project", 0.0) / steps, 4)}
+    if wl["method"] == "jacobi":
+        # dominant kernel = the Jacobi iterations: 16 B/cell/iteration algorithmic (SURVEY §8d stage C).  The 2-D
+        # kernel is temporally blocked (several iterations per launch on register-resident tiles), so the
+        # algorithmic figure can exceed the HBM peak; `frac_of_launch_traffic` is the same time against the
+        # bytes a launch really has to move (12 R + 4 W per cell per LAUNCH).
+        algo_bytes = 16.0 * cells * iters * steps
+        achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
+        per_launch = jacobi_launch_iters if D == 1 else 1
+        nlaunch = (iters + per_launch - 1) // per_launch
+        launch_bytes = 16.0 * cells * nlaunch * steps
+        tkey = f"k_jacobi2d_blocked @{wl['res'][1]}x{wl['res'][2]}"
+        traffic, tsrc = ncu_traffic(tkey) if D == 1 else (None, None)
+        roof = {"bound": "hbm",
+                "kernel": f"k_jacobi2d_blocked ({per_launch} iterations per launch)" if D == 1
+                else "k_jacobi3d_vec (1 iteration per launch)",
+                "achieved": round(achieved, 1) if achieved else None, "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 4) if achieved else None,
+                "traffic": traffic, "traffic_source": tsrc,
+                "algorithmic_bytes_per_launch": 16.0 * cells * per_launch,
+                "launch_ms": round(dom_ms / steps / nlaunch, 5) if dom_ms > 0 else None,
+                "frac_of_launch_traffic": round(launch_bytes / (dom_ms / 1e3) / 1e9 / hbm_peak, 4) if dom_ms > 0 else None,
+                "peak_source": peak_src, "stage_ms_per_step": round(dom_ms / steps, 4),
+                "step_hbm_frac": round(step_bytes_per_cell(wl) * cells * steps / (total_ms / 1e3) / 1e9 / hbm_peak, 4),
+                "stencil_group": group}
+        return roof
+    # dominant kernel = the tcgen05 conv layer with the largest share of the step, timed per launch with
+    # CUDA events (fnx_profile_*).  achieved = ALGORITHMIC fp32-equivalent FLOPs (2*Cin*Cout*k*k*H*W) per
+    # launch / launch time; the kernel executes 3x that on the tensor pipe (split-fp16: hi*hi, hi*lo,
+    # lo*hi), reported beside it.  Peak = measured bf16 burst (kind::f16 and bf16 share the rate).
+    tc_peak = peaks.get("bf16_tflops", 1590.0)
+    peak_src_tc = ("MEASURED_PEAKS.json bf16_tflops (measured, burst)" if "bf16_tflops" in peaks
+                   else "fallback 1590 TFLOP/s")
+    agg = {}
+    for r in layer_recs:
+        key = (r.cin, r.cout, r.ksize, r.h, r.w, r.tensor)
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1; a[1] += r.ms
+    layers = []
+    for (cin, cout, k, h, w, tensor), (n, ms) in agg.items():
+        fl = 2.0 * cin * cout * k * k * h * w
+        layers.append({"layer": f"{cin}->{cout} k{k} @{h}x{w}", "tensor": bool(tensor), "launches": n,
+                       "ms_per_launch": round(ms / n, 4), "algorithmic_tflops": round(fl / (ms / n / 1e3) / 1e12, 2)})
+    cnn_ms = sum(v[1] for v in agg.values()) / max(steps, 1)
+    top = max((kv for kv in agg.items() if kv[0][5]), key=lambda kv: kv[1][1], default=None)
+    if top is None:
+        return {"bound": "tensor", "kernel": None, "achieved": None, "peak": round(tc_peak, 1), "unit": "TFLOP/s",
+                "frac": None, "traffic": None, "peak_source": peak_src_tc}
+    (cin, cout, k, h, w, _), (n, ms) = top
+    fl = 2.0 * cin * cout * k * k * h * w
+    achieved = fl / (ms / n / 1e3) / 1e12
+    traffic, tsrc = ncu_traffic(f"k_conv_tc {cin}->{cout} k{k} @{h}x{w}")
+    return {"bound": "tensor", "kernel": f"k_conv_tc (tcgen05 split-fp16 implicit GEMM) {cin}->{cout} k{k} @{h}x{w}",
+            "achieved": round(achieved, 2), "peak": round(tc_peak, 1), "unit": "TFLOP/s",
+            "frac": round(achieved / tc_peak, 4), "traffic": traffic, "traffic_source": tsrc,
+            "peak_source": peak_src_tc, "launch_ms": round(ms / n, 4), "launches_timed": n,
+            "algorithmic_flop_per_launch": fl, "executed_tensor_tflops": round(3 * achieved, 2),
+            "executed_tensor_frac": round(3 * achieved / tc_peak, 4),
+            "share_of_step": round((ms / steps) / (total_ms / steps), 4),
+            "conv_launch_ms_per_step": round(cnn_ms, 4), "stage_ms_per_step": round(dom_ms / steps, 4),
+            "forward_algorithmic_tflops": round(CNN_FLOP_PER_CELL * cells * steps / (dom_ms / 1e3) / 1e12, 2)
+            if dom_ms > 0 else None,
+            "algorithmic_flop_per_cell": CNN_FLOP_PER_CELL, "layers": layers}
+
+
+def make_record(args, name, wl, world, total_cells, cells, steps, warmup, total_ms, e2e_ms, e2e_steps, roof, h2d, d2h,
+                launches, clocks, t_wall, flush, graphed, parallelism, grid, scaling):
+    """One record of the contract's JSON line.  cells = cells one GPU computes per step."""
+    value = total_cells * steps / (total_ms / 1e3) / 1e6
+    e2e_value = total_cells * e2e_steps / (e2e_ms / 1e3) / 1e6
+    return {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(total_ms / steps, 4),
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (seeded N(0,0.5^2) velocity, U[0,1) density, plume inlet BCs, border obstacles)",
+        "config": {"workload": name, "baseline_config": wl["baseline_config"], "grid": grid, "measured_grid": grid,
+                   "pressure": pressure_name(wl), "cells_per_gpu": cells, "parallelism": parallelism,
+                   "l2": "flushed between timed steps" if flush else "working set larger than L2, no flush",
+                   "launch": "CUDA graph replay of the fused step" if graphed else "direct kernel launches",
+                   "arithmetic": ("fp32 stencils (bit-exact vs the reference's ATen CPU path)"
+                                  + ("; CNN convs fp32-equivalent on tcgen05: two-term fp16 expansion (hi+lo, 22 "
+                                     "significant bits) of activations and weights, 3 MMA terms, fp32 TMEM "
+                                     "accumulation -- 1e-5 parity vs torch fp32 (tests/test_gpu_cnn.py)"
+                                     if wl["method"] == "convnet" else "")),
+                   "algorithmic_bytes_per_cell_step": step_bytes_per_cell(wl)},
+        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "wall_s": round(t_wall, 3),
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+def run_single(args, name, guard, local_rank=0, want_cpu_baseline=True):
+    """One workload on one GPU through the public lib.simulate."""
+    import importlib
+    import torch
+    from fluidnet_cxx_b200 import _native
+    from fluidnet_cxx_b200.lib import fluid
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+
+    wl = WORKLOADS[name]
+    dev = torch.device("cuda", local_rank)
+    lib = _native.load()
+    D, H, W = wl["res"]
+    cells = D * H * W
+    mconf = workload_mconf(wl)
+    nc = 3 if D > 1 else 2
+    net = None
+    if wl["method"] == "convnet":
+        from fluidnet_cxx_b200.lib.pretrained import load_scalenet
+        net, mconf_net = load_scalenet(dev)
+        m = dict(mconf_net); m.update(mconf); mconf = m
+        net.mconf = mconf; net.scale.mconf = mconf
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # ---- synthetic state, built on the HOST (pinned) and copied in ------------------------------
+    guard.beat(f"{name}: state")
+    U_np, rho_np = synthetic_state_numpy(D, H, W, seed=0)
+    host = {"p": torch.zeros(1, 1, D, H, W).pin_memory(), "U": torch.from_numpy(U_np).pin_memory(),
+            "flags": torch.zeros(1, 1, D, H, W).pin_memory(), "density": torch.from_numpy(rho_np).pin_memory()}
+    bd = {k: torch.zeros_like(v, device=dev) for k, v in host.items()}
+    init_state(fluid, wl, mconf, bd, U_np, rho_np, lambda a: torch.from_numpy(a).to(dev))
+    for k in ("flags", "U", "density"):
+        host[k].copy_(bd[k])
+    torch.cuda.synchronize()
+
+    working_set = cells * 4 * (1 + nc + 1 + 1 + 2 * nc + 2)   # state + masks
+    flush = working_set < 2 * L2_BYTES
+    flush_buf = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev) if flush else None
+
+    def one_step():
+        with torch.no_grad():
+            sim.simulate(mconf, bd, net, wl["method"])
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for i in range(warmup):
+        guard.beat(f"{name}: warm-up step {i}")
+        one_step()
+    torch.cuda.synchronize()
+
+    # ---- pass 1: the timed region of `value` (public API; CUDA-graph replay where the step is small) ----
+    guard.beat(f"{name}: timed steps")
+    step_ms = []
+    torch.cuda.synchronize()
+    sampler.mark_begin()
+    t_wall0 = time.perf_counter()
+    for _ in range(steps):
+        if flush:
+            flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_step()
+        e1.record()
+        step_ms.append((e0, e1))
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.mark_end()
+    total_ms = sum(a.elapsed_time(b) for a, b in step_ms)
+    graphed = bool(sim.graphs_enabled() and cells <= sim.GRAPH_MAX_CELLS)
+
+    # ---- pass 2: the same steps issued stage by stage with CUDA events around every stage (stage hook)
+    # and, for the CNN, around every conv launch (fnx_profile_*): roofline inputs.  The launch count is
+    # taken here (a graph replay re-issues exactly these kernels).
+    guard.beat(f"{name}: per-stage pass")
+    stage_events = {}
+
+    def hook(stage, when):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        stage_events.setdefault(stage, []).append(ev)
+    sim.set_stage_hook(hook)
+    one_step()
+    torch.cuda.synchronize()
+    stage_events.clear()
+    if wl["method"] == "convnet":
+        lib.fnx_profile_enable(1)
+    n0 = lib.fnx_launch_count()
+    for _ in range(steps):
+        if flush:
+            flush_buf.zero_()
+        one_step()
+    torch.cuda.synchronize()
+    launches = lib.fnx_launch_count() - n0
+    layer_recs = []
+    if wl["method"] == "convnet":
+        buf = (_native.ProfileRec * 4096)()
+        n = lib.fnx_profile_fetch(buf, 4096)
+        lib.fnx_profile_enable(0)
+        layer_recs = [buf[i] for i in range(max(0, min(n, 4096)))]
+    stage_ms = {k: sum(v[2 * i].elapsed_time(v[2 * i + 1]) for i in range(len(v) // 2)) for k, v in stage_events.items()}
+    sim.set_stage_hook(None)
+    clocks = sampler.stop()
+
+    # ---- e2e: host (pinned) state in, results out, every step -----------------------------------
+    guard.beat(f"{name}: e2e steps")
+    e2e_steps = max(3, min(steps, 10))
+    h2d = sum(host[k].numel() * 4 for k in ("p", "U", "flags", "density"))
+    d2h = sum(host[k].numel() * 4 for k in ("p", "U", "density"))
+    out_host = {k: torch.empty_like(host[k]).pin_memory() for k in ("p", "U", "density")}
+    masks = {k: bd[k] for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask") if k in bd}
+
+    def e2e_step():
+        d = {k: host[k].to(dev, non_blocking=True) for k in ("p", "U", "flags", "density")}
+        d.update(masks)
+        with torch.no_grad():
+            sim.simulate(mconf, d, net, wl["method"])
+        for k in ("p", "U", "density"):
+            out_host[k].copy_(d[k], non_blocking=True)
+        return d
+
+    e2e_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+
+    roof = build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs)
+    out = make_record(args, name, wl, 1, cells, cells, steps, warmup, total_ms, e2e_ms, e2e_steps, roof, h2d, d2h,
+                      int(launches), clocks, t_wall, flush, graphed, "1 GPU", [D, H, W], args.scaling)
+    del bd, host, out_host, flush_buf, masks
+    sim.clear_graph_cache()
+    torch.cuda.empty_cache()
+    if want_cpu_baseline:
+        guard.beat(f"{name}: cpu_baseline")
+        guard_prev, guard.timeout_s = guard.timeout_s, max(guard.timeout_s, 600.0)
+        out["cpu_baseline"] = cpu_baseline(wl, *wl["cpu_steps"][::-1])
+        guard.timeout_s = guard_prev
+    else:
+        out["cpu_baseline"] = None
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def run_distributed(args, name, scaling, guard, transport):
+    """N > 1: slab decomposition along the outermost spatial axis (fluidnet_cxx_b200/lib/distributed.py).
+    strong = the workload grid itself cut into N slabs; weak = N slabs of the workload grid stacked.
+    value = global cells * steps / max-over-ranks time.  Returns the record on rank 0, None elsewhere."""
     import importlib
     import torch
     import torch.distributed as dist
@@ -185,12 +487,10 @@ def run_ours_distributed(args):
     from fluidnet_cxx_b200.lib import fluid
     D = importlib.import_module("fluidnet_cxx_b200.lib.distributed")
 
-    wl = WORKLOADS[args.workload]
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    wl = WORKLOADS[name]
+    rank, world = dist.get_rank(), dist.get_world_size()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
     lib = _native.load()
     Dz, H, W = wl["res"]
     is3d = Dz > 1
@@ -207,37 +507,19 @@ def run_ours_distributed(args):
     ghost = D.GHOST_CONVNET if wl["method"] == "convnet" else D.GHOST_JACOBI
     axis = 2 if is3d else 3
     rows_owned = Dz if is3d else H
-    if args.scaling == "strong":
+    if scaling == "strong":
         if rows_owned % world:
             raise SystemExit(f"bench.py: {rows_owned} rows do not split over {world} GPUs")
         rows_owned //= world
     ghost = min(ghost, rows_owned // 4 * 4)
     gD, gH = (rows_owned * world, H) if is3d else (1, rows_owned * world)
-    decomp = D.SlabDecomposition(rows_owned * world, ghost, axis=axis)
+    decomp = D.SlabDecomposition(rows_owned * world, ghost, axis=axis, transport=transport)
     cells_global = gD * gH * W
-    transport = "nccl"
-    if args.transport in ("auto", "peer"):
-        # probe the peer-memory path on every rank (symmetric allocation + rendezvous); all ranks agree
-        ok = 1.0
-        try:
-            decomp.transport = "peer"
-            decomp.peer = D.PeerMemoryTransport(decomp)
-            decomp.peer.region("probe", 64, torch.float32, dev)
-            torch.cuda.synchronize()
-        except Exception as e:      # noqa: BLE001
-            ok = 0.0
-            if rank == 0:
-                print(f"[bench] peer-memory transport unavailable ({e!r}); using NCCL send/recv", file=sys.stderr)
-        t_ok = torch.tensor([ok], device=dev)
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        if t_ok.item() >= 1.0:
-            transport = "peer"
-        else:
-            decomp.transport, decomp.peer = "nccl", None
-            if args.transport == "peer":
-                raise SystemExit("bench.py: --transport peer requested but peer memory could not be set up")
+    steps, warmup = args.steps, max(args.warmup, 3)
+    tag = f"{name}/{scaling}"
 
     # the same seeded global state on every rank (pinned host), window rows copied in
+    guard.beat(f"{tag}: state")
     U_np, rho_np = synthetic_state_numpy(gD, gH, W, seed=0)
     host = {"p": torch.zeros(1, 1, gD, gH, W).pin_memory(), "U": torch.from_numpy(U_np).pin_memory(),
             "flags": torch.zeros(1, 1, gD, gH, W).pin_memory(), "density": torch.from_numpy(rho_np).pin_memory()}
@@ -272,40 +554,42 @@ def run_ours_distributed(args):
         def cnn(self, *a):
             return self._timed(super().cnn, *a)
     ops = TimedOps()
+    ops.events = []
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
 
-    # pass 1 (value): the public stepper -- the whole step incl. NCCL halo exchange replayed as one CUDA
-    # graph when the step is launch-bound; pass 2 below re-issues it kernel by kernel for the roofline
+    # pass 1 (value): the public stepper -- the step replayed as CUDA graphs when it is launch-bound;
+    # pass 2 below re-issues it kernel by kernel for the roofline
+    guard.beat(f"{tag}: stepper set-up / graph capture")
     use_graph = window_cells <= (1 << 22) and os.environ.get("FLUIDNET_B200_GRAPHS", "1") != "0"
     stepper = D.GraphedDistributedStep(mconf, bd, net, wl["method"], decomp, use_graph=use_graph)
     graphed = stepper.graphed
+    guard.beat(f"{tag}: graph-vs-direct check")
     graph_check = stepper.verify() if graphed else None     # graphs vs direct launches, owned rows
     if rank == 0 and stepper.capture_error:
         print(f"[bench] CUDA-graph capture of the distributed step failed, using direct launches: "
               f"{stepper.capture_error}", file=sys.stderr)
 
-    def one_step():
-        stepper.step()
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        one_step()
+    for i in range(warmup):
+        guard.beat(f"{tag}: warm-up step {i}")
+        stepper.step()
     barrier()
     step_ms = []
     barrier()
     sampler.mark_begin()
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(steps):
+        guard.beat(f"{tag}: timed step {i}")
         if flush:
             flush_buf.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        one_step()
+        stepper.step()
         e1.record()
         step_ms.append((e0, e1))
     barrier()
@@ -314,6 +598,7 @@ def run_ours_distributed(args):
     total_ms = sum(a.elapsed_time(b) for a, b in step_ms)
 
     # pass 2: direct launches with per-stage / per-layer events
+    guard.beat(f"{tag}: per-stage pass")
     bd = stepper.state
 
     def one_step():
@@ -325,16 +610,12 @@ def run_ours_distributed(args):
     if wl["method"] == "convnet":
         lib.fnx_profile_enable(1)
     n0 = lib.fnx_launch_count()
-    step_ms = []
     barrier()
-    for _ in range(args.steps):
+    for i in range(steps):
+        guard.beat(f"{tag}: per-stage step {i}")
         if flush:
             flush_buf.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         one_step()
-        e1.record()
-        step_ms.append((e0, e1))
     barrier()
     launches = lib.fnx_launch_count() - n0
     dom_ms = sum(a.elapsed_time(b) for a, b in ops.events)
@@ -347,11 +628,13 @@ def run_ours_distributed(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: this rank's window rows in from pinned host memory, owned rows out, every step ----
-    e2e_steps = max(3, min(args.steps, 10))
+    guard.beat(f"{tag}: e2e steps")
+    e2e_steps = max(3, min(steps, 10))
     win, own = decomp._sl(decomp.r0, decomp.r1), decomp._sl(decomp.lo, decomp.hi)
     h2d = sum(host[k][win].numel() * 4 for k in ("p", "U", "flags", "density"))
     d2h = sum(host[k][own].numel() * 4 for k in ("p", "U", "density"))
     out_host = {k: torch.empty_like(host[k][own]).pin_memory() for k in ("p", "U", "density")}
+
     def e2e_step():
         for k in ("p", "U", "flags", "density"):
             stepper.state[k][win].copy_(host[k][win], non_blocking=True)
@@ -375,284 +658,64 @@ def run_ours_distributed(args):
     tb = torch.tensor([float(h2d), float(d2h), float(launches)], dtype=torch.float64, device=dev)
     dist.all_reduce(tb)
     h2d_all, d2h_all, launches_all = (int(x) for x in tb.tolist())
+    out = None
     if rank == 0:
-        out = make_report(args, wl, world, cells_global, window_cells, total_ms, e2e_ms, e2e_steps, dom_ms, layer_recs,
-                          h2d_all, d2h_all, launches_all, clocks, t_wall, flush, graphed,
-                          parallelism=(f"{world} GPUs: slab decomposition along {'D' if is3d else 'H'} "
+        roof = build_roofline(wl, steps, window_cells, total_ms, {"pressure": dom_ms}, layer_recs)
+        out = make_record(args, name, wl, world, cells_global, window_cells, steps, warmup, total_ms, e2e_ms, e2e_steps,
+                          roof, h2d_all, d2h_all, launches_all, clocks, t_wall, flush, graphed,
+                          parallelism=(f"{world} GPUs, {scaling} scaling: slab decomposition along {'D' if is3d else 'H'} "
                                        f"({rows_owned} owned + {ghost} ghost rows per interior side), halo exchange by "
                                        + ("stores into the neighbours' inboxes over NVLink peer memory"
-                                          if transport == "peer" else "NCCL send/recv")
+                                          if decomp.transport == "peer" else "NCCL send/recv")
                                        + f", global grid {gD}x{gH}x{W}"),
-                          grid=[gD, gH, W])
+                          grid=[gD, gH, W], scaling=scaling)
         out["cpu_baseline"] = None
-        out["scaling"] = args.scaling
         if graph_check is not None:
             out["config"]["graph_vs_direct_max_abs_diff"] = graph_check
+    del stepper, bd, host, out_host, flush_buf, ops
+    torch.cuda.empty_cache()
+    barrier()
+    return out
+
+
+def run_ours(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    from fluidnet_cxx_b200.lib.hang_guard import HangGuard
+    guard = HangGuard(args.hang_timeout, who=f"bench.py rank {rank}/{world}")
+    name = args.workload or DEFAULT_WORKLOAD
+    if world == 1:
+        out = run_single(args, name, guard, local_rank, want_cpu_baseline=not args.no_cpu_baseline)
+        if args.workload is None and not args.no_also:
+            out["also"] = [run_single(args, w, guard, local_rank, want_cpu_baseline=not args.no_cpu_baseline)
+                           for w in ALSO_SINGLE]
+        guard.stop()
+        print(json.dumps(out), flush=True)
+        return
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    guard.beat("init_process_group")
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=max(60.0, 1.5 * args.hang_timeout)))
+    out = run_distributed(args, name, args.scaling, guard, args.transport)
+    if args.workload is None and not args.no_also:
+        other = "weak" if args.scaling == "strong" else "strong"
+        also = [run_distributed(args, name, other, guard, args.transport)]
+        if rank == 0:
+            out["also"] = also
+    guard.stop()
+    if rank == 0:
         print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def run_ours(args):
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        return run_ours_distributed(args)
-    import torch
-    import torch.distributed as dist
-    from fluidnet_cxx_b200 import _native
-    from fluidnet_cxx_b200.lib import fluid
-    import importlib
-    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
-
-    wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _native.load()
-
-    D, H, W = wl["res"]
-    cells = D * H * W
-    mconf = workload_mconf(wl)
-    nc = 3 if D > 1 else 2
-    net = None
-    if wl["method"] == "convnet":
-        from fluidnet_cxx_b200.lib.pretrained import load_scalenet
-        net, mconf_net = load_scalenet(dev)
-        m = dict(mconf_net); m.update(mconf); mconf = m
-        net.mconf = mconf; net.scale.mconf = mconf
-
-    # ---- synthetic state, built on the HOST (pinned) and copied in ------------------------------
-    U_np, rho_np = synthetic_state_numpy(D, H, W, seed=rank)
-    host = {"p": torch.zeros(1, 1, D, H, W).pin_memory(), "U": torch.from_numpy(U_np).pin_memory(),
-            "flags": torch.zeros(1, 1, D, H, W).pin_memory(), "density": torch.from_numpy(rho_np).pin_memory()}
-    bd = {k: torch.zeros_like(v, device=dev) for k, v in host.items()}
-    init_state(fluid, wl, mconf, bd, U_np, rho_np, lambda a: torch.from_numpy(a).to(dev))
-    for k in ("flags", "U", "density"):
-        host[k].copy_(bd[k])
-    torch.cuda.synchronize()
-
-    working_set = cells * 4 * (1 + nc + 1 + 1 + 2 * nc + 2)   # state + masks
-    flush = working_set < 2 * L2_BYTES
-    flush_buf = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev) if flush else None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def one_step():
-        with torch.no_grad():
-            sim.simulate(mconf, bd, net, wl["method"])
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        one_step()
-    barrier()
-
-    # ---- pass 1: the timed region of `value` (public API; CUDA-graph replay where the step is small) ----
-    n0 = lib.fnx_launch_count()
-    step_ms = []
-    barrier()
-    sampler.mark_begin()
-    t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        if flush:
-            flush_buf.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        one_step()
-        e1.record()
-        step_ms.append((e0, e1))
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    sampler.mark_end()
-    times = [a.elapsed_time(b) for a, b in step_ms]
-    total_ms = sum(times)
-    graphed = bool(sim.graphs_enabled() and cells <= sim.GRAPH_MAX_CELLS)
-
-    # ---- pass 2: the same steps issued kernel by kernel, with CUDA events around the pressure stage
-    # (stage hook) and, for the CNN, around every conv launch (fnx_profile_*): roofline inputs.  The
-    # launch count is taken here (a graph replay re-issues exactly these kernels).
-    stage_events = []
-
-    def hook(name, when):
-        if name == "pressure":
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            stage_events.append(ev)
-    sim.set_stage_hook(hook)
-    one_step()
-    torch.cuda.synchronize()
-    stage_events.clear()
-    if wl["method"] == "convnet":
-        lib.fnx_profile_enable(1)
-    n0 = lib.fnx_launch_count()
-    for _ in range(args.steps):
-        if flush:
-            flush_buf.zero_()
-        one_step()
-    torch.cuda.synchronize()
-    launches = lib.fnx_launch_count() - n0
-    layer_recs = []
-    if wl["method"] == "convnet":
-        buf = (_native.ProfileRec * 4096)()
-        n = lib.fnx_profile_fetch(buf, 4096)
-        lib.fnx_profile_enable(0)
-        layer_recs = [buf[i] for i in range(max(0, min(n, 4096)))]
-    dom_ms = sum(stage_events[2 * i].elapsed_time(stage_events[2 * i + 1]) for i in range(len(stage_events) // 2))
-    sim.set_stage_hook(None)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- e2e: host (pinned) state in, results out, every step -----------------------------------
-    e2e_steps = max(3, min(args.steps, 10))
-    h2d = sum(host[k].numel() * 4 for k in ("p", "U", "flags", "density"))
-    d2h = sum(host[k].numel() * 4 for k in ("p", "U", "density"))
-    out_host = {k: torch.empty_like(host[k]).pin_memory() for k in ("p", "U", "density")}
-    masks = {k: bd[k] for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask") if k in bd}
-
-    def e2e_step():
-        d = {k: host[k].to(dev, non_blocking=True) for k in ("p", "U", "flags", "density")}
-        d.update(masks)
-        with torch.no_grad():
-            sim.simulate(mconf, d, net, wl["method"])
-        for k in ("p", "U", "density"):
-            out_host[k].copy_(d[k], non_blocking=True)
-        return d
-
-    e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-
-    if rank == 0:
-        out = make_report(args, wl, world, cells * world, cells, total_ms, e2e_ms, e2e_steps, dom_ms, layer_recs, h2d, d2h,
-                          int(launches), clocks, t_wall, flush, graphed, parallelism="1 GPU", grid=[D, H, W])
-        out["cpu_baseline"] = cpu_baseline(wl, steps=1, warmup=0) if not args.no_cpu_baseline else None
-        print(json.dumps(out), flush=True)
-
-
-def ncu_traffic(kernel_key):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r1_traffic.json), or None when that kernel / size has not been captured."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            return json.load(f).get(kernel_key)
-    except OSError:
-        return None
-
-
-def make_report(args, wl, world, total_cells, cells, total_ms, e2e_ms, e2e_steps, dom_ms, layer_recs, h2d, d2h, launches,
-                clocks, t_wall, flush, graphed, parallelism, grid):
-    """The one JSON line of the contract (rank 0).  cells = cells one GPU computes per step."""
-    D = grid[0] if world == 1 else wl["res"][0]
-    if True:
-        peaks = {}
-        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            with open(pk) as f:
-                peaks = json.load(f)
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        value = total_cells * args.steps / (total_ms / 1e3) / 1e6
-        e2e_value = total_cells * e2e_steps / (e2e_ms / 1e3) / 1e6
-        iters = wl["jacobi_iters"]
-        step_bytes = (80 if D == 1 else 104) + 16 * iters
-        if wl["method"] == "jacobi":
-            # dominant kernel = temporally blocked Jacobi: 16 B/cell/iteration algorithmic (SURVEY §8d stage C)
-            algo_bytes = 16.0 * cells * iters * args.steps
-            achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
-            roof = {"bound": "hbm", "kernel": "k_jacobi2d_blocked (8 iterations per launch)" if D == 1
-                    else "k_jacobi3d_vec (1 iteration per launch)",
-                    "achieved": round(achieved, 1) if achieved else None, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(achieved / hbm_peak, 4) if achieved else None,
-                    "traffic": ncu_traffic(f"k_jacobi2d_blocked @{wl['res'][1]}x{wl['res'][2]}") if D == 1 else None,
-                    "algorithmic_bytes_per_launch": 16.0 * cells * (8 if D == 1 else 1),
-                    "peak_source": peak_src, "stage_ms_per_step": round(dom_ms / args.steps, 4),
-                    "step_hbm_frac": round(step_bytes * cells * args.steps / (total_ms / 1e3) / 1e9 / hbm_peak, 4)}
-            pressure = f"jacobi x{iters}"
-        else:
-            # dominant kernel = the tcgen05 conv layer with the largest share of the step, timed per
-            # launch with CUDA events (fnx_profile_*).  achieved = ALGORITHMIC fp32-equivalent FLOPs
-            # (2*Cin*Cout*k*k*H*W) per launch / launch time; the kernel executes 3x that on the tensor
-            # pipe (split-fp16: hi*hi, hi*lo, lo*hi), reported beside it.  Peak = measured bf16 burst
-            # (kind::f16 and bf16 share the rate).
-            tc_peak = peaks.get("bf16_tflops", 1590.0)
-            peak_src_tc = ("MEASURED_PEAKS.json bf16_tflops (measured, burst)" if "bf16_tflops" in peaks
-                           else "fallback 1590 TFLOP/s")
-            agg = {}
-            for r in layer_recs:
-                key = (r.cin, r.cout, r.ksize, r.h, r.w, r.tensor)
-                a = agg.setdefault(key, [0, 0.0])
-                a[0] += 1; a[1] += r.ms
-            layers = []
-            for (cin, cout, k, h, w, tensor), (n, ms) in agg.items():
-                fl = 2.0 * cin * cout * k * k * h * w
-                layers.append({"layer": f"{cin}->{cout} k{k} @{h}x{w}", "tensor": bool(tensor), "launches": n,
-                               "ms_per_launch": round(ms / n, 4), "algorithmic_tflops": round(fl / (ms / n / 1e3) / 1e12, 2)})
-            cnn_ms = sum(v[1] for v in agg.values()) / max(args.steps, 1)
-            top = max((kv for kv in agg.items() if kv[0][5]), key=lambda kv: kv[1][1], default=None)
-            if top is not None:
-                (cin, cout, k, h, w, _), (n, ms) = top
-                fl = 2.0 * cin * cout * k * k * h * w
-                achieved = fl / (ms / n / 1e3) / 1e12
-                roof = {"bound": "tensor", "kernel": f"k_conv_tc (tcgen05 split-fp16 implicit GEMM) {cin}->{cout} k{k} @{h}x{w}",
-                        "achieved": round(achieved, 2), "peak": round(tc_peak, 1), "unit": "TFLOP/s",
-                        "frac": round(achieved / tc_peak, 4),
-                        "traffic": ncu_traffic(f"k_conv_tc {cin}->{cout} k{k} @{h}x{w}"), "peak_source": peak_src_tc,
-                        "launch_ms": round(ms / n, 4), "launches_timed": n, "algorithmic_flop_per_launch": fl,
-                        "executed_tensor_tflops": round(3 * achieved, 2),
-                        "executed_tensor_frac": round(3 * achieved / tc_peak, 4),
-                        "share_of_step": round((ms / args.steps) / (total_ms / args.steps), 4),
-                        "conv_launch_ms_per_step": round(cnn_ms, 4),
-                        "stage_ms_per_step": round(dom_ms / args.steps, 4),
-                        "forward_algorithmic_tflops": round(CNN_FLOP_PER_CELL * cells * args.steps / (dom_ms / 1e3) / 1e12, 2)
-                        if dom_ms > 0 else None,
-                        "algorithmic_flop_per_cell": CNN_FLOP_PER_CELL, "layers": layers}
-            else:
-                roof = {"bound": "tensor", "kernel": None, "achieved": None, "peak": round(tc_peak, 1), "unit": "TFLOP/s",
-                        "frac": None, "traffic": None, "peak_source": peak_src_tc}
-            pressure = "ScaleNet (MultiScaleNet, shipped weights)"
-        out = {
-            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (seeded N(0,0.5^2) velocity, U[0,1) density, plume inlet BCs, border obstacles)",
-            "config": {"workload": args.workload, "baseline_config": wl["baseline_config"], "grid": grid,
-                       "pressure": pressure, "cells_per_gpu": cells,
-                       "parallelism": parallelism,
-                       "l2": "flushed between timed steps" if flush else "working set larger than L2, no flush",
-                       "launch": "CUDA graph replay of the fused step" if graphed else "direct kernel launches",
-                       "arithmetic": ("fp32 stencils (bit-exact vs the reference's ATen CPU path)"
-                                      + ("; CNN convs fp32-equivalent on tcgen05: two-term fp16 expansion (hi+lo, 22 "
-                                         "significant bits) of activations and weights, 3 MMA terms, fp32 TMEM "
-                                         "accumulation -- 1e-5 parity vs torch fp32 (tests/test_gpu_cnn.py)"
-                                         if wl["method"] == "convnet" else "")),
-                       "algorithmic_bytes_per_cell_step": step_bytes},
-            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": roof,
-            "wall_s": round(t_wall, 3),
-        }
-        return out
-
-
 # ---------------------------------------------------------------------------------------------
 def reference_step_runner(wl, res):
     """The reference's own CPU path (oracle/_ref) on a res x res sample of the workload."""
-    import numpy as np
     import torch
     import ref_loader
     if not ref_loader.available():
@@ -676,20 +739,33 @@ def reference_step_runner(wl, res):
     return step
 
 
-def cpu_baseline(wl, steps, warmup):
+def _all_host_threads():
     import torch
     try:
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except (AttributeError, RuntimeError):
         pass
+
+
+def sample_text(wl, res, steps, warm):
+    import torch
+    full = res == wl["res"][1] == wl["res"][2]
+    return (f"{steps} timed step(s) (+{warm} warm-up) of the reference's ATen CPU path (patched build oracle/_ref, "
+            f"torch {torch.__version__}, {os.cpu_count()} host CPUs) on a {res}x{res} grid"
+            + (" = the full workload" if full else
+               f": same physics, reduced grid (minutes per step at the full {wl['res'][1]}x{wl['res'][2]} size)"))
+
+
+def cpu_baseline(wl, steps, warmup):
+    import torch
+    _all_host_threads()
     res = wl["cpu_sample_res"]
     if res is None:
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                 "sample": "none: the reference asserts 3-D off (advection.py:58,108); no CPU reference exists"}
     step = reference_step_runner(wl, res)
-    kind = "reference"
     if step is None:
-        return {"value": None, "unit": UNIT, "cores": 0, "kind": kind, "sample": "oracle/_ref not built"}
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -697,17 +773,18 @@ def cpu_baseline(wl, steps, warmup):
         step()
     dt = time.perf_counter() - t0
     return {"value": round(res * res * steps / dt / 1e6, 4), "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": kind, "seconds": round(dt, 2),
-            "sample": f"{steps} step(s) of the same physics on a {res}x{res} grid (reference ATen CPU path, "
-                      f"patched build oracle/_ref, torch {torch.__version__}, {os.cpu_count()} host CPUs)"}
+            "kind": "reference", "seconds": round(dt, 2), "sample": sample_text(wl, res, steps, warmup)}
 
 
 def run_reference(args):
+    """The reference arm: the reference's own ATen CPU implementation of the step (oracle/_ref) with every
+    host thread, the requested --steps / --warmup, on a bounded sample of the default workload."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload]
+    name = args.workload or DEFAULT_WORKLOAD
+    wl = WORKLOADS[name]
     res = wl["cpu_sample_res"]
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "the reference has no runnable 3-D path"}))
@@ -715,16 +792,12 @@ def run_reference(args):
     import torch
     # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm is the only work on this box while
     # it runs, give it every host thread
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except (AttributeError, RuntimeError):
-        pass
+    _all_host_threads()
     step = reference_step_runner(wl, res)
     if step is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"}))
         return
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
@@ -732,18 +805,22 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     value = res * res * steps / dt / 1e6
-    full = res == wl["res"][1] == wl["res"][2]
-    sample = (f"{steps} timed step(s) (+{warm} warm-up) of the reference's ATen CPU path (oracle/_ref) on a {res}x{res} "
-              f"grid" + (" = the full workload" if full else
-                         f": same physics, reduced grid (minutes per step at the full {wl['res'][1]}x{wl['res'][2]} size)"))
+    sample = sample_text(wl, res, steps, warm)
+    cores = torch.get_num_threads()
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
            "steps": steps, "warmup": warm, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the GPU arm)",
-           "config": {"workload": args.workload, "baseline_config": wl["baseline_config"], "grid": [1, res, res],
-                      "pressure": f"jacobi x{wl['jacobi_iters']}" if wl["method"] == "jacobi" else "ScaleNet"},
-           "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+           "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic (same generator as the GPU arm)",
+           "config": {"workload": name, "baseline_config": wl["baseline_config"], "grid": list(wl["res"]),
+                      "measured_grid": [1, res, res], "pressure": pressure_name(wl), "cells_per_gpu": 0,
+                      "parallelism": f"CPU, {cores} threads (ATen intra-op parallelism)", "l2": "n/a (CPU)",
+                      "launch": "reference lib.simulate, op by op",
+                      "arithmetic": "fp32 ATen CPU (the reference's own path)",
+                      "algorithmic_bytes_per_cell_step": step_bytes_per_cell(wl)},
+           "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "reference",
                             "sample": sample},
            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    assert tuple(out["config"]) == CONFIG_KEYS
     print(json.dumps(out), flush=True)
 
 
@@ -753,15 +830,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help=f"run this workload only (default: {DEFAULT_WORKLOAD}, plus the sub-records under 'also')")
+    ap.add_argument("--no-also", action="store_true", help="default workload only, no sub-records")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--transport", default="nccl", choices=["auto", "peer", "nccl"],
-                    help="N > 1 halo exchange: nccl = batched send/recv between CUDA-graph segments (default: "
-                         "measured equal or faster on 2 and 8 B200s); peer = stores into the neighbour's inbox over "
-                         "NVLink peer memory, whole step in one CUDA graph; auto = peer when it can be set up")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = N slabs of the workload grid stacked along H/D (default); "
-                         "strong = the workload grid itself split into N slabs")
+    ap.add_argument("--transport", default="nccl", choices=["peer", "nccl"],
+                    help="N > 1 halo exchange: nccl = batched send/recv between CUDA-graph segments; peer = stores "
+                         "into the neighbour's inbox over NVLink peer memory, whole step in one CUDA graph")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = the workload grid itself split into N slabs (default); "
+                         "weak = N slabs of the workload grid stacked along H/D")
+    ap.add_argument("--hang-timeout", type=float, default=120.0,
+                    help="seconds without progress before the run is ended with a diagnosis (0 = off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

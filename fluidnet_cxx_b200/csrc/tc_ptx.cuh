@@ -54,8 +54,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded wait: a barrier that does not flip within ~4e9 clocks (about 2 s at 1.9 GHz; a conv launch
+// lasts well under 1 ms) is a protocol deadlock, not a slow producer.  Trap instead of spinning forever,
+// so the failure surfaces as a CUDA error at the next synchronisation of the host (and of every peer
+// waiting on this rank) instead of a hung job.  The fast path (first try succeeds) is unchanged.
+#ifndef FNX_MBAR_TIMEOUT_CLOCKS
+#define FNX_MBAR_TIMEOUT_CLOCKS 4000000000LL
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > FNX_MBAR_TIMEOUT_CLOCKS) __trap();
   }
 }
 

@@ -25,8 +25,8 @@ _stage_hook = None
 
 
 def set_stage_hook(fn):
-    """fn(stage_name, 'begin'|'end') is called around the pressure stage of the fused step
-    (bench.py records CUDA events there); None restores the single-call path."""
+    """fn(stage_name, 'begin'|'end') is called around the stages of the fused step ('advect_forces',
+    'pressure', 'project'; bench.py records CUDA events there); None restores the single-call path."""
     global _stage_hook
     _stage_hook = fn
 
@@ -274,10 +274,14 @@ def _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div):
         prm = _step_params(mconf, dt, 0)
         prm.apply_wall_bcs = 0
         prm.density_const_passes = 1
+        if _stage_hook is not None:
+            _stage_hook("advect_forces", "begin")
         N.check(lib.fnx_step_advect_forces_div(ctypes.byref(prm), N.ptr(rho_in), N.ptr(U_in), N.ptr(flags),
                                                N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), rows_ptr,
                                                N.ptr(density), N.ptr(U), None, B, D, H, W, is3d,
                                                ws.data_ptr(), ws.numel(), st), "simulate")
+        if _stage_hook is not None:
+            _stage_hook("advect_forces", "end")
         net.eval()
         if _stage_hook is not None:
             _stage_hook("pressure", "begin")
@@ -305,18 +309,22 @@ def _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div):
         prm.apply_wall_bcs = 1
         prm.density_const_passes = 2
         div = torch.empty_like(flags)
+        _stage_hook("advect_forces", "begin")
         N.check(lib.fnx_step_advect_forces_div(ctypes.byref(prm), N.ptr(rho_in), N.ptr(U_in), N.ptr(flags),
                                                N.ptr(UBC), N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), rows_ptr,
                                                N.ptr(density), N.ptr(U), N.ptr(div), B, D, H, W, is3d,
                                                ws.data_ptr(), ws.numel(), st), "simulate")
+        _stage_hook("advect_forces", "end")
         wj = N.workspaces.get(U.device, "jacobi", lib.fnx_jacobi_workspace(B, D, H, W, prm.jacobi_iters))
         _stage_hook("pressure", "begin")
         N.check(lib.fnx_solve_linear_system_jacobi(N.ptr(flags), N.ptr(div), N.ptr(p), residual.data_ptr(), B, D, H,
                                                    W, is3d, 0.0, prm.jacobi_iters, None, wj.data_ptr(), wj.numel(),
                                                    st), "simulate")
         _stage_hook("pressure", "end")
+        _stage_hook("project", "begin")
         N.check(lib.fnx_step_project_bcs(N.ptr(p), N.ptr(U), N.ptr(flags), N.ptr(UBC), N.ptr(UBCInv), rows_ptr, 1,
                                          B, D, H, W, is3d, st), "simulate")
+        _stage_hook("project", "end")
     batch_dict['U'], batch_dict['density'], batch_dict['p'] = U, density, p
 
 

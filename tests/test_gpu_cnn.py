@@ -343,3 +343,84 @@ def test_conv_tc_power_of_two_scaling_is_exact():
     # and the result is invariant to where the tile grid falls: a shifted crop gives the same pixels
     crop = _tc_conv(lib, N, x[:, 100:360, 37:300].contiguous(), w, b, 0, 1)[2:130]
     assert torch.equal(crop[:, 1:-1, 1:-1], base[:, 101:359, 38:299])
+
+
+# ---------------------------------------------------------------------------------------------
+# Full-size parity against the REFERENCE model itself (oracle/_ref: the reference's FluidNet /
+# MultiScaleNet classes with the shipped weights, torch fp32 conv2d / interpolate / std on the host
+# CPU) at the BASELINE.json sizes: 512^2 plume (configs[1]) and 1024^2 Rayleigh-Taylor (configs[2]).
+# Tolerance = the north star's 1e-5 relative (max norm) on p and U, written here.
+def _reference_scalenet():
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref (the patched reference build) is not present on this box")
+    return ref_loader.load_scalenet()
+
+
+def _bench_state(name, seed=0):
+    """The synthetic state of bench.py's workload `name` (same generator), as CPU tensors."""
+    import bench
+    wl = bench.WORKLOADS[name]
+    reflib, ref_net, mconf_net = _reference_scalenet()
+    mconf = dict(mconf_net)
+    mconf.update(bench.workload_mconf(wl))
+    D, H, W = wl["res"]
+    U_np, rho_np = bench.synthetic_state_numpy(D, H, W, seed=seed)
+    bd = {"p": torch.zeros(1, 1, D, H, W), "U": torch.zeros(1, 2, D, H, W), "flags": torch.zeros(1, 1, D, H, W),
+          "density": torch.zeros(1, 1, D, H, W)}
+    bench.init_state(reflib.fluid, wl, mconf, bd, U_np, rho_np, torch.from_numpy)
+    return reflib, ref_net, mconf, bd
+
+
+@pytest.mark.parametrize("name", ["plume512_scalenet", "rt1024_scalenet"])
+def test_fluidnet_forward_full_size_vs_reference_cpu(net, name):
+    """FluidNet.forward (std normalisation, divergence, 17 convs, resizes, velocity update, wall BCs,
+    periodic seam for RT) on the full BASELINE grid vs the reference model on CPU: 1e-5 rel on p and U."""
+    model, mconf_net = net
+    reflib, ref_net, mconf, bd = _bench_state(name)
+    ref_net.mconf = mconf
+    ref_net.scale.mconf = mconf
+    data = torch.cat((bd["p"], bd["U"], bd["flags"], bd["density"]), 1)
+    with torch.no_grad():
+        p_ref, U_ref = ref_net(data.clone())
+    old = model.mconf
+    try:
+        model.mconf = mconf
+        model.scale.mconf = mconf
+        with torch.no_grad():
+            p, U = model(data.cuda())
+        assert rel_err(p.cpu().numpy(), p_ref.numpy()) < RTOL, name
+        assert rel_err(U.cpu().numpy(), U_ref.numpy()) < RTOL, name
+        assert np.array_equal(U.cpu().numpy() == 0, U_ref.numpy() == 0), name
+    finally:
+        model.mconf = old
+        model.scale.mconf = old
+
+
+@pytest.mark.parametrize("name", ["plume512_scalenet", "rt1024_scalenet"])
+def test_convnet_step_full_size_vs_reference_cpu(net, name):
+    """One whole lib.simulate(..., 'convnet') step of the bench workload at full size vs the reference's
+    own lib.simulate on CPU (advection + forces bit-exact, then the CNN projection): 1e-5 rel on p, U;
+    density (no CNN arithmetic on its path) bit-exact."""
+    model, mconf_net = net
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    reflib, ref_net, mconf, bd = _bench_state(name)
+    ref_net.mconf = mconf
+    ref_net.scale.mconf = mconf
+    dev = {k: v.cuda() for k, v in bd.items()}
+    with torch.no_grad():
+        reflib.simulate(mconf, bd, ref_net, "convnet")
+    old = model.mconf
+    try:
+        model.mconf = mconf
+        model.scale.mconf = mconf
+        sim.clear_graph_cache()
+        with torch.no_grad():
+            sim.simulate(mconf, dev, model, "convnet")
+        assert n_bad(dev["density"].cpu().numpy(), bd["density"].numpy()) == 0, name
+        assert rel_err(dev["p"].cpu().numpy(), bd["p"].numpy()) < RTOL, name
+        assert rel_err(dev["U"].cpu().numpy(), bd["U"].numpy()) < RTOL, name
+    finally:
+        sim.clear_graph_cache()
+        model.mconf = old
+        model.scale.mconf = old

@@ -350,3 +350,34 @@ def test_viscosity_and_correct_scalar_golden():
         simulate(mconf, bd, None, "jacobi")
         for k in ("p", "U", "density"):
             assert n_mismatch(bd[k].cpu().numpy(), z[f"sim/step{it}_{k}"]) == 0, (it, k)
+
+
+# ---------------------------------------------------------------------------------------------
+# getCentered (the output / statistics step of plume.py:238-243; reference grid.py:7-30)
+# ---------------------------------------------------------------------------------------------
+def _get_centered_reference(U):
+    """grid.py:7-30 restated on CPU tensors (pure slicing arithmetic: 0.5 * (a + b), last row / column /
+    plane left at 0); when oracle/_ref is on the box the reference function itself is used instead."""
+    try:
+        import ref_loader
+        if ref_loader.available():
+            return ref_loader.load().fluid.getCentered(U)
+    except Exception:      # noqa: BLE001 - fall through to the restatement
+        pass
+    is3d = U.size(2) > 1
+    cx = torch.zeros_like(U[:, 0]); cy = torch.zeros_like(U[:, 0]); cz = torch.zeros_like(U[:, 0])
+    cx[:, :, :, :-1] = 0.5 * (U[:, 0, :, :, 0:-1] + U[:, 0, :, :, 1:])
+    cy[:, :, :-1, :] = 0.5 * (U[:, 1, :, 0:-1, :] + U[:, 1, :, 1:, :])
+    if is3d:
+        cz[:, :-1, :, :] = 0.5 * (U[:, 2, 0:-1, :, :] + U[:, 2, 1:, :, :])
+    return torch.stack((cx, cy, cz), dim=1)
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 1, 33, 47), (2, 2, 1, 128, 128), (1, 3, 9, 17, 21), (1, 2, 1, 1024, 1024)])
+def test_get_centered_vs_reference(fluid, shape):
+    g = torch.Generator().manual_seed(shape[3])
+    U = torch.randn(shape, generator=g)
+    want = _get_centered_reference(U).numpy()
+    got = host(fluid.getCentered(U.cuda()))
+    assert got.shape == want.shape
+    assert n_mismatch(got, want) == 0
