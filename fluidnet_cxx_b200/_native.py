@@ -26,7 +26,8 @@ class StepParams(ctypes.Structure):
                 ("buoyancy3", _c_float * 3), ("gravity3", _c_float * 3),
                 ("rho_star", _c_float), ("jacobi_iters", _c_int),
                 ("apply_wall_bcs", _c_int), ("density_const_passes", _c_int),
-                ("row_begin", _c_int), ("row_end", _c_int)]
+                ("row_begin", _c_int), ("row_end", _c_int),
+                ("held_row_begin", _c_int), ("held_row_end", _c_int)]
 
 
 class ActMeta(ctypes.Structure):
@@ -69,6 +70,7 @@ SIGNATURES = {
     "fnx_solve_linear_system_jacobi": (_I, [_P, _P, _P, _P] + _GRID + [_F, _I, ctypes.POINTER(_I), _P, _S, _P]),
     "fnx_jacobi_iterate": (_I, [_P, _P, _P, _P] + _GRID + [_I, _I, _I, _P, _S, _P]),
     "fnx_step_project_bcs_rows": (_I, [_P] * 6 + [_I] + _GRID + [_I, _I, _P]),
+    "fnx_step_project_bcs_held": (_I, [_P] * 6 + [_I] + _GRID + [_I, _I, _I, _I, _P]),
     "fnx_velocity_divergence": (_I, [_P, _P, _P] + _GRID + [_P]),
     "fnx_velocity_update": (_I, [_P, _P, _P] + _GRID + [_P]),
     "fnx_set_wall_bcs": (_I, [_P, _P] + _GRID + [_P]),

@@ -28,6 +28,7 @@ UNITS = {
     "stencils.cu": ["-fmad=false"],
     "jacobi_blocked.cu": ["-fmad=false"],
     "step.cu": ["-fmad=false"],
+    "step2d.cu": ["-fmad=false"],
     "host_util.cpp": [],
     "conv.cu": [],
     "conv_tc.cu": [],

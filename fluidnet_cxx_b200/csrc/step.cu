@@ -9,10 +9,24 @@
 #include "fluid_common.cuh"
 #include "host_util.h"
 #include "stencil_device.cuh"
+#include "step2d.h"
+
+#include <stdlib.h>
 
 namespace fnx {
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// FNX_STEP2D=0 routes the 2-D step through the generic one-thread-per-cell kernels below (the 3-D
+// path), kept as the cross-check of the fused 2-D kernels (tests/test_gpu_parity.py)
+static bool use_clean() {
+  const char* e = getenv("FNX_STEP2D_CLEAN");
+  return !(e && e[0] == '0');
+}
+static bool use_step2d() {
+  const char* e = getenv("FNX_STEP2D");
+  return !(e && e[0] == '0');
+}
 
 // ---- unbiased std (model.py:18) ----------------------------------------------------------
 // pass 1: per-batch sum -> mean; pass 2: sum (x-mean)^2; both in double (torch accumulates the
@@ -307,10 +321,11 @@ int fnx_step_advect_forces_div(const fnx_step_params* prm, const float* density_
   if (!prm) return fnx_set_error(FNX_ERR_ARG, "step: null params");
   if (B < 1 || D < 1 || H < 2 || W < 2 || (is3d && D < 2) || (!is3d && D != 1) || (long long)D * H * W >= (1LL << 31))
     return fnx_set_error(FNX_ERR_ARG, "step: unsupported grid B=%d D=%d H=%d W=%d is3d=%d", B, D, H, W, is3d);
-  if (!workspace || workspace_bytes < fnx_step_workspace(B, D, H, W, is3d))
+  const int Hheld = (prm->held_row_end > prm->held_row_begin) ? prm->held_row_end - prm->held_row_begin : H;
+  if (!workspace || workspace_bytes < fnx_step_workspace(B, D, Hheld, W, is3d))
     return fnx_set_error(FNX_ERR_WORKSPACE, "step: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t n = (size_t)B * D * H * W;
+  const size_t n = (size_t)B * D * Hheld * W;
   const int nc = is3d ? 3 : 2;
   char* ws = (char*)workspace;
   float* rho_fwd = (float*)ws_take(ws, n * sizeof(float));
@@ -322,6 +337,30 @@ int fnx_step_advect_forces_div(const fnx_step_params* prm, const float* density_
   if (prm->row_end > prm->row_begin) {  // slab window (domain-decomposed step): only these rows are computed
     if (prm->row_begin < 0 || prm->row_end > D * H) return fnx_set_error(FNX_ERR_ARG, "step: row window out of range");
     g.row0 = prm->row_begin; g.row1 = prm->row_end;
+  }
+  const bool held = prm->held_row_end > prm->held_row_begin;   // arrays hold these rows only
+  if (held && (is3d || !use_step2d() || !fnx_step2d_supported(H, W)))
+    return fnx_set_error(FNX_ERR_ARG, "step: row-window arrays (held_row_*) are a 2-D feature of the fused kernels");
+  if (!is3d && use_step2d() && fnx_step2d_supported(H, W)) {
+    // 2-D: fused advection (forward pass staged in shared memory) + tiled forces/divergence (step2d.cu)
+    fnx_step2d_win w;
+    w.H = H; w.W = W; w.row0 = g.row0; w.row1 = g.row1;
+    w.ya0 = held ? prm->held_row_begin : 0; w.ya1 = held ? prm->held_row_end : H;
+    FNX_TRY(fnx_step2d_check_window(w));
+    const bool ubc2 = UBC && UBCInvMask, rbc2 = densityBC && densityBCInvMask;
+    fnx_step2d_masks mk;
+    mk.UBC = ubc2 ? UBC : nullptr; mk.UBCInv = ubc2 ? UBCInvMask : nullptr;
+    mk.rBC = rbc2 ? densityBC : nullptr; mk.rBCInv = rbc2 ? densityBCInvMask : nullptr;
+    mk.rows = mask_rows;
+    float* rho_mid = rbc2 ? rho_fwd : nullptr;   // one-pass density of the masked rows (what addBuoyancy reads)
+    // the interior fast path (FNX_STEP2D_CLEAN=0 switches it off: generic fused kernel only) keeps its list of
+    // declined tiles in the slot of the traced-index array the fused kernels do not need
+    int* tile_ws = use_clean() && fnx_step2d_tile_ws_ints(w, B) * sizeof(int) <= n * sizeof(int) ? fidx : nullptr;
+    FNX_TRY(fnx_step2d_advect(w, prm->dt, prm->maccormack_strength, prm->sample_outside_fluid, density_in, U_in, flags,
+                              mk, prm->density_const_passes, density_out, rho_mid, U1, B, tile_ws, st));
+    FNX_TRY(fnx_step2d_forces_div(w, prm, density_out, rho_mid, U1, flags, mk, U_out, div, B, st));
+    FNX_CUDA_TRY("step", cudaGetLastError());
+    return FNX_OK;
   }
   StepMasks m;
   const bool ubc = UBC && UBCInvMask, rbc = densityBC && densityBCInvMask;
@@ -363,12 +402,37 @@ int fnx_step_project_bcs(const float* pressure, float* U, const float* flags, co
 int fnx_step_project_bcs_rows(const float* pressure, float* U, const float* flags, const float* UBC,
                               const float* UBCInvMask, const unsigned char* mask_rows, int apply_wall_bcs, int B,
                               int D, int H, int W, int is3d, int row_begin, int row_end, void* stream) {
+  return fnx_step_project_bcs_held(pressure, U, flags, UBC, UBCInvMask, mask_rows, apply_wall_bcs, B, D, H, W, is3d,
+                                   row_begin, row_end, 0, 0, stream);
+}
+
+int fnx_step_project_bcs_held(const float* pressure, float* U, const float* flags, const float* UBC,
+                              const float* UBCInvMask, const unsigned char* mask_rows, int apply_wall_bcs, int B,
+                              int D, int H, int W, int is3d, int row_begin, int row_end, int held_row_begin,
+                              int held_row_end, void* stream) {
   if (B < 1 || D < 1 || H < 2 || W < 2 || (is3d && D < 2) || (!is3d && D != 1))
     return fnx_set_error(FNX_ERR_ARG, "step: unsupported grid B=%d D=%d H=%d W=%d is3d=%d", B, D, H, W, is3d);
   Grid g = make_grid(B, D, H, W);
   if (row_end > row_begin) {
     if (row_begin < 0 || row_end > D * H) return fnx_set_error(FNX_ERR_ARG, "step: row window out of range");
     g.row0 = row_begin; g.row1 = row_end;
+  }
+  const bool held = held_row_end > held_row_begin;
+  if (held && (is3d || !use_step2d() || !fnx_step2d_supported(H, W)))
+    return fnx_set_error(FNX_ERR_ARG, "step: row-window arrays (held_row_*) are a 2-D feature of the fused kernels");
+  if (!is3d && use_step2d() && fnx_step2d_supported(H, W)) {
+    fnx_step2d_win w;
+    w.H = H; w.W = W; w.row0 = g.row0; w.row1 = g.row1;
+    w.ya0 = held ? held_row_begin : 0; w.ya1 = held ? held_row_end : H;
+    if (!(0 <= w.ya0 && w.ya0 <= w.row0 && w.row1 <= w.ya1 && w.ya1 <= H) || (w.ya0 > 0 && w.row0 - w.ya0 < 1))
+      return fnx_set_error(FNX_ERR_ARG, "step: bad row window");
+    const bool ubc2 = UBC && UBCInvMask;
+    fnx_step2d_masks mk;
+    mk.UBC = ubc2 ? UBC : nullptr; mk.UBCInv = ubc2 ? UBCInvMask : nullptr;
+    mk.rBC = nullptr; mk.rBCInv = nullptr; mk.rows = mask_rows;
+    FNX_TRY(fnx_step2d_project(w, pressure, U, flags, mk, apply_wall_bcs, B, (cudaStream_t)stream));
+    FNX_CUDA_TRY("step", cudaGetLastError());
+    return FNX_OK;
   }
   StepMasks m;
   const bool ubc = UBC && UBCInvMask;

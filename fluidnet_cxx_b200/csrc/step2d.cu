@@ -1,0 +1,918 @@
+// step2d.cu -- the 2-D stencil stages of lib.simulate (pytorch/lib/simulate.py:28-171) as three
+// window-aware sm_100a kernels.  Compiled with -fmad=false (bit-exact vs the reference's ATen path).
+//
+//   k2_advect      advectScalar + advectVelocity (MacCormack, fluids_init.cpp:265-382, 656-807) +
+//                  setConstVals (simulate.py:96) in ONE kernel: the forward (semi-Lagrangian) pass
+//                  of a 64x32 output tile and of a 2-cell apron around it is computed into SHARED
+//                  MEMORY (rho_fwd, U_fwd, the traced cell index), then the backward pass /
+//                  correction / clamp of the tile samples it from there.  The forward fields never
+//                  travel through HBM (the two-kernel version wrote and re-read 16 B/cell of them
+//                  and re-read every input).  A backward sample that leaves the staged apron
+//                  (|u| dt > 1 cell) recomputes the forward value of the cells it needs from global
+//                  memory through an out-of-line copy of the same per-cell function: any velocity is
+//                  handled, with identical results.
+//   k2_forces_div  addBuoyancy / addGravity -> [setWallBcs] -> setConstVals -> velocityDivergence
+//                  (simulate.py:98-145): the forced velocity of a tile + one row / column is computed
+//                  once into shared memory, the divergence reads its neighbours from there.
+//   k2_project     velocityUpdate -> [setWallBcs] -> setConstVals (simulate.py:154-168), in place.
+//
+// Per-cell arithmetic, operation order and quirks are those of the per-op
+// device functions (advect_device.cuh, advect_cells.cuh, stencil_device.cuh) the op-level entry points
+// and the 3-D path keep using; tests/test_gpu_parity.py holds the two implementations equal bit for
+// bit, and both equal to the reference's golden outputs.
+//
+// Windows.  Every array argument may hold only rows [ya0, ya1) of the global H x W grid (a slab of
+// the domain-decomposed step): the kernels index with GLOBAL coordinates through "virtual base"
+// pointers (base - ya0*W), channel c of a multi-channel field lives `cs` elements after channel
+// c-1, and every data-dependent row index is clamped to the rows that exist.  With ya0 = 0, ya1 = H
+// the clamps are the reference's own clamps to the grid.
+#include <cuda_runtime.h>
+
+#include "../../include/fluidstep.h"
+#include "fluid_common.cuh"
+#include "host_util.h"
+#include "stencil_device.cuh"
+#include "step2d.h"
+
+namespace fnx {
+namespace s2 {
+
+// ---- advection ------------------------------------------------------------------------------------
+constexpr int TX = 64, TY = 32;          // output tile
+constexpr int AP = 2;                    // apron of forward values around it
+constexpr int SW = TX + 2 * AP, SH = TY + 2 * AP;
+constexpr int NT = 256;                  // threads: 64 x 4
+
+struct Adv {
+  int H, W;
+  int row0, row1;        // rows written
+  int ycl, ych;          // clamp of a bilinear sample's lower row:   [max(0,ya0), min(H-2, ya1-2)]
+  int yrl, yrh;          // clamp of a cell row index:                [max(0,ya0), min(H-1, ya1-1)]
+  int yf0, yf1;          // rows whose forward value can be computed (all +-1 neighbours exist)
+  float dt, mdt, hs;
+  int sample_outside;
+  const float* rho;      // virtual bases of this batch item
+  const float* u0;
+  const float* u1;
+  const float* fl;
+};
+
+struct Tap {
+  int x0, y0;
+  float s0, s1, t0, t1;
+};
+
+// grid.cpp:28-52 (Q3): weights clamped to [0,1] before the index clamp; positions beyond 1e9 and NaN
+// take the int64 truncation of the ATen path (out of line: never on the hot path)
+__device__ __noinline__ void taps_big(const Adv& a, float px, float py, Tap& t) {
+  const long long ix = trunc_ll(px), iy = trunc_ll(py);
+  const float s1 = px - (float)ix, t1 = py - (float)iy;
+  const float s0 = 1.f - s1, t0 = 1.f - t1;
+  t.x0 = (int)clampll(ix, 0, a.W - 2);
+  t.y0 = (int)clampll(clampll(iy, 0, a.H - 2), a.ycl, a.ych);
+  t.s1 = clamp01(s1); t.t1 = clamp01(t1);
+  t.s0 = clamp01(s0); t.t0 = clamp01(t0);
+}
+
+__device__ __forceinline__ Tap make_tap(const Adv& a, float x, float y) {
+  Tap t;
+  const float px = x - 0.5f, py = y - 0.5f;
+  if ((fabsf(px) < 1.0e9f) & (fabsf(py) < 1.0e9f)) {
+    const int ix = __float2int_rz(px), iy = __float2int_rz(py);
+    const float s1 = px - (float)ix, t1 = py - (float)iy;
+    const float s0 = 1.f - s1, t0 = 1.f - t1;
+    int x0 = ix < 0 ? 0 : ix, y0 = iy < a.ycl ? a.ycl : iy;
+    t.x0 = x0 > a.W - 2 ? a.W - 2 : x0;
+    t.y0 = y0 > a.ych ? a.ych : y0;
+    t.s1 = clamp01(s1); t.t1 = clamp01(t1);
+    t.s0 = clamp01(s0); t.t0 = clamp01(t0);
+  } else {
+    taps_big(a, px, py, t);
+  }
+  return t;
+}
+
+// grid.cpp:54-75: (Ia*t0 + Ib*t1)*s0 + (Ic*t0 + Id*t1)*s1 with a=(y0,x0) b=(y0+1,x0) c=(y0,x0+1) d=(y0+1,x0+1)
+__device__ __forceinline__ float bilerp(float Ia, float Ib, float Ic, float Id, const Tap& t) {
+  return (Ia * t.t0 + Ib * t.t1) * t.s0 + (Ic * t.t0 + Id * t.t1) * t.s1;
+}
+
+// grid.cpp:78-96
+__device__ __forceinline__ void mix1(float va, bool fa, float vb, bool fb, float wa, float wb, float& v, bool& fl) {
+  if (!fa && !fb) { v = 0.f; fl = false; }
+  else if (!fa) { v = vb; fl = true; }
+  else if (!fb) { v = va; fl = true; }
+  else { v = va * wa + vb * wb; fl = true; }
+}
+
+// grid.cpp:118-269 interpolWithFluid on four corner values + their fluid bits; all-fluid (the common
+// case) is the plain formula, no fluid corner falls back to it as well
+__device__ __forceinline__ float bilerp_fluid(float Ia, float Ib, float Ic, float Id, bool fa, bool fb, bool fc,
+                                              bool fd, const Tap& t) {
+  if (fa & fb & fc & fd) return bilerp(Ia, Ib, Ic, Id, t);
+  float ab, cd, v;
+  bool fab, fcd, fv;
+  mix1(Ia, fa, Ib, fb, t.t0, t.t1, ab, fab);
+  mix1(Ic, fc, Id, fd, t.t0, t.t1, cd, fcd);
+  mix1(ab, fab, cd, fcd, t.s0, t.s1, v, fv);
+  return fv ? v : bilerp(Ia, Ib, Ic, Id, t);
+}
+
+__device__ __forceinline__ float sample_g(const Adv& a, const float* __restrict__ f, float x, float y) {
+  const Tap t = make_tap(a, x, y);
+  const float* p = f + t.y0 * a.W + t.x0;
+  return bilerp(__ldg(p), __ldg(p + a.W), __ldg(p + 1), __ldg(p + a.W + 1), t);
+}
+
+__device__ __forceinline__ float sample_g_fluid(const Adv& a, const float* __restrict__ f, float x, float y) {
+  const Tap t = make_tap(a, x, y);
+  const int o = t.y0 * a.W + t.x0;
+  const float* p = f + o;
+  const float* q = a.fl + o;
+  return bilerp_fluid(__ldg(p), __ldg(p + a.W), __ldg(p + 1), __ldg(p + a.W + 1), __ldg(q) == kFluid,
+                      __ldg(q + a.W) == kFluid, __ldg(q + 1) == kFluid, __ldg(q + a.W + 1) == kFluid, t);
+}
+
+// ---- line trace, 2-D (calc_line_trace.cpp:259-424) --------------------------------------------------
+__device__ __forceinline__ bool ood(const Adv& a, float x, float y) {  // :16-27
+  return x <= 0.f || x >= (float)a.W || y <= 0.f || y >= (float)a.H;
+}
+__device__ __forceinline__ bool blocked(const Adv& a, float x, float y) {  // :33-64
+  if (ood(a, x, y)) return false;
+  int r = __float2int_rz(y);
+  r = r < a.yrl ? a.yrl : (r > a.yrh ? a.yrh : r);
+  return __ldg(a.fl + r * a.W + __float2int_rz(x)) != kFluid;
+}
+
+// the step that leaves the grid or enters a non-fluid cell (:323-412); always ends the trace.
+// (px,py) trace start, (bx,by) current position (in/out), (nx,ny) the offending step, (dx,dy) direction
+__device__ __noinline__ void trace_stop(const Adv& a, float px, float py, float dirx, float diry, float nx, float ny,
+                                        float& bx, float& by) {
+  if (ood(a, nx, ny)) {
+    // calcRayBorderIntersection from the trace's START position (:175-257, Q11)
+    float min_step = CUDART_INF_F;
+    const float nxt[2] = {nx, ny}, pos[2] = {px, py}, dimf[2] = {(float)a.W, (float)a.H};
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+      if (nxt[k] <= kHitMargin) {
+        const float d = nxt[k] - pos[k];
+        if (fabsf(d) >= kEpsilon) min_step = min_t(min_step, (kHitMargin - pos[k]) / d);
+      }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const float lim = dimf[k] - kHitMargin;
+      if (nxt[k] >= lim) {
+        const float d = nxt[k] - pos[k];
+        if (fabsf(d) >= kEpsilon) min_step = min_t(min_step, (lim - pos[k]) / d);
+      }
+    }
+    const bool hit = (min_step >= 0.f) && (min_step < CUDART_INF_F);
+    float ix = nx, iy = ny;  // clampToDomain is a no-op in the reference (Q9)
+    if (hit) {
+      ix = min_step * (nx - px) + px;
+      iy = min_step * (ny - py) + py;
+    }
+    if (!blocked(a, ix, iy)) { bx = ix; by = iy; return; }
+    nx = ix; ny = iy;
+  }
+  if (blocked(a, nx, ny)) {
+    bool stopped = false;
+    for (int count = 0; count < 4; count++) {
+      if (!blocked(a, nx, ny)) break;
+      // HitBoundingBox as the ATen code evaluates it (:73-149, Q10) on the cell's inflated box
+      const float o[2] = {bx, by}, dir[2] = {dirx, diry}, nn[2] = {nx, ny};
+      float minB[2], maxB[2], cand[2], maxT[2], coord[2];
+      bool mid[2], inside = true;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const float ctr = (float)__float2int_rz(nn[k]) + 0.5f;
+        minB[k] = ctr - 0.5f - kHitMargin;
+        maxB[k] = ctr + 0.5f + kHitMargin;
+        const bool lt = o[k] < minB[k], gt = o[k] > maxB[k];
+        mid[k] = (o[k] >= minB[k]) && (o[k] <= maxB[k]);
+        cand[k] = 0.f;
+        if (lt) cand[k] = minB[k];
+        if (gt) cand[k] = maxB[k];
+        if (lt || gt) inside = false;
+      }
+      const bool outside = !inside;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        maxT[k] = 0.f;
+        if (outside && !mid[k] && dir[k] != 0.f) maxT[k] = (cand[k] - o[k]) / dir[k];
+        if ((outside && mid[k]) || dir[k] == 0.f) maxT[k] = -1.f;
+      }
+      const int wp = maxT[1] > maxT[0] ? 1 : 0;  // argmax keeps the first maximum
+      const float T = wp ? maxT[1] : maxT[0];
+      bool ret = !(T < 0.f && outside);
+      const float err_tol = 1e-6f;
+#pragma unroll
+      for (int k = 0; k < 2; k++) coord[k] = (k == wp) ? cand[k] : (o[k] + T * dir[k]);
+#pragma unroll
+      for (int k = 0; k < 2; k++)
+        if (k != wp && (coord[k] < minB[k] - err_tol || coord[k] > maxB[k] + err_tol)) ret = false;
+      if (!ret) { stopped = true; break; }
+      nx = coord[0]; ny = coord[1];
+    }
+    if (!stopped) { bx = nx; by = ny; }
+    return;
+  }
+  // unreachable from trace2 (it only calls with an offending step); kept for completeness
+  bx = nx; by = ny;
+}
+
+// trace from the centre (px,py) of an INTERIOR FLUID cell (so the start is neither outside the grid
+// nor blocked, :283-288) along (dx,dy); returns the end position
+__device__ __forceinline__ void trace2(const Adv& a, float px, float py, float dx, float dy, float& bx, float& by) {
+  bx = px; by = py;
+  float acc = dx * dx;  // at::norm(2): acc += x*x in fp32, then sqrt
+  acc = acc + dy * dy;
+  const float length = sqrtf(acc);
+  if (length <= kEpsilon) return;
+  const float dirx = dx / length, diry = dy / length;
+  float cur = 0.f;
+  while (cur < length - kHitMargin) {  // :310-314
+    const float rem = length - cur;
+    const float step = rem < 1.f ? rem : 1.f;
+    const float nx = bx + dirx * step, ny = by + diry * step;
+    if (ood(a, nx, ny) || blocked(a, nx, ny)) {
+      trace_stop(a, px, py, dirx, diry, nx, ny, bx, by);
+      return;
+    }
+    bx = nx; by = ny;
+    cur = cur + step;
+  }
+}
+
+struct Fwd {
+  float rho, u0, u1;
+  unsigned idx;  // traced cell (j0 << 16 | i0)
+};
+
+// forward pass of cell (j,i): SemiLagrangeEulerFluidNetSavePos (:69-133) + SemiLagrangeEulerFluidNetMAC
+// (:388-451; no line trace Q2, solid-cell channel mix-up Q1)
+__device__ __forceinline__ Fwd fwd_cell(const Adv& a, int j, int i) {
+  Fwd f;
+  const int c = j * a.W + i;
+  f.idx = ((unsigned)j << 16) | (unsigned)i;
+  const bool border = (i < 1) | (i > a.W - 2) | (j < 1) | (j > a.H - 2);
+  if (border) {
+    f.rho = 0.f; f.u0 = 0.f; f.u1 = 0.f;
+    return f;
+  }
+  if (__ldg(a.fl + c) != kFluid) {
+    f.rho = __ldg(a.rho + c);  // don't advect solid geometry
+    f.u0 = __ldg(a.u1 + c);    // Q1
+    f.u1 = 0.f;
+    return f;
+  }
+  const int W = a.W;
+  const float px = (float)i + 0.5f, py = (float)j + 0.5f;
+  const float ux = __ldg(a.u0 + c), uxr = __ldg(a.u0 + c + 1), uxd = __ldg(a.u0 + c - W), uxdr = __ldg(a.u0 + c - W + 1);
+  const float vy = __ldg(a.u1 + c), vyl = __ldg(a.u1 + c - 1), vyu = __ldg(a.u1 + c + W), vyul = __ldg(a.u1 + c + W - 1);
+  // scalar: centred velocity (grid.cpp:300-309), line trace, fluid-aware sample
+  {
+    const float cx = 0.5f * (ux + uxr), cy = 0.5f * (vy + vyu);
+    float bx, by;
+    trace2(a, px, py, a.mdt * cx, a.mdt * cy, bx, by);
+    f.rho = a.sample_outside ? sample_g(a, a.rho, bx, by) : sample_g_fluid(a, a.rho, bx, by);
+    const int i0 = trunc_clamp0(bx, W - 1);
+    int j0 = trunc_clamp0(by, a.H - 1);
+    j0 = j0 < a.yrl ? a.yrl : (j0 > a.yrh ? a.yrh : j0);
+    f.idx = ((unsigned)j0 << 16) | (unsigned)i0;
+  }
+  // velocity: face-centred velocities (grid.cpp:314-402), sum order ((a+b)+c)+d
+  {
+    const float vx_y = 0.25f * (((vy + vyl) + vyu) + vyul);  // v at the x face
+    f.u0 = sample_g(a, a.u0, px + ux * a.mdt, py + vx_y * a.mdt);
+    const float vy_x = 0.25f * (((ux + uxd) + uxr) + uxdr);  // u at the y face
+    f.u1 = sample_g(a, a.u1, px + vy_x * a.mdt, py + vy * a.mdt);
+  }
+  return f;
+}
+
+__device__ __noinline__ void fwd_cell_far(const Adv& a, int j, int i, Fwd& f) { f = fwd_cell(a, j, i); }
+
+struct Smem {
+  float rho[SH][SW];
+  float u0[SH][SW];
+  float u1[SH][SW];
+  unsigned idx[SH][SW];
+};
+
+// forward value `which` (0 rho, 1 u0, 2 u1) at the four corners of a tap: from the staged apron, or
+// recomputed when the sample leaves it
+template <int WHICH>
+__device__ __forceinline__ void fwd_corners(const Adv& a, const Smem& s, int ty0, int tx0, const Tap& t, float& Ia,
+                                            float& Ib, float& Ic, float& Id) {
+  const int ly = t.y0 - (ty0 - AP), lx = t.x0 - (tx0 - AP);
+  if ((unsigned)ly < (unsigned)(SH - 1) && (unsigned)lx < (unsigned)(SW - 1) && t.y0 >= a.yf0 && t.y0 + 1 < a.yf1) {
+    const float(*f)[SW] = WHICH == 0 ? s.rho : (WHICH == 1 ? s.u0 : s.u1);
+    Ia = f[ly][lx]; Ib = f[ly + 1][lx]; Ic = f[ly][lx + 1]; Id = f[ly + 1][lx + 1];
+    return;
+  }
+  Fwd f;
+  float v[4];
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    const int jj = t.y0 + (k & 1), ii = t.x0 + (k >> 1);
+    if (jj >= a.yf0 && jj < a.yf1) fwd_cell_far(a, jj, ii, f);
+    else { f.rho = 0.f; f.u0 = 0.f; f.u1 = 0.f; }   // rows at the edge of a slab's memory: stale-halo territory
+    v[k] = WHICH == 0 ? f.rho : (WHICH == 1 ? f.u0 : f.u1);
+  }
+  Ia = v[0]; Ib = v[1]; Ic = v[2]; Id = v[3];
+}
+
+struct Masks {   // setConstVals (simulate.py:4-26); virtual bases, NULL = no mask
+  const float* u0bc; const float* u0inv; const float* u1bc; const float* u1inv;
+  const float* rbc; const float* rinv;
+  const unsigned char* rows;   // per row: bit0 = U masks differ from identity, bit1 = density masks (NULL: test every cell)
+};
+
+__global__ void __launch_bounds__(NT, 3)
+    k2_advect(const __grid_constant__ Adv a, const __grid_constant__ Masks m, int rho_passes, float* __restrict__ rho_out, float* __restrict__ rho_mid,
+              float* __restrict__ u0_out, float* __restrict__ u1_out, int tiles_x, const int* __restrict__ tile_count,
+              const int* __restrict__ tile_list) {
+  __shared__ Smem s;
+  // with a tile list (written by k2_advect_clean) only the tiles that kernel could not take are done here
+  int tile = blockIdx.x;
+  if (tile_list) {
+    if (tile >= *tile_count) return;
+    tile = tile_list[tile];
+  }
+  const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
+  const int tx0 = tile_x * TX, ty0 = a.row0 + tile_y * TY;
+  const int W = a.W, H = a.H;
+
+  // ---- phase 1: forward pass of the tile and its apron into shared memory ----
+  for (int e = threadIdx.x; e < SW * SH; e += NT) {
+    const int ly = e / SW, lx = e - ly * SW;
+    const int j = ty0 - AP + ly, i = tx0 - AP + lx;
+    if (i < 0 || i >= W || j < a.yf0 || j >= a.yf1) continue;  // never sampled (samples clamp to existing rows)
+    const Fwd f = fwd_cell(a, j, i);
+    s.rho[ly][lx] = f.rho; s.u0[ly][lx] = f.u0; s.u1[ly][lx] = f.u1; s.idx[ly][lx] = f.idx;
+  }
+  __syncthreads();
+
+  // ---- phase 2: backward pass + MacCormack correction + clamp + setConstVals of the tile ----
+  const int lxo = threadIdx.x & (TX - 1), lyo = threadIdx.x / TX;
+  const int i = tx0 + lxo;
+  if (i >= W) return;
+#pragma unroll 1
+  for (int r = lyo; r < TY; r += NT / TX) {
+    const int j = ty0 + r;
+    if (j >= a.row1) break;
+    const int c = j * W + i;
+    const int ly = r + AP, lx = lxo + AP;
+    const bool border = (i < 1) | (i > W - 2) | (j < 1) | (j > H - 2);
+    const float fc = __ldg(a.fl + c);
+    const bool fluid = fc == kFluid;
+    float rho_v, u0_v = 0.f, u1_v = 0.f;
+    // ---------------- scalar (fluids_init.cpp:322-382) ----------------
+    {
+      const float fw = s.rho[ly][lx];
+      float v = fw;
+      float ux = 0.f, uxr = 0.f, vy = 0.f, vyu = 0.f;
+      if (fluid) {
+        float bwd = 0.f;  // border cells of the backward pass are zeroed (:354-363)
+        if (!border) {
+          ux = __ldg(a.u0 + c); uxr = __ldg(a.u0 + c + 1); vy = __ldg(a.u1 + c); vyu = __ldg(a.u1 + c + W);
+          const float cx = 0.5f * (ux + uxr), cy = 0.5f * (vy + vyu);
+          float bx, by;
+          trace2(a, (float)i + 0.5f, (float)j + 0.5f, a.dt * cx, a.dt * cy, bx, by);
+          const Tap t = make_tap(a, bx, by);
+          float Ia, Ib, Ic, Id;
+          fwd_corners<0>(a, s, ty0, tx0, t, Ia, Ib, Ic, Id);
+          if (a.sample_outside) {
+            bwd = bilerp(Ia, Ib, Ic, Id, t);
+          } else {
+            const float* q = a.fl + t.y0 * W + t.x0;
+            bwd = bilerp_fluid(Ia, Ib, Ic, Id, __ldg(q) == kFluid, __ldg(q + W) == kFluid, __ldg(q + 1) == kFluid,
+                               __ldg(q + W + 1) == kFluid, t);
+          }
+        }
+        v = fw + a.hs * (__ldg(a.rho + c) - bwd);  // MacCormackCorrect :135-148
+      }
+      if (!border) {
+        // getClampBounds :154-222: 3x3 neighbourhood of the forward-traced cell, fluid cells only
+        const unsigned id = s.idx[ly][lx];
+        const int j0 = (int)(id >> 16), i0 = (int)(id & 0xffffu);
+        float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+        bool any = false;
+        const int jlo = a.yrl, jhi = a.yrh;
+        if (i0 >= 1 && i0 <= W - 2 && j0 - 1 >= jlo && j0 + 1 <= jhi) {
+          const float* sp = a.rho + (j0 - 1) * W + (i0 - 1);
+          const float* fp = a.fl + (j0 - 1) * W + (i0 - 1);
+#pragma unroll
+          for (int dj = 0; dj < 3; dj++)
+#pragma unroll
+            for (int di = 0; di < 3; di++) {
+              if (a.sample_outside || __ldg(fp + dj * W + di) == kFluid) {
+                const float sv = __ldg(sp + dj * W + di);
+                mn = min_t(mn, sv); mx = max_t(mx, sv);
+                any = true;
+              }
+            }
+        } else {
+          for (int dj = -1; dj <= 1; dj++) {
+            const int jj = j0 + dj;
+            if (jj < 0 || jj >= H || jj < jlo || jj > jhi) continue;
+            for (int di = -1; di <= 1; di++) {
+              const int ii = i0 + di;
+              if (ii < 0 || ii >= W) continue;
+              const int q = jj * W + ii;
+              if (a.sample_outside || __ldg(a.fl + q) == kFluid) {
+                const float sv = __ldg(a.rho + q);
+                mn = min_t(mn, sv); mx = max_t(mx, sv);
+                any = true;
+              }
+            }
+          }
+        }
+        v = any ? max_t(mn, min_t(mx, v)) : fw;
+      }
+      rho_v = v;
+      // ---------------- velocity (fluids_init.cpp:700-807) ----------------
+      if (!border) {
+        if (!fluid) { ux = __ldg(a.u0 + c); uxr = __ldg(a.u0 + c + 1); vy = __ldg(a.u1 + c); vyu = __ldg(a.u1 + c + W); }
+        const float uxd = __ldg(a.u0 + c - W), uxdr = __ldg(a.u0 + c - W + 1);
+        const float vyl = __ldg(a.u1 + c - 1), vyul = __ldg(a.u1 + c + W - 1);
+        const float px = (float)i + 0.5f, py = (float)j + 0.5f;
+        const float fi = (float)i, fj = (float)j;
+        const bool solid = !fluid;
+#pragma unroll
+        for (int comp = 0; comp < 2; comp++) {
+          float velx, vely;
+          if (comp == 0) { velx = ux; vely = 0.25f * (((vy + vyl) + vyu) + vyul); }
+          else { velx = 0.25f * (((ux + uxd) + uxr) + uxdr); vely = vy; }
+          const float* oc = comp == 0 ? a.u0 : a.u1;
+          const float fw = comp == 0 ? s.u0[ly][lx] : s.u1[ly][lx];
+          // correction skipped when the cell or its lower neighbour along `comp` is not fluid (:470-487)
+          bool skip = solid;
+          if (!skip && __ldg(a.fl + c - (comp == 0 ? 1 : W)) != kFluid) skip = true;   // interior: index > 0
+          float v = fw;
+          const float vdx = velx * a.dt, vdy = vely * a.dt;
+          if (!skip) {
+            const Tap t = make_tap(a, px + vdx, py + vdy);
+            float Ia, Ib, Ic, Id;
+            if (comp == 0) fwd_corners<1>(a, s, ty0, tx0, t, Ia, Ib, Ic, Id);
+            else fwd_corners<2>(a, s, ty0, tx0, t, Ia, Ib, Ic, Id);
+            const float bwd = bilerp(Ia, Ib, Ic, Id, t);
+            v = fw + a.hs * ((comp == 0 ? ux : vy) - bwd);
+          }
+          // doClampComponentMAC :500-614: min/max of orig over the 2x2 blocks at trunc(pos -/+ vel*dt) (Q5)
+          float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+          for (int l = 0; l < 2; l++) {
+            const int q0 = trunc_x86_clamp0(l == 0 ? fi - vdx : fi + vdx, W - 2);
+            int q1 = trunc_x86_clamp0(l == 0 ? fj - vdy : fj + vdy, H - 2);
+            q1 = q1 < a.ycl ? a.ycl : (q1 > a.ych ? a.ych : q1);
+            const float* b0 = oc + q1 * W + q0;
+            float sv;
+            sv = __ldg(b0); mn = min_t(mn, sv); mx = max_t(mx, sv);
+            sv = __ldg(b0 + 1); mn = min_t(mn, sv); mx = max_t(mx, sv);
+            sv = __ldg(b0 + W); mn = min_t(mn, sv); mx = max_t(mx, sv);
+            sv = __ldg(b0 + W + 1); mn = min_t(mn, sv); mx = max_t(mx, sv);
+          }
+          v = max_t(min_t(v, mx), mn);
+          if (comp == 0) u0_v = v; else u1_v = v;
+        }
+      }
+    }
+    // ---------------- setConstVals (simulate.py:96) ----------------
+    const unsigned char rb = m.rows ? m.rows[j] : (unsigned char)3;
+    if (m.u0bc && (rb & 1)) {
+      u0_v = const_vals_apply(u0_v, __ldg(m.u0inv + c), __ldg(m.u0bc + c));
+      u1_v = const_vals_apply(u1_v, __ldg(m.u1inv + c), __ldg(m.u1bc + c));
+    }
+    u0_out[c] = u0_v;
+    u1_out[c] = u1_v;
+    if (m.rbc && (rb & 2)) {
+      const float inv = __ldg(m.rinv + c), bc = __ldg(m.rbc + c);
+      rho_v = const_vals_apply(rho_v, inv, bc);
+      if (rho_mid) rho_mid[c] = rho_v;        // the density addBuoyancy reads (one pass)
+      for (int t = 0; t < rho_passes; t++) rho_v = const_vals_apply(rho_v, inv, bc);   // simulate.py:133,168
+    }
+    rho_out[c] = rho_v;
+  }
+}
+
+// ---- advection, interior fast path --------------------------------------------------------------------
+// A tile is CLEAN when, on the tile and the two cells around it, every cell is Fluid, no cell computed
+// is a border cell, every row is held in memory, no value is NaN and |u| dt <= 0.95 cells.  Then (with
+// exactly the same arithmetic as the generic path, which it is tested against bit for bit):
+//   * no border / flag test can fire and every fluid-aware sample is the plain bilinear formula;
+//   * a line trace never leaves the grid nor meets a blocked cell: it is its free-step loop;
+//   * every back-traced position stays within one cell of its start, so every index clamp, the weight
+//     clamp to [0,1] and the |x| < 1e9 guard are identities and the apron of forward values is ONE cell;
+//   * the min / max of the MacCormack clamps run over values known not to be NaN, where the
+//     reference's compare-and-select equals fminf / fmaxf (up to the sign of a zero, which the parity
+//     convention of this repo -- and every consumer of these fields -- treats as equal).
+// Tiles that are not clean are appended to a list and done by the generic kernel.
+constexpr int CA = 1;                               // apron of the clean path
+constexpr int CSW = TX + 2 * CA, CSH = TY + 2 * CA;
+constexpr int CR = 2;                               // scanned margin
+struct SmemC {
+  float rho[CSH][CSW];
+  float u0[CSH][CSW];
+  float u1[CSH][CSW];
+  unsigned idx[CSH][CSW];
+};
+
+__device__ __forceinline__ void trace_free(float px, float py, float dx, float dy, float& bx, float& by) {
+  bx = px; by = py;
+  float acc = dx * dx;
+  acc = acc + dy * dy;
+  const float length = sqrtf(acc);
+  if (length <= kEpsilon) return;
+  const float dirx = dx / length, diry = dy / length;
+  float cur = 0.f;
+  while (cur < length - kHitMargin) {
+    const float rem = length - cur;
+    const float step = rem < 1.f ? rem : 1.f;
+    bx = bx + dirx * step; by = by + diry * step;
+    cur = cur + step;
+  }
+}
+
+struct TapC {
+  int ix, iy;
+  float s0, s1, t0, t1;
+};
+__device__ __forceinline__ TapC tap_c(float x, float y) {
+  TapC t;
+  const float px = x - 0.5f, py = y - 0.5f;
+  t.ix = __float2int_rz(px); t.iy = __float2int_rz(py);
+  t.s1 = px - (float)t.ix; t.t1 = py - (float)t.iy;
+  t.s0 = 1.f - t.s1; t.t0 = 1.f - t.t1;
+  return t;
+}
+__device__ __forceinline__ float bilerp_c(float Ia, float Ib, float Ic, float Id, const TapC& t) {
+  return (Ia * t.t0 + Ib * t.t1) * t.s0 + (Ic * t.t0 + Id * t.t1) * t.s1;
+}
+__device__ __forceinline__ float gather_g(const float* __restrict__ f, int W, float x, float y) {
+  const TapC t = tap_c(x, y);
+  const float* p = f + t.iy * W + t.ix;
+  return bilerp_c(__ldg(p), __ldg(p + W), __ldg(p + 1), __ldg(p + W + 1), t);
+}
+
+__global__ void __launch_bounds__(NT, 4)
+    k2_advect_clean(const __grid_constant__ Adv a, const __grid_constant__ Masks m, int rho_passes, int ya0, int ya1,
+                    float* __restrict__ rho_out, float* __restrict__ rho_mid, float* __restrict__ u0_out,
+                    float* __restrict__ u1_out, int tiles_x, int* __restrict__ slow_count, int* __restrict__ slow_list) {
+  __shared__ SmemC s;
+  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+  const int tx0 = tile_x * TX, ty0 = a.row0 + tile_y * TY;
+  const int W = a.W, H = a.H;
+
+  // ---- classification ----
+  int ok = (tx0 - CA >= 1) && (tx0 + TX - 1 + CA <= W - 2) && (ty0 - CA >= 1) && (ty0 + TY - 1 + CA <= H - 2) &&
+           (ty0 - CR >= ya0) && (ty0 + TY + CR <= ya1);
+  if (ok) {
+    const float adt = fabsf(a.dt);
+    constexpr int RW = TX + 2 * CR, RH = TY + 2 * CR;
+    for (int e = threadIdx.x; e < RW * RH; e += NT) {
+      const int ly = e / RW, lx = e - ly * RW;
+      const int c = (ty0 - CR + ly) * W + (tx0 - CR + lx);
+      const float f = __ldg(a.fl + c), u = __ldg(a.u0 + c), v = __ldg(a.u1 + c), r = __ldg(a.rho + c);
+      ok &= (f == kFluid) & (fabsf(u) * adt <= 0.95f) & (fabsf(v) * adt <= 0.95f) & (r == r);
+    }
+  }
+  ok = __syncthreads_and(ok);
+  if (!ok) {
+    if (threadIdx.x == 0) slow_list[atomicAdd(slow_count, 1)] = blockIdx.x;
+    return;
+  }
+
+  // ---- phase 1: forward pass of the tile + one cell around it ----
+  for (int e = threadIdx.x; e < CSW * CSH; e += NT) {
+    const int ly = e / CSW, lx = e - ly * CSW;
+    const int j = ty0 - CA + ly, i = tx0 - CA + lx;
+    const int c = j * W + i;
+    const float px = (float)i + 0.5f, py = (float)j + 0.5f;
+    const float ux = __ldg(a.u0 + c), uxr = __ldg(a.u0 + c + 1), uxd = __ldg(a.u0 + c - W), uxdr = __ldg(a.u0 + c - W + 1);
+    const float vy = __ldg(a.u1 + c), vyl = __ldg(a.u1 + c - 1), vyu = __ldg(a.u1 + c + W), vyul = __ldg(a.u1 + c + W - 1);
+    const float cx = 0.5f * (ux + uxr), cy = 0.5f * (vy + vyu);
+    float bx, by;
+    trace_free(px, py, a.mdt * cx, a.mdt * cy, bx, by);
+    s.rho[ly][lx] = gather_g(a.rho, W, bx, by);
+    s.idx[ly][lx] = ((unsigned)__float2int_rz(by) << 16) | (unsigned)__float2int_rz(bx);
+    const float vx_y = 0.25f * (((vy + vyl) + vyu) + vyul);
+    s.u0[ly][lx] = gather_g(a.u0, W, px + ux * a.mdt, py + vx_y * a.mdt);
+    const float vy_x = 0.25f * (((ux + uxd) + uxr) + uxdr);
+    s.u1[ly][lx] = gather_g(a.u1, W, px + vy_x * a.mdt, py + vy * a.mdt);
+  }
+  __syncthreads();
+
+  // ---- phase 2: backward pass + correction + clamp + setConstVals ----
+  const int lxo = threadIdx.x & (TX - 1), lyo = threadIdx.x / TX;
+  const int i = tx0 + lxo;
+  const int lbase_x = tx0 - CA, lbase_y = ty0 - CA;
+#pragma unroll 1
+  for (int r = lyo; r < TY; r += NT / TX) {
+    const int j = ty0 + r;
+    if (j >= a.row1) break;
+    const int c = j * W + i;
+    const int ly = r + CA, lx = lxo + CA;
+    const float px = (float)i + 0.5f, py = (float)j + 0.5f;
+    const float ux = __ldg(a.u0 + c), uxr = __ldg(a.u0 + c + 1), uxd = __ldg(a.u0 + c - W), uxdr = __ldg(a.u0 + c - W + 1);
+    const float vy = __ldg(a.u1 + c), vyl = __ldg(a.u1 + c - 1), vyu = __ldg(a.u1 + c + W), vyul = __ldg(a.u1 + c + W - 1);
+    float rho_v, u0_v, u1_v;
+    {  // scalar
+      const float fw = s.rho[ly][lx];
+      const float cx = 0.5f * (ux + uxr), cy = 0.5f * (vy + vyu);
+      float bx, by;
+      trace_free(px, py, a.dt * cx, a.dt * cy, bx, by);
+      const TapC t = tap_c(bx, by);
+      const float* f = &s.rho[t.iy - lbase_y][t.ix - lbase_x];
+      const float bwd = bilerp_c(f[0], f[CSW], f[1], f[CSW + 1], t);
+      float v = fw + a.hs * (__ldg(a.rho + c) - bwd);
+      const unsigned id = s.idx[ly][lx];
+      const float* sp = a.rho + ((int)(id >> 16) - 1) * W + ((int)(id & 0xffffu) - 1);
+      float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+      for (int dj = 0; dj < 3; dj++)
+#pragma unroll
+        for (int di = 0; di < 3; di++) {
+          const float sv = __ldg(sp + dj * W + di);
+          mn = fminf(mn, sv); mx = fmaxf(mx, sv);
+        }
+      rho_v = max_t(mn, min_t(mx, v));
+    }
+    {  // velocity
+      const float fi = (float)i, fj = (float)j;
+#pragma unroll
+      for (int comp = 0; comp < 2; comp++) {
+        float velx, vely;
+        if (comp == 0) { velx = ux; vely = 0.25f * (((vy + vyl) + vyu) + vyul); }
+        else { velx = 0.25f * (((ux + uxd) + uxr) + uxdr); vely = vy; }
+        const float* oc = comp == 0 ? a.u0 : a.u1;
+        const float fw = comp == 0 ? s.u0[ly][lx] : s.u1[ly][lx];
+        const float vdx = velx * a.dt, vdy = vely * a.dt;
+        const TapC t = tap_c(px + vdx, py + vdy);
+        const float* f = comp == 0 ? &s.u0[t.iy - lbase_y][t.ix - lbase_x] : &s.u1[t.iy - lbase_y][t.ix - lbase_x];
+        const float bwd = bilerp_c(f[0], f[CSW], f[1], f[CSW + 1], t);
+        float v = fw + a.hs * ((comp == 0 ? ux : vy) - bwd);
+        float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+          const int q0 = __float2int_rz(l == 0 ? fi - vdx : fi + vdx);
+          const int q1 = __float2int_rz(l == 0 ? fj - vdy : fj + vdy);
+          const float* b0 = oc + q1 * W + q0;
+          const float s00 = __ldg(b0), s01 = __ldg(b0 + 1), s10 = __ldg(b0 + W), s11 = __ldg(b0 + W + 1);
+          mn = fminf(fminf(mn, s00), fminf(s01, fminf(s10, s11)));
+          mx = fmaxf(fmaxf(mx, s00), fmaxf(s01, fmaxf(s10, s11)));
+        }
+        v = max_t(min_t(v, mx), mn);
+        if (comp == 0) u0_v = v; else u1_v = v;
+      }
+    }
+    const unsigned char rb = m.rows ? m.rows[j] : (unsigned char)3;
+    if (m.u0bc && (rb & 1)) {
+      u0_v = const_vals_apply(u0_v, __ldg(m.u0inv + c), __ldg(m.u0bc + c));
+      u1_v = const_vals_apply(u1_v, __ldg(m.u1inv + c), __ldg(m.u1bc + c));
+    }
+    u0_out[c] = u0_v;
+    u1_out[c] = u1_v;
+    if (m.rbc && (rb & 2)) {
+      const float inv = __ldg(m.rinv + c), bc = __ldg(m.rbc + c);
+      rho_v = const_vals_apply(rho_v, inv, bc);
+      if (rho_mid) rho_mid[c] = rho_v;
+      for (int t = 0; t < rho_passes; t++) rho_v = const_vals_apply(rho_v, inv, bc);
+    }
+    rho_out[c] = rho_v;
+  }
+}
+
+// ---- forces + BCs + divergence ----------------------------------------------------------------------
+constexpr int FX = 128, FY = 8;          // output tile; forced velocity staged for (FY+1) x (FX+1)
+struct Frc {
+  int H, W, row0, row1;
+  int use_buoyancy, use_gravity, wall_bcs;
+  float bs0, bs1, gf0, gf1, rho_star;
+};
+
+// velocity component `comp` of cell (j,i) after addBuoyancy -> addGravity -> [setWallBcs] -> setConstVals
+// (simulate.py:98-133) from the post-advection fields
+template <int COMP>
+__device__ __forceinline__ float forced(const Frc& g, int j, int i, const float* __restrict__ u,
+                                        const float* __restrict__ rho, const float* __restrict__ rho_mid,
+                                        const float* __restrict__ fl, const Masks& m) {
+  const int c = j * g.W + i;
+  float v = __ldg(u + c);
+  const float fc = __ldg(fl + c);
+  const int idx = COMP == 0 ? i : j;
+  const int cn = c - (COMP == 0 ? 1 : g.W);
+  const float fn = idx > 0 ? __ldg(fl + cn) : fc;
+  const bool border = (i < 1) | (i > g.W - 2) | (j < 1) | (j > g.H - 2);
+  if (!border) {
+    if (g.use_buoyancy && fc == kFluid && fn == kFluid) {
+      // density as addBuoyancy sees it: after ONE setConstVals pass (rho_mid on masked rows)
+      const int jn = COMP == 0 ? j : j - 1;
+      const float* rc_p = (rho_mid && (!m.rows || (m.rows[j] & 2))) ? rho_mid : rho;
+      const float* rn_p = (rho_mid && (!m.rows || (m.rows[jn] & 2))) ? rho_mid : rho;
+      v = buoyancy_apply(v, fc, fn, __ldg(rc_p + c), __ldg(rn_p + cn), COMP == 0 ? g.bs0 : g.bs1, g.rho_star);
+    }
+    if (g.use_gravity) v = gravity_apply(v, fc, fn, COMP == 0 ? g.gf0 : g.gf1);
+  }
+  if (g.wall_bcs) v = wall_bcs_apply(v, fc, fn);
+  const unsigned char rb = m.rows ? m.rows[j] : (unsigned char)3;
+  if (m.u0bc && (rb & 1)) {
+    v = COMP == 0 ? const_vals_apply(v, __ldg(m.u0inv + c), __ldg(m.u0bc + c))
+                  : const_vals_apply(v, __ldg(m.u1inv + c), __ldg(m.u1bc + c));
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+    k2_forces_div(Frc g, Masks m, const float* __restrict__ rho, const float* __restrict__ rho_mid,
+                  const float* __restrict__ u0, const float* __restrict__ u1, const float* __restrict__ fl,
+                  float* __restrict__ u0_out, float* __restrict__ u1_out, float* __restrict__ div, int tiles_x) {
+  __shared__ float su[FY + 1][FX + 1];
+  __shared__ float sv[FY + 1][FX + 1];
+  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+  const int tx0 = tile_x * FX, ty0 = g.row0 + tile_y * FY;
+  for (int e = threadIdx.x; e < (FY + 1) * (FX + 1); e += 256) {
+    const int ly = e / (FX + 1), lx = e - ly * (FX + 1);
+    const int j = ty0 + ly, i = tx0 + lx;
+    if (i >= g.W || j >= g.H || j > g.row1) continue;   // row1 itself (one past the window) feeds the divergence
+    // the x face of column tx0+FX is only needed by row < FY, the y face of row ty0+FY only by lx < FX
+    if (ly < FY) su[ly][lx] = forced<0>(g, j, i, u0, rho, rho_mid, fl, m);
+    if (lx < FX) sv[ly][lx] = forced<1>(g, j, i, u1, rho, rho_mid, fl, m);
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & (FX - 1);
+  const int i = tx0 + lx;
+  if (i >= g.W) return;
+  for (int ly = threadIdx.x / FX; ly < FY; ly += 256 / FX) {
+    const int j = ty0 + ly;
+    if (j >= g.row1) break;
+    const int c = j * g.W + i;
+    const float a = su[ly][lx], b = sv[ly][lx];
+    u0_out[c] = a;
+    u1_out[c] = b;
+    if (div) {
+      float d = 0.f;
+      const bool border = (i < 1) | (i > g.W - 2) | (j < 1) | (j > g.H - 2);
+      if (!border) d = a - su[ly][lx + 1] + b - sv[ly + 1][lx];   // velocity_divergence.py:61-66 (Q15)
+      if (__ldg(fl + c) == kObstacle) d = 0.f;
+      div[c] = d;
+    }
+  }
+}
+
+// ---- velocityUpdate + [setWallBcs] + setConstVals, in place -------------------------------------------
+__global__ void __launch_bounds__(256)
+    k2_project(int H, int W, int row0, int row1, const float* __restrict__ p, float* __restrict__ u0,
+               float* __restrict__ u1, const float* __restrict__ fl, Masks m, int wall_bcs) {
+  const int i = blockIdx.x * 128 + (threadIdx.x & 127);
+  const int j = row0 + blockIdx.y * 2 + (threadIdx.x >> 7);
+  if (i >= W || j >= row1) return;
+  const int c = j * W + i;
+  const float fc = __ldg(fl + c);
+  const bool interior = !((i < 1) | (i > W - 2) | (j < 1) | (j > H - 2));
+  const float P = __ldg(p + c);
+  const float fl_l = i > 0 ? __ldg(fl + c - 1) : fc, fl_d = j > 0 ? __ldg(fl + c - W) : fc;
+  float a = u0[c], b = u1[c];
+  if (interior) {
+    a = velocity_update_apply(a, fc, fl_l, P, __ldg(p + c - 1));
+    b = velocity_update_apply(b, fc, fl_d, P, __ldg(p + c - W));
+  }
+  if (wall_bcs) {
+    a = wall_bcs_apply(a, fc, fl_l);
+    b = wall_bcs_apply(b, fc, fl_d);
+  }
+  const unsigned char rb = m.rows ? m.rows[j] : (unsigned char)3;
+  if (m.u0bc && (rb & 1)) {
+    a = const_vals_apply(a, __ldg(m.u0inv + c), __ldg(m.u0bc + c));
+    b = const_vals_apply(b, __ldg(m.u1inv + c), __ldg(m.u1bc + c));
+  }
+  u0[c] = a;
+  u1[c] = b;
+}
+
+}  // namespace s2
+}  // namespace fnx
+
+using namespace fnx;
+using namespace fnx::s2;
+
+namespace {
+inline const float* vb(const float* p, long long off) { return p ? p - off : nullptr; }
+inline float* vb(float* p, long long off) { return p ? p - off : nullptr; }
+}  // namespace
+
+bool fnx_step2d_supported(int H, int W) { return H >= 4 && W >= 4 && H < 65536 && W < 65536; }
+
+size_t fnx_step2d_tile_ws_ints(const fnx_step2d_win& w, int B) {
+  const int tiles_x = (w.W + TX - 1) / TX, tiles_y = (w.row1 - w.row0 + TY - 1) / TY;
+  return (size_t)B * ((size_t)tiles_x * tiles_y + 1);
+}
+
+int fnx_step2d_check_window(const fnx_step2d_win& w) {
+  if (w.H < 4 || w.W < 4) return fnx_set_error(FNX_ERR_ARG, "step2d: grid too small");
+  if (!(0 <= w.ya0 && w.ya0 <= w.row0 && w.row0 < w.row1 && w.row1 <= w.ya1 && w.ya1 <= w.H))
+    return fnx_set_error(FNX_ERR_ARG, "step2d: bad window rows [%d,%d) in memory rows [%d,%d) of %d", w.row0, w.row1,
+                         w.ya0, w.ya1, w.H);
+  // a computed row reads its +-1 neighbours and the forward apron reads +-1 around +-2: three existing
+  // rows beyond the window on every interior side
+  if ((w.ya0 > 0 && w.row0 - w.ya0 < 3) || (w.ya1 < w.H && w.ya1 - w.row1 < 3))
+    return fnx_set_error(FNX_ERR_ARG, "step2d: a slab needs >= 3 rows of memory beyond the computed window");
+  return FNX_OK;
+}
+
+int fnx_step2d_advect(const fnx_step2d_win& w, float dt, float maccormack_strength, int sample_outside,
+                      const float* rho, const float* U, const float* flags, const fnx_step2d_masks& mk, int rho_passes,
+                      float* rho_out, float* rho_mid, float* U_out, int B, int* tile_ws, cudaStream_t st) {
+  const long long off = (long long)w.ya0 * w.W;
+  const long long plane = (long long)(w.ya1 - w.ya0) * w.W;   // elements per channel / batch item of a 1-channel field
+  const int tiles_x = (w.W + TX - 1) / TX, tiles_y = (w.row1 - w.row0 + TY - 1) / TY;
+  const int ntiles = tiles_x * tiles_y;
+  for (int b = 0; b < B; b++) {
+    Adv a;
+    a.H = w.H; a.W = w.W; a.row0 = w.row0; a.row1 = w.row1;
+    a.ycl = w.ya0; a.ych = (w.H - 2 < w.ya1 - 2) ? w.H - 2 : w.ya1 - 2;
+    a.yrl = w.ya0; a.yrh = (w.H - 1 < w.ya1 - 1) ? w.H - 1 : w.ya1 - 1;
+    a.yf0 = w.ya0 == 0 ? 0 : w.ya0 + 1;
+    a.yf1 = w.ya1 == w.H ? w.H : w.ya1 - 1;
+    a.dt = dt; a.mdt = -dt; a.hs = maccormack_strength * 0.5f;
+    a.sample_outside = sample_outside;
+    a.rho = vb(rho + b * plane, off);
+    a.u0 = vb(U + (2 * b) * plane, off);
+    a.u1 = vb(U + (2 * b + 1) * plane, off);
+    a.fl = vb(flags + b * plane, off);
+    Masks m;
+    m.u0bc = vb(mk.UBC ? mk.UBC + (2 * b) * plane : nullptr, off);
+    m.u1bc = vb(mk.UBC ? mk.UBC + (2 * b + 1) * plane : nullptr, off);
+    m.u0inv = vb(mk.UBCInv ? mk.UBCInv + (2 * b) * plane : nullptr, off);
+    m.u1inv = vb(mk.UBCInv ? mk.UBCInv + (2 * b + 1) * plane : nullptr, off);
+    m.rbc = vb(mk.rBC ? mk.rBC + b * plane : nullptr, off);
+    m.rinv = vb(mk.rBCInv ? mk.rBCInv + b * plane : nullptr, off);
+    m.rows = mk.rows ? mk.rows + (long long)b * (w.ya1 - w.ya0) - w.ya0 : nullptr;
+    float* ro = vb(rho_out + b * plane, off);
+    float* rm = vb(rho_mid ? rho_mid + b * plane : nullptr, off);
+    float* uo0 = vb(U_out + (2 * b) * plane, off);
+    float* uo1 = vb(U_out + (2 * b + 1) * plane, off);
+    if (tile_ws) {
+      // interior fast path first; the tiles it declines come back in a list for the generic kernel
+      int* count = tile_ws + (size_t)b * (ntiles + 1);
+      int* list = count + 1;
+      if (cudaMemsetAsync(count, 0, sizeof(int), st) != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "step2d: memset failed");
+      k2_advect_clean<<<ntiles, NT, 0, st>>>(a, m, rho_passes, w.ya0, w.ya1, ro, rm, uo0, uo1, tiles_x, count, list);
+      k2_advect<<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, count, list);
+    } else {
+      k2_advect<<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, nullptr, nullptr);
+    }
+  }
+  fnx_count_launches(tile_ws ? 2 * B : B);
+  return FNX_OK;
+}
+
+int fnx_step2d_forces_div(const fnx_step2d_win& w, const fnx_step_params* prm, const float* rho, const float* rho_mid,
+                          const float* U, const float* flags, const fnx_step2d_masks& mk, float* U_out, float* div, int B,
+                          cudaStream_t st) {
+  const long long off = (long long)w.ya0 * w.W;
+  const long long plane = (long long)(w.ya1 - w.ya0) * w.W;
+  const int tiles_x = (w.W + FX - 1) / FX, tiles_y = (w.row1 - w.row0 + FY - 1) / FY;
+  Frc g;
+  g.H = w.H; g.W = w.W; g.row0 = w.row0; g.row1 = w.row1;
+  g.use_buoyancy = prm->use_buoyancy; g.use_gravity = prm->use_gravity; g.wall_bcs = prm->apply_wall_bcs;
+  g.bs0 = prm->buoyancy3[0] * prm->dt; g.bs1 = prm->buoyancy3[1] * prm->dt;   // gravity*dt, one fp32 product
+  g.gf0 = prm->gravity3[0] * prm->dt; g.gf1 = prm->gravity3[1] * prm->dt;
+  g.rho_star = prm->rho_star;
+  for (int b = 0; b < B; b++) {
+    Masks m;
+    m.u0bc = vb(mk.UBC ? mk.UBC + (2 * b) * plane : nullptr, off);
+    m.u1bc = vb(mk.UBC ? mk.UBC + (2 * b + 1) * plane : nullptr, off);
+    m.u0inv = vb(mk.UBCInv ? mk.UBCInv + (2 * b) * plane : nullptr, off);
+    m.u1inv = vb(mk.UBCInv ? mk.UBCInv + (2 * b + 1) * plane : nullptr, off);
+    m.rbc = nullptr; m.rinv = nullptr;
+    m.rows = mk.rows ? mk.rows + (long long)b * (w.ya1 - w.ya0) - w.ya0 : nullptr;
+    k2_forces_div<<<tiles_x * tiles_y, 256, 0, st>>>(
+        g, m, vb(rho + b * plane, off), vb(rho_mid ? rho_mid + b * plane : nullptr, off), vb(U + (2 * b) * plane, off),
+        vb(U + (2 * b + 1) * plane, off), vb(flags + b * plane, off), vb(U_out + (2 * b) * plane, off),
+        vb(U_out + (2 * b + 1) * plane, off), vb(div ? div + b * plane : nullptr, off), tiles_x);
+  }
+  fnx_count_launches(B);
+  return FNX_OK;
+}
+
+int fnx_step2d_project(const fnx_step2d_win& w, const float* p, float* U, const float* flags, const fnx_step2d_masks& mk,
+                       int wall_bcs, int B, cudaStream_t st) {
+  const long long off = (long long)w.ya0 * w.W;
+  const long long plane = (long long)(w.ya1 - w.ya0) * w.W;
+  dim3 grid((w.W + 127) / 128, (w.row1 - w.row0 + 1) / 2);
+  for (int b = 0; b < B; b++) {
+    Masks m;
+    m.u0bc = vb(mk.UBC ? mk.UBC + (2 * b) * plane : nullptr, off);
+    m.u1bc = vb(mk.UBC ? mk.UBC + (2 * b + 1) * plane : nullptr, off);
+    m.u0inv = vb(mk.UBCInv ? mk.UBCInv + (2 * b) * plane : nullptr, off);
+    m.u1inv = vb(mk.UBCInv ? mk.UBCInv + (2 * b + 1) * plane : nullptr, off);
+    m.rbc = nullptr; m.rinv = nullptr;
+    m.rows = mk.rows ? mk.rows + (long long)b * (w.ya1 - w.ya0) - w.ya0 : nullptr;
+    k2_project<<<grid, 256, 0, st>>>(w.H, w.W, w.row0, w.row1, vb(p + b * plane, off), vb(U + (2 * b) * plane, off),
+                                     vb(U + (2 * b + 1) * plane, off), vb(flags + b * plane, off), m, wall_bcs);
+  }
+  fnx_count_launches(B);
+  return FNX_OK;
+}

@@ -140,6 +140,11 @@ typedef struct fnx_step_params {
    * (D*H) row space are computed (arrays stay global-sized, coordinates stay global, so the rows
    * computed are bit-identical to the single-GPU step); 0,0 = the whole grid */
   int row_begin, row_end;
+  /* 2-D only: the array arguments hold rows [held_row_begin, held_row_end) of the global H x W grid
+   * (pointers address the first held row; a 2-channel field holds its channels held-rows apart; the
+   * workspace and mask_rows are sized for the held rows).  The window must lie >= 3 rows inside the held
+   * rows on every side that is not a grid edge.  0,0 = the arrays hold the whole grid. */
+  int held_row_begin, held_row_end;
 } fnx_step_params;
 
 size_t fnx_step_workspace(int B, int D, int H, int W, int is3d);
@@ -165,6 +170,12 @@ int fnx_step_project_bcs_rows(const float *pressure, float *U, const float *flag
                               const float *UBCInvMask, const unsigned char *mask_rows,
                               int apply_wall_bcs, int B, int D, int H, int W, int is3d,
                               int row_begin, int row_end, void *stream);
+/* the same on arrays that hold rows [held_row_begin, held_row_end) only (2-D; see fnx_step_params) */
+int fnx_step_project_bcs_held(const float *pressure, float *U, const float *flags, const float *UBC,
+                              const float *UBCInvMask, const unsigned char *mask_rows,
+                              int apply_wall_bcs, int B, int D, int H, int W, int is3d,
+                              int row_begin, int row_end, int held_row_begin, int held_row_end,
+                              void *stream);
 /* whole Jacobi step; p and residual as in fnx_solve_linear_system_jacobi (p_tol = 0) */
 int fnx_step_jacobi(const fnx_step_params *prm, const float *density_in, const float *U_in,
                     const float *flags, const float *UBC, const float *UBCInvMask,

@@ -381,3 +381,65 @@ def test_get_centered_vs_reference(fluid, shape):
     got = host(fluid.getCentered(U.cuda()))
     assert got.shape == want.shape
     assert n_mismatch(got, want) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# (4) the fused 2-D step kernels (csrc/step2d.cu: forward pass staged in shared memory, tiled
+# forces / divergence) against the op-by-op sequence AND the generic one-thread-per-cell kernels
+# (FNX_STEP2D=0), on inputs that exercise every slow path: obstacles and Empty cells inside the
+# domain (line-trace stops, fluid-aware interpolation), velocities of several cells per step
+# (backward samples leaving the staged apron), odd sizes (partial tiles), both sampling modes,
+# with and without imposed-value masks, convnet (no wall BCs, no divergence) and Jacobi variants.
+# ---------------------------------------------------------------------------------------------
+FUSED_CASES = [
+    # seed, H, W, border, nboxes, vscale, dt, empty, sample_outside, masks
+    (30, 96, 160, "obstacle", 12, 3.0, 0.3, False, False, True),
+    (31, 130, 70, "fluid", 6, 9.0, 0.5, True, False, False),
+    (32, 257, 131, "obstacle", 30, 1.0, 1.0, True, True, True),
+    (33, 64, 64, "obstacle", 0, 0.5, 0.1, False, False, True),
+    (34, 37, 203, "obstacle", 8, 20.0, 0.5, True, False, True),
+    (35, 512, 384, "obstacle", 60, 2.0, 0.4, True, False, True),
+    # mostly CLEAN tiles (interior fast path of k2_advect_clean) with a few obstacles / fast cells mixed in
+    (36, 300, 420, "obstacle", 3, 1.0, 0.2, False, False, True),
+    (37, 200, 330, "fluid", 2, 2.0, 0.3, True, True, True),
+    (38, 1024, 1024, "obstacle", 5, 0.5, 0.1, False, False, False),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: f"s{c[0]}_{c[1]}x{c[2]}")
+def test_fused_2d_step_equals_ops_and_generic(fluid, case):
+    import importlib
+    import os
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    seed, H, W, border, nboxes, vscale, dt, we, so, masks = case
+    f, U, rho, p = random_case(seed, 1, H, W, border, nboxes, vscale, we)
+    mconf = plume_mconf(jacobiIter=11, dt=dt, sampleOutsideFluid=so, buoyancyScale=0.7, operatingDensity=0.05)
+    base = {"p": cu(p), "U": cu(U), "flags": cu(f), "density": cu(rho)}
+    if masks:
+        rng = np.random.RandomState(seed + 100)
+        inv = np.ones((1, 2, 1, H, W), np.float32); bc = np.zeros((1, 2, 1, H, W), np.float32)
+        rinv = np.ones((1, 1, 1, H, W), np.float32); rbc = np.zeros((1, 1, 1, H, W), np.float32)
+        rows = [0, 1, 2, 3, H // 2]
+        for r in rows:
+            sel = rng.rand(W) < 0.5
+            inv[0, :, 0, r, sel] = 0; bc[0, 0, 0, r, sel] = 1.5; bc[0, 1, 0, r, sel] = -0.5
+            rinv[0, 0, 0, r, sel] = 0; rbc[0, 0, 0, r, sel] = 0.8
+        base.update({"UBC": cu(bc), "UBCInvMask": cu(inv), "densityBC": cu(rbc), "densityBCInvMask": cu(rinv)})
+    sim.clear_graph_cache()
+    runs = {}
+    for mode in ("fused", "ops", "generic"):
+        bd = {k: v.clone() for k, v in base.items()}
+        for _ in range(2):
+            if mode == "ops":
+                sim._simulate_ops(mconf, bd, None, "jacobi", float(mconf["dt"]), False)
+            else:
+                if mode == "generic":
+                    os.environ["FNX_STEP2D"] = "0"
+                try:
+                    sim._simulate_fused(mconf, bd, None, "jacobi", float(mconf["dt"]), False)
+                finally:
+                    os.environ.pop("FNX_STEP2D", None)
+        runs[mode] = {k: host(bd[k]) for k in ("p", "U", "density")}
+    for k in ("p", "U", "density"):
+        assert n_mismatch(runs["fused"][k], runs["ops"][k]) == 0, ("fused vs ops", k, n_mismatch(runs["fused"][k], runs["ops"][k]))
+        assert n_mismatch(runs["fused"][k], runs["generic"][k]) == 0, ("fused vs generic", k)
