@@ -41,7 +41,7 @@ struct Row4 {
 // one Jacobi sweep over the lane's 8x4 patch.  `p` holds the old values and receives the new.
 // up/dn: rows adjacent to the strip (old values).  SLOW applies the Neumann/fixed masks.
 template <bool SLOW, bool RESID>
-__device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const Row4 (&dv)[JB_R], const Row4& up,
+__device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const float4* __restrict__ sdv, const Row4& up,
                                              const Row4& dn, unsigned Lb, unsigned Rb, unsigned Ub,
                                              unsigned Db, unsigned fixedb, float& acc) {
   Row4 prev = up;
@@ -49,6 +49,8 @@ __device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const Row4 (&dv)[J
   for (int rr = 0; rr < JB_R; rr++) {
     const Row4 cur = p[rr];
     const Row4 down = rr < JB_R - 1 ? p[rr + 1] : dn;
+    const float4 d4 = sdv[rr * (JB_TW / 4)];  // this lane's 4 divergence values of row rr (shared memory)
+    const float dvr[JB_C] = {d4.x, d4.y, d4.z, d4.w};
     const float left = __shfl_up_sync(0xffffffffu, cur.v[JB_C - 1], 1);
     const float right = __shfl_down_sync(0xffffffffu, cur.v[0], 1);
     Row4 nw;
@@ -65,7 +67,7 @@ __device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const Row4 (&dv)[J
         if (Ub & bit) p3 = cur.v[c];
         if (Db & bit) p4 = cur.v[c];
       }
-      float pn = (p1 + p2 + p3 + p4 + dv[rr].v[c]) * 0.25f;
+      float pn = (p1 + p2 + p3 + p4 + dvr[c]) * 0.25f;
       if (SLOW) {
         if (fixedb & (1u << (rr * JB_C + c))) pn = 0.f;
       }
@@ -80,12 +82,17 @@ __device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const Row4 (&dv)[J
   }
 }
 
+// The divergence tile lives in SHARED memory (read once per sweep with one LDS.128 per row), not in
+// registers: with p (32 values) alone a thread needs < 85 registers, so TWO 12-warp CTAs (or three 8-warp
+// ones) are resident per SM = 24 warps (the version that also kept div in registers ran one 16-warp
+// CTA at 128 registers: 25 % occupancy, issue slots half empty).
 template <int NW, bool FIRST, bool RESID>
-__global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 2 : 1))
+__global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
     k_jacobi2d_blocked(int H, int W, int row0, int row1, int iters, int vec_ok, const float* __restrict__ flags,
                        const float* __restrict__ div, const float* __restrict__ prev,
                        float* __restrict__ cur, double* __restrict__ ssq) {
   constexpr int TH = NW * JB_R;
+  extern __shared__ __align__(16) float sdv_all[];      // [TH][JB_TW] divergence tile
   __shared__ __align__(16) float xch[2][NW][2][JB_TW];  // [parity][warp][top|bottom][column]
   __shared__ unsigned xob[NW][32];
   __shared__ double wsum[NW];
@@ -97,7 +104,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 2 : 1))
   flags += boff; div += boff; cur += boff;
   if (!FIRST) prev += boff;
 
-  Row4 p[JB_R], dv[JB_R];
+  Row4 p[JB_R];
+  float4* const sdv = reinterpret_cast<float4*>(sdv_all) + (w * JB_R) * (JB_TW / 4) + lane;
   unsigned obw = 0, fixedb = 0;
   const bool xvec = vec_ok && gx0 >= 0 && gx0 + JB_C <= W;
 #pragma unroll
@@ -110,21 +118,23 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 2 : 1))
       const float4 f4 = __ldg(reinterpret_cast<const float4*>(flags + o));
       const float4 d4 = __ldg(reinterpret_cast<const float4*>(div + o));
       f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w;
-      dv[rr].v[0] = d4.x; dv[rr].v[1] = d4.y; dv[rr].v[2] = d4.z; dv[rr].v[3] = d4.w;
+      sdv[rr * (JB_TW / 4)] = d4;
       if (!FIRST) {
         const float4 p4 = __ldg(reinterpret_cast<const float4*>(prev + o));
         p[rr].v[0] = p4.x; p[rr].v[1] = p4.y; p[rr].v[2] = p4.z; p[rr].v[3] = p4.w;
       }
     } else {
+      float dvv[JB_C];
 #pragma unroll
       for (int c = 0; c < JB_C; c++) {
         const int gx = gx0 + c;
         const bool inb = yin && gx >= 0 && gx < W;
         const long long o = (long long)gy * W + gx;
         f[c] = inb ? __ldg(flags + o) : -1.f;  // -1: outside the domain
-        dv[rr].v[c] = inb ? __ldg(div + o) : 0.f;
+        dvv[c] = inb ? __ldg(div + o) : 0.f;
         if (!FIRST) p[rr].v[c] = inb ? __ldg(prev + o) : 0.f;
       }
+      sdv[rr * (JB_TW / 4)] = make_float4(dvv[0], dvv[1], dvv[2], dvv[3]);
     }
 #pragma unroll
     for (int c = 0; c < JB_C; c++) {
@@ -166,8 +176,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 2 : 1))
       dn.v[0] = d4.x; dn.v[1] = d4.y; dn.v[2] = d4.z; dn.v[3] = d4.w;
     }
     if (RESID) acc = 0.f;  // only the last iteration's |p - p_prev|^2 survives
-    if (slow) jacobi_sweep<true, RESID>(p, dv, up, dn, Lb, Rb, Ub, Db, fixedb, acc);
-    else jacobi_sweep<false, RESID>(p, dv, up, dn, Lb, Rb, Ub, Db, fixedb, acc);
+    if (slow) jacobi_sweep<true, RESID>(p, sdv, up, dn, Lb, Rb, Ub, Db, fixedb, acc);
+    else jacobi_sweep<false, RESID>(p, sdv, up, dn, Lb, Rb, Ub, Db, fixedb, acc);
   }
 
   // write back the cells whose dependency cone stayed inside the tile: warps 1..NW-2, lanes 2..29
@@ -224,10 +234,19 @@ static void launch_blocked(bool first, bool resid, dim3 grid, cudaStream_t st, i
                            int iters, int vec_ok,
                            const float* flags, const float* div, const float* prev, float* cur, double* ssq) {
   const int threads = NW * 32;
-  if (first && resid) k_jacobi2d_blocked<NW, true, true><<<grid, threads, 0, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
-  else if (first) k_jacobi2d_blocked<NW, true, false><<<grid, threads, 0, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
-  else if (resid) k_jacobi2d_blocked<NW, false, true><<<grid, threads, 0, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
-  else k_jacobi2d_blocked<NW, false, false><<<grid, threads, 0, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+  constexpr size_t dsm = (size_t)NW * JB_R * JB_TW * sizeof(float);   // the divergence tile
+  static bool attr_done = false;   // per instantiation (NW); > 48 KB of dynamic shared memory must be opted in
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    attr_done = true;
+  }
+  if (first && resid) k_jacobi2d_blocked<NW, true, true><<<grid, threads, dsm, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+  else if (first) k_jacobi2d_blocked<NW, true, false><<<grid, threads, dsm, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+  else if (resid) k_jacobi2d_blocked<NW, false, true><<<grid, threads, dsm, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+  else k_jacobi2d_blocked<NW, false, false><<<grid, threads, dsm, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
 }
 
 int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
@@ -238,12 +257,12 @@ int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_i
   auto wbuf = [&](int l) { return ((nL - 1 - l) % 2 == 0) ? p : scratch; };
   // float4 path: rows 16-byte aligned in every buffer
   const int vec_ok = (W % 4 == 0) && ((((uintptr_t)flags | (uintptr_t)div | (uintptr_t)p | (uintptr_t)scratch | (uintptr_t)p_init) & 15) == 0);
-  // tall tiles (16 warps) waste less halo work; short tiles keep small grids on more SMs
+  // tall tiles (12 warps) waste less halo work; short tiles keep small grids on more SMs
   static const char* force = getenv("FNX_JACOBI_NW");
   bool tall = (long long)H * W * B >= (1LL << 21);
-  if (force) tall = atoi(force) >= 16;
+  if (force) tall = atoi(force) >= 12;
   constexpr int OW = JB_TW - 2 * JB_HALO;
-  const int oh = (tall ? 16 : 8) * JB_R - 2 * JB_HALO;
+  const int oh = (tall ? 12 : 8) * JB_R - 2 * JB_HALO;
   dim3 grid((W + OW - 1) / OW, (row1 - row0 + oh - 1) / oh, B);
   int done = 0;
   for (int l = 0; l < nL; l++) {
@@ -252,7 +271,7 @@ int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_i
     const bool first = l == 0 && p_init == nullptr, resid = l == nL - 1 && ssq != nullptr;
     const float* prev = l == 0 ? p_init : wbuf(l - 1);
     float* cur = wbuf(l);
-    if (tall) launch_blocked<16>(first, resid, grid, st, H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+    if (tall) launch_blocked<12>(first, resid, grid, st, H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
     else launch_blocked<8>(first, resid, grid, st, H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
     done += iters;
     fnx_count_launches(1);

@@ -40,7 +40,7 @@ namespace s2 {
 // ---- advection ------------------------------------------------------------------------------------
 constexpr int TX = 64, TY = 32;          // output tile
 constexpr int AP = 2;                    // apron of forward values around it
-constexpr int SW = TX + 2 * AP, SH = TY + 2 * AP;
+constexpr int SW = TX + 2 * AP;
 constexpr int NT = 256;                  // threads: 64 x 4
 
 struct Adv {
@@ -293,20 +293,22 @@ __device__ __forceinline__ Fwd fwd_cell(const Adv& a, int j, int i) {
 
 __device__ __noinline__ void fwd_cell_far(const Adv& a, int j, int i, Fwd& f) { f = fwd_cell(a, j, i); }
 
-struct Smem {
-  float rho[SH][SW];
-  float u0[SH][SW];
-  float u1[SH][SW];
-  unsigned idx[SH][SW];
+template <int TYY>
+struct Smem {   // forward values of a TX x TYY tile + apron
+  static constexpr int SHH = TYY + 2 * AP;
+  float rho[SHH][SW];
+  float u0[SHH][SW];
+  float u1[SHH][SW];
+  unsigned idx[SHH][SW];
 };
 
 // forward value `which` (0 rho, 1 u0, 2 u1) at the four corners of a tap: from the staged apron, or
 // recomputed when the sample leaves it
-template <int WHICH>
-__device__ __forceinline__ void fwd_corners(const Adv& a, const Smem& s, int ty0, int tx0, const Tap& t, float& Ia,
+template <int WHICH, int TYY>
+__device__ __forceinline__ void fwd_corners(const Adv& a, const Smem<TYY>& s, int ty0, int tx0, const Tap& t, float& Ia,
                                             float& Ib, float& Ic, float& Id) {
   const int ly = t.y0 - (ty0 - AP), lx = t.x0 - (tx0 - AP);
-  if ((unsigned)ly < (unsigned)(SH - 1) && (unsigned)lx < (unsigned)(SW - 1) && t.y0 >= a.yf0 && t.y0 + 1 < a.yf1) {
+  if ((unsigned)ly < (unsigned)(Smem<TYY>::SHH - 1) && (unsigned)lx < (unsigned)(SW - 1) && t.y0 >= a.yf0 && t.y0 + 1 < a.yf1) {
     const float(*f)[SW] = WHICH == 0 ? s.rho : (WHICH == 1 ? s.u0 : s.u1);
     Ia = f[ly][lx]; Ib = f[ly + 1][lx]; Ic = f[ly][lx + 1]; Id = f[ly + 1][lx + 1];
     return;
@@ -329,23 +331,29 @@ struct Masks {   // setConstVals (simulate.py:4-26); virtual bases, NULL = no ma
   const unsigned char* rows;   // per row: bit0 = U masks differ from identity, bit1 = density masks (NULL: test every cell)
 };
 
+// TYY = rows per CTA.  TY for the whole grid; with a tile list (written by k2_advect_clean: only the tiles
+// that kernel declined are done here -- a few per cent of a plume grid, the ring along the walls) each
+// listed TX x TY tile is cut into TY / TYY CTAs so that the few tiles left spread over all SMs.
+template <int TYY>
 __global__ void __launch_bounds__(NT, 3)
     k2_advect(const __grid_constant__ Adv a, const __grid_constant__ Masks m, int rho_passes, float* __restrict__ rho_out, float* __restrict__ rho_mid,
               float* __restrict__ u0_out, float* __restrict__ u1_out, int tiles_x, const int* __restrict__ tile_count,
               const int* __restrict__ tile_list) {
-  __shared__ Smem s;
-  // with a tile list (written by k2_advect_clean) only the tiles that kernel could not take are done here
-  int tile = blockIdx.x;
+  __shared__ Smem<TYY> s;
+  constexpr int SUB = TY / TYY, SH_ = Smem<TYY>::SHH;
+  int tile = blockIdx.x / SUB;
+  const int sub = blockIdx.x - tile * SUB;
   if (tile_list) {
     if (tile >= *tile_count) return;
     tile = tile_list[tile];
   }
   const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
-  const int tx0 = tile_x * TX, ty0 = a.row0 + tile_y * TY;
+  const int tx0 = tile_x * TX, ty0 = a.row0 + tile_y * TY + sub * TYY;
   const int W = a.W, H = a.H;
+  if (ty0 >= a.row1) return;
 
   // ---- phase 1: forward pass of the tile and its apron into shared memory ----
-  for (int e = threadIdx.x; e < SW * SH; e += NT) {
+  for (int e = threadIdx.x; e < SW * SH_; e += NT) {
     const int ly = e / SW, lx = e - ly * SW;
     const int j = ty0 - AP + ly, i = tx0 - AP + lx;
     if (i < 0 || i >= W || j < a.yf0 || j >= a.yf1) continue;  // never sampled (samples clamp to existing rows)
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(NT, 3)
   const int i = tx0 + lxo;
   if (i >= W) return;
 #pragma unroll 1
-  for (int r = lyo; r < TY; r += NT / TX) {
+  for (int r = lyo; r < TYY; r += NT / TX) {
     const int j = ty0 + r;
     if (j >= a.row1) break;
     const int c = j * W + i;
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(NT, 3)
           trace2(a, (float)i + 0.5f, (float)j + 0.5f, a.dt * cx, a.dt * cy, bx, by);
           const Tap t = make_tap(a, bx, by);
           float Ia, Ib, Ic, Id;
-          fwd_corners<0>(a, s, ty0, tx0, t, Ia, Ib, Ic, Id);
+          fwd_corners<0, TYY>(a, s, ty0, tx0, t, Ia, Ib, Ic, Id);
           if (a.sample_outside) {
             bwd = bilerp(Ia, Ib, Ic, Id, t);
           } else {
@@ -455,8 +463,8 @@ __global__ void __launch_bounds__(NT, 3)
           if (!skip) {
             const Tap t = make_tap(a, px + vdx, py + vdy);
             float Ia, Ib, Ic, Id;
-            if (comp == 0) fwd_corners<1>(a, s, ty0, tx0, t, Ia, Ib, Ic, Id);
-            else fwd_corners<2>(a, s, ty0, tx0, t, Ia, Ib, Ic, Id);
+            if (comp == 0) fwd_corners<1, TYY>(a, s, ty0, tx0, t, Ia, Ib, Ic, Id);
+            else fwd_corners<2, TYY>(a, s, ty0, tx0, t, Ia, Ib, Ic, Id);
             const float bwd = bilerp(Ia, Ib, Ic, Id, t);
             v = fw + a.hs * ((comp == 0 ? ux : vy) - bwd);
           }
@@ -685,79 +693,104 @@ __global__ void __launch_bounds__(NT, 4)
 }
 
 // ---- forces + BCs + divergence ----------------------------------------------------------------------
-constexpr int FX = 128, FY = 8;          // output tile; forced velocity staged for (FY+1) x (FX+1)
+// One thread per column marching DOWN a strip of FR rows: the forced velocity (addBuoyancy ->
+// addGravity -> [setWallBcs] -> setConstVals, simulate.py:98-133) of every face is computed ONCE; the
+// divergence takes the right neighbour's x face from the next lane (warp shuffle; a warp owns 31 output
+// columns + 1 overlap lane) and the upper neighbour's y face from the previous iteration (a register);
+// flags / density of the lower row are loaded once and carried to the next iteration.
+constexpr int FW = 31, FWARPS = 4, FR = 32;   // output columns per warp, warps per CTA, rows per strip
 struct Frc {
   int H, W, row0, row1;
   int use_buoyancy, use_gravity, wall_bcs;
   float bs0, bs1, gf0, gf1, rho_star;
 };
 
-// velocity component `comp` of cell (j,i) after addBuoyancy -> addGravity -> [setWallBcs] -> setConstVals
-// (simulate.py:98-133) from the post-advection fields
-template <int COMP>
-__device__ __forceinline__ float forced(const Frc& g, int j, int i, const float* __restrict__ u,
-                                        const float* __restrict__ rho, const float* __restrict__ rho_mid,
-                                        const float* __restrict__ fl, const Masks& m) {
-  const int c = j * g.W + i;
-  float v = __ldg(u + c);
-  const float fc = __ldg(fl + c);
-  const int idx = COMP == 0 ? i : j;
-  const int cn = c - (COMP == 0 ? 1 : g.W);
-  const float fn = idx > 0 ? __ldg(fl + cn) : fc;
-  const bool border = (i < 1) | (i > g.W - 2) | (j < 1) | (j > g.H - 2);
+// one velocity component of one cell: u after the forces, wall BCs and imposed values.  fc / fn flags of
+// the cell and of its lower neighbour along the component (the cell itself at index 0, Q13), rc / rn the
+// densities addBuoyancy sees there
+__device__ __forceinline__ float forced1(const Frc& g, float u, float fc, float fn, float rc, float rn, bool border,
+                                         float bs, float gf, bool masked, float inv, float bc) {
   if (!border) {
-    if (g.use_buoyancy && fc == kFluid && fn == kFluid) {
-      // density as addBuoyancy sees it: after ONE setConstVals pass (rho_mid on masked rows)
-      const int jn = COMP == 0 ? j : j - 1;
-      const float* rc_p = (rho_mid && (!m.rows || (m.rows[j] & 2))) ? rho_mid : rho;
-      const float* rn_p = (rho_mid && (!m.rows || (m.rows[jn] & 2))) ? rho_mid : rho;
-      v = buoyancy_apply(v, fc, fn, __ldg(rc_p + c), __ldg(rn_p + cn), COMP == 0 ? g.bs0 : g.bs1, g.rho_star);
-    }
-    if (g.use_gravity) v = gravity_apply(v, fc, fn, COMP == 0 ? g.gf0 : g.gf1);
+    if (g.use_buoyancy) u = buoyancy_apply(u, fc, fn, rc, rn, bs, g.rho_star);
+    if (g.use_gravity) u = gravity_apply(u, fc, fn, gf);
   }
-  if (g.wall_bcs) v = wall_bcs_apply(v, fc, fn);
-  const unsigned char rb = m.rows ? m.rows[j] : (unsigned char)3;
-  if (m.u0bc && (rb & 1)) {
-    v = COMP == 0 ? const_vals_apply(v, __ldg(m.u0inv + c), __ldg(m.u0bc + c))
-                  : const_vals_apply(v, __ldg(m.u1inv + c), __ldg(m.u1bc + c));
-  }
-  return v;
+  if (g.wall_bcs) u = wall_bcs_apply(u, fc, fn);
+  if (masked) u = const_vals_apply(u, inv, bc);
+  return u;
 }
 
-__global__ void __launch_bounds__(256)
-    k2_forces_div(Frc g, Masks m, const float* __restrict__ rho, const float* __restrict__ rho_mid,
-                  const float* __restrict__ u0, const float* __restrict__ u1, const float* __restrict__ fl,
-                  float* __restrict__ u0_out, float* __restrict__ u1_out, float* __restrict__ div, int tiles_x) {
-  __shared__ float su[FY + 1][FX + 1];
-  __shared__ float sv[FY + 1][FX + 1];
+__global__ void __launch_bounds__(32 * FWARPS)
+    k2_forces_div(const __grid_constant__ Frc g, const __grid_constant__ Masks m, const float* __restrict__ rho,
+                  const float* __restrict__ rho_mid, const float* __restrict__ u0, const float* __restrict__ u1,
+                  const float* __restrict__ fl, float* __restrict__ u0_out, float* __restrict__ u1_out,
+                  float* __restrict__ div, int tiles_x) {
   const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
-  const int tx0 = tile_x * FX, ty0 = g.row0 + tile_y * FY;
-  for (int e = threadIdx.x; e < (FY + 1) * (FX + 1); e += 256) {
-    const int ly = e / (FX + 1), lx = e - ly * (FX + 1);
-    const int j = ty0 + ly, i = tx0 + lx;
-    if (i >= g.W || j >= g.H || j > g.row1) continue;   // row1 itself (one past the window) feeds the divergence
-    // the x face of column tx0+FX is only needed by row < FY, the y face of row ty0+FY only by lx < FX
-    if (ly < FY) su[ly][lx] = forced<0>(g, j, i, u0, rho, rho_mid, fl, m);
-    if (lx < FX) sv[ly][lx] = forced<1>(g, j, i, u1, rho, rho_mid, fl, m);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int W = g.W, H = g.H;
+  const int i = (tile_x * FWARPS + w) * FW + lane;
+  const int jb = g.row0 + tile_y * FR;                        // lowest row of the strip
+  int jt = jb + FR;                                           // one above its highest row
+  jt = jt > g.row1 ? g.row1 : jt;
+  const bool in = i < W;                                      // lanes beyond the grid only feed shuffles
+  const bool out = in && lane < FW;
+  const bool cborder = (i < 1) | (i > W - 2);
+  const unsigned full = 0xffffffffu;
+  auto rows_of = [&](int j) -> unsigned { return m.rows ? (unsigned)m.rows[j] : 3u; };
+  auto rho_of = [&](int j) -> const float* { return (rho_mid && (rows_of(j) & 2u)) ? rho_mid : rho; };
+
+  // the row above the strip only contributes its y face (it exists unless the strip ends at the grid's top)
+  const bool top = jt < H;
+  int j = top ? jt : jt - 1;
+  float fc = 0.f, rc = 0.f;
+  if (in) {
+    fc = __ldg(fl + j * W + i);
+    rc = __ldg(rho_of(j) + j * W + i);
   }
-  __syncthreads();
-  const int lx = threadIdx.x & (FX - 1);
-  const int i = tx0 + lx;
-  if (i >= g.W) return;
-  for (int ly = threadIdx.x / FX; ly < FY; ly += 256 / FX) {
-    const int j = ty0 + ly;
-    if (j >= g.row1) break;
-    const int c = j * g.W + i;
-    const float a = su[ly][lx], b = sv[ly][lx];
-    u0_out[c] = a;
-    u1_out[c] = b;
-    if (div) {
-      float d = 0.f;
-      const bool border = (i < 1) | (i > g.W - 2) | (j < 1) | (j > g.H - 2);
-      if (!border) d = a - su[ly][lx + 1] + b - sv[ly + 1][lx];   // velocity_divergence.py:61-66 (Q15)
-      if (__ldg(fl + c) == kObstacle) d = 0.f;
-      div[c] = d;
+  float fv_up = 0.f;
+  for (; j >= jb; j--) {
+    const int c = j * W + i;
+    const bool face_only = j == jt;                           // first iteration when `top`
+    // lower row: loaded once, becomes this column's (fc, rc) in the next iteration
+    float fb = fc, rb = rc;
+    if (in && j > 0) {
+      fb = __ldg(fl + c - W);
+      rb = __ldg(rho_of(j - 1) + c - W);
     }
+    // left neighbour from the previous lane; lane 0 reads it (column 0 is its own neighbour, Q13)
+    float fl_l = __shfl_up_sync(full, fc, 1), r_l = __shfl_up_sync(full, rc, 1);
+    if (lane == 0) {
+      fl_l = fc; r_l = rc;
+      if (in && i > 0) {
+        fl_l = __ldg(fl + c - 1);
+        r_l = __ldg(rho_of(j) + c - 1);
+      }
+    }
+    const unsigned rbits = rows_of(j);
+    const bool masked = m.u0bc != nullptr && (rbits & 1u);
+    const bool border = cborder | (j < 1) | (j > H - 2);
+    float a = 0.f, b = 0.f;
+    if (in) {
+      float i0 = 0.f, b0 = 0.f, i1 = 0.f, b1 = 0.f;
+      if (masked) {
+        i0 = __ldg(m.u0inv + c); b0 = __ldg(m.u0bc + c);
+        i1 = __ldg(m.u1inv + c); b1 = __ldg(m.u1bc + c);
+      }
+      b = forced1(g, __ldg(u1 + c), fc, j > 0 ? fb : fc, rc, rb, border, g.bs1, g.gf1, masked, i1, b1);
+      if (!face_only) a = forced1(g, __ldg(u0 + c), fc, fl_l, rc, r_l, border, g.bs0, g.gf0, masked, i0, b0);
+    }
+    const float a_right = __shfl_down_sync(full, a, 1);
+    if (!face_only && out) {
+      u0_out[c] = a;
+      u1_out[c] = b;
+      if (div) {
+        float d = 0.f;
+        if (!border) d = a - a_right + b - fv_up;             // velocity_divergence.py:61-66 (Q15)
+        if (fc == kObstacle) d = 0.f;
+        div[c] = d;
+      }
+    }
+    fv_up = b;
+    fc = fb; rc = rb;
   }
 }
 
@@ -859,9 +892,9 @@ int fnx_step2d_advect(const fnx_step2d_win& w, float dt, float maccormack_streng
       int* list = count + 1;
       if (cudaMemsetAsync(count, 0, sizeof(int), st) != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "step2d: memset failed");
       k2_advect_clean<<<ntiles, NT, 0, st>>>(a, m, rho_passes, w.ya0, w.ya1, ro, rm, uo0, uo1, tiles_x, count, list);
-      k2_advect<<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, count, list);
+      k2_advect<8><<<ntiles * (TY / 8), NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, count, list);
     } else {
-      k2_advect<<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, nullptr, nullptr);
+      k2_advect<TY><<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, nullptr, nullptr);
     }
   }
   fnx_count_launches(tile_ws ? 2 * B : B);
@@ -873,7 +906,7 @@ int fnx_step2d_forces_div(const fnx_step2d_win& w, const fnx_step_params* prm, c
                           cudaStream_t st) {
   const long long off = (long long)w.ya0 * w.W;
   const long long plane = (long long)(w.ya1 - w.ya0) * w.W;
-  const int tiles_x = (w.W + FX - 1) / FX, tiles_y = (w.row1 - w.row0 + FY - 1) / FY;
+  const int tiles_x = (w.W + FW * FWARPS - 1) / (FW * FWARPS), tiles_y = (w.row1 - w.row0 + FR - 1) / FR;
   Frc g;
   g.H = w.H; g.W = w.W; g.row0 = w.row0; g.row1 = w.row1;
   g.use_buoyancy = prm->use_buoyancy; g.use_gravity = prm->use_gravity; g.wall_bcs = prm->apply_wall_bcs;
@@ -888,7 +921,7 @@ int fnx_step2d_forces_div(const fnx_step2d_win& w, const fnx_step_params* prm, c
     m.u1inv = vb(mk.UBCInv ? mk.UBCInv + (2 * b + 1) * plane : nullptr, off);
     m.rbc = nullptr; m.rinv = nullptr;
     m.rows = mk.rows ? mk.rows + (long long)b * (w.ya1 - w.ya0) - w.ya0 : nullptr;
-    k2_forces_div<<<tiles_x * tiles_y, 256, 0, st>>>(
+    k2_forces_div<<<tiles_x * tiles_y, 32 * FWARPS, 0, st>>>(
         g, m, vb(rho + b * plane, off), vb(rho_mid ? rho_mid + b * plane : nullptr, off), vb(U + (2 * b) * plane, off),
         vb(U + (2 * b + 1) * plane, off), vb(flags + b * plane, off), vb(U_out + (2 * b) * plane, off),
         vb(U_out + (2 * b + 1) * plane, off), vb(div ? div + b * plane : nullptr, off), tiles_x);
