@@ -42,6 +42,19 @@ class ConvLayer(ctypes.Structure):
                 ("w_scale", _c_float), ("w_norm", _c_float), ("b_max", _c_float), ("w_replicas", _c_int)]
 
 
+HALO_MAX_PEERS, HALO_MAX_FIELDS = 8, 4
+
+
+class HaloDesc(ctypes.Structure):
+    """struct fnx_halo_desc (include/fluidstep.h)."""
+    _fields_ = [("n_peers", _c_int), ("n_fields", _c_int),
+                ("src", (_c_void_p * HALO_MAX_FIELDS) * HALO_MAX_PEERS),
+                ("dst", (_c_void_p * HALO_MAX_FIELDS) * HALO_MAX_PEERS),
+                ("count", _c_size_t * HALO_MAX_PEERS),
+                ("flag_out", _c_void_p * HALO_MAX_PEERS), ("flag_in", _c_void_p * HALO_MAX_PEERS),
+                ("epoch", _c_void_p), ("done", _c_void_p)]
+
+
 class ProfileRec(ctypes.Structure):
     """struct fnx_profile_rec (include/fluidstep.h)."""
     _fields_ = [("cin", _c_int), ("cout", _c_int), ("ksize", _c_int), ("h", _c_int), ("w", _c_int),
@@ -70,6 +83,8 @@ SIGNATURES = {
     "fnx_solve_linear_system_jacobi": (_I, [_P, _P, _P, _P] + _GRID + [_F, _I, ctypes.POINTER(_I), _P, _S, _P]),
     "fnx_jacobi_iterate": (_I, [_P, _P, _P, _P] + _GRID + [_I, _I, _I, _P, _S, _P]),
     "fnx_step_project_bcs_rows": (_I, [_P] * 6 + [_I] + _GRID + [_I, _I, _P]),
+    "fnx_jacobi_iterate_held": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _S, _P]),
+    "fnx_halo_exchange": (_I, [ctypes.POINTER(HaloDesc), _P]),
     "fnx_step_project_bcs_held": (_I, [_P] * 6 + [_I] + _GRID + [_I, _I, _I, _I, _P]),
     "fnx_velocity_divergence": (_I, [_P, _P, _P] + _GRID + [_P]),
     "fnx_velocity_update": (_I, [_P, _P, _P] + _GRID + [_P]),

@@ -30,6 +30,7 @@ UNITS = {
     "step.cu": ["-fmad=false"],
     "step2d.cu": ["-fmad=false"],
     "host_util.cpp": [],
+    "halo.cu": [],
     "conv.cu": [],
     "conv_tc.cu": [],
 }

@@ -88,7 +88,7 @@ __device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const float4* __re
 // CTA at 128 registers: 25 % occupancy, issue slots half empty).
 template <int NW, bool FIRST, bool RESID>
 __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
-    k_jacobi2d_blocked(int H, int W, int row0, int row1, int iters, int vec_ok, const float* __restrict__ flags,
+    k_jacobi2d_blocked(int H, int W, int row0, int row1, int ya0, int ya1, int iters, int vec_ok, const float* __restrict__ flags,
                        const float* __restrict__ div, const float* __restrict__ prev,
                        float* __restrict__ cur, double* __restrict__ ssq) {
   constexpr int TH = NW * JB_R;
@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
   constexpr int OW = JB_TW - 2 * JB_HALO, OH = TH - 2 * JB_HALO;
   const int gx0 = blockIdx.x * OW - JB_HALO + lane * JB_C;
   const int gy0 = row0 + blockIdx.y * OH - JB_HALO + w * JB_R;  // [row0, row1): rows this launch writes
-  const long long boff = (long long)blockIdx.z * H * W;
+  // the arrays hold rows [ya0, ya1) of the grid (a slab; 0, H = everything) and are addressed through
+  // virtual bases with global row indices; rows that are not held read as "outside" (they lie in the halo
+  // of a slab, whose values never reach the rows written)
+  const long long boff = (long long)blockIdx.z * (ya1 - ya0) * W - (long long)ya0 * W;
   flags += boff; div += boff; cur += boff;
   if (!FIRST) prev += boff;
 
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
 #pragma unroll
   for (int rr = 0; rr < JB_R; rr++) {
     const int gy = gy0 + rr;
-    const bool yin = gy >= 0 && gy < H;
+    const bool yin = gy >= ya0 && gy < ya1;
     float f[JB_C];
     if (xvec && yin) {
       const long long o = (long long)gy * W + gx0;
@@ -231,7 +234,7 @@ static int jacobi_block_iters() {
 
 template <int NW>
 static void launch_blocked(bool first, bool resid, dim3 grid, cudaStream_t st, int H, int W, int row0, int row1,
-                           int iters, int vec_ok,
+                           int ya0, int ya1, int iters, int vec_ok,
                            const float* flags, const float* div, const float* prev, float* cur, double* ssq) {
   const int threads = NW * 32;
   constexpr size_t dsm = (size_t)NW * JB_R * JB_TW * sizeof(float);   // the divergence tile
@@ -243,15 +246,28 @@ static void launch_blocked(bool first, bool resid, dim3 grid, cudaStream_t st, i
     cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
     attr_done = true;
   }
-  if (first && resid) k_jacobi2d_blocked<NW, true, true><<<grid, threads, dsm, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
-  else if (first) k_jacobi2d_blocked<NW, true, false><<<grid, threads, dsm, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
-  else if (resid) k_jacobi2d_blocked<NW, false, true><<<grid, threads, dsm, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
-  else k_jacobi2d_blocked<NW, false, false><<<grid, threads, dsm, st>>>(H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+  if (first && resid) k_jacobi2d_blocked<NW, true, true><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
+  else if (first) k_jacobi2d_blocked<NW, true, false><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
+  else if (resid) k_jacobi2d_blocked<NW, false, true><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
+  else k_jacobi2d_blocked<NW, false, false><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
 }
+
+int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
+                               double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
+                               cudaStream_t st);
 
 int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
                           double* ssq, int B, int H, int W, int max_iter, int row0, int row1, cudaStream_t st) {
+  return fnx_jacobi_2d_blocked_held(flags, div, p_init, p, scratch, ssq, B, H, W, max_iter, row0, row1, 0, H, st);
+}
+
+int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
+                               double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
+                               cudaStream_t st) {
   if (row1 <= row0) { row0 = 0; row1 = H; }
+  if (!(0 <= ya0 && ya0 <= row0 && row1 <= ya1 && ya1 <= H))
+    return fnx_set_error(FNX_ERR_ARG, "jacobi_2d_blocked: rows [%d,%d) not inside the held rows [%d,%d) of %d", row0, row1,
+                         ya0, ya1, H);
   const int T = jacobi_block_iters();
   const int nL = (max_iter + T - 1) / T;
   auto wbuf = [&](int l) { return ((nL - 1 - l) % 2 == 0) ? p : scratch; };
@@ -259,7 +275,7 @@ int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_i
   const int vec_ok = (W % 4 == 0) && ((((uintptr_t)flags | (uintptr_t)div | (uintptr_t)p | (uintptr_t)scratch | (uintptr_t)p_init) & 15) == 0);
   // tall tiles (12 warps) waste less halo work; short tiles keep small grids on more SMs
   static const char* force = getenv("FNX_JACOBI_NW");
-  bool tall = (long long)H * W * B >= (1LL << 21);
+  bool tall = (long long)(row1 - row0) * W * B >= (1LL << 21);
   if (force) tall = atoi(force) >= 12;
   constexpr int OW = JB_TW - 2 * JB_HALO;
   const int oh = (tall ? 12 : 8) * JB_R - 2 * JB_HALO;
@@ -271,8 +287,8 @@ int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_i
     const bool first = l == 0 && p_init == nullptr, resid = l == nL - 1 && ssq != nullptr;
     const float* prev = l == 0 ? p_init : wbuf(l - 1);
     float* cur = wbuf(l);
-    if (tall) launch_blocked<12>(first, resid, grid, st, H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
-    else launch_blocked<8>(first, resid, grid, st, H, W, row0, row1, iters, vec_ok, flags, div, prev, cur, ssq);
+    if (tall) launch_blocked<12>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
+    else launch_blocked<8>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
     done += iters;
     fnx_count_launches(1);
   }

@@ -472,6 +472,9 @@ static void launch_jacobi_iter(const Grid& g, bool first, bool resid, const floa
 int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
                           double* ssq, int B, int H, int W, int max_iter, int row0, int row1,
                           cudaStream_t st);  // jacobi_blocked.cu
+int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
+                               double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
+                               cudaStream_t st);  // jacobi_blocked.cu
 
 
 // 3-D fixed iteration count: mask once, then the 4-cells-per-thread kernel (needs W % 4 == 0 and 16-byte
@@ -770,6 +773,22 @@ int fnx_jacobi_iterate(const float* flags, const float* div, const float* p_init
   }
   FNX_LAUNCH_CHECK("jacobi_iterate", 0);
   return FNX_OK;
+}
+
+// 2-D, arrays holding rows [held_row_begin, held_row_end) only (a slab of the domain-decomposed step):
+// `iters` iterations continued from p_init (NULL = from p = 0), rows [row_begin, row_end) written.
+// More than 8 iterations ping-pong through `workspace` (held rows x W floats).
+int fnx_jacobi_iterate_held(const float* flags, const float* div, const float* p_init, float* p, int B, int H, int W,
+                            int iters, int row_begin, int row_end, int held_row_begin, int held_row_end,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 1 || H < 2 || W < 2) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate_held: bad grid");
+  if (iters < 1) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate_held: At least 1 iteration of the solver is needed.");
+  if (p_init == p) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate_held: p_init must not alias p");
+  const size_t n = (size_t)B * (held_row_end - held_row_begin) * W;
+  if (iters > 8 && (!workspace || workspace_bytes < n * sizeof(float)))
+    return fnx_set_error(FNX_ERR_WORKSPACE, "jacobi_iterate_held: workspace too small");
+  return fnx_jacobi_2d_blocked_held(flags, div, p_init, p, (float*)workspace, nullptr, B, H, W, iters, row_begin, row_end,
+                                    held_row_begin, held_row_end, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -719,6 +719,85 @@ __device__ __forceinline__ float forced1(const Frc& g, float u, float fc, float 
   return u;
 }
 
+// MASKED = false: no row of the strip (nor the row below / above it) carries imposed values, so the row
+// byte map, the mask loads and the choice between the one-pass and the final density drop out (the
+// plume inlet touches 4 rows of the grid); chosen per CTA at run time.
+template <bool MASKED>
+__device__ __forceinline__ void forces_strip(const Frc& g, const Masks& m, const float* __restrict__ rho,
+                                             const float* __restrict__ rho_mid, const float* __restrict__ u0,
+                                             const float* __restrict__ u1, const float* __restrict__ fl,
+                                             float* __restrict__ u0_out, float* __restrict__ u1_out,
+                                             float* __restrict__ div, int i, int jb, int jt, int lane) {
+  const int W = g.W, H = g.H;
+  const bool in = i < W;                                      // lanes beyond the grid only feed shuffles
+  const bool out = in && lane < FW;
+  const bool cborder = (i < 1) | (i > W - 2);
+  const unsigned full = 0xffffffffu;
+  auto rows_of = [&](int j) -> unsigned { return MASKED ? (m.rows ? (unsigned)m.rows[j] : 3u) : 0u; };
+  auto rho_of = [&](int j) -> const float* { return (MASKED && rho_mid && (rows_of(j) & 2u)) ? rho_mid : rho; };
+  const int ic = in ? i : W - 1;                              // clamped column: every lane loads something valid
+
+  // the row above the strip only contributes its y face (it exists unless the strip ends at the grid's top)
+  const bool top = jt < H;
+  int j = top ? jt : jt - 1;
+  float fc = __ldg(fl + j * W + ic), rc = __ldg(rho_of(j) + j * W + ic);
+  float fv_up = 0.f;
+  constexpr int U = 4;                                        // rows in flight per thread
+  while (j >= jb) {
+    // loads of up to U rows first (independent of the arithmetic below)
+    float au[U], av[U], fbv[U], rbv[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int jj = j - k;
+      const int c = (jj < jb ? jb : jj) * W + ic;
+      au[k] = __ldg(u0 + c);
+      av[k] = __ldg(u1 + c);
+      const int cb = jj > 0 ? c - W : c;
+      fbv[k] = __ldg(fl + cb);
+      rbv[k] = __ldg(rho_of(jj > 0 ? jj - 1 : 0) + cb);
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      if (j < jb) break;
+      const int c = j * W + ic;
+      const bool face_only = j == jt;                         // first iteration when `top`
+      const float fb = j > 0 ? fbv[k] : fc, rb = j > 0 ? rbv[k] : rc;
+      // left neighbour from the previous lane; lane 0 reads it (column 0 is its own neighbour, Q13)
+      float fl_l = __shfl_up_sync(full, fc, 1), r_l = __shfl_up_sync(full, rc, 1);
+      if (lane == 0) {
+        fl_l = fc; r_l = rc;
+        if (i > 0 && in) {
+          fl_l = __ldg(fl + c - 1);
+          r_l = __ldg(rho_of(j) + c - 1);
+        }
+      }
+      const bool masked = MASKED && m.u0bc != nullptr && (rows_of(j) & 1u);
+      const bool border = cborder | (j < 1) | (j > H - 2);
+      float i0 = 0.f, b0 = 0.f, i1 = 0.f, b1 = 0.f;
+      if (masked) {
+        i0 = __ldg(m.u0inv + c); b0 = __ldg(m.u0bc + c);
+        i1 = __ldg(m.u1inv + c); b1 = __ldg(m.u1bc + c);
+      }
+      const float b = forced1(g, av[k], fc, j > 0 ? fb : fc, rc, rb, border, g.bs1, g.gf1, masked, i1, b1);
+      const float a = forced1(g, au[k], fc, fl_l, rc, r_l, border, g.bs0, g.gf0, masked, i0, b0);
+      const float a_right = __shfl_down_sync(full, a, 1);
+      if (!face_only && out) {
+        u0_out[c] = a;
+        u1_out[c] = b;
+        if (div) {
+          float d = 0.f;
+          if (!border) d = a - a_right + b - fv_up;           // velocity_divergence.py:61-66 (Q15)
+          if (fc == kObstacle) d = 0.f;
+          div[c] = d;
+        }
+      }
+      fv_up = b;
+      fc = fb; rc = rb;
+      j--;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(32 * FWARPS)
     k2_forces_div(const __grid_constant__ Frc g, const __grid_constant__ Masks m, const float* __restrict__ rho,
                   const float* __restrict__ rho_mid, const float* __restrict__ u0, const float* __restrict__ u1,
@@ -726,72 +805,21 @@ __global__ void __launch_bounds__(32 * FWARPS)
                   float* __restrict__ div, int tiles_x) {
   const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int W = g.W, H = g.H;
   const int i = (tile_x * FWARPS + w) * FW + lane;
   const int jb = g.row0 + tile_y * FR;                        // lowest row of the strip
   int jt = jb + FR;                                           // one above its highest row
   jt = jt > g.row1 ? g.row1 : jt;
-  const bool in = i < W;                                      // lanes beyond the grid only feed shuffles
-  const bool out = in && lane < FW;
-  const bool cborder = (i < 1) | (i > W - 2);
-  const unsigned full = 0xffffffffu;
-  auto rows_of = [&](int j) -> unsigned { return m.rows ? (unsigned)m.rows[j] : 3u; };
-  auto rho_of = [&](int j) -> const float* { return (rho_mid && (rows_of(j) & 2u)) ? rho_mid : rho; };
-
-  // the row above the strip only contributes its y face (it exists unless the strip ends at the grid's top)
-  const bool top = jt < H;
-  int j = top ? jt : jt - 1;
-  float fc = 0.f, rc = 0.f;
-  if (in) {
-    fc = __ldg(fl + j * W + i);
-    rc = __ldg(rho_of(j) + j * W + i);
+  // does any row this strip touches (jb-1 .. jt) carry imposed values?
+  int any = 0;
+  if (m.u0bc || rho_mid) {
+    if (!m.rows) any = 1;
+    else
+      for (int r = jb - 1 + (int)threadIdx.x; r <= jt; r += 32 * FWARPS)
+        if (r >= 0 && r < g.H && m.rows[r]) any = 1;
   }
-  float fv_up = 0.f;
-  for (; j >= jb; j--) {
-    const int c = j * W + i;
-    const bool face_only = j == jt;                           // first iteration when `top`
-    // lower row: loaded once, becomes this column's (fc, rc) in the next iteration
-    float fb = fc, rb = rc;
-    if (in && j > 0) {
-      fb = __ldg(fl + c - W);
-      rb = __ldg(rho_of(j - 1) + c - W);
-    }
-    // left neighbour from the previous lane; lane 0 reads it (column 0 is its own neighbour, Q13)
-    float fl_l = __shfl_up_sync(full, fc, 1), r_l = __shfl_up_sync(full, rc, 1);
-    if (lane == 0) {
-      fl_l = fc; r_l = rc;
-      if (in && i > 0) {
-        fl_l = __ldg(fl + c - 1);
-        r_l = __ldg(rho_of(j) + c - 1);
-      }
-    }
-    const unsigned rbits = rows_of(j);
-    const bool masked = m.u0bc != nullptr && (rbits & 1u);
-    const bool border = cborder | (j < 1) | (j > H - 2);
-    float a = 0.f, b = 0.f;
-    if (in) {
-      float i0 = 0.f, b0 = 0.f, i1 = 0.f, b1 = 0.f;
-      if (masked) {
-        i0 = __ldg(m.u0inv + c); b0 = __ldg(m.u0bc + c);
-        i1 = __ldg(m.u1inv + c); b1 = __ldg(m.u1bc + c);
-      }
-      b = forced1(g, __ldg(u1 + c), fc, j > 0 ? fb : fc, rc, rb, border, g.bs1, g.gf1, masked, i1, b1);
-      if (!face_only) a = forced1(g, __ldg(u0 + c), fc, fl_l, rc, r_l, border, g.bs0, g.gf0, masked, i0, b0);
-    }
-    const float a_right = __shfl_down_sync(full, a, 1);
-    if (!face_only && out) {
-      u0_out[c] = a;
-      u1_out[c] = b;
-      if (div) {
-        float d = 0.f;
-        if (!border) d = a - a_right + b - fv_up;             // velocity_divergence.py:61-66 (Q15)
-        if (fc == kObstacle) d = 0.f;
-        div[c] = d;
-      }
-    }
-    fv_up = b;
-    fc = fb; rc = rb;
-  }
+  any = __syncthreads_or(any);
+  if (any) forces_strip<true>(g, m, rho, rho_mid, u0, u1, fl, u0_out, u1_out, div, i, jb, jt, lane);
+  else forces_strip<false>(g, m, rho, rho_mid, u0, u1, fl, u0_out, u1_out, div, i, jb, jt, lane);
 }
 
 // ---- velocityUpdate + [setWallBcs] + setConstVals, in place -------------------------------------------
@@ -892,7 +920,9 @@ int fnx_step2d_advect(const fnx_step2d_win& w, float dt, float maccormack_streng
       int* list = count + 1;
       if (cudaMemsetAsync(count, 0, sizeof(int), st) != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "step2d: memset failed");
       k2_advect_clean<<<ntiles, NT, 0, st>>>(a, m, rho_passes, w.ya0, w.ya1, ro, rm, uo0, uo1, tiles_x, count, list);
-      k2_advect<8><<<ntiles * (TY / 8), NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, count, list);
+      // (cutting the listed tiles into 8-row CTAs measured slower, 75 vs 63 us at 4096^2: the apron overhead
+      // of a thin tile outweighs the better spread -- the leftover pass is instruction-bound, not latency-bound)
+      k2_advect<TY><<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, count, list);
     } else {
       k2_advect<TY><<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, nullptr, nullptr);
     }

@@ -84,6 +84,31 @@ int fnx_jacobi_iterate(const float *flags, const float *div, const float *p_init
                        int D, int H, int W, int is3d, int iters, int row_begin, int row_end,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* 2-D, arrays that hold rows [held_row_begin, held_row_end) of the H x W grid only (a slab): */
+int fnx_jacobi_iterate_held(const float *flags, const float *div, const float *p_init, float *p,
+                            int B, int H, int W, int iters, int row_begin, int row_end,
+                            int held_row_begin, int held_row_end, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
+/* ---- halo exchange over NVLink peer memory (no reference counterpart: SURVEY.md section 8e) ----
+ * One kernel per exchange: copy `count[k]` floats of each of `n_fields` fields from src[k][f] (this
+ * GPU) to dst[k][f] (peer-mapped memory of neighbour k), then raise *flag_out[k] (in neighbour k's
+ * memory) to the next epoch and wait until every *flag_in[k] (in this GPU's memory, raised by
+ * neighbour k's matching call) has reached it.  `epoch` / `done`: two zero-initialised device words
+ * owned by this exchange site.  Capturable in CUDA graphs; waits are bounded (trap on timeout). */
+#define FNX_HALO_MAX_PEERS 8
+#define FNX_HALO_MAX_FIELDS 4
+typedef struct fnx_halo_desc {
+  int n_peers, n_fields;
+  const float *src[FNX_HALO_MAX_PEERS][FNX_HALO_MAX_FIELDS];
+  float *dst[FNX_HALO_MAX_PEERS][FNX_HALO_MAX_FIELDS];
+  size_t count[FNX_HALO_MAX_PEERS];
+  unsigned *flag_out[FNX_HALO_MAX_PEERS];
+  const unsigned *flag_in[FNX_HALO_MAX_PEERS];
+  unsigned *epoch, *done;
+} fnx_halo_desc;
+int fnx_halo_exchange(const fnx_halo_desc *d, void *stream);
+
 /* ---- lib.fluid stencils ----------------------------------------------------- */
 /* velocity_divergence.py:4-74 : div (B,1,D,H,W) out */
 int fnx_velocity_divergence(const float *U, const float *flags, float *div, int B, int D, int H,

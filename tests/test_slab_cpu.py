@@ -1,0 +1,130 @@
+"""The schedule of the window-based slab step (fluidnet_cxx_b200.lib.slab.schedule: ghost widths, row
+windows of every stage, which rows every exchange moves) replayed on CPU with the C oracle as compute.
+
+Every virtual rank works on arrays whose rows OUTSIDE its held rows are poisoned (the real rank does not
+even allocate them) and only the rows the schedule says a stage writes are taken from that stage's
+result.  If a ghost width or a window were one row too small, poison would reach an owned row: the
+gathered owned rows must equal the single-domain oracle step BIT FOR BIT."""
+import numpy as np
+import pytest
+import torch
+
+from test_distributed_cpu import MCONF, OracleOps, global_state, jacobi_numpy
+
+
+def single_domain(st, steps):
+    """the single-domain oracle step (simulate.py:28-171, jacobi branch) from state `st`"""
+    ops = OracleOps()
+    H = st["flags"].shape[3]
+    bd = {k: torch.from_numpy(v.copy()) for k, v in st.items()}
+    out = []
+    for _ in range(steps):
+        rho, U, div = ops.advect_forces_div(MCONF, MCONF["dt"], bd, True, True, (0, H))
+        p, _ = ops.o.solveLinearSystemJacobi(bd["flags"].numpy(), div.numpy(), False, 0.0, MCONF["jacobiIter"])
+        U = ops.project(torch.from_numpy(p), U, bd, (0, H))
+        bd["U"], bd["density"], bd["p"] = U, rho, torch.from_numpy(p)
+        out.append({k: bd[k].numpy().copy() for k in ("p", "U", "density")})
+    return out
+
+
+def poison(shape, rng, scale):
+    return (rng.standard_normal(shape) * scale + 3.0 * scale).astype(np.float32)
+
+
+# fast = True: the velocity is scaled so that max |u| dt = 0.95 cells, the limit the ghost widths are sized
+# for (one step only: the projected velocity of the next step is not bounded by construction)
+@pytest.mark.parametrize("world,H,K,fast", [(2, 64, 1, False), (3, 96, 1, True), (4, 128, 1, False), (2, 96, 2, True),
+                                            (3, 144, 2, False), (2, 64, 1, True)])
+def test_slab_schedule_bit_exact(world, H, K, fast):
+    from fluidnet_cxx_b200.lib import slab
+    W, steps, seed = 40, (1 if fast else 2), 11
+    iters = MCONF["jacobiIter"]
+    ops = OracleOps()
+    st = global_state(H, W, seed)
+    if fast:
+        st["U"] = (st["U"] * np.float32(0.95 / (np.abs(st["U"]).max() * MCONF["dt"]))).astype(np.float32)
+    ref = single_domain(st, steps)
+    rng = np.random.RandomState(99)
+    geo = [slab.geometry(H, world, r, K) for r in range(world)]
+    scheds = [slab.schedule(H, world, r, iters, K)[1] for r in range(world)]
+    assert len({len(s) for s in scheds}) == 1 and all([o[0] for o in s] == [o[0] for o in scheds[0]] for s in scheds)
+
+    def held_only(name, g):
+        full = st[name]
+        out = poison(full.shape, rng, 0.5 if name == "U" else 1.0)
+        out[:, :, :, g["ya0"]:g["ya1"]] = full[:, :, :, g["ya0"]:g["ya1"]]
+        return out
+    R = []
+    for g in geo:
+        R.append({"U": [held_only("U", g), poison(st["U"].shape, rng, 0.5)],
+                  "rho": [held_only("density", g), poison(st["density"].shape, rng, 1.0)],
+                  "P": [poison(st["p"].shape, rng, 1.0), poison(st["p"].shape, rng, 1.0)],
+                  "div": poison(st["p"].shape, rng, 1.0),
+                  # static fields: a rank holds its rows of the flags / masks only (outside: walls, harmless and never owned)
+                  "bd": {k: torch.from_numpy(np.where(np.arange(H)[None, None, None, :, None] // 1 >= g["ya0"], st[k], st[k]).copy())
+                         for k in ("flags", "UBC", "UBCInvMask", "densityBC", "densityBCInvMask")}})
+        f = R[-1]["bd"]["flags"].numpy()
+        f[:, :, :, :g["ya0"]] = 2.0
+        f[:, :, :, g["ya1"]:] = 2.0
+    par = 0
+    for step in range(steps):
+        for i in range(len(scheds[0])):
+            kind = scheds[0][i][0]
+            if kind == "X":
+                for r, g in enumerate(geo):
+                    _, what, rows = scheds[r][i]
+                    for q, first in ((r - 1, g["lo"]), (r + 1, g["hi"] - rows)):
+                        if q < 0 or q >= world:
+                            continue
+                        sl = slice(first, first + rows)
+                        assert geo[q]["ya0"] <= sl.start and sl.stop <= geo[q]["ya1"], "push outside the neighbour's held rows"
+                        if what == "state":
+                            R[q]["U"][par][:, :, :, sl] = R[r]["U"][par][:, :, :, sl]
+                            R[q]["rho"][par][:, :, :, sl] = R[r]["rho"][par][:, :, :, sl]
+                        else:
+                            R[q]["P"][what][:, :, :, sl] = R[r]["P"][what][:, :, :, sl]
+                continue
+            for r, g in enumerate(geo):
+                op = scheds[r][i]
+                me = R[r]
+                if kind == "advect":
+                    w0, w1 = op[1], op[2]
+                    bd = dict(me["bd"])
+                    bd["U"], bd["density"] = torch.from_numpy(me["U"][par]), torch.from_numpy(me["rho"][par])
+                    rho, U, div = ops.advect_forces_div(MCONF, MCONF["dt"], bd, True, True, (0, H))
+                    me["rho"][1 - par][:, :, :, w0:w1] = rho.numpy()[:, :, :, w0:w1]
+                    me["U"][1 - par][:, :, :, w0:w1] = U.numpy()[:, :, :, w0:w1]
+                    me["div"][:, :, :, w0:w1] = div.numpy()[:, :, :, w0:w1]
+                elif kind == "jacobi":
+                    _, src, dst, it, r0, r1 = op
+                    p = jacobi_numpy(me["bd"]["flags"].numpy(), me["div"], None if src is None else me["P"][src], it)
+                    me["P"][dst][:, :, :, r0:r1] = p[:, :, :, r0:r1]
+                else:
+                    _, pbuf, lo, hi = op
+                    U = ops.project(torch.from_numpy(me["P"][pbuf]), torch.from_numpy(me["U"][1 - par]), me["bd"], (0, H))
+                    me["U"][1 - par][:, :, :, lo:hi] = U.numpy()[:, :, :, lo:hi]
+                    me["p_final"] = pbuf
+        par ^= 1
+        for k, pick in (("U", lambda me: me["U"][par]), ("density", lambda me: me["rho"][par]),
+                        ("p", lambda me: me["P"][me["p_final"]])):
+            got = np.concatenate([pick(R[r])[:, :, :, geo[r]["lo"]:geo[r]["hi"]] for r in range(world)], axis=3)
+            want = ref[step][k]
+            bad = int(np.sum(~((got == want) | (np.isnan(got) & np.isnan(want)))))
+            assert bad == 0, f"world {world} K {K} step {step} field {k}: {bad} owned cells differ from the single-domain step"
+
+
+def test_slab_geometry():
+    from fluidnet_cxx_b200.lib import slab
+    g = slab.geometry(4096, 8, 3)
+    assert (g["lo"], g["hi"], g["G"], g["dg"], g["ya0"], g["ya1"], g["rows_held"]) == (1536, 2048, 16, 8, 1520, 2064, 544)
+    assert slab.geometry(4096, 8, 0)["ya0"] == 0 and slab.geometry(4096, 8, 7)["ya1"] == 4096
+    assert slab.geometry(100, 1, 0)["rows_held"] == 100
+    with pytest.raises(ValueError):
+        slab.geometry(100, 3, 0)
+    with pytest.raises(ValueError):
+        slab.geometry(64, 8, 0)           # 8 rows per slab < ghost width
+    # every rank's schedule has the same shape (the exchanges pair up)
+    shapes = {tuple(o[0] for o in slab.schedule(1024, 4, r, 100)[1]) for r in range(4)}
+    assert len(shapes) == 1
+    _, ops = slab.schedule(1024, 4, 1, 100)
+    assert sum(1 for o in ops if o[0] == "X") == 1 + 12 + 1 and sum(o[3] for o in ops if o[0] == "jacobi") == 100
