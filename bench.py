@@ -678,6 +678,191 @@ def run_distributed(args, name, scaling, guard, transport):
     return out
 
 
+def plume_held_state(wl, mconf, gH, W, seed=0):
+    """held(name, r0, r1) -> rows [r0, r1) of the GLOBAL initial state of a 2-D plume workload as CPU tensors
+    (1, C, 1, r1-r0, W), built without ever materialising the global grid on a GPU: emptyDomain (util.py:5-49)
+    and createPlumeBCs (init_conditions.py:4-83) only touch the border ring and rows 0:4."""
+    import numpy as np
+    import torch
+    from fluidnet_cxx_b200.lib.fluid import init_conditions
+    U_np, rho_np = synthetic_state_numpy(1, gH, W, seed=seed)
+    small = {"p": torch.zeros(1, 1, 1, 8, W), "U": torch.zeros(1, 2, 1, 8, W), "flags": torch.zeros(1, 1, 1, 8, W),
+             "density": torch.zeros(1, 1, 1, 8, W)}
+    init_conditions.createPlumeBCs(small, mconf["injectionDensity"], mconf["injectionVelocity"], mconf["sourceRadius"])
+    ident = {"UBC": 0.0, "UBCInvMask": 1.0, "densityBC": 0.0, "densityBCInvMask": 1.0}
+
+    def held(name, r0, r1):
+        if name == "U":
+            return torch.from_numpy(np.ascontiguousarray(U_np[:, :, :, r0:r1]))
+        if name == "density":
+            return torch.from_numpy(np.ascontiguousarray(rho_np[:, :, :, r0:r1]))
+        if name == "flags":
+            f = torch.ones(1, 1, 1, r1 - r0, W)
+            f[..., 0] = 2.0; f[..., W - 1] = 2.0
+            if r0 == 0:
+                f[:, :, :, 0] = 2.0
+            if r1 == gH:
+                f[:, :, :, -1] = 2.0
+            return f
+        if name in ident:
+            c = 2 if name.startswith("U") else 1
+            t = torch.full((1, c, 1, r1 - r0, W), ident[name])
+            n = max(0, min(8, r1) - r0) if r0 < 8 else 0
+            if n > 0:
+                t[:, :, :, :n] = small[name][:, :, :, r0:r0 + n]
+            return t
+        return None
+    return held
+
+
+def run_distributed_slab(args, name, scaling, guard):
+    """N > 1, 2-D Jacobi workloads: the window-based slab step (fluidnet_cxx_b200/lib/slab.py): every rank
+    holds its rows + ghost rows only, halos travel by one peer-memory kernel per exchange, the whole step
+    is one CUDA graph.  strong = the workload grid cut into N slabs; weak = N workload grids stacked."""
+    import torch
+    import torch.distributed as dist
+    from fluidnet_cxx_b200 import _native
+    from fluidnet_cxx_b200.lib import slab
+
+    wl = WORKLOADS[name]
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    lib = _native.load()
+    _, H, W = wl["res"]
+    mconf = workload_mconf(wl)
+    gH = H if scaling == "strong" else H * world
+    if gH % world:
+        raise SystemExit(f"bench.py: {gH} rows do not split over {world} GPUs")
+    steps, warmup = args.steps, max(args.warmup, 3)
+    tag = f"{name}/{scaling}/slab"
+    guard.beat(f"{tag}: state")
+    held = plume_held_state(wl, mconf, gH, W)
+    topo = slab.ProcessTopology(dev)
+    K = int(os.environ.get("FNX_SLAB_K", "1"))
+    step = slab.SlabJacobiStep(topo, mconf, gH, W, held, K=K)
+    g = step.g
+    cells_global = gH * W
+    owned_cells = g["Hs"] * W
+    held_cells = g["rows_held"] * W
+
+    # pinned host copies of this rank's held rows (inputs of the e2e leg) -- allocated BEFORE any timed region
+    host_in = {k: held(k, g["ya0"], g["ya1"]).pin_memory() for k in ("U", "density", "flags")}
+    host_out = {k: torch.empty((1, c, 1, g["Hs"], W)).pin_memory() for k, c in (("p", 1), ("U", 2), ("density", 1))}
+    working_set = held_cells * 4 * 14
+    flush = working_set < 2 * L2_BYTES
+    flush_buf = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev) if flush else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    guard.beat(f"{tag}: direct steps + graph capture")
+    for _ in range(2):
+        step.step()
+    barrier()
+    graphed = step.capture()
+    barrier()
+    reach = step.max_reach()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for i in range(warmup):
+        guard.beat(f"{tag}: warm-up step {i}")
+        step.step()
+    barrier()
+    guard.beat(f"{tag}: timed steps")
+    ev = []
+    sampler.mark_begin()
+    t_wall0 = time.perf_counter()
+    for i in range(steps):
+        if flush:
+            flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step.step()
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.mark_end()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # pass 2: the same phases launched one by one with events per kind (exchange / advect+forces / jacobi / project)
+    guard.beat(f"{tag}: per-stage pass")
+    kinds = [op[0] for op in slab.schedule(gH, world, rank, step.iters, K)[1]]
+    stage = {}
+    n0 = lib.fnx_launch_count()
+    nstage = max(3, min(steps, 10))
+    for _ in range(nstage):
+        for kind, ph in zip(kinds, step.phases()):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ph()
+            e1.record()
+            stage.setdefault(kind, []).append((e0, e1))
+        step.advance()
+    barrier()
+    launches = (lib.fnx_launch_count() - n0) * steps // nstage
+    stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) * steps / nstage for k, v in stage.items()}
+    clocks = sampler.stop() if rank == 0 else None
+
+    # e2e: held rows in from pinned host memory, owned rows out, every step
+    guard.beat(f"{tag}: e2e steps")
+    e2e_steps = max(3, min(steps, 10))
+    h2d = sum(v.numel() * 4 for v in host_in.values())
+    d2h = sum(v.numel() * 4 for v in host_out.values())
+
+    def e2e_step():
+        step.held("U").copy_(host_in["U"], non_blocking=True)
+        step.held("density").copy_(host_in["density"], non_blocking=True)
+        step.flags.copy_(host_in["flags"], non_blocking=True)
+        step.step()
+        for k in ("p", "U", "density"):
+            host_out[k].copy_(step.owned(k), non_blocking=True)
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([total_ms, e2e_ms] + [stage_ms.get(k, 0.0) for k in ("X", "advect", "jacobi", "project")],
+                     dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, x_ms, adv_ms, jac_ms, prj_ms = t.tolist()
+    tb = torch.tensor([float(h2d), float(d2h), float(launches), float(torch.cuda.max_memory_allocated(dev))],
+                      dtype=torch.float64, device=dev)
+    dist.all_reduce(tb)
+    h2d_all, d2h_all, launches_all, mem_all = (int(x) for x in tb.tolist())
+    out = None
+    if rank == 0:
+        roof = build_roofline(wl, steps, owned_cells, total_ms, {"pressure": jac_ms, "advect_forces": adv_ms, "project": prj_ms},
+                              [])
+        roof["exchange_ms_per_step"] = round(x_ms / steps, 4)
+        roof["exchanges_per_step"] = kinds.count("X")
+        out = make_record(args, name, wl, world, cells_global, owned_cells, steps, warmup, total_ms, e2e_ms, e2e_steps, roof,
+                          h2d_all, d2h_all, launches_all, clocks, t_wall, flush, graphed,
+                          parallelism=(f"{world} GPUs, {scaling} scaling: row slabs ({g['Hs']} owned rows, {g['G']} ghost rows "
+                                       f"held per interior side, every rank allocates its window only), halo rows stored "
+                                       f"straight into the neighbours' ghost rows over NVLink peer memory by one kernel "
+                                       f"per exchange ({kinds.count('X')} per step, no NCCL in the data path), whole step "
+                                       f"replayed as one CUDA graph; global grid 1x{gH}x{W}"),
+                          grid=[1, gH, W], scaling=scaling)
+        out["cpu_baseline"] = None
+        out["config"]["max_u_dt_cells"] = round(reach, 3)
+        out["config"]["device_bytes_all_ranks_peak"] = mem_all
+    del step, host_in, host_out, flush_buf
+    torch.cuda.empty_cache()
+    barrier()
+    return out
+
+
+
 def run_ours(args):
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -700,10 +885,15 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     guard.beat("init_process_group")
     dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=max(60.0, 1.5 * args.hang_timeout)))
-    out = run_distributed(args, name, args.scaling, guard, args.transport)
+    def run_n(nm, scaling):
+        w = WORKLOADS[nm]
+        if w["method"] == "jacobi" and w["res"][0] == 1 and w.get("case") != "rt" and args.transport != "nccl":
+            return run_distributed_slab(args, nm, scaling, guard)
+        return run_distributed(args, nm, scaling, guard, "nccl" if args.transport == "window" else args.transport)
+    out = run_n(name, args.scaling)
     if args.workload is None and not args.no_also:
         other = "weak" if args.scaling == "strong" else "strong"
-        also = [run_distributed(args, name, other, guard, args.transport)]
+        also = [run_n(name, other)]
         if rank == 0:
             out["also"] = also
     guard.stop()
@@ -827,16 +1017,18 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help=f"run this workload only (default: {DEFAULT_WORKLOAD}, plus the sub-records under 'also')")
     ap.add_argument("--no-also", action="store_true", help="default workload only, no sub-records")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--transport", default="nccl", choices=["peer", "nccl"],
-                    help="N > 1 halo exchange: nccl = batched send/recv between CUDA-graph segments; peer = stores "
-                         "into the neighbour's inbox over NVLink peer memory, whole step in one CUDA graph")
+    ap.add_argument("--transport", default="window", choices=["window", "peer", "nccl"],
+                    help="N > 1: window (default) = per-rank row windows + one peer-memory halo kernel per exchange, "
+                         "whole step one CUDA graph (lib/slab.py; 2-D Jacobi workloads, others fall back to nccl); "
+                         "nccl / peer = the global-array decomposition of lib/distributed.py with batched NCCL "
+                         "send/recv, or stores into the neighbour's inbox")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N > 1: strong = the workload grid itself split into N slabs (default); "
                          "weak = N slabs of the workload grid stacked along H/D")

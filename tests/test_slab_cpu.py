@@ -128,3 +128,24 @@ def test_slab_geometry():
     assert len(shapes) == 1
     _, ops = slab.schedule(1024, 4, 1, 100)
     assert sum(1 for o in ops if o[0] == "X") == 1 + 12 + 1 and sum(o[3] for o in ops if o[0] == "jacobi") == 100
+
+
+def test_bench_held_state_equals_global_init():
+    """bench.plume_held_state builds a rank's rows of the initial state directly; they must be the rows of the
+    state bench.init_state builds on the whole grid (here with the reference's own emptyDomain / createPlumeBCs)."""
+    import bench
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built")
+    reflib = ref_loader.load()
+    H, W = 96, 72
+    wl = dict(bench.WORKLOADS["plume4096_jacobi100"], res=(1, H, W))
+    mconf = bench.workload_mconf(wl)
+    U_np, rho_np = bench.synthetic_state_numpy(1, H, W, 0)
+    bd = {"p": torch.zeros(1, 1, 1, H, W), "U": torch.zeros(1, 2, 1, H, W), "flags": torch.zeros(1, 1, 1, H, W),
+          "density": torch.zeros(1, 1, 1, H, W)}
+    bench.init_state(reflib.fluid, wl, mconf, bd, U_np, rho_np, torch.from_numpy)
+    held = bench.plume_held_state(wl, mconf, H, W)
+    for r0, r1 in ((0, 40), (2, 50), (30, 96), (0, 96), (5, 9)):
+        for k in ("U", "density", "flags", "UBC", "UBCInvMask", "densityBC", "densityBCInvMask"):
+            assert torch.equal(held(k, r0, r1), bd[k][:, :, :, r0:r1]), (k, r0, r1)
