@@ -628,19 +628,39 @@ def run_distributed(args, name, scaling, guard, transport):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: this rank's window rows in from pinned host memory, owned rows out, every step ----
+    # Contiguous pinned buffers <-> contiguous device staging buffers (true asynchronous DMA), then device-side
+    # copies into / out of the strided window.  (Round 1 copied the strided window views directly: torch stages
+    # such copies through pageable host memory, i.e. synchronously, and that e2e leg is where the 4-GPU run of
+    # round 1 stopped making progress; every buffer is also allocated up front now, no cudaHostAlloc between
+    # collectives.)
     guard.beat(f"{tag}: e2e steps")
     e2e_steps = max(3, min(steps, 10))
     win, own = decomp._sl(decomp.r0, decomp.r1), decomp._sl(decomp.lo, decomp.hi)
-    h2d = sum(host[k][win].numel() * 4 for k in ("p", "U", "flags", "density"))
-    d2h = sum(host[k][own].numel() * 4 for k in ("p", "U", "density"))
-    out_host = {k: torch.empty_like(host[k][own]).pin_memory() for k in ("p", "U", "density")}
+    host_win = {k: host[k][win].contiguous().pin_memory() for k in ("p", "U", "flags", "density")}
+    dev_win = {k: torch.empty_like(v, device=dev) for k, v in host_win.items()}
+    out_host = {k: torch.empty(host[k][own].shape).pin_memory() for k in ("p", "U", "density")}
+    dev_out = {k: torch.empty(v.shape, device=dev) for k, v in out_host.items()}
+    h2d = sum(v.numel() * 4 for v in host_win.values())
+    d2h = sum(v.numel() * 4 for v in out_host.values())
+    barrier()
+
+    e2e_sync = os.environ.get("FNX_E2E_MODE", "sync") == "sync"
 
     def e2e_step():
         for k in ("p", "U", "flags", "density"):
-            stepper.state[k][win].copy_(host[k][win], non_blocking=True)
+            dev_win[k].copy_(host_win[k], non_blocking=True)
+            stepper.state[k][win].copy_(dev_win[k])
+        if e2e_sync:
+            # DMA copies and NCCL send/recv are kept apart: with host<->device copies queued around the NCCL
+            # calls this leg stopped making progress at 4 ranks (every rank parked in the next barrier, no conv
+            # barrier time-out); see DESIGN.md "the 4-GPU hang"
+            torch.cuda.synchronize()
         stepper.step()
+        if e2e_sync:
+            torch.cuda.synchronize()
         for k in ("p", "U", "density"):
-            out_host[k].copy_(stepper.state[k][own], non_blocking=True)
+            dev_out[k].copy_(stepper.state[k][own])
+            out_host[k].copy_(dev_out[k], non_blocking=True)
 
     e2e_step()
     barrier()
@@ -672,7 +692,7 @@ def run_distributed(args, name, scaling, guard, transport):
         out["cpu_baseline"] = None
         if graph_check is not None:
             out["config"]["graph_vs_direct_max_abs_diff"] = graph_check
-    del stepper, bd, host, out_host, flush_buf, ops
+    del stepper, bd, host, out_host, flush_buf, ops, host_win, dev_win, dev_out
     torch.cuda.empty_cache()
     barrier()
     return out
@@ -739,7 +759,7 @@ def run_distributed_slab(args, name, scaling, guard):
     guard.beat(f"{tag}: state")
     held = plume_held_state(wl, mconf, gH, W)
     topo = slab.ProcessTopology(dev)
-    K = int(os.environ.get("FNX_SLAB_K", "1"))
+    K = int(os.environ.get("FNX_SLAB_K", "3"))   # Jacobi launches per pressure exchange (measured: 1.52 / 1.43 / 1.41 ms at K = 1 / 2 / 3, 2 GPUs strong)
     step = slab.SlabJacobiStep(topo, mconf, gH, W, held, K=K)
     g = step.g
     cells_global = gH * W

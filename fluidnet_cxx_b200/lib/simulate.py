@@ -150,16 +150,47 @@ def clear_graph_cache():
     _graph_seen.clear()
 
 
+def _native_net(net):
+    """This package's FluidNet for `net`, or None.
+
+    The reference drivers do not use lib.FluidNet: they execute the model class saved next to the weights
+    (plume.py:87-96,131: trained_models/.../*_saved.py), whose forward is eager torch code (std, cat, masks,
+    lib.fluid calls) around `lib.MultiScaleNet`.  Under compat.install() that MultiScaleNet is this package's
+    tcgen05 network; when the instance has the saved model's structure and the shipped configuration, its
+    forward is routed through FluidNet.forward (same arithmetic: tests/test_gpu_cnn.py pins it against the
+    saved model's own CPU outputs) sharing the instance's weights, so the drivers take the fused, graph-replayed
+    path.  Anything else (other model variants, foreign modules) keeps running its own forward."""
+    from .model import FluidNet
+    from .multi_scale_net import MultiScaleNet
+    if isinstance(net, FluidNet):
+        return net
+    if net is None or type(net).__name__ != 'FluidNet' or not hasattr(net, 'mconf'):
+        return None
+    ms = getattr(net, 'multiScale', None)
+    if not isinstance(ms, MultiScaleNet):
+        return None
+    cached = net.__dict__.get('_fnx_native')
+    if cached is not None and cached.mconf is net.mconf and cached.multiScale is ms:
+        return cached
+    try:
+        native = FluidNet(net.mconf, dropout=False)
+        native._check_config()
+    except (NotImplementedError, AssertionError, KeyError):
+        return None
+    native.multiScale = ms            # the instance's own (already loaded, already on the device) weights
+    native.eval()
+    net.__dict__['_fnx_native'] = native
+    return native
+
+
 def _graphable(batch_dict, net, sim_method):
     if not graphs_enabled() or _stage_hook is not None:
         return False
     f = batch_dict['flags']
     if f.numel() > GRAPH_MAX_CELLS or torch.cuda.is_current_stream_capturing():
         return False
-    if sim_method == 'convnet':
-        from .model import FluidNet
-        if not isinstance(net, FluidNet):     # a foreign nn.Module: its launches may not be capturable
-            return False
+    if sim_method == 'convnet' and _native_net(net) is None:
+        return False                          # a foreign nn.Module: its launches may not be capturable
     return True
 
 
@@ -186,8 +217,9 @@ def _graph_key(mconf, batch_dict, net, sim_method):
     conf = tuple(_freeze(mconf.get(k)) for k in _STEP_KEYS)
     netk = None
     if sim_method == 'convnet':
-        netk = (id(net), net.multiScale._plan_key(batch_dict['U'].device),
-                tuple(_freeze(net.mconf.get(k)) for k in _NET_KEYS))
+        nn_ = _native_net(net)
+        netk = (id(net), nn_.multiScale._plan_key(batch_dict['U'].device),
+                tuple(_freeze(nn_.mconf.get(k)) for k in _NET_KEYS))
     return (str(batch_dict['U'].device), sim_method, state, masks, conf, netk)
 
 
@@ -286,7 +318,7 @@ def _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div):
         if _stage_hook is not None:
             _stage_hook("pressure", "begin")
         data = torch.cat((batch_dict['p'], U, flags, density), 1)
-        p, U = net(data)
+        p, U = (_native_net(net) or net)(data)
         if _stage_hook is not None:
             _stage_hook("pressure", "end")
         if UBC is not None:

@@ -54,7 +54,7 @@ def geometry(H, world, rank, K=1):
 def schedule(H, world, rank, iters, K=1):
     """The step of one rank as a list of operations on row intervals (pure bookkeeping, shared by the
     CUDA stepper below and by the CPU test that replays it with the oracle on NaN-poisoned arrays):
-      ("X", what, rows)            exchange `rows` boundary rows; what = "state" or a pressure buffer index
+      ("X", what, rows)            exchange `rows` boundary rows; what = "state" or a pressure buffer index (0..3)
       ("advect", w0, w1)           advect + forces + divergence on rows [w0, w1)
       ("jacobi", src, dst, it, r0, r1)   `it` iterations, pressure buffer src (None = from zero) -> dst, rows written
       ("project", p, lo, hi)       velocity update + BCs on the owned rows, pressure buffer p
@@ -66,17 +66,24 @@ def schedule(H, world, rank, iters, K=1):
     if multi:
         ops.append(("X", "state", g["G"]))
     ops.append(("advect", max(0, lo - dg - 1), min(H, hi + dg + 1)) if multi else ("advect", 0, H))
+    # Pressure buffers: 0 / 1 receive the result of a chunk (the only buffers ever pushed into, alternating
+    # from chunk to chunk), 2 / 3 hold the intermediate launches of a chunk (their ghost rows are computed
+    # locally).  A neighbour may still be inside chunk c -- reading the ghost rows of buffer (c-1) % 2 and
+    # of the intermediates -- when this rank pushes the result of chunk c: it goes into buffer c % 2, which
+    # nobody reads before the wait of that exchange.
     n_launch = (iters + JACOBI_LAUNCH_ITERS - 1) // JACOBI_LAUNCH_ITERS
-    src, dst = None, 0
+    src = None
     for l in range(n_launch):
         it = min(JACOBI_LAUNCH_ITERS, iters - l * JACOBI_LAUNCH_ITERS)
-        in_chunk = l % K
+        chunk, in_chunk = divmod(l, K)
+        n_in_chunk = min(K, n_launch - chunk * K)
         if multi and l > 0 and in_chunk == 0:
             ops.append(("X", src, dg))
-        margin = JACOBI_LAUNCH_ITERS * (min(K, n_launch - (l - in_chunk)) - 1 - in_chunk) if multi else 0
+        margin = JACOBI_LAUNCH_ITERS * (n_in_chunk - 1 - in_chunk) if multi else 0
         r0, r1 = (max(0, lo - margin), min(H, hi + margin)) if multi else (0, H)
+        dst = chunk % 2 if in_chunk == n_in_chunk - 1 else 2 + in_chunk % 2
         ops.append(("jacobi", src, dst, it, r0, r1))
-        src, dst = dst, 1 - dst
+        src = dst
     if multi:
         ops.append(("X", src, 4))      # velocityUpdate reads one row below the slab (4 rows keep 16-byte units)
     ops.append(("project", src, lo, hi))
@@ -195,7 +202,7 @@ class SlabJacobiStep:
         # ---- symmetric arena: state ping-pong, pressure ping-pong, flags of the exchange sites.  Every rank
         # reserves room for the tallest slab (interior ranks hold Hs + 2G rows, edge ranks fewer) so that a
         # field starts at the same offset everywhere; a rank's tensor covers its own held rows only.
-        self.arena = ar = _Arena(topo, 8 * _align(plane_max) + _align(n_sites * 2 * 4) + 4096)
+        self.arena = ar = _Arena(topo, 10 * _align(plane_max) + _align(n_sites * 2 * 4) + 4096)
 
         def field(channels):
             start = ar.off
@@ -204,7 +211,7 @@ class SlabJacobiStep:
             return t
         self.U = [field(2), field(2)]
         self.rho = [field(1), field(1)]
-        self.P = [field(1), field(1)]
+        self.P = [field(1), field(1), field(1), field(1)]   # see schedule(): 0/1 exchanged, 2/3 intermediates
         self.site_flags = ar.take((n_sites, 2), torch.int32)
         # ---- local (never pushed into) ----
         z = lambda c: torch.zeros((1, c, 1, Rh, W), dtype=torch.float32, device=dev)  # noqa: E731

@@ -106,6 +106,24 @@ def stage_sources():
     # the python wrappers `import fluidnet_cpp` (top-level module name, build/)
 
 
+def stage_drivers():
+    """UNMODIFIED copies of the reference's two simulation drivers, their YAML configs and the shipped
+    model directory under oracle/_ref/drivers/ (git-ignored like the rest of oracle/_ref; it travels to the
+    GPU box so tests/test_gpu_drivers.py can run `pytorch/plume.py` / `pytorch/rayleighTaylor.py` as they
+    are against the B200 library through tools/run_reference_driver.py)."""
+    d = os.path.join(OUT, "drivers")
+    if os.path.isdir(d):
+        shutil.rmtree(d)
+    os.makedirs(os.path.join(d, "pytorch"))
+    for f in ("plume.py", "rayleighTaylor.py", "plumeConfig.yaml", "rayleighTaylorConfig.yaml", "trainConfig.yaml"):
+        shutil.copy(os.path.join(REF, "pytorch", f), os.path.join(d, "pytorch"))
+    md = os.path.join(d, MODEL_DIR)
+    os.makedirs(md)
+    for f in ("ScaleNet_ShortTerm_LongTermLoss_saved.py", "convModel_mconf.pth", "convModel_conf.pth",
+              "convModel_lastEpoch_best.pth"):
+        shutil.copy(os.path.join(REF, MODEL_DIR, f), md)
+
+
 def build_extension():
     import torch  # noqa: F401
     from torch.utils.cpp_extension import load
@@ -123,7 +141,12 @@ def main():
     if not os.path.isdir(REF):
         print(f"[oracle/build_ref] {REF} not present; keeping prebuilt oracle/_ref as is")
         return 0
+    if "--drivers-only" in sys.argv:
+        stage_drivers()
+        print("[oracle/build_ref] staged", os.path.join(OUT, "drivers"))
+        return 0
     stage_sources()
+    stage_drivers()
     build_extension()
     print("[oracle/build_ref] built", os.path.join(OUT, "build", "fluidnet_cpp.so"))
     return 0

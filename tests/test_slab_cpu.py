@@ -32,10 +32,18 @@ def poison(shape, rng, scale):
 
 
 # fast = True: the velocity is scaled so that max |u| dt = 0.95 cells, the limit the ghost widths are sized
-# for (one step only: the projected velocity of the next step is not bounded by construction)
-@pytest.mark.parametrize("world,H,K,fast", [(2, 64, 1, False), (3, 96, 1, True), (4, 128, 1, False), (2, 96, 2, True),
-                                            (3, 144, 2, False), (2, 64, 1, True)])
-def test_slab_schedule_bit_exact(world, H, K, fast):
+# for (one step only: the projected velocity of the next step is not bounded by construction).
+# order: how the virtual ranks are interleaved.  On the GPUs nothing keeps two ranks in lockstep between two
+# exchanges: a rank pushes its rows into the neighbour as soon as IT is ready, and only its own progress
+# past an exchange depends on the neighbours.  "lockstep" runs every operation on all ranks in turn;
+# "ahead" / "behind" let the lowest / highest runnable rank run as far as its exchanges allow before anyone
+# else moves; "random" picks the next rank at random.  A push that lands in rows the receiver still reads
+# (a write-after-read hazard of the schedule) corrupts owned rows under the skewed orders.
+@pytest.mark.parametrize("world,H,K,fast,order", [
+    (2, 64, 1, False, "lockstep"), (3, 96, 1, True, "ahead"), (4, 128, 1, False, "random"), (2, 96, 2, True, "behind"),
+    (3, 144, 2, False, "ahead"), (2, 64, 1, True, "behind"), (3, 144, 3, False, "ahead"), (4, 160, 3, False, "behind"),
+    (3, 120, 3, True, "random"), (4, 128, 2, False, "random")])
+def test_slab_schedule_bit_exact(world, H, K, fast, order):
     from fluidnet_cxx_b200.lib import slab
     W, steps, seed = 40, (1 if fast else 2), 11
     iters = MCONF["jacobiIter"]
@@ -48,6 +56,7 @@ def test_slab_schedule_bit_exact(world, H, K, fast):
     geo = [slab.geometry(H, world, r, K) for r in range(world)]
     scheds = [slab.schedule(H, world, r, iters, K)[1] for r in range(world)]
     assert len({len(s) for s in scheds}) == 1 and all([o[0] for o in s] == [o[0] for o in scheds[0]] for s in scheds)
+    nops = len(scheds[0])
 
     def held_only(name, g):
         full = st[name]
@@ -58,59 +67,99 @@ def test_slab_schedule_bit_exact(world, H, K, fast):
     for g in geo:
         R.append({"U": [held_only("U", g), poison(st["U"].shape, rng, 0.5)],
                   "rho": [held_only("density", g), poison(st["density"].shape, rng, 1.0)],
-                  "P": [poison(st["p"].shape, rng, 1.0), poison(st["p"].shape, rng, 1.0)],
+                  "P": [poison(st["p"].shape, rng, 1.0) for _ in range(4)],
                   "div": poison(st["p"].shape, rng, 1.0),
-                  # static fields: a rank holds its rows of the flags / masks only (outside: walls, harmless and never owned)
-                  "bd": {k: torch.from_numpy(np.where(np.arange(H)[None, None, None, :, None] // 1 >= g["ya0"], st[k], st[k]).copy())
-                         for k in ("flags", "UBC", "UBCInvMask", "densityBC", "densityBCInvMask")}})
+                  "bd": {k: torch.from_numpy(st[k].copy()) for k in ("flags", "UBC", "UBCInvMask", "densityBC", "densityBCInvMask")}})
+        # a rank holds its rows of the static fields only: outside, walls (harmless, never owned, never read by the kernels)
         f = R[-1]["bd"]["flags"].numpy()
         f[:, :, :, :g["ya0"]] = 2.0
         f[:, :, :, g["ya1"]:] = 2.0
-    par = 0
-    for step in range(steps):
-        for i in range(len(scheds[0])):
-            kind = scheds[0][i][0]
-            if kind == "X":
-                for r, g in enumerate(geo):
-                    _, what, rows = scheds[r][i]
-                    for q, first in ((r - 1, g["lo"]), (r + 1, g["hi"] - rows)):
-                        if q < 0 or q >= world:
-                            continue
-                        sl = slice(first, first + rows)
-                        assert geo[q]["ya0"] <= sl.start and sl.stop <= geo[q]["ya1"], "push outside the neighbour's held rows"
-                        if what == "state":
-                            R[q]["U"][par][:, :, :, sl] = R[r]["U"][par][:, :, :, sl]
-                            R[q]["rho"][par][:, :, :, sl] = R[r]["rho"][par][:, :, :, sl]
-                        else:
-                            R[q]["P"][what][:, :, :, sl] = R[r]["P"][what][:, :, :, sl]
-                continue
-            for r, g in enumerate(geo):
-                op = scheds[r][i]
-                me = R[r]
-                if kind == "advect":
-                    w0, w1 = op[1], op[2]
-                    bd = dict(me["bd"])
-                    bd["U"], bd["density"] = torch.from_numpy(me["U"][par]), torch.from_numpy(me["rho"][par])
-                    rho, U, div = ops.advect_forces_div(MCONF, MCONF["dt"], bd, True, True, (0, H))
-                    me["rho"][1 - par][:, :, :, w0:w1] = rho.numpy()[:, :, :, w0:w1]
-                    me["U"][1 - par][:, :, :, w0:w1] = U.numpy()[:, :, :, w0:w1]
-                    me["div"][:, :, :, w0:w1] = div.numpy()[:, :, :, w0:w1]
-                elif kind == "jacobi":
-                    _, src, dst, it, r0, r1 = op
-                    p = jacobi_numpy(me["bd"]["flags"].numpy(), me["div"], None if src is None else me["P"][src], it)
-                    me["P"][dst][:, :, :, r0:r1] = p[:, :, :, r0:r1]
+
+    def run_op(r, step, i):
+        """operation i of time step `step` on rank r (an exchange: the PUSH half only)"""
+        g, op, me, par = geo[r], scheds[r][i], R[r], step % 2
+        kind = op[0]
+        if kind == "X":
+            _, what, rows = op
+            for q, first in ((r - 1, g["lo"]), (r + 1, g["hi"] - rows)):
+                if q < 0 or q >= world:
+                    continue
+                sl = slice(first, first + rows)
+                assert geo[q]["ya0"] <= sl.start and sl.stop <= geo[q]["ya1"], "push outside the neighbour's held rows"
+                if what == "state":
+                    R[q]["U"][par][:, :, :, sl] = me["U"][par][:, :, :, sl]
+                    R[q]["rho"][par][:, :, :, sl] = me["rho"][par][:, :, :, sl]
                 else:
-                    _, pbuf, lo, hi = op
-                    U = ops.project(torch.from_numpy(me["P"][pbuf]), torch.from_numpy(me["U"][1 - par]), me["bd"], (0, H))
-                    me["U"][1 - par][:, :, :, lo:hi] = U.numpy()[:, :, :, lo:hi]
-                    me["p_final"] = pbuf
-        par ^= 1
-        for k, pick in (("U", lambda me: me["U"][par]), ("density", lambda me: me["rho"][par]),
-                        ("p", lambda me: me["P"][me["p_final"]])):
-            got = np.concatenate([pick(R[r])[:, :, :, geo[r]["lo"]:geo[r]["hi"]] for r in range(world)], axis=3)
+                    R[q]["P"][what][:, :, :, sl] = me["P"][what][:, :, :, sl]
+        elif kind == "advect":
+            w0, w1 = op[1], op[2]
+            bd = dict(me["bd"])
+            bd["U"], bd["density"] = torch.from_numpy(me["U"][par]), torch.from_numpy(me["rho"][par])
+            rho, U, div = ops.advect_forces_div(MCONF, MCONF["dt"], bd, True, True, (0, H))
+            me["rho"][1 - par][:, :, :, w0:w1] = rho.numpy()[:, :, :, w0:w1]
+            me["U"][1 - par][:, :, :, w0:w1] = U.numpy()[:, :, :, w0:w1]
+            me["div"][:, :, :, w0:w1] = div.numpy()[:, :, :, w0:w1]
+        elif kind == "jacobi":
+            _, src, dst, it, r0, r1 = op
+            p = jacobi_numpy(me["bd"]["flags"].numpy(), me["div"], None if src is None else me["P"][src], it)
+            me["P"][dst][:, :, :, r0:r1] = p[:, :, :, r0:r1]
+        else:
+            _, pbuf, lo, hi = op
+            U = ops.project(torch.from_numpy(me["P"][pbuf]), torch.from_numpy(me["U"][1 - par]), me["bd"], (0, H))
+            me["U"][1 - par][:, :, :, lo:hi] = U.numpy()[:, :, :, lo:hi]
+            me["p_final"] = pbuf
+
+    # discrete-event replay: pc[r] = next operation (step * nops + i); pushed[r] = exchanges whose push rank r has done
+    total = steps * nops
+    pc = [0] * world
+    pushed = [set() for _ in range(world)]
+    snapshots = {}
+    pick = np.random.RandomState(5)
+
+    def runnable(r):
+        if pc[r] >= total:
+            return False
+        step, i = divmod(pc[r], nops)
+        if scheds[r][i][0] == "X" and pc[r] in pushed[r]:
+            # waiting half of the exchange: every neighbour must have pushed at this site
+            return all(pc[r] in pushed[q] for q in (r - 1, r + 1) if 0 <= q < world)
+        return True
+
+    def advance(r):
+        step, i = divmod(pc[r], nops)
+        if scheds[r][i][0] == "X":
+            if pc[r] not in pushed[r]:
+                run_op(r, step, i)
+                pushed[r].add(pc[r])
+                return                      # the wait half is a separate event
+        else:
+            run_op(r, step, i)
+        pc[r] += 1
+        if pc[r] % nops == 0:               # end of a time step on this rank: keep its owned rows for the comparison
+            par = (step + 1) % 2
+            me, g = R[r], geo[r]
+            snapshots[(step, r)] = {"U": me["U"][par][:, :, :, g["lo"]:g["hi"]].copy(),
+                                    "density": me["rho"][par][:, :, :, g["lo"]:g["hi"]].copy(),
+                                    "p": me["P"][me["p_final"]][:, :, :, g["lo"]:g["hi"]].copy()}
+
+    while any(p < total for p in pc):
+        ready = [r for r in range(world) if runnable(r)]
+        assert ready, "deadlock in the schedule"
+        if order == "lockstep":
+            r = min(ready, key=lambda q: pc[q])
+            advance(r)
+        elif order == "random":
+            advance(int(pick.choice(ready)))
+        else:
+            r = ready[0] if order == "ahead" else ready[-1]
+            while runnable(r):
+                advance(r)
+    for step in range(steps):
+        for k in ("p", "U", "density"):
+            got = np.concatenate([snapshots[(step, r)][k] for r in range(world)], axis=3)
             want = ref[step][k]
             bad = int(np.sum(~((got == want) | (np.isnan(got) & np.isnan(want)))))
-            assert bad == 0, f"world {world} K {K} step {step} field {k}: {bad} owned cells differ from the single-domain step"
+            assert bad == 0, f"world {world} K {K} {order} step {step} field {k}: {bad} owned cells differ"
 
 
 def test_slab_geometry():
