@@ -54,6 +54,11 @@ WORKLOADS = {
     # BASELINE.json configs[4] with the Jacobi projection
     "plume256cube_jacobi40": dict(res=(256, 256, 256), method="jacobi", jacobi_iters=40, cpu_sample_res=None,
                                   cpu_steps=(0, 0), baseline_config="256x256x256 3D synthetic grid, Jacobi 40 iter"),
+    # BASELINE.json configs[4] as written: CNN pressure on the 256^3 grid.  The reference has no 3-D model
+    # (model.py:93); the slice-wise projection FluidNet.forward_fields_3d is this package's definition (parity unpinned)
+    "cube256_scalenet_slicewise": dict(res=(256, 256, 256), method="convnet", jacobi_iters=0, cpu_sample_res=None,
+                                       cpu_steps=(0, 0),
+                                       baseline_config="256x256x256 3D synthetic grid, CNN pressure (slice-wise ScaleNet)"),
     # BASELINE.json configs[1]
     "plume512_scalenet": dict(res=(1, 512, 512), method="convnet", jacobi_iters=0, cpu_sample_res=512,
                               cpu_steps=(1, 5), baseline_config="512x512 2D plume, ScaleNet CNN pressure, fp32"),
@@ -216,7 +221,7 @@ def ncu_traffic(kernel_key):
 
 
 # ---------------------------------------------------------------------------------------------
-def build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs, jacobi_launch_iters=8):
+def build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs, jacobi_launch_iters=8, rec_steps=None):
     """The roofline object of one record.  stage_ms = {"advect_forces", "pressure", "project"} totals
     (ms over `steps` steps of the per-kernel pass)."""
     peaks = load_peaks()
@@ -278,7 +283,8 @@ def build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs, jacobi_laun
         fl = 2.0 * cin * cout * k * k * h * w
         layers.append({"layer": f"{cin}->{cout} k{k} @{h}x{w}", "tensor": bool(tensor), "launches": n,
                        "ms_per_launch": round(ms / n, 4), "algorithmic_tflops": round(fl / (ms / n / 1e3) / 1e12, 2)})
-    cnn_ms = sum(v[1] for v in agg.values()) / max(steps, 1)
+    rec_steps = rec_steps or steps             # steps the per-layer records cover
+    cnn_ms = sum(v[1] for v in agg.values()) / max(rec_steps, 1)
     top = max((kv for kv in agg.items() if kv[0][5]), key=lambda kv: kv[1][1], default=None)
     if top is None:
         return {"bound": "tensor", "kernel": None, "achieved": None, "peak": round(tc_peak, 1), "unit": "TFLOP/s",
@@ -293,7 +299,7 @@ def build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs, jacobi_laun
             "peak_source": peak_src_tc, "launch_ms": round(ms / n, 4), "launches_timed": n,
             "algorithmic_flop_per_launch": fl, "executed_tensor_tflops": round(3 * achieved, 2),
             "executed_tensor_frac": round(3 * achieved / tc_peak, 4),
-            "share_of_step": round((ms / steps) / (total_ms / steps), 4),
+            "share_of_step": round((ms / rec_steps) / (total_ms / steps), 4),
             "conv_launch_ms_per_step": round(cnn_ms, 4), "stage_ms_per_step": round(dom_ms / steps, 4),
             "forward_algorithmic_tflops": round(CNN_FLOP_PER_CELL * cells * steps / (dom_ms / 1e3) / 1e12, 2)
             if dom_ms > 0 else None,
@@ -416,19 +422,22 @@ def run_single(args, name, guard, local_rank=0, want_cpu_baseline=True):
     if wl["method"] == "convnet":
         lib.fnx_profile_enable(1)
     n0 = lib.fnx_launch_count()
-    for _ in range(steps):
+    nstage = min(steps, 10 if D == 1 else 1)      # (a 3-D CNN step is 256 forwards: one profiled step is plenty)
+    for _ in range(nstage):
         if flush:
             flush_buf.zero_()
         one_step()
     torch.cuda.synchronize()
-    launches = lib.fnx_launch_count() - n0
+    launches = (lib.fnx_launch_count() - n0) * steps // nstage
     layer_recs = []
     if wl["method"] == "convnet":
-        buf = (_native.ProfileRec * 4096)()
-        n = lib.fnx_profile_fetch(buf, 4096)
+        cap = 8192
+        buf = (_native.ProfileRec * cap)()
+        n = lib.fnx_profile_fetch(buf, cap)
         lib.fnx_profile_enable(0)
-        layer_recs = [buf[i] for i in range(max(0, min(n, 4096)))]
-    stage_ms = {k: sum(v[2 * i].elapsed_time(v[2 * i + 1]) for i in range(len(v) // 2)) for k, v in stage_events.items()}
+        layer_recs = [buf[i] for i in range(max(0, min(n, cap)))]
+    stage_ms = {k: sum(v[2 * i].elapsed_time(v[2 * i + 1]) for i in range(len(v) // 2)) * steps / nstage
+                for k, v in stage_events.items()}
     sim.set_stage_hook(None)
     clocks = sampler.stop()
 
@@ -459,7 +468,7 @@ def run_single(args, name, guard, local_rank=0, want_cpu_baseline=True):
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1)
 
-    roof = build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs)
+    roof = build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs, rec_steps=nstage)
     out = make_record(args, name, wl, 1, cells, cells, steps, warmup, total_ms, e2e_ms, e2e_steps, roof, h2d, d2h,
                       int(launches), clocks, t_wall, flush, graphed, "1 GPU", [D, H, W], args.scaling)
     del bd, host, out_host, flush_buf, masks
@@ -599,7 +608,7 @@ def run_distributed(args, name, scaling, guard, transport):
 
     # pass 2: direct launches with per-stage / per-layer events
     guard.beat(f"{tag}: per-stage pass")
-    bd = stepper.state
+    bd = dict(stepper.state)      # a COPY of the dict: simulate_distributed re-binds its entries (see GraphedDistributedStep)
 
     def one_step():
         with torch.no_grad():
@@ -644,17 +653,14 @@ def run_distributed(args, name, scaling, guard, transport):
     d2h = sum(v.numel() * 4 for v in out_host.values())
     barrier()
 
-    e2e_sync = os.environ.get("FNX_E2E_MODE", "sync") == "sync"
+    e2e_sync = os.environ.get("FNX_E2E_MODE", "async") == "sync"
 
     def e2e_step():
         for k in ("p", "U", "flags", "density"):
             dev_win[k].copy_(host_win[k], non_blocking=True)
             stepper.state[k][win].copy_(dev_win[k])
         if e2e_sync:
-            # DMA copies and NCCL send/recv are kept apart: with host<->device copies queued around the NCCL
-            # calls this leg stopped making progress at 4 ranks (every rank parked in the next barrier, no conv
-            # barrier time-out); see DESIGN.md "the 4-GPU hang"
-            torch.cuda.synchronize()
+            torch.cuda.synchronize()      # (experiment switch of the round-2 hang hunt; DESIGN.md "the 4-GPU hang")
         stepper.step()
         if e2e_sync:
             torch.cuda.synchronize()

@@ -251,6 +251,10 @@ __device__ __forceinline__ void line_trace(const Grid& g, const float* __restric
   for (int a = 0; a < NA; a++) acc = acc + delta[a] * delta[a];
   const float length = sqrtf(acc);
   if (length <= kEpsilon) return;
+  // An infinite displacement (|delta| beyond 1.8e19: garbage input) has direction delta / inf = 0: the march
+  // below would never move and never end -- the reference's loop (calc_line_trace.cpp:310) does not end
+  // either, so there is no result to match; keep the start position instead of hanging the GPU.
+  if (!(length < CUDART_INF_F)) return;
   float dir[NA], next[NA];
 #pragma unroll
   for (int a = 0; a < NA; a++) dir[a] = delta[a] / length;

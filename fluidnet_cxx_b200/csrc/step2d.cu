@@ -229,6 +229,7 @@ __device__ __forceinline__ void trace2(const Adv& a, float px, float py, float d
   acc = acc + dy * dy;
   const float length = sqrtf(acc);
   if (length <= kEpsilon) return;
+  if (!(length < CUDART_INF_F)) return;   // infinite displacement: the reference's march never ends (advect_device.cuh)
   const float dirx = dx / length, diry = dy / length;
   float cur = 0.f;
   while (cur < length - kHitMargin) {  // :310-314

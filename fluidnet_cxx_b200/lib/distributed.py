@@ -522,6 +522,12 @@ class GraphedDistributedStep:
                 schedule.append((graph, comm))
         self.schedule = schedule
         self.outs = {k: work[k] for k in ('p', 'U', 'density')}
+        # A CUDA graph holds raw pointers, not references: the tensors it READS must stay alive and must stay
+        # the ones `state` names.  (Round 1 lost both: bench.py's per-stage pass re-bound the entries of
+        # `stepper.state`, the original tensors were freed and re-used by the allocator, and every later replay
+        # advected whatever bytes landed there -- at 4 ranks an infinite velocity, i.e. a line trace that never
+        # ends: the "4-GPU hang".)
+        self._inputs = {k: self.state[k] for k in ('p', 'U', 'density', 'flags')}
 
     def verify(self):
         """one step through the graphs and one by direct launches from the same state: max |difference|
@@ -537,6 +543,10 @@ class GraphedDistributedStep:
 
     def step(self):
         if self.graphed:
+            for k in ('p', 'U', 'density'):
+                if self.state[k] is not self._inputs[k]:       # someone re-bound an entry: take its rows, keep our buffer
+                    self._inputs[k][self._win].copy_(self.state[k][self._win])
+                    self.state[k] = self._inputs[k]
             for graph, comm in self.schedule:
                 graph.replay()
                 if comm is not None:

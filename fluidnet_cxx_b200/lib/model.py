@@ -82,6 +82,10 @@ class FluidNet(nn.Module):
 
     def forward(self, input_):
         self._check_config()
+        if input_.dim() == 5 and input_.size(2) > 1:
+            # 3-D extension (no reference counterpart, see forward_fields_3d): cat(p, U(3), flags, density)
+            assert input_.size(1) >= 5, 'a 3-D input carries (p, Ux, Uy, Uz, flags[, density])'
+            return self.forward_fields_3d(input_[:, 1:4].contiguous(), input_[:, 4:5].contiguous())
         assert input_.dim() == 5 and input_.size(2) == 1 and input_.size(1) >= 4, 'Input can only be 2D'
         lib = N.load()
         B, _, _, H, W = (int(s) for s in input_.shape)
@@ -114,3 +118,30 @@ class FluidNet(nn.Module):
                                             N.ptr(U_temp), B, H, W, 0, st), "FluidNet")
             self._seam(self.mconf, U_out, U_temp)
         return p, U_out
+
+    def forward_fields_3d(self, U, flags, scale=None):
+        """SLICE-WISE 3-D pressure projection -- an extension defined by this package, not by the reference.
+
+        The reference's model is 2-D only (`assert self.is3D == False`, model.py:93; Conv2d layers) and no 3-D
+        weights exist, yet BASELINE.json configs[4] asks for a CNN pressure on a 256^3 grid (SURVEY.md section 8c:
+        "must be defined by the build ... parity unpinned").  Definition used here, the 2-D wrapper's steps
+        (*_saved.py:135-232) with the 3-D stencils and the trained 2-D network applied to every z-slice:
+            s  = max(std(U), threshold)                      (all three components)
+            x  = [velocityDivergence_3D(U) / s, occupancy]   per slice k: (2, H, W)
+            p~ = MultiScaleNet(x[k]) for every k             (D independent 2-D forwards, one batch)
+            U' = setWallBcs(velocityUpdate_3D(p~, U / s) * s) ;  p = p~ * s
+        A z-invariant state with Uz = 0 reproduces the 2-D model slice by slice (tests/test_gpu_cnn.py)."""
+        from .fluid import ops as F
+        B, C, D, H, W = (int(v) for v in U.shape)
+        assert C == 3 and D > 1, 'forward_fields_3d expects a (B, 3, D, H, W) MAC velocity'
+        s = self.scale(U) if scale is None else scale                     # (B,1,1,1,1)
+        div = F.velocityDivergence(U, flags)                              # (B,1,D,H,W)
+        x = torch.empty((B * D, 2, H, W), dtype=torch.float32, device=U.device)
+        x[:, 0] = (div / s)[:, 0].reshape(B * D, H, W)
+        x[:, 1] = F.flagsToOccupancy(flags)[:, 0].reshape(B * D, H, W)
+        p_net = self.multiScale(x).view(B, 1, D, H, W)                    # one 2-D forward per slice
+        v = (U / s).contiguous()
+        F.velocityUpdate(pressure=p_net, U=v, flags=flags)
+        v = F.setWallBcs((v * s).contiguous(), flags)
+        return (p_net * s).contiguous(), v
+

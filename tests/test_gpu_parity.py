@@ -443,3 +443,29 @@ def test_fused_2d_step_equals_ops_and_generic(fluid, case):
     for k in ("p", "U", "density"):
         assert n_mismatch(runs["fused"][k], runs["ops"][k]) == 0, ("fused vs ops", k, n_mismatch(runs["fused"][k], runs["ops"][k]))
         assert n_mismatch(runs["fused"][k], runs["generic"][k]) == 0, ("fused vs generic", k)
+
+
+def test_infinite_displacement_terminates(fluid, oracle):
+    """A velocity whose displacement overflows fp32 (|u| dt > 1.8e19: length = inf, direction = delta/inf = 0) makes
+    the reference's line-trace march stand still forever (calc_line_trace.cpp:310; there is no reference result).
+    The kernels keep the start position instead -- this is the input that hung the 4-GPU run of round 1 once a
+    freed CUDA-graph input buffer fed garbage to the advection.  Must terminate and agree with the oracle."""
+    f, U, rho, p = random_case(41, 1, 70, 90, "obstacle", 4, 0.5, False)
+    U[0, 0, 0, 30, 40] = 3.0e30
+    U[0, 1, 0, 31, 41] = -2.5e31
+    U[0, 0, 0, 50, 20] = np.inf
+    tf, tU, tr = cu(f), cu(U), cu(rho)
+    got = fluid.advectScalar(0.1, tr, tU, tf, "maccormackFluidNet", 1, False, 0.6)
+    torch.cuda.synchronize()
+    ref = oracle.advectScalar(0.1, rho, U, f, "maccormackFluidNet", 1, False, 0.6)
+    assert n_mismatch(host(got), ref) == 0
+    # and through the fused step kernels (generic path: these tiles are not "clean")
+    import importlib
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    mconf = plume_mconf(jacobiIter=4)
+    bd = {"p": cu(p), "U": tU.clone(), "flags": tf, "density": tr.clone()}
+    bd2 = {k: v.clone() for k, v in bd.items()}
+    sim._simulate_fused(mconf, bd, None, "jacobi", 0.1, False)
+    sim._simulate_ops(mconf, bd2, None, "jacobi", 0.1, False)
+    torch.cuda.synchronize()
+    assert n_mismatch(host(bd["density"]), host(bd2["density"])) == 0
