@@ -403,7 +403,7 @@ def run_single(args, name, guard, local_rank=0, want_cpu_baseline=True):
     t_wall = time.perf_counter() - t_wall0
     sampler.mark_end()
     total_ms = sum(a.elapsed_time(b) for a, b in step_ms)
-    graphed = bool(sim.graphs_enabled() and cells <= sim.GRAPH_MAX_CELLS)
+    graphed = bool(sim._fusable(mconf, bd, wl["method"]) and sim._graphable(bd, net, wl["method"]))
 
     # ---- pass 2: the same steps issued stage by stage with CUDA events around every stage (stage hook)
     # and, for the CNN, around every conv launch (fnx_profile_*): roofline inputs.  The launch count is

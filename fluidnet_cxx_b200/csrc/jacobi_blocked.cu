@@ -273,11 +273,24 @@ int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float
   auto wbuf = [&](int l) { return ((nL - 1 - l) % 2 == 0) ? p : scratch; };
   // float4 path: rows 16-byte aligned in every buffer
   const int vec_ok = (W % 4 == 0) && ((((uintptr_t)flags | (uintptr_t)div | (uintptr_t)p | (uintptr_t)scratch | (uintptr_t)p_init) & 15) == 0);
-  // tall tiles (12 warps) waste less halo work; short tiles keep small grids on more SMs
+  // Tile height: 12-warp tiles (96 rows, 2 CTAs per SM) waste less halo work, 8-warp tiles (64 rows, 3 CTAs per
+  // SM) quantise better: a launch costs about (waves of CTAs) x (rows of a tile), and a slab of a strong-scaled
+  // grid is only one or two waves deep -- pick the cheaper shape for this launch.
   static const char* force = getenv("FNX_JACOBI_NW");
-  bool tall = (long long)(row1 - row0) * W * B >= (1LL << 21);
-  if (force) tall = atoi(force) >= 12;
   constexpr int OW = JB_TW - 2 * JB_HALO;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+  }
+  auto cost = [&](int nw) {
+    const long long ctas = (long long)((W + OW - 1) / OW) * ((row1 - row0 + nw * JB_R - 2 * JB_HALO - 1) / (nw * JB_R - 2 * JB_HALO)) * B;
+    const long long slots = (long long)sms * (nw <= 8 ? 3 : 2);
+    return ((ctas + slots - 1) / slots) * (long long)(nw * JB_R);
+  };
+  bool tall = cost(12) < cost(8);
+  if (force) tall = atoi(force) >= 12;
   const int oh = (tall ? 12 : 8) * JB_R - 2 * JB_HALO;
   dim3 grid((W + OW - 1) / OW, (row1 - row0 + oh - 1) / oh, B);
   int done = 0;

@@ -446,10 +446,12 @@ def test_slicewise_3d_reduces_to_2d_model(net):
     with torch.no_grad():
         p2, V2 = model.forward_fields(U2.contiguous(), fl2, scale=s)
         p3, V3 = model.forward_fields_3d(U3.contiguous(), fl3, scale=s)
-    for k in range(D):
+    # interior slices (the first / last plane is the border ring of the 3-D stencils: divergence 0, velocity untouched)
+    for k in range(1, D - 1):
         assert rel_err(p3[0, 0, k].cpu().numpy(), p2[0, 0, 0].cpu().numpy()) < 1e-6, k
         assert rel_err(V3[0, 0:2, k].cpu().numpy(), V2[0, :, 0].cpu().numpy()) < 1e-6, k
-    assert float(V3[0, 2].abs().max()) == 0.0       # no z pressure gradient in a z-invariant field, Uz stays 0
+    # no z pressure gradient between identical interior slices: Uz stays 0 there
+    assert float(V3[0, 2, 2:D - 1].abs().max()) == 0.0
 
 
 def test_slicewise_3d_step_fused_graph_ops_agree(net):
