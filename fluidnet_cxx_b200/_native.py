@@ -174,6 +174,11 @@ def ptr(t):
         raise RuntimeError(f"fluidnet_cxx_b200 expects float32 tensors, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError("fluidnet_cxx_b200 expects contiguous tensors")
+    if t.device.index != torch.cuda.current_device():
+        # the C-ABI launches on the current device / its current stream (the reference's ATen ops guard the
+        # device themselves): refuse loudly instead of launching on the wrong GPU
+        raise RuntimeError(f"tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "wrap the call in `with torch.cuda.device(tensor.device):`")
     return t.data_ptr()
 
 
@@ -189,7 +194,11 @@ class _Workspaces:
         self._retired = []   # outgrown buffers stay alive: captured CUDA graphs may still point at them
 
     def get(self, device, tag, nbytes):
-        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        # one buffer per (device, STREAM, tag): two simulations on different streams or threads never share
+        # scratch (work on one stream is ordered, so re-use within a stream is safe; a CUDA-graph capture runs
+        # on its own stream and therefore gets buffers of its own, which live as long as this registry)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, torch.cuda.current_stream(idx).cuda_stream, tag)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             if buf is not None:

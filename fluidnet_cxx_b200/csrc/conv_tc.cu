@@ -394,10 +394,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
                 __align__(16) __half2 hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
+                  // two-term fp16 expansion of a pair with the packed conversions (cvt.rn.f16x2.f32: one
+                  // instruction per pair and direction instead of one per value plus a pack)
                   const float u0 = f[gg * 8 + 2 * i] * s_out, u1 = f[gg * 8 + 2 * i + 1] * s_out;
-                  const __half h0 = __float2half_rn(u0), h1 = __float2half_rn(u1);
-                  hi[i] = __halves2half2(h0, h1);
-                  lo[i] = __halves2half2(__float2half_rn(u0 - __half2float(h0)), __float2half_rn(u1 - __half2float(h1)));
+                  const __half2 h = __floats2half2_rn(u0, u1);
+                  const float2 hb = __half22float2(h);
+                  hi[i] = h;
+                  lo[i] = __floats2half2_rn(u0 - hb.x, u1 - hb.y);
                 }
                 const size_t off = (((size_t)((c0 >> 3) + gg) * a.Hp + (y + PAD)) * a.Wp + (px + PAD)) * 8;
                 *reinterpret_cast<uint4*>(yh + off) = *reinterpret_cast<const uint4*>(hi);

@@ -82,7 +82,11 @@ class PeerMemoryTransport:
             raise RuntimeError("peer transport: inbox allocation during graph capture (warm up first)")
         t = self.symm.empty((2, int(nelem)), dtype=dtype, device=device)
         hdl = self.symm.rendezvous(t, self.group)
-        base = 2 * len(self.regions) + 2            # channel 0/1 are left to hdl.barrier
+        # channels come from a counter that only grows: a regrown tag must never land on the pair of another
+        # tag (channel 0/1 are left to hdl.barrier)
+        self._next_channel = getattr(self, "_next_channel", 2)
+        base = self._next_channel
+        self._next_channel += 2
         r = {"t": t, "hdl": hdl, "nelem": int(nelem), "data": base, "ack": base + 1}
         self.regions[tag] = r
         # credits: every neighbour may write my inbox once before my first ack
@@ -399,6 +403,13 @@ def step_phases(mconf, bd, net, sim_method, decomp, ops, bufs):
     dt = float(mconf['dt'])
     g = decomp.ghost
     multi = decomp.world > 1
+    if bd['U'].size(0) != 1:
+        raise NotImplementedError("the slab-decomposed step handles one simulation per call (B = 1): the ScaleNet "
+                                  "normalisation is reduced over the whole batch tensor")
+    for conf in (mconf, getattr(net, 'mconf', None) or {}):
+        if multi and (conf.get('periodic-x') or conf.get('periodic-y')):
+            raise NotImplementedError("periodic seams across slabs are not implemented: the seam row lives on another "
+                                      "rank (simulate.py:120-128); run periodic configurations on one GPU")
     if multi:
         need = RA + (CNN_REACH if sim_method == 'convnet' else 1)
         if g < need:

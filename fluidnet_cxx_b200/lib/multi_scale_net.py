@@ -78,6 +78,9 @@ class MultiScaleNet(nn.Module):
         def fill(dst, conv, relu):
             w = conv.weight.detach().contiguous().float()
             b = conv.bias.detach().contiguous().float()
+            if w.device != device or b.device != device:
+                raise RuntimeError(f"MultiScaleNet parameters live on {w.device} but the input is on {device}: "
+                                   "move the model first (net.to(device)); there is no CPU path")
             keep.extend([w, b])
             cout, cin, k, _ = w.shape
             dst.weight, dst.bias = w.data_ptr(), b.data_ptr()
@@ -137,7 +140,13 @@ class MultiScaleNet(nn.Module):
         plan = cache["plan"]
         assert c == plan.data_channels, "MultiScaleNet: wrong number of input channels"
         st = N.stream_of(x)
-        ws = cache["ws"].get((h, w))
+        # one workspace per (resolution, stream): simulations on different streams never share activations.  A
+        # CUDA-graph capture (its own stream) re-uses the workspace of the eager warm-up call that precedes it --
+        # zero-filling a fresh one would put the memset of the whole workspace into every replay.
+        wkey = (h, w, st)
+        ws = cache["ws"].get(wkey)
+        if ws is None and torch.cuda.is_current_stream_capturing():
+            ws = next((v for k, v in cache["ws"].items() if k[:2] == (h, w)), None)
         if ws is None:
             nbytes = lib.fnx_msnet_workspace(ctypes.byref(plan), h, w)
             if nbytes == 0:
@@ -147,7 +156,7 @@ class MultiScaleNet(nn.Module):
             N.check(lib.fnx_msnet_workspace_init(ws.data_ptr(), ws.numel(), st), "MultiScaleNet.workspace_init")
             if len(cache["ws"]) >= 4:    # a few resolutions stay resident (captured graphs point at them)
                 cache["ws"].pop(next(iter(cache["ws"])))
-            cache["ws"][(h, w)] = ws
+            cache["ws"][wkey] = ws
         y = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
         N.check(lib.fnx_msnet_forward(ctypes.byref(plan), N.ptr(x), N.ptr(y), n, h, w, ws.data_ptr(), ws.numel(), st),
                 "MultiScaleNet.forward")

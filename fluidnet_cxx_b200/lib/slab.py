@@ -18,8 +18,9 @@ Schedule of a step (K = Jacobi launches per exchange, 8 iterations per launch; d
   advect + forces + divergence      on [lo-dg-1, hi+dg+1)  (MacCormack reads rows j-2 .. j+4 for |u| dt <= 1)
                                     -> divergence valid on [lo-dg, hi+dg)
   Jacobi chunk 0                    K launches from p = 0, writing [lo-8(K-1-l), hi+8(K-1-l)) in launch l
-  repeat: X(p) dg ghost rows, Jacobi chunk (K launches, last one writes the owned rows only)
-  X(p)                              the row below the slab for the pressure gradient
+  repeat: X(p) dg+1 ghost rows, Jacobi chunk (K launches, the last one writes rows [lo-1, hi))
+                                    (every launch also computes row lo-1: the pressure gradient of the owned rows reads
+                                     it, and one redundant row is cheaper than one more exchange per step)
   project + BCs                     owned rows
 A rank only pushes into ghost rows of the buffer its neighbour will read AFTER the neighbour's matching
 wait, and never touches a ghost row of a buffer between its own signal and the next push into it: every
@@ -41,7 +42,7 @@ def geometry(H, world, rank, K=1):
         raise ValueError(f"{H} rows do not split evenly over {world} ranks")
     Hs = H // world
     dg = JACOBI_LAUNCH_ITERS * K
-    G = dg + 8
+    G = dg + 8          # state ghost rows: divergence on [lo-dg-1, hi+dg) + MacCormack reach (2 rows for |u| dt < 1) + slack
     if world > 1 and Hs < G:
         raise ValueError(f"slab height {Hs} is smaller than the ghost width {G}")
     lo, hi = rank * Hs, (rank + 1) * Hs
@@ -65,12 +66,15 @@ def schedule(H, world, rank, iters, K=1):
     ops = []
     if multi:
         ops.append(("X", "state", g["G"]))
-    ops.append(("advect", max(0, lo - dg - 1), min(H, hi + dg + 1)) if multi else ("advect", 0, H))
+    ops.append(("advect", max(0, lo - dg - 2), min(H, hi + dg + 1)) if multi else ("advect", 0, H))
     # Pressure buffers: 0 / 1 receive the result of a chunk (the only buffers ever pushed into, alternating
     # from chunk to chunk), 2 / 3 hold the intermediate launches of a chunk (their ghost rows are computed
     # locally).  A neighbour may still be inside chunk c -- reading the ghost rows of buffer (c-1) % 2 and
     # of the intermediates -- when this rank pushes the result of chunk c: it goes into buffer c % 2, which
     # nobody reads before the wait of that exchange.
+    # The pressure gradient of the owned rows reads p one row BELOW the slab: every Jacobi launch also computes
+    # row lo-1 (one redundant row instead of one more exchange per step), so the exchanges carry dg + 1 rows.
+    lo_p = max(0, lo - 1) if multi else 0
     n_launch = (iters + JACOBI_LAUNCH_ITERS - 1) // JACOBI_LAUNCH_ITERS
     src = None
     for l in range(n_launch):
@@ -78,14 +82,17 @@ def schedule(H, world, rank, iters, K=1):
         chunk, in_chunk = divmod(l, K)
         n_in_chunk = min(K, n_launch - chunk * K)
         if multi and l > 0 and in_chunk == 0:
-            ops.append(("X", src, dg))
+            ops.append(("X", src, dg + 1))
         margin = JACOBI_LAUNCH_ITERS * (n_in_chunk - 1 - in_chunk) if multi else 0
-        r0, r1 = (max(0, lo - margin), min(H, hi + margin)) if multi else (0, H)
+        r0, r1 = (max(0, lo_p - margin), min(H, hi + margin)) if multi else (0, H)
         dst = chunk % 2 if in_chunk == n_in_chunk - 1 else 2 + in_chunk % 2
         ops.append(("jacobi", src, dst, it, r0, r1))
         src = dst
-    if multi:
-        ops.append(("X", src, 4))      # velocityUpdate reads one row below the slab (4 rows keep 16-byte units)
+    if multi and n_launch <= K:
+        # a step without any pressure exchange (a single chunk) still needs ONE hand-shake after the stencil
+        # stage: the neighbours' next state push lands in ghost rows of the new state that this rank's
+        # advect / forces kernels have just written, and only a flag received after those kernels orders the two
+        ops.append(("X", src, 4))
     ops.append(("project", src, lo, hi))
     return g, ops
 
@@ -198,7 +205,7 @@ class SlabJacobiStep:
         plane_max = Rmax * W * 4
         n_launch = (self.iters + JACOBI_LAUNCH_ITERS - 1) // JACOBI_LAUNCH_ITERS
         self.n_chunks = (n_launch + K - 1) // K
-        n_sites = 2 * (2 + self.n_chunks)
+        n_sites = 2 * (2 + self.n_chunks)      # per parity: state + (n_chunks - 1) pressure exchanges
         # ---- symmetric arena: state ping-pong, pressure ping-pong, flags of the exchange sites.  Every rank
         # reserves room for the tallest slab (interior ranks hold Hs + 2G rows, edge ranks fewer) so that a
         # field starts at the same offset everywhere; a rank's tensor covers its own held rows only.

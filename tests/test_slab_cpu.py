@@ -176,7 +176,13 @@ def test_slab_geometry():
     shapes = {tuple(o[0] for o in slab.schedule(1024, 4, r, 100)[1]) for r in range(4)}
     assert len(shapes) == 1
     _, ops = slab.schedule(1024, 4, 1, 100)
-    assert sum(1 for o in ops if o[0] == "X") == 1 + 12 + 1 and sum(o[3] for o in ops if o[0] == "jacobi") == 100
+    # K = 1: the state exchange + one pressure exchange between consecutive launches (none after the last:
+    # every launch also computes the row below the slab that the pressure gradient reads)
+    assert sum(1 for o in ops if o[0] == "X") == 1 + 12 and sum(o[3] for o in ops if o[0] == "jacobi") == 100
+    _, ops3 = slab.schedule(1024, 4, 1, 100, 3)
+    assert sum(1 for o in ops3 if o[0] == "X") == 1 + 4
+    _, one = slab.schedule(1024, 4, 1, 20, 3)           # a single chunk keeps one hand-shake after the stencil stage
+    assert [o[0] for o in one].count("X") == 2
 
 
 def test_bench_held_state_equals_global_init():
