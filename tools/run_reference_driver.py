@@ -11,7 +11,15 @@ library (SURVEY.md section 7 "hazards" H1-H4):
   H3  `lib.FluidNetDataset` tolerates a missing dataset; `lib.simulate` accepts the legacy 5-argument call;
   H4  the driver copies `<modelDir>/<name>_saved.py` into ./lib/ and executes it: the launcher runs the driver
       from a scratch directory that has a ./lib/ folder; `import lib` resolves to fluidnet_cxx_b200.lib
-      (compat.install), so the saved model's `from lib import fluid, MultiScaleNet` gets the tcgen05 network.
+      (compat.install), so the saved model's `from lib import fluid, MultiScaleNet` gets the tcgen05 network;
+  H5  rayleighTaylor.py:112-115 updates `conf` with the pickled training configuration `<model>_conf.pth`, whose
+      `modelDir` is the training machine's RELATIVE path (`data2/model_divL2_5divLT_ScaleNet_New` for the shipped
+      model) and then loads the weights from there: the launcher links that relative path, inside the scratch
+      directory the driver runs from, to the model directory given by --modelDir / the YAML;
+  H6  rayleighTaylor.py:253-257 appends `[[it*dt, distance]]` -- a Python float next to a (n, 1) CUDA tensor -- to a
+      NumPy array every step.  NumPy of the reference's day built an object array out of that; NumPy >= 1.24 refuses
+      the ragged list and never converts CUDA tensors: `np.append` falls back to the old object-array result (tensor
+      moved to the host) when NumPy rejects the arguments.
 """
 import importlib
 import os
@@ -87,9 +95,56 @@ def prepare():
             return _tload(*a, **kw)
         tload._fnx_shim = True
         torch.load = tload
+    import numpy as np
+    if not getattr(np.append, "_fnx_shim", False):
+        _append = np.append
+
+        def append(arr, values, axis=None):
+            try:
+                return _append(arr, values, axis)
+            except (ValueError, TypeError):
+                rows = [[(v.detach().cpu() if isinstance(v, torch.Tensor) else v) for v in row] for row in values]
+                obj = np.empty((len(rows), len(rows[0])), dtype=object)
+                for i, row in enumerate(rows):
+                    for j, v in enumerate(row):
+                        obj[i, j] = v
+                return _append(np.asarray(arr, dtype=object), obj, axis)
+        append._fnx_shim = True
+        np.append = append
     import fluidnet_cxx_b200.compat as compat
     compat.install()
     return stubbed
+
+
+def _link_pickled_model_dir(argv, work):
+    """hazard H5: make the relative `modelDir` pickled in <modelDir>/<modelFilename>_conf.pth resolve, from the
+    scratch directory, to the real model directory"""
+    import torch
+    import yaml
+    model_dir = argv[argv.index("--modelDir") + 1] if "--modelDir" in argv else None
+    model_name = argv[argv.index("--modelFilename") + 1] if "--modelFilename" in argv else None
+    if "--simConf" in argv:
+        try:
+            with open(argv[argv.index("--simConf") + 1]) as f:
+                sc = yaml.safe_load(f) or {}
+            model_dir = model_dir or sc.get("modelDir")
+            model_name = model_name or sc.get("modelFilename")
+        except (OSError, yaml.YAMLError):
+            pass
+    if not model_dir or not model_name:
+        return
+    cpath = os.path.join(model_dir, model_name + "_conf.pth")
+    if not os.path.isfile(cpath):
+        return
+    try:
+        pickled = torch.load(cpath, weights_only=False, map_location="cpu").get("modelDir")
+    except Exception:       # noqa: BLE001 - nothing to link
+        return
+    if not pickled or os.path.isabs(pickled) or os.path.exists(os.path.join(work, pickled)):
+        return
+    link = os.path.join(work, pickled)
+    os.makedirs(os.path.dirname(link) or work, exist_ok=True)
+    os.symlink(os.path.abspath(model_dir), link)
 
 
 def main():
@@ -110,6 +165,7 @@ def main():
             os.path.basename(driver))
         if default and os.path.exists(os.path.join(os.path.dirname(driver), default)):
             argv += ["--simConf", os.path.join(os.path.dirname(driver), default)]
+    _link_pickled_model_dir(argv, work)
     os.chdir(work)
     sys.argv = argv
     runpy.run_path(driver, run_name="__main__")
