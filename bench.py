@@ -236,7 +236,8 @@ def build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs, jacobi_laun
     group = None
     if wl["method"] == "jacobi" and grp_ms > 0:
         gbs = grp_bytes / (grp_ms / 1e3) / 1e9
-        group = {"kernels": "k_step_advect_fwd + k_step_advect_bwd + k_step_forces_div + k_step_project",
+        group = {"kernels": ("k2_advect_clean + k2_advect + k2_forces_div + k2_project (csrc/step2d.cu)" if D == 1 else
+                             "k_step_advect_fwd + k_step_advect_bwd + k_step_forces_div + k_step_project (csrc/step.cu)"),
                  "algorithmic_bytes_per_cell": 80 if D == 1 else 104, "ms_per_step": round(grp_ms / steps, 4),
                  "achieved": round(gbs, 1), "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
                  "advect_forces_ms_per_step": round(stage_ms.get("advect_forces", 0.0) / steps, 4),
@@ -311,7 +312,7 @@ def make_record(args, name, wl, world, total_cells, cells, steps, warmup, total_
     """One record of the contract's JSON line.  cells = cells one GPU computes per step."""
     value = total_cells * steps / (total_ms / 1e3) / 1e6
     e2e_value = total_cells * e2e_steps / (e2e_ms / 1e3) / 1e6
-    return {
+    rec = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": round(total_ms / steps, 4),
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
@@ -333,6 +334,8 @@ def make_record(args, name, wl, world, total_cells, cells, steps, warmup, total_
         "roofline": roof,
         "wall_s": round(t_wall, 3),
     }
+    assert tuple(rec["config"]) == CONFIG_KEYS
+    return rec
 
 
 # ---------------------------------------------------------------------------------------------
@@ -697,7 +700,7 @@ def run_distributed(args, name, scaling, guard, transport):
                           grid=[gD, gH, W], scaling=scaling)
         out["cpu_baseline"] = None
         if graph_check is not None:
-            out["config"]["graph_vs_direct_max_abs_diff"] = graph_check
+            out["multi_gpu"] = {"graph_vs_direct_max_abs_diff": graph_check}
     del stepper, bd, host, out_host, flush_buf, ops, host_win, dev_win, dev_out
     torch.cuda.empty_cache()
     barrier()
@@ -880,8 +883,9 @@ def run_distributed_slab(args, name, scaling, guard):
                                        f"replayed as one CUDA graph; global grid 1x{gH}x{W}"),
                           grid=[1, gH, W], scaling=scaling)
         out["cpu_baseline"] = None
-        out["config"]["max_u_dt_cells"] = round(reach, 3)
-        out["config"]["device_bytes_all_ranks_peak"] = mem_all
+        # (kept out of `config`: both arms of the driver's comparison carry exactly CONFIG_KEYS there)
+        out["multi_gpu"] = {"max_u_dt_cells": round(reach, 3), "device_bytes_all_ranks_peak": mem_all,
+                            "jacobi_launches_per_exchange": K, "ghost_rows": g["G"]}
     del step, host_in, host_out, flush_buf
     torch.cuda.empty_cache()
     barrier()

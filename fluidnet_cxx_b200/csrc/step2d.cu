@@ -799,6 +799,70 @@ __device__ __forceinline__ void forces_strip(const Frc& g, const Masks& m, const
   }
 }
 
+// The common strip: no imposed values on its rows, every row it touches (jb-1 .. jt) inside the grid and
+// jt - jb a multiple of 4: no row test, no mask, no clamp left in the loop; running row pointers.
+__device__ __forceinline__ void forces_strip_fast(const Frc& g, const float* __restrict__ rho, const float* __restrict__ u0,
+                                                  const float* __restrict__ u1, const float* __restrict__ fl,
+                                                  float* __restrict__ u0_out, float* __restrict__ u1_out,
+                                                  float* __restrict__ div, int i, int jb, int jt, int lane) {
+  const int W = g.W;
+  const bool in = i < W;
+  const bool out = in && lane < FW;
+  const bool border = (i < 1) | (i > W - 2);                  // rows jb .. jt-1 are interior rows
+  const unsigned full = 0xffffffffu;
+  const int ic = in ? i : W - 1;
+  const bool lead = lane == 0 && in && i > 0;                 // lane 0 reads its left neighbour itself
+  const float* pf = fl + jt * W + ic;
+  const float* pr = rho + jt * W + ic;
+  const float* pa = u0 + jt * W + ic;
+  const float* pb = u1 + jt * W + ic;
+  float* oa = u0_out + jt * W + ic;
+  float* ob = u1_out + jt * W + ic;
+  float* od = div ? div + jt * W + ic : nullptr;
+  // the row above the strip: its y face only
+  float fc = __ldg(pf), rc = __ldg(pr);
+  float fb = __ldg(pf - W), rb = __ldg(pr - W);
+  float fv_up = forced1(g, __ldg(pb), fc, fb, rc, rb, border | (jt > g.H - 2), g.bs1, g.gf1, false, 0.f, 0.f);
+  fc = fb; rc = rb;
+  for (int j = jt - 1; j >= jb; j -= 4) {
+    pf -= 4 * W; pr -= 4 * W; pa -= 4 * W; pb -= 4 * W; oa -= 4 * W; ob -= 4 * W;
+    if (od) od -= 4 * W;
+    // rows j, j-1, j-2, j-3 live at +3W, +2W, +W, 0 of the moved pointers; their lower rows one W below
+    float au[4], av[4], fbv[4], rbv[4], fl_l0[4], r_l0[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int o = (3 - k) * W;
+      au[k] = __ldg(pa + o);
+      av[k] = __ldg(pb + o);
+      fbv[k] = __ldg(pf + o - W);
+      rbv[k] = __ldg(pr + o - W);
+      fl_l0[k] = 0.f; r_l0[k] = 0.f;
+      if (lead) { fl_l0[k] = __ldg(pf + o - 1); r_l0[k] = __ldg(pr + o - 1); }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int o = (3 - k) * W;
+      float fl_l = __shfl_up_sync(full, fc, 1), r_l = __shfl_up_sync(full, rc, 1);
+      if (lane == 0) { fl_l = lead ? fl_l0[k] : fc; r_l = lead ? r_l0[k] : rc; }
+      const float b = forced1(g, av[k], fc, fbv[k], rc, rbv[k], border, g.bs1, g.gf1, false, 0.f, 0.f);
+      const float a = forced1(g, au[k], fc, fl_l, rc, r_l, border, g.bs0, g.gf0, false, 0.f, 0.f);
+      const float a_right = __shfl_down_sync(full, a, 1);
+      if (out) {
+        oa[o] = a;
+        ob[o] = b;
+        if (od) {
+          float d = 0.f;
+          if (!border) d = a - a_right + b - fv_up;           // velocity_divergence.py:61-66 (Q15)
+          if (fc == kObstacle) d = 0.f;
+          od[o] = d;
+        }
+      }
+      fv_up = b;
+      fc = fbv[k]; rc = rbv[k];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(32 * FWARPS)
     k2_forces_div(const __grid_constant__ Frc g, const __grid_constant__ Masks m, const float* __restrict__ rho,
                   const float* __restrict__ rho_mid, const float* __restrict__ u0, const float* __restrict__ u1,
@@ -820,6 +884,8 @@ __global__ void __launch_bounds__(32 * FWARPS)
   }
   any = __syncthreads_or(any);
   if (any) forces_strip<true>(g, m, rho, rho_mid, u0, u1, fl, u0_out, u1_out, div, i, jb, jt, lane);
+  else if (jb >= 1 && jt <= g.H - 1 && ((jt - jb) & 3) == 0 && jt > jb)
+    forces_strip_fast(g, rho, u0, u1, fl, u0_out, u1_out, div, i, jb, jt, lane);
   else forces_strip<false>(g, m, rho, rho_mid, u0, u1, fl, u0_out, u1_out, div, i, jb, jt, lane);
 }
 
@@ -851,6 +917,54 @@ __global__ void __launch_bounds__(256)
   }
   u0[c] = a;
   u1[c] = b;
+}
+
+// four consecutive cells of a row per thread (16-byte loads / stores); W % 4 == 0 and 16-byte aligned rows
+__global__ void __launch_bounds__(128)
+    k2_project4(int H, int W, int row0, int row1, const float* __restrict__ p, float* __restrict__ u0,
+                float* __restrict__ u1, const float* __restrict__ fl, Masks m, int wall_bcs) {
+  const int i0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int j = row0 + blockIdx.y;
+  if (i0 >= W || j >= row1) return;
+  const int c = j * W + i0;
+  const float4 P4 = __ldg(reinterpret_cast<const float4*>(p + c));
+  const float4 F4 = __ldg(reinterpret_cast<const float4*>(fl + c));
+  float4 A4 = *reinterpret_cast<const float4*>(u0 + c);
+  float4 B4 = *reinterpret_cast<const float4*>(u1 + c);
+  float4 Pd4 = P4, Fd4 = F4;                 // row below (the cell itself at j = 0, Q13)
+  if (j > 0) {
+    Pd4 = __ldg(reinterpret_cast<const float4*>(p + c - W));
+    Fd4 = __ldg(reinterpret_cast<const float4*>(fl + c - W));
+  }
+  float pl = 0.f, fll = F4.x;                // left neighbour of the first cell
+  if (i0 > 0) { pl = __ldg(p + c - 1); fll = __ldg(fl + c - 1); }
+  const float P[4] = {P4.x, P4.y, P4.z, P4.w}, F[4] = {F4.x, F4.y, F4.z, F4.w};
+  const float Pd[4] = {Pd4.x, Pd4.y, Pd4.z, Pd4.w}, Fd[4] = {Fd4.x, Fd4.y, Fd4.z, Fd4.w};
+  float a[4] = {A4.x, A4.y, A4.z, A4.w}, b[4] = {B4.x, B4.y, B4.z, B4.w};
+  const bool rborder = (j < 1) | (j > H - 2);
+  const unsigned char rb = m.rows ? m.rows[j] : (unsigned char)3;
+  const bool masked = m.u0bc && (rb & 1);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int i = i0 + k;
+    const float fc = F[k];
+    const float fl_l = k == 0 ? fll : F[k - 1], p_l = k == 0 ? pl : P[k - 1];
+    const float fl_d = j > 0 ? Fd[k] : fc;
+    if (!(rborder | (i < 1) | (i > W - 2))) {
+      a[k] = velocity_update_apply(a[k], fc, fl_l, P[k], p_l);
+      b[k] = velocity_update_apply(b[k], fc, fl_d, P[k], Pd[k]);
+    }
+    if (wall_bcs) {
+      a[k] = wall_bcs_apply(a[k], fc, fl_l);
+      b[k] = wall_bcs_apply(b[k], fc, fl_d);
+    }
+    if (masked) {
+      a[k] = const_vals_apply(a[k], __ldg(m.u0inv + c + k), __ldg(m.u0bc + c + k));
+      b[k] = const_vals_apply(b[k], __ldg(m.u1inv + c + k), __ldg(m.u1bc + c + k));
+    }
+  }
+  *reinterpret_cast<float4*>(u0 + c) = make_float4(a[0], a[1], a[2], a[3]);
+  *reinterpret_cast<float4*>(u1 + c) = make_float4(b[0], b[1], b[2], b[3]);
 }
 
 }  // namespace s2
@@ -974,8 +1088,18 @@ int fnx_step2d_project(const fnx_step2d_win& w, const float* p, float* U, const 
     m.u1inv = vb(mk.UBCInv ? mk.UBCInv + (2 * b + 1) * plane : nullptr, off);
     m.rbc = nullptr; m.rinv = nullptr;
     m.rows = mk.rows ? mk.rows + (long long)b * (w.ya1 - w.ya0) - w.ya0 : nullptr;
-    k2_project<<<grid, 256, 0, st>>>(w.H, w.W, w.row0, w.row1, vb(p + b * plane, off), vb(U + (2 * b) * plane, off),
-                                     vb(U + (2 * b + 1) * plane, off), vb(flags + b * plane, off), m, wall_bcs);
+    const float* pp = vb(p + b * plane, off);
+    float* pu0 = vb(U + (2 * b) * plane, off);
+    float* pu1 = vb(U + (2 * b + 1) * plane, off);
+    const float* pfl = vb(flags + b * plane, off);
+    const bool vec = (w.W % 4 == 0) && ((((uintptr_t)pp | (uintptr_t)pu0 | (uintptr_t)pu1 | (uintptr_t)pfl) & 15) == 0) &&
+                     (w.row1 - w.row0) <= 65535;
+    if (vec) {
+      dim3 g4((w.W / 4 + 127) / 128, w.row1 - w.row0);
+      k2_project4<<<g4, 128, 0, st>>>(w.H, w.W, w.row0, w.row1, pp, pu0, pu1, pfl, m, wall_bcs);
+    } else {
+      k2_project<<<grid, 256, 0, st>>>(w.H, w.W, w.row0, w.row1, pp, pu0, pu1, pfl, m, wall_bcs);
+    }
   }
   fnx_count_launches(B);
   return FNX_OK;
