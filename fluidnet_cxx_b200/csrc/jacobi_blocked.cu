@@ -86,11 +86,78 @@ __device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const float4* __re
 // registers: with p (32 values) alone a thread needs < 85 registers, so TWO 12-warp CTAs (or three 8-warp
 // ones) are resident per SM = 24 warps (the version that also kept div in registers ran one 16-warp
 // CTA at 128 registers: 25 % occupancy, issue slots half empty).
-template <int NW, bool FIRST, bool RESID>
+// The flags never change during a solve and every launch of a solve has the same tile geometry: the five mask
+// words of a thread (Neumann L/R/U/D and "fixed" bits of its 8x4 cells) are computed ONCE per solve by
+// k_jacobi2d_tilemask and re-loaded (20 bytes per thread) by the launches (PRE = true), instead of decoding 32
+// fp32 flags per thread in every launch -- a third of a launch's instructions and a quarter of its traffic.
+template <int NW>
+__device__ __forceinline__ void tile_masks(int H, int W, int ya0, int ya1, int gx0, int gy0, int vec_ok,
+                                           const float* __restrict__ flags, unsigned (&xob)[NW][32], int w, int lane,
+                                           unsigned& Lb, unsigned& Rb, unsigned& Ub, unsigned& Db, unsigned& fixedb) {
+  unsigned obw = 0;
+  fixedb = 0;
+  const bool xvec = vec_ok && gx0 >= 0 && gx0 + JB_C <= W;
+#pragma unroll
+  for (int rr = 0; rr < JB_R; rr++) {
+    const int gy = gy0 + rr;
+    const bool yin = gy >= ya0 && gy < ya1;
+    float f[JB_C];
+    if (xvec && yin) {
+      const float4 f4 = __ldg(reinterpret_cast<const float4*>(flags + (long long)gy * W + gx0));
+      f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < JB_C; c++) {
+        const int gx = gx0 + c;
+        const bool inb = yin && gx >= 0 && gx < W;
+        f[c] = inb ? __ldg(flags + (long long)gy * W + gx) : -1.f;  // -1: outside the domain
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < JB_C; c++) {
+      const int gx = gx0 + c;
+      const bool ob = f[c] == kObstacle;
+      const bool border = (gx < 1) | (gx > W - 2) | (gy < 1) | (gy > H - 2);  // also covers outside
+      if (ob) obw |= 1u << (rr * JB_C + c);
+      if (ob || border) fixedb |= 1u << (rr * JB_C + c);
+    }
+  }
+  // Neumann masks: which neighbours are Obstacle cells
+  xob[w][lane] = obw;
+  __syncthreads();
+  const unsigned obl = __shfl_up_sync(0xffffffffu, obw, 1), obr = __shfl_down_sync(0xffffffffu, obw, 1);
+  const unsigned obu = w > 0 ? xob[w - 1][lane] : 0u, obd = w < NW - 1 ? xob[w + 1][lane] : 0u;
+  Lb = (obw << 1) & 0xEEEEEEEEu; Rb = (obw >> 1) & 0x77777777u;
+  if (lane > 0) Lb |= (obl >> 3) & 0x11111111u;
+  if (lane < 31) Rb |= (obr << 3) & 0x88888888u;
+  Ub = (obw << JB_C) | (obu >> (JB_C * (JB_R - 1)));
+  Db = (obw >> JB_C) | (obd << (JB_C * (JB_R - 1)));
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32)
+    k_jacobi2d_tilemask(int H, int W, int row0, int ya0, int ya1, int vec_ok, const float* __restrict__ flags,
+                        uint4* __restrict__ m4, unsigned* __restrict__ m1) {
+  constexpr int TH = NW * JB_R;
+  constexpr int OW = JB_TW - 2 * JB_HALO, OH = TH - 2 * JB_HALO;
+  __shared__ unsigned xob[NW][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int gx0 = blockIdx.x * OW - JB_HALO + lane * JB_C;
+  const int gy0 = row0 + blockIdx.y * OH - JB_HALO + w * JB_R;
+  flags += (long long)blockIdx.z * (ya1 - ya0) * W - (long long)ya0 * W;
+  unsigned Lb, Rb, Ub, Db, fixedb;
+  tile_masks<NW>(H, W, ya0, ya1, gx0, gy0, vec_ok, flags, xob, w, lane, Lb, Rb, Ub, Db, fixedb);
+  const size_t t = ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (NW * 32) + threadIdx.x;
+  m4[t] = make_uint4(Lb, Rb, Ub, Db);
+  m1[t] = fixedb;
+}
+
+template <int NW, bool FIRST, bool RESID, bool PRE>
 __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
     k_jacobi2d_blocked(int H, int W, int row0, int row1, int ya0, int ya1, int iters, int vec_ok, const float* __restrict__ flags,
                        const float* __restrict__ div, const float* __restrict__ prev,
-                       float* __restrict__ cur, double* __restrict__ ssq) {
+                       float* __restrict__ cur, double* __restrict__ ssq, const uint4* __restrict__ m4,
+                       const unsigned* __restrict__ m1) {
   constexpr int TH = NW * JB_R;
   extern __shared__ __align__(16) float sdv_all[];      // [TH][JB_TW] divergence tile
   __shared__ __align__(16) float xch[2][NW][2][JB_TW];  // [parity][warp][top|bottom][column]
@@ -109,19 +176,14 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
 
   Row4 p[JB_R];
   float4* const sdv = reinterpret_cast<float4*>(sdv_all) + (w * JB_R) * (JB_TW / 4) + lane;
-  unsigned obw = 0, fixedb = 0;
   const bool xvec = vec_ok && gx0 >= 0 && gx0 + JB_C <= W;
 #pragma unroll
   for (int rr = 0; rr < JB_R; rr++) {
     const int gy = gy0 + rr;
     const bool yin = gy >= ya0 && gy < ya1;
-    float f[JB_C];
     if (xvec && yin) {
       const long long o = (long long)gy * W + gx0;
-      const float4 f4 = __ldg(reinterpret_cast<const float4*>(flags + o));
-      const float4 d4 = __ldg(reinterpret_cast<const float4*>(div + o));
-      f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w;
-      sdv[rr * (JB_TW / 4)] = d4;
+      sdv[rr * (JB_TW / 4)] = __ldg(reinterpret_cast<const float4*>(div + o));
       if (!FIRST) {
         const float4 p4 = __ldg(reinterpret_cast<const float4*>(prev + o));
         p[rr].v[0] = p4.x; p[rr].v[1] = p4.y; p[rr].v[2] = p4.z; p[rr].v[3] = p4.w;
@@ -133,32 +195,25 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
         const int gx = gx0 + c;
         const bool inb = yin && gx >= 0 && gx < W;
         const long long o = (long long)gy * W + gx;
-        f[c] = inb ? __ldg(flags + o) : -1.f;  // -1: outside the domain
         dvv[c] = inb ? __ldg(div + o) : 0.f;
         if (!FIRST) p[rr].v[c] = inb ? __ldg(prev + o) : 0.f;
       }
       sdv[rr * (JB_TW / 4)] = make_float4(dvv[0], dvv[1], dvv[2], dvv[3]);
     }
+    if (FIRST) {
 #pragma unroll
-    for (int c = 0; c < JB_C; c++) {
-      const int gx = gx0 + c;
-      if (FIRST) p[rr].v[c] = 0.f;
-      const bool ob = f[c] == kObstacle;
-      const bool border = (gx < 1) | (gx > W - 2) | (gy < 1) | (gy > H - 2);  // also covers outside
-      if (ob) obw |= 1u << (rr * JB_C + c);
-      if (ob || border) fixedb |= 1u << (rr * JB_C + c);
+      for (int c = 0; c < JB_C; c++) p[rr].v[c] = 0.f;
     }
   }
-  // Neumann masks: which neighbours are Obstacle cells
-  xob[w][lane] = obw;
-  __syncthreads();
-  const unsigned obl = __shfl_up_sync(0xffffffffu, obw, 1), obr = __shfl_down_sync(0xffffffffu, obw, 1);
-  const unsigned obu = w > 0 ? xob[w - 1][lane] : 0u, obd = w < NW - 1 ? xob[w + 1][lane] : 0u;
-  unsigned Lb = (obw << 1) & 0xEEEEEEEEu, Rb = (obw >> 1) & 0x77777777u;
-  if (lane > 0) Lb |= (obl >> 3) & 0x11111111u;
-  if (lane < 31) Rb |= (obr << 3) & 0x88888888u;
-  const unsigned Ub = (obw << JB_C) | (obu >> (JB_C * (JB_R - 1)));
-  const unsigned Db = (obw >> JB_C) | (obd << (JB_C * (JB_R - 1)));
+  unsigned Lb, Rb, Ub, Db, fixedb;
+  if (PRE) {
+    const size_t t = ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (NW * 32) + threadIdx.x;
+    const uint4 q = __ldg(m4 + t);
+    Lb = q.x; Rb = q.y; Ub = q.z; Db = q.w;
+    fixedb = __ldg(m1 + t);
+  } else {
+    tile_masks<NW>(H, W, ya0, ya1, gx0, gy0, vec_ok, flags, xob, w, lane, Lb, Rb, Ub, Db, fixedb);
+  }
   const bool slow = __any_sync(0xffffffffu, (Lb | Rb | Ub | Db | fixedb) != 0u);
 
   float acc = 0.f;
@@ -232,38 +287,49 @@ static int jacobi_block_iters() {
   return t;
 }
 
-template <int NW>
+template <int NW, bool PRE>
 static void launch_blocked(bool first, bool resid, dim3 grid, cudaStream_t st, int H, int W, int row0, int row1,
                            int ya0, int ya1, int iters, int vec_ok,
-                           const float* flags, const float* div, const float* prev, float* cur, double* ssq) {
+                           const float* flags, const float* div, const float* prev, float* cur, double* ssq,
+                           const uint4* m4, const unsigned* m1) {
   const int threads = NW * 32;
   constexpr size_t dsm = (size_t)NW * JB_R * JB_TW * sizeof(float);   // the divergence tile
-  static bool attr_done = false;   // per instantiation (NW); > 48 KB of dynamic shared memory must be opted in
+  static bool attr_done = false;   // per instantiation; > 48 KB of dynamic shared memory must be opted in
   if (!attr_done) {
-    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, true, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, false, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, true, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, false, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
     attr_done = true;
   }
-  if (first && resid) k_jacobi2d_blocked<NW, true, true><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
-  else if (first) k_jacobi2d_blocked<NW, true, false><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
-  else if (resid) k_jacobi2d_blocked<NW, false, true><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
-  else k_jacobi2d_blocked<NW, false, false><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
+  if (first && resid) k_jacobi2d_blocked<NW, true, true, PRE><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+  else if (first) k_jacobi2d_blocked<NW, true, false, PRE><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+  else if (resid) k_jacobi2d_blocked<NW, false, true, PRE><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+  else k_jacobi2d_blocked<NW, false, false, PRE><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+}
+
+// bytes of tile-mask scratch that make a multi-launch solve on a (B, H, W) grid skip the per-launch flag decode
+size_t fnx_jacobi_2d_tilemask_bytes(int B, int H, int W) {
+  constexpr int OW = JB_TW - 2 * JB_HALO;
+  const size_t tx = (size_t)(W + OW - 1) / OW;
+  const size_t a = (size_t)((H + 47) / 48) * 256, b = (size_t)((H + 79) / 80) * 384;   // threads per tile column, NW = 8 / 12
+  return (size_t)B * tx * (a > b ? a : b) * 20 + 512;
 }
 
 int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
                                double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
-                               cudaStream_t st);
+                               void* tile_ws, size_t tile_ws_bytes, cudaStream_t st);
 
 int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
-                          double* ssq, int B, int H, int W, int max_iter, int row0, int row1, cudaStream_t st) {
-  return fnx_jacobi_2d_blocked_held(flags, div, p_init, p, scratch, ssq, B, H, W, max_iter, row0, row1, 0, H, st);
+                          double* ssq, int B, int H, int W, int max_iter, int row0, int row1, void* tile_ws,
+                          size_t tile_ws_bytes, cudaStream_t st) {
+  return fnx_jacobi_2d_blocked_held(flags, div, p_init, p, scratch, ssq, B, H, W, max_iter, row0, row1, 0, H, tile_ws,
+                                    tile_ws_bytes, st);
 }
 
 int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
                                double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
-                               cudaStream_t st) {
+                               void* tile_ws, size_t tile_ws_bytes, cudaStream_t st) {
   if (row1 <= row0) { row0 = 0; row1 = H; }
   if (!(0 <= ya0 && ya0 <= row0 && row1 <= ya1 && ya1 <= H))
     return fnx_set_error(FNX_ERR_ARG, "jacobi_2d_blocked: rows [%d,%d) not inside the held rows [%d,%d) of %d", row0, row1,
@@ -293,6 +359,19 @@ int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float
   if (force) tall = atoi(force) >= 12;
   const int oh = (tall ? 12 : 8) * JB_R - 2 * JB_HALO;
   dim3 grid((W + OW - 1) / OW, (row1 - row0 + oh - 1) / oh, B);
+  // tile masks once per solve (worth it from the second launch on)
+  const size_t nthr = (size_t)grid.x * grid.y * grid.z * (tall ? 384 : 256);
+  static const char* nopre = getenv("FNX_JACOBI_NO_TILEMASK");
+  const bool pre = nL >= 2 && tile_ws && tile_ws_bytes >= nthr * 20 + 256 && !(nopre && nopre[0] == '1');
+  uint4* m4 = nullptr;
+  unsigned* m1 = nullptr;
+  if (pre) {
+    m4 = reinterpret_cast<uint4*>(((uintptr_t)tile_ws + 15) & ~(uintptr_t)15);
+    m1 = reinterpret_cast<unsigned*>(m4 + nthr);
+    if (tall) k_jacobi2d_tilemask<12><<<grid, 384, 0, st>>>(H, W, row0, ya0, ya1, vec_ok, flags, m4, m1);
+    else k_jacobi2d_tilemask<8><<<grid, 256, 0, st>>>(H, W, row0, ya0, ya1, vec_ok, flags, m4, m1);
+    fnx_count_launches(1);
+  }
   int done = 0;
   for (int l = 0; l < nL; l++) {
     const int iters = (max_iter - done) < T ? (max_iter - done) : T;
@@ -300,8 +379,10 @@ int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float
     const bool first = l == 0 && p_init == nullptr, resid = l == nL - 1 && ssq != nullptr;
     const float* prev = l == 0 ? p_init : wbuf(l - 1);
     float* cur = wbuf(l);
-    if (tall) launch_blocked<12>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
-    else launch_blocked<8>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq);
+    if (tall && pre) launch_blocked<12, true>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+    else if (tall) launch_blocked<12, false>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+    else if (pre) launch_blocked<8, true>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+    else launch_blocked<8, false>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
     done += iters;
     fnx_count_launches(1);
   }

@@ -470,11 +470,12 @@ static void launch_jacobi_iter(const Grid& g, bool first, bool resid, const floa
 }
 
 int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
-                          double* ssq, int B, int H, int W, int max_iter, int row0, int row1,
-                          cudaStream_t st);  // jacobi_blocked.cu
+                          double* ssq, int B, int H, int W, int max_iter, int row0, int row1, void* tile_ws,
+                          size_t tile_ws_bytes, cudaStream_t st);  // jacobi_blocked.cu
 int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
                                double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
-                               cudaStream_t st);  // jacobi_blocked.cu
+                               void* tile_ws, size_t tile_ws_bytes, cudaStream_t st);  // jacobi_blocked.cu
+size_t fnx_jacobi_2d_tilemask_bytes(int B, int H, int W);  // jacobi_blocked.cu
 
 
 // 3-D fixed iteration count: mask once, then the 4-cells-per-thread kernel (needs W % 4 == 0 and 16-byte
@@ -675,7 +676,8 @@ size_t fnx_jacobi_workspace(int B, int D, int H, int W, int max_iter) {
   (void)max_iter;
   size_t n = (size_t)B * D * H * W;
   return align256(n * sizeof(float)) + align256(sizeof(JacobiCtrl)) + align256((size_t)B * sizeof(double)) +
-         (D > 1 ? align256(n) : 0);  // 3-D: one neighbour-mask byte per cell
+         (D > 1 ? align256(n)                                      // 3-D: one neighbour-mask byte per cell
+                : align256(fnx_jacobi_2d_tilemask_bytes(B, H, W)));  // 2-D: per-thread tile masks of the blocked kernel
 }
 
 int fnx_solve_linear_system_jacobi(const float* flags, const float* div, float* p, float* residual, int B,
@@ -698,7 +700,9 @@ int fnx_solve_linear_system_jacobi(const float* flags, const float* div, float* 
   const bool tol = p_tol > 0.f;
   if (!tol && !is3d) {
     // fixed iteration count, 2-D: temporally blocked shared-memory kernel
-    int e = fnx_jacobi_2d_blocked(flags, div, nullptr, p, scratch, ssq, B, H, W, max_iter, 0, 0, st);
+    void* tmask = (char*)ssq + align256((size_t)B * sizeof(double));
+    int e = fnx_jacobi_2d_blocked(flags, div, nullptr, p, scratch, ssq, B, H, W, max_iter, 0, 0, tmask,
+                                  fnx_jacobi_2d_tilemask_bytes(B, H, W), st);
     if (e) return e;
     k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, max_iter - 1, residual);
     FNX_LAUNCH_CHECK("solve_linear_system", 1);
@@ -758,7 +762,13 @@ int fnx_jacobi_iterate(const float* flags, const float* div, const float* p_init
     if (row_begin < 0 || row_end > D * H) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate: row window out of range");
     g.row0 = row_begin; g.row1 = row_end;
   }
-  if (!is3d) return fnx_jacobi_2d_blocked(flags, div, p_init, p, scratch, nullptr, B, H, W, iters, row_begin, row_end, st);
+  if (!is3d) {
+    const size_t nn = (size_t)B * g.n;
+    void* tmask = (char*)workspace + align256(nn * sizeof(float)) + align256(sizeof(JacobiCtrl)) +
+                  align256((size_t)B * sizeof(double));
+    return fnx_jacobi_2d_blocked(flags, div, p_init, p, scratch, nullptr, B, H, W, iters, row_begin, row_end, tmask,
+                                 fnx_jacobi_2d_tilemask_bytes(B, H, W), st);
+  }
   if (jacobi3d_vec_ok(g, flags, div, p, scratch) && (((uintptr_t)p_init) & 15) == 0) {
     const size_t n = (size_t)B * g.n;
     unsigned char* mask = (unsigned char*)workspace + align256(n * sizeof(float)) + align256(sizeof(JacobiCtrl)) +
@@ -788,7 +798,7 @@ int fnx_jacobi_iterate_held(const float* flags, const float* div, const float* p
   if (iters > 8 && (!workspace || workspace_bytes < n * sizeof(float)))
     return fnx_set_error(FNX_ERR_WORKSPACE, "jacobi_iterate_held: workspace too small");
   return fnx_jacobi_2d_blocked_held(flags, div, p_init, p, (float*)workspace, nullptr, B, H, W, iters, row_begin, row_end,
-                                    held_row_begin, held_row_end, (cudaStream_t)stream);
+                                    held_row_begin, held_row_end, nullptr, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

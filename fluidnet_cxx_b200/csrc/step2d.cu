@@ -332,24 +332,23 @@ struct Masks {   // setConstVals (simulate.py:4-26); virtual bases, NULL = no ma
   const unsigned char* rows;   // per row: bit0 = U masks differ from identity, bit1 = density masks (NULL: test every cell)
 };
 
-// TYY = rows per CTA.  TY for the whole grid; with a tile list (written by k2_advect_clean: only the tiles
-// that kernel declined are done here -- a few per cent of a plume grid, the ring along the walls) each
-// listed TX x TY tile is cut into TY / TYY CTAs so that the few tiles left spread over all SMs.
+// TYY = rows per tile (32 on large grids; 16 / 8 on small ones, where a launch is a handful of tiles per SM
+// and its duration is the latency of ONE tile).  With a tile list (written by k2_advect_clean) only the tiles
+// that kernel declined are done here -- a few per cent of a plume grid, the ring along the walls.
 template <int TYY>
 __global__ void __launch_bounds__(NT, 3)
     k2_advect(const __grid_constant__ Adv a, const __grid_constant__ Masks m, int rho_passes, float* __restrict__ rho_out, float* __restrict__ rho_mid,
               float* __restrict__ u0_out, float* __restrict__ u1_out, int tiles_x, const int* __restrict__ tile_count,
               const int* __restrict__ tile_list) {
   __shared__ Smem<TYY> s;
-  constexpr int SUB = TY / TYY, SH_ = Smem<TYY>::SHH;
-  int tile = blockIdx.x / SUB;
-  const int sub = blockIdx.x - tile * SUB;
+  constexpr int SH_ = Smem<TYY>::SHH;
+  int tile = blockIdx.x;
   if (tile_list) {
     if (tile >= *tile_count) return;
     tile = tile_list[tile];
   }
   const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
-  const int tx0 = tile_x * TX, ty0 = a.row0 + tile_y * TY + sub * TYY;
+  const int tx0 = tile_x * TX, ty0 = a.row0 + tile_y * TYY;
   const int W = a.W, H = a.H;
   if (ty0 >= a.row1) return;
 
@@ -519,9 +518,11 @@ __global__ void __launch_bounds__(NT, 3)
 //     convention of this repo -- and every consumer of these fields -- treats as equal).
 // Tiles that are not clean are appended to a list and done by the generic kernel.
 constexpr int CA = 1;                               // apron of the clean path
-constexpr int CSW = TX + 2 * CA, CSH = TY + 2 * CA;
+constexpr int CSW = TX + 2 * CA;
 constexpr int CR = 2;                               // scanned margin
+template <int TYY>
 struct SmemC {
+  static constexpr int CSH = TYY + 2 * CA;
   float rho[CSH][CSW];
   float u0[CSH][CSW];
   float u1[CSH][CSW];
@@ -565,21 +566,23 @@ __device__ __forceinline__ float gather_g(const float* __restrict__ f, int W, fl
   return bilerp_c(__ldg(p), __ldg(p + W), __ldg(p + 1), __ldg(p + W + 1), t);
 }
 
+template <int TYY>
 __global__ void __launch_bounds__(NT, 4)
     k2_advect_clean(const __grid_constant__ Adv a, const __grid_constant__ Masks m, int rho_passes, int ya0, int ya1,
                     float* __restrict__ rho_out, float* __restrict__ rho_mid, float* __restrict__ u0_out,
                     float* __restrict__ u1_out, int tiles_x, int* __restrict__ slow_count, int* __restrict__ slow_list) {
-  __shared__ SmemC s;
+  __shared__ SmemC<TYY> s;
+  constexpr int CSH = SmemC<TYY>::CSH;
   const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
-  const int tx0 = tile_x * TX, ty0 = a.row0 + tile_y * TY;
+  const int tx0 = tile_x * TX, ty0 = a.row0 + tile_y * TYY;
   const int W = a.W, H = a.H;
 
   // ---- classification ----
-  int ok = (tx0 - CA >= 1) && (tx0 + TX - 1 + CA <= W - 2) && (ty0 - CA >= 1) && (ty0 + TY - 1 + CA <= H - 2) &&
-           (ty0 - CR >= ya0) && (ty0 + TY + CR <= ya1);
+  int ok = (tx0 - CA >= 1) && (tx0 + TX - 1 + CA <= W - 2) && (ty0 - CA >= 1) && (ty0 + TYY - 1 + CA <= H - 2) &&
+           (ty0 - CR >= ya0) && (ty0 + TYY + CR <= ya1);
   if (ok) {
     const float adt = fabsf(a.dt);
-    constexpr int RW = TX + 2 * CR, RH = TY + 2 * CR;
+    constexpr int RW = TX + 2 * CR, RH = TYY + 2 * CR;
     for (int e = threadIdx.x; e < RW * RH; e += NT) {
       const int ly = e / RW, lx = e - ly * RW;
       const int c = (ty0 - CR + ly) * W + (tx0 - CR + lx);
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(NT, 4)
   const int i = tx0 + lxo;
   const int lbase_x = tx0 - CA, lbase_y = ty0 - CA;
 #pragma unroll 1
-  for (int r = lyo; r < TY; r += NT / TX) {
+  for (int r = lyo; r < TYY; r += NT / TX) {
     const int j = ty0 + r;
     if (j >= a.row1) break;
     const int c = j * W + i;
@@ -981,7 +984,7 @@ inline float* vb(float* p, long long off) { return p ? p - off : nullptr; }
 bool fnx_step2d_supported(int H, int W) { return H >= 4 && W >= 4 && H < 65536 && W < 65536; }
 
 size_t fnx_step2d_tile_ws_ints(const fnx_step2d_win& w, int B) {
-  const int tiles_x = (w.W + TX - 1) / TX, tiles_y = (w.row1 - w.row0 + TY - 1) / TY;
+  const int tiles_x = (w.W + TX - 1) / TX, tiles_y = (w.row1 - w.row0 + 7) / 8;   // the smallest tile height
   return (size_t)B * ((size_t)tiles_x * tiles_y + 1);
 }
 
@@ -1002,7 +1005,11 @@ int fnx_step2d_advect(const fnx_step2d_win& w, float dt, float maccormack_streng
                       float* rho_out, float* rho_mid, float* U_out, int B, int* tile_ws, cudaStream_t st) {
   const long long off = (long long)w.ya0 * w.W;
   const long long plane = (long long)(w.ya1 - w.ya0) * w.W;   // elements per channel / batch item of a 1-channel field
-  const int tiles_x = (w.W + TX - 1) / TX, tiles_y = (w.row1 - w.row0 + TY - 1) / TY;
+  // tile height: 32 rows, or 16 / 8 on small grids (fewer than ~8 / ~2 tiles of 32 rows per SM slot)
+  const int tiles_x = (w.W + TX - 1) / TX;
+  const int n32 = tiles_x * ((w.row1 - w.row0 + 31) / 32);
+  const int th = n32 > 1184 ? 32 : (n32 > 296 ? 16 : 8);
+  const int tiles_y = (w.row1 - w.row0 + th - 1) / th;
   const int ntiles = tiles_x * tiles_y;
   for (int b = 0; b < B; b++) {
     Adv a;
@@ -1029,18 +1036,24 @@ int fnx_step2d_advect(const fnx_step2d_win& w, float dt, float maccormack_streng
     float* rm = vb(rho_mid ? rho_mid + b * plane : nullptr, off);
     float* uo0 = vb(U_out + (2 * b) * plane, off);
     float* uo1 = vb(U_out + (2 * b + 1) * plane, off);
-    if (tile_ws) {
-      // interior fast path first; the tiles it declines come back in a list for the generic kernel
-      int* count = tile_ws + (size_t)b * (ntiles + 1);
-      int* list = count + 1;
-      if (cudaMemsetAsync(count, 0, sizeof(int), st) != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "step2d: memset failed");
-      k2_advect_clean<<<ntiles, NT, 0, st>>>(a, m, rho_passes, w.ya0, w.ya1, ro, rm, uo0, uo1, tiles_x, count, list);
-      // (cutting the listed tiles into 8-row CTAs measured slower, 75 vs 63 us at 4096^2: the apron overhead
-      // of a thin tile outweighs the better spread -- the leftover pass is instruction-bound, not latency-bound)
-      k2_advect<TY><<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, count, list);
-    } else {
-      k2_advect<TY><<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, nullptr, nullptr);
-    }
+#define FNX_ADV_LAUNCH(T)                                                                                              \
+  do {                                                                                                               \
+    if (tile_ws) {                                                                                                   \
+      k2_advect_clean<T><<<ntiles, NT, 0, st>>>(a, m, rho_passes, w.ya0, w.ya1, ro, rm, uo0, uo1, tiles_x, count, list); \
+      k2_advect<T><<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, count, list);                 \
+    } else {                                                                                                         \
+      k2_advect<T><<<ntiles, NT, 0, st>>>(a, m, rho_passes, ro, rm, uo0, uo1, tiles_x, nullptr, nullptr);            \
+    }                                                                                                                \
+  } while (0)
+    // interior fast path first; the tiles it declines come back in a list for the generic kernel
+    int* count = tile_ws ? tile_ws + (size_t)b * (ntiles + 1) : nullptr;
+    int* list = tile_ws ? count + 1 : nullptr;
+    if (tile_ws && cudaMemsetAsync(count, 0, sizeof(int), st) != cudaSuccess)
+      return fnx_set_error(FNX_ERR_CUDA, "step2d: memset failed");
+    if (th == 32) FNX_ADV_LAUNCH(32);
+    else if (th == 16) FNX_ADV_LAUNCH(16);
+    else FNX_ADV_LAUNCH(8);
+#undef FNX_ADV_LAUNCH
   }
   fnx_count_launches(tile_ws ? 2 * B : B);
   return FNX_OK;

@@ -27,21 +27,20 @@ def main():
     step, conv1024, conv512 = sys.argv[1:4]
     t = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from round-2 ncu --set full captures "
                      "(profiles/r2_ncu_*_summary.txt); bench.py copies the matching entry into roofline.traffic"}
-    jac = [r for r in rows_of(step) if "k_jacobi2d_blocked" in r["name"] and "(bool)0, (bool)0" in r["name"]
-           or "k_jacobi2d_blocked" in r["name"] and ", 0, 0>" in r["name"]]
-    if jac:
+    jac = [r for r in rows_of(step) if "k_jacobi2d_blocked<" in r["name"] and
+           any(tag in r["name"] for tag in ("<8, 0, 0,", "<12, 0, 0,", "(int)8, (bool)0, (bool)0", "(int)12, (bool)0, (bool)0"))]
+    if jac:     # the middle launches of a solve: continued from p, no residual
         t["k_jacobi2d_blocked @4096x4096"] = int(sum(r["bytes"] for r in jac) / len(jac))
+    # conv reports: exactly ONE MultiScaleNet forward (tools/prof_msnet.py, 16 tcgen05 launches in the order of
+    # multi_scale_net.py:109-127: quarter 4, half 6, full 6); the full-resolution 64->128 / 128->64 layers are launches 12 / 13
     for rep, res in ((conv1024, 1024), (conv512, 512)):
         if rep == "-":
             continue
-        c = [r for r in rows_of(rep) if "k_conv_tc<3, 64," in r["name"] or "k_conv_tc<(int)3, (int)64," in r["name"]]
-        if c:
-            top = max(c, key=lambda r: r["us"])
-            t[f"k_conv_tc 128->64 k3 @{res}x{res}"] = int(top["bytes"])
-        c = [r for r in rows_of(rep) if "k_conv_tc<3, 128," in r["name"] or "k_conv_tc<(int)3, (int)128," in r["name"]]
-        if c:
-            top = max(c, key=lambda r: r["us"])
-            t[f"k_conv_tc 64->128 k3 @{res}x{res}"] = int(top["bytes"])
+        c = [r for r in rows_of(rep) if "k_conv_tc" in r["name"]]
+        if len(c) >= 16:
+            c = c[-16:]
+            t[f"k_conv_tc 64->128 k3 @{res}x{res}"] = int(c[12]["bytes"])
+            t[f"k_conv_tc 128->64 k3 @{res}x{res}"] = int(c[13]["bytes"])
     print(json.dumps(t, indent=2))
 
 
