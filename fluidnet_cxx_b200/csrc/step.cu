@@ -16,6 +16,9 @@
 namespace fnx {
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+#ifndef FNX_STEP2D_MIN_CELLS
+#define FNX_STEP2D_MIN_CELLS (1LL << 20)
+#endif
 
 // FNX_STEP2D=0 routes the 2-D step through the generic one-thread-per-cell kernels below (the 3-D
 // path), kept as the cross-check of the fused 2-D kernels (tests/test_gpu_parity.py)
@@ -23,9 +26,15 @@ static bool use_clean() {
   const char* e = getenv("FNX_STEP2D_CLEAN");
   return !(e && e[0] == '0');
 }
-static bool use_step2d() {
+// The fused 2-D kernels pay a fixed latency (a tile of 2 048 cells per CTA, two dependent advection kernels, a
+// 32-row march per thread in the forces kernel): below ~1 M cells the grid is a handful of tiles per SM and the
+// one-thread-per-cell kernels are faster (measured: 512^2 ScaleNet step 0.597 vs 0.621 ms, 128^2 Jacobi-28 step
+// 0.103 vs 0.124 ms).  FNX_STEP2D=1 / 0 forces one or the other; held-row (slab) arrays always take the fused ones.
+static bool use_step2d(long long cells = (1LL << 40)) {
   const char* e = getenv("FNX_STEP2D");
-  return !(e && e[0] == '0');
+  if (e && e[0] == '0') return false;
+  if (e && e[0] == '1') return true;
+  return cells >= FNX_STEP2D_MIN_CELLS;
 }
 
 // ---- unbiased std (model.py:18) ----------------------------------------------------------
@@ -339,9 +348,9 @@ int fnx_step_advect_forces_div(const fnx_step_params* prm, const float* density_
     g.row0 = prm->row_begin; g.row1 = prm->row_end;
   }
   const bool held = prm->held_row_end > prm->held_row_begin;   // arrays hold these rows only
-  if (held && (is3d || !use_step2d() || !fnx_step2d_supported(H, W)))
+  if (held && (is3d || !fnx_step2d_supported(H, W)))
     return fnx_set_error(FNX_ERR_ARG, "step: row-window arrays (held_row_*) are a 2-D feature of the fused kernels");
-  if (!is3d && use_step2d() && fnx_step2d_supported(H, W)) {
+  if (!is3d && fnx_step2d_supported(H, W) && (held || use_step2d((long long)(g.row1 - g.row0) * W))) {
     // 2-D: fused advection (forward pass staged in shared memory) + tiled forces/divergence (step2d.cu)
     fnx_step2d_win w;
     w.H = H; w.W = W; w.row0 = g.row0; w.row1 = g.row1;
@@ -418,9 +427,9 @@ int fnx_step_project_bcs_held(const float* pressure, float* U, const float* flag
     g.row0 = row_begin; g.row1 = row_end;
   }
   const bool held = held_row_end > held_row_begin;
-  if (held && (is3d || !use_step2d() || !fnx_step2d_supported(H, W)))
+  if (held && (is3d || !fnx_step2d_supported(H, W)))
     return fnx_set_error(FNX_ERR_ARG, "step: row-window arrays (held_row_*) are a 2-D feature of the fused kernels");
-  if (!is3d && use_step2d() && fnx_step2d_supported(H, W)) {
+  if (!is3d && fnx_step2d_supported(H, W) && (held || use_step2d((long long)(g.row1 - g.row0) * W))) {
     fnx_step2d_win w;
     w.H = H; w.W = W; w.row0 = g.row0; w.row1 = g.row1;
     w.ya0 = held ? held_row_begin : 0; w.ya1 = held ? held_row_end : H;

@@ -433,8 +433,8 @@ def test_fused_2d_step_equals_ops_and_generic(fluid, case):
             if mode == "ops":
                 sim._simulate_ops(mconf, bd, None, "jacobi", float(mconf["dt"]), False)
             else:
-                if mode == "generic":
-                    os.environ["FNX_STEP2D"] = "0"
+                # the library picks by grid size (fused kernels from ~1 M cells): force each one here
+                os.environ["FNX_STEP2D"] = "0" if mode == "generic" else "1"
                 try:
                     sim._simulate_fused(mconf, bd, None, "jacobi", float(mconf["dt"]), False)
                 finally:
