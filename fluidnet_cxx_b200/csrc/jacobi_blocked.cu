@@ -327,9 +327,29 @@ int fnx_jacobi_2d_blocked(const float* flags, const float* div, const float* p_i
                                     tile_ws_bytes, st);
 }
 
+static int jacobi_2d_blocked_impl(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
+                                  double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
+                                  void* tile_ws, size_t tile_ws_bytes, int mask_mode, cudaStream_t st);
+
 int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
                                double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
                                void* tile_ws, size_t tile_ws_bytes, cudaStream_t st) {
+  return jacobi_2d_blocked_impl(flags, div, p_init, p, scratch, ssq, B, H, W, max_iter, row0, row1, ya0, ya1, tile_ws,
+                                tile_ws_bytes, 0, st);
+}
+
+// mask_mode 1: only compute the tile masks of this launch geometry into tile_ws (no iteration);
+// mask_mode 2: tile_ws already holds them (computed by a mask_mode-1 call with the same geometry): use, do not recompute
+int fnx_jacobi_2d_blocked_masks(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
+                                int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1, void* tile_ws,
+                                size_t tile_ws_bytes, int mask_mode, cudaStream_t st) {
+  return jacobi_2d_blocked_impl(flags, div, p_init, p, scratch, nullptr, B, H, W, max_iter, row0, row1, ya0, ya1, tile_ws,
+                                tile_ws_bytes, mask_mode, st);
+}
+
+static int jacobi_2d_blocked_impl(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
+                                  double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
+                                  void* tile_ws, size_t tile_ws_bytes, int mask_mode, cudaStream_t st) {
   if (row1 <= row0) { row0 = 0; row1 = H; }
   if (!(0 <= ya0 && ya0 <= row0 && row1 <= ya1 && ya1 <= H))
     return fnx_set_error(FNX_ERR_ARG, "jacobi_2d_blocked: rows [%d,%d) not inside the held rows [%d,%d) of %d", row0, row1,
@@ -362,15 +382,24 @@ int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float
   // tile masks once per solve (worth it from the second launch on)
   const size_t nthr = (size_t)grid.x * grid.y * grid.z * (tall ? 384 : 256);
   static const char* nopre = getenv("FNX_JACOBI_NO_TILEMASK");
-  const bool pre = nL >= 2 && tile_ws && tile_ws_bytes >= nthr * 20 + 256 && !(nopre && nopre[0] == '1');
+  const bool room = tile_ws && tile_ws_bytes >= nthr * 20 + 256;
+  if (mask_mode != 0 && !room) return fnx_set_error(FNX_ERR_WORKSPACE, "jacobi_2d_blocked: tile-mask buffer too small");
+  const bool pre = mask_mode != 0 || (nL >= 2 && room && !(nopre && nopre[0] == '1'));
   uint4* m4 = nullptr;
   unsigned* m1 = nullptr;
   if (pre) {
     m4 = reinterpret_cast<uint4*>(((uintptr_t)tile_ws + 15) & ~(uintptr_t)15);
     m1 = reinterpret_cast<unsigned*>(m4 + nthr);
-    if (tall) k_jacobi2d_tilemask<12><<<grid, 384, 0, st>>>(H, W, row0, ya0, ya1, vec_ok, flags, m4, m1);
-    else k_jacobi2d_tilemask<8><<<grid, 256, 0, st>>>(H, W, row0, ya0, ya1, vec_ok, flags, m4, m1);
-    fnx_count_launches(1);
+    if (mask_mode != 2) {
+      if (tall) k_jacobi2d_tilemask<12><<<grid, 384, 0, st>>>(H, W, row0, ya0, ya1, vec_ok, flags, m4, m1);
+      else k_jacobi2d_tilemask<8><<<grid, 256, 0, st>>>(H, W, row0, ya0, ya1, vec_ok, flags, m4, m1);
+      fnx_count_launches(1);
+    }
+    if (mask_mode == 1) {
+      cudaError_t e1 = cudaGetLastError();
+      if (e1 != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "jacobi_2d_blocked: %s", cudaGetErrorString(e1));
+      return FNX_OK;
+    }
   }
   int done = 0;
   for (int l = 0; l < nL; l++) {

@@ -476,6 +476,9 @@ int fnx_jacobi_2d_blocked_held(const float* flags, const float* div, const float
                                double* ssq, int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1,
                                void* tile_ws, size_t tile_ws_bytes, cudaStream_t st);  // jacobi_blocked.cu
 size_t fnx_jacobi_2d_tilemask_bytes(int B, int H, int W);  // jacobi_blocked.cu
+int fnx_jacobi_2d_blocked_masks(const float* flags, const float* div, const float* p_init, float* p, float* scratch,
+                                int B, int H, int W, int max_iter, int row0, int row1, int ya0, int ya1, void* tile_ws,
+                                size_t tile_ws_bytes, int mask_mode, cudaStream_t st);  // jacobi_blocked.cu
 
 
 // 3-D fixed iteration count: mask once, then the 4-cells-per-thread kernel (needs W % 4 == 0 and 16-byte
@@ -799,6 +802,26 @@ int fnx_jacobi_iterate_held(const float* flags, const float* div, const float* p
     return fnx_set_error(FNX_ERR_WORKSPACE, "jacobi_iterate_held: workspace too small");
   return fnx_jacobi_2d_blocked_held(flags, div, p_init, p, (float*)workspace, nullptr, B, H, W, iters, row_begin, row_end,
                                     held_row_begin, held_row_end, nullptr, 0, (cudaStream_t)stream);
+}
+
+// Tile masks of one launch geometry for fnx_jacobi_iterate_held_masked (the flags are static during a simulation:
+// a slab stepper computes them once per launch shape instead of decoding the flags in every launch).
+size_t fnx_jacobi_tilemask_bytes(int B, int rows, int W) { return fnx_jacobi_2d_tilemask_bytes(B, rows, W); }
+
+int fnx_jacobi_tilemask_held(const float* flags, int B, int H, int W, int row_begin, int row_end, int held_row_begin,
+                             int held_row_end, void* masks, size_t mask_bytes, void* stream) {
+  return fnx_jacobi_2d_blocked_masks(flags, flags, nullptr, nullptr, nullptr, B, H, W, 1, row_begin, row_end, held_row_begin,
+                                     held_row_end, masks, mask_bytes, 1, (cudaStream_t)stream);
+}
+
+// one launch (iters <= 8) with masks computed by fnx_jacobi_tilemask_held for the SAME (row_begin, row_end, held rows)
+int fnx_jacobi_iterate_held_masked(const float* flags, const float* div, const float* p_init, float* p, int B, int H, int W,
+                                   int iters, int row_begin, int row_end, int held_row_begin, int held_row_end,
+                                   const void* masks, size_t mask_bytes, void* stream) {
+  if (iters < 1 || iters > 8) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate_held_masked: 1..8 iterations per call");
+  if (p_init == p) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate_held_masked: p_init must not alias p");
+  return fnx_jacobi_2d_blocked_masks(flags, div, p_init, p, nullptr, B, H, W, iters, row_begin, row_end, held_row_begin,
+                                     held_row_end, const_cast<void*>(masks), mask_bytes, 2, (cudaStream_t)stream);
 }
 
 }  // extern "C"

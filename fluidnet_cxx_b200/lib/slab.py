@@ -240,6 +240,7 @@ class SlabJacobiStep:
         self.ws_j = torch.empty(Rh * W * 4 + 256, dtype=torch.uint8, device=dev)
         self._descs = []
         self._n_sites = 0
+        self._mask_cache = {}
         self._plans = [self._build_plan(par) for par in (0, 1)]
         self._graphs = [None, None]
         self.use_graph = bool(use_graph) and isinstance(topo, ProcessTopology)
@@ -313,9 +314,10 @@ class SlabJacobiStep:
             elif op[0] == "jacobi":
                 _, src, dst, it, r0, r1 = op
                 src_t, dst_t = (None if src is None else self.P[src]), self.P[dst]
-                phases.append(lambda src_t=src_t, dst_t=dst_t, it=it, r0=r0, r1=r1: N.check(lib.fnx_jacobi_iterate_held(
-                    N.ptr(self.flags), N.ptr(self.div), N.ptr(src_t), N.ptr(dst_t), 1, H, W, it, r0, r1, ya0, ya1,
-                    self.ws_j.data_ptr(), self.ws_j.numel(), st()), "slab jacobi"))
+                mk = self._tile_masks(r0, r1, ya0, ya1)
+                phases.append(lambda src_t=src_t, dst_t=dst_t, it=it, r0=r0, r1=r1, mk=mk: N.check(
+                    lib.fnx_jacobi_iterate_held_masked(N.ptr(self.flags), N.ptr(self.div), N.ptr(src_t), N.ptr(dst_t), 1, H, W,
+                                                       it, r0, r1, ya0, ya1, mk.data_ptr(), mk.numel(), st()), "slab jacobi"))
             else:
                 _, pbuf, lo, hi = op
                 p_final = self.P[pbuf]
@@ -323,6 +325,25 @@ class SlabJacobiStep:
                     N.ptr(p_final), N.ptr(U_out), N.ptr(self.flags), N.ptr(m["UBC"]), N.ptr(m["UBCInvMask"]), mrows, 1, 1, 1,
                     H, W, 0, lo, hi, ya0 if multi else 0, ya1 if multi else 0, st()), "slab project"))
         return dict(phases=phases, p=p_final)
+
+    def _tile_masks(self, r0, r1, ya0, ya1):
+        """per-thread Neumann / fixed-cell masks of the Jacobi launch that writes rows [r0, r1): the flags are static
+        during a simulation, so they are decoded once per launch shape (refresh_flags() after changing them)"""
+        key = (r0, r1, ya0, ya1)
+        mk = self._mask_cache.get(key)
+        if mk is None:
+            nbytes = self.lib.fnx_jacobi_tilemask_bytes(1, r1 - r0, self.W)
+            mk = torch.empty(nbytes, dtype=torch.uint8, device=self.flags.device)
+            self._mask_cache[key] = mk
+            N.check(self.lib.fnx_jacobi_tilemask_held(N.ptr(self.flags), 1, self.H, self.W, r0, r1, ya0, ya1, mk.data_ptr(),
+                                                      mk.numel(), N.stream_of(self.flags)), "slab tile masks")
+        return mk
+
+    def refresh_flags(self):
+        """call after writing new cell types into `self.flags` (obstacles moved): re-derives what depends on them"""
+        for (r0, r1, ya0, ya1), mk in self._mask_cache.items():
+            N.check(self.lib.fnx_jacobi_tilemask_held(N.ptr(self.flags), 1, self.H, self.W, r0, r1, ya0, ya1, mk.data_ptr(),
+                                                      mk.numel(), N.stream_of(self.flags)), "slab tile masks")
 
     def phases(self):
         return self._plans[self.parity]["phases"]

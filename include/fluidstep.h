@@ -90,6 +90,16 @@ int fnx_jacobi_iterate_held(const float *flags, const float *div, const float *p
                             int held_row_begin, int held_row_end, void *workspace,
                             size_t workspace_bytes, void *stream);
 
+/* the tile masks of one launch shape (flags are static during a simulation), and a launch (1..8 iterations) using them */
+size_t fnx_jacobi_tilemask_bytes(int B, int rows, int W);
+int fnx_jacobi_tilemask_held(const float *flags, int B, int H, int W, int row_begin, int row_end,
+                             int held_row_begin, int held_row_end, void *masks, size_t mask_bytes,
+                             void *stream);
+int fnx_jacobi_iterate_held_masked(const float *flags, const float *div, const float *p_init, float *p,
+                                   int B, int H, int W, int iters, int row_begin, int row_end,
+                                   int held_row_begin, int held_row_end, const void *masks,
+                                   size_t mask_bytes, void *stream);
+
 /* ---- halo exchange over NVLink peer memory (no reference counterpart: SURVEY.md section 8e) ----
  * One kernel per exchange: copy `count[k]` floats of each of `n_fields` fields from src[k][f] (this
  * GPU) to dst[k][f] (peer-mapped memory of neighbour k), then raise *flag_out[k] (in neighbour k's
