@@ -516,7 +516,7 @@ def run_distributed(args, name, scaling, guard, transport):
         net, mconf_net = load_scalenet(dev)
         m = dict(mconf_net); m.update(mconf); mconf = m
         net.mconf = mconf; net.scale.mconf = mconf
-    ghost = D.GHOST_CONVNET if wl["method"] == "convnet" else D.GHOST_JACOBI
+    ghost = (D.GHOST_CONVNET_3D if Dz > 1 else D.GHOST_CONVNET) if wl["method"] == "convnet" else D.GHOST_JACOBI
     axis = 2 if is3d else 3
     rows_owned = Dz if is3d else H
     if scaling == "strong":

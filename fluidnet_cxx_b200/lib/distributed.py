@@ -36,6 +36,11 @@ RA = 12
 CNN_REACH = 54 - 9
 GHOST_JACOBI = 48      # k = 32 iterations between pressure exchanges
 GHOST_CONVNET = 64
+# 3-D slabs along D with the slice-wise CNN projection (FluidNet.forward_fields_3d): the network itself does not couple
+# planes; only the 3-D divergence (planes k, k+1) and the z pressure gradient (k, k-1) do, so the CNN stage needs the
+# owned planes +- CNN3D_PLANES and the ghost width is RA + CNN3D_PLANES rounded up
+CNN3D_PLANES = 2
+GHOST_CONVNET_3D = 16
 
 
 def jacobi_chunk(ghost):
@@ -365,6 +370,8 @@ class CudaLocalOps:
         fluid.setConstVals(x, inv_mask, bc)
 
     def cnn(self, net, U, flags, scale):
+        if U.size(1) == 3:
+            return net.forward_fields_3d(U, flags, scale=scale)
         return net.forward_fields(U, flags, scale=scale)
 
 
@@ -411,7 +418,8 @@ def step_phases(mconf, bd, net, sim_method, decomp, ops, bufs):
             raise NotImplementedError("periodic seams across slabs are not implemented: the seam row lives on another "
                                       "rank (simulate.py:120-128); run periodic configurations on one GPU")
     if multi:
-        need = RA + (CNN_REACH if sim_method == 'convnet' else 1)
+        is3d_cnn = sim_method == 'convnet' and decomp.axis == 2
+        need = RA + (CNN3D_PLANES if is3d_cnn else (CNN_REACH if sim_method == 'convnet' else 1))
         if g < need:
             raise ValueError(f"ghost width {g} < {need} rows needed by the {sim_method} step")
     plane = bd['flags'].size(3) if decomp.axis == 2 else 1     # 3-D slabs along D: H rows per plane
@@ -449,10 +457,21 @@ def step_phases(mconf, bd, net, sim_method, decomp, ops, bufs):
         if multi:
             yield lambda: decomp.all_reduce(part)
         scale = _std_finish(decomp, part, decomp.owned(U).numel(), net.mconf['normalizeInputThreshold'])
-        # the CNN runs on a compact copy of the window (translation invariant), results go back in place
-        p_w, U_w = ops.cnn(net, decomp.window(U), decomp.window(bd['flags']), scale)
-        p = decomp.put_window(ops.p_buffer(bd['flags'], bd.get('p')), p_w)
-        U = decomp.put_window(U, U_w)
+        if decomp.axis == 2:
+            # 3-D, slice-wise projection: a compact copy of the owned planes +- CNN3D_PLANES (the first / last plane of
+            # the copy is treated as a border plane by the 3-D stencils: that only touches ghost planes)
+            c0 = max(decomp.lo - CNN3D_PLANES, decomp.r0)
+            c1 = min(decomp.hi + CNN3D_PLANES, decomp.r1)
+            sl = decomp._sl(c0, c1)
+            p_w, U_w = ops.cnn(net, U[sl].contiguous(), bd['flags'][sl].contiguous(), scale)
+            p = ops.p_buffer(bd['flags'], bd.get('p'))
+            p[sl] = p_w
+            U[sl] = U_w
+        else:
+            # the CNN runs on a compact copy of the window (translation invariant), results go back in place
+            p_w, U_w = ops.cnn(net, decomp.window(U), decomp.window(bd['flags']), scale)
+            p = decomp.put_window(ops.p_buffer(bd['flags'], bd.get('p')), p_w)
+            U = decomp.put_window(U, U_w)
         if 'UBC' in bd and 'UBCInvMask' in bd:
             ops.set_const(U, bd['UBCInvMask'], bd['UBC'])
         if 'densityBC' in bd and 'densityBCInvMask' in bd:

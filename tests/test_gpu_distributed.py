@@ -192,3 +192,62 @@ def test_graphed_stepper_single_rank(method):
                 err = float((stepper.state[k] - ref_bd[k]).abs().max() / ref_bd[k].abs().max())
                 assert err < 1e-5, (i, k, err)
     assert stepper.verify() == 0.0
+
+
+def test_virtual_ranks_convnet_3d_slicewise():
+    """BASELINE configs[4] as this package defines it (slice-wise CNN projection, parity unpinned): slabs along D,
+    two virtual ranks with the real kernels == the single-GPU 3-D convnet step (CNN tolerance)."""
+    from fluidnet_cxx_b200.lib import fluid
+    from fluidnet_cxx_b200.lib.distributed import GHOST_CONVNET_3D, SlabDecomposition, simulate_distributed
+    from fluidnet_cxx_b200.lib.pretrained import load_scalenet
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from test_gpu_parity import plume_mconf, plume_state
+    model, mconf_net = load_scalenet("cuda")
+    mconf = dict(mconf_net)
+    mconf.update(plume_mconf(simMethod="convnet"))
+    model.mconf = mconf
+    model.scale.mconf = mconf
+    D, res, world = 48, 40, 2
+    state = plume_state(fluid, res, mconf, depth=D)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    state["U"] = torch.randn(state["U"].shape, device="cuda", generator=g) * 0.3
+    state["density"] = torch.rand(state["density"].shape, device="cuda", generator=g)
+    ref_bd = {k: v.clone() for k, v in state.items()}
+    sim.clear_graph_cache()
+    ref = []
+    with torch.no_grad():
+        for _ in range(2):
+            sim._simulate_fused(mconf, ref_bd, model, "convnet", float(mconf["dt"]), False)
+            ref.append({k: ref_bd[k].clone() for k in ("p", "U", "density")})
+    comm = ThreadComm(world)
+    ops_cls = locked_ops()
+    results, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            torch.cuda.set_device(0)
+            dec = SlabDecomposition(D, GHOST_CONVNET_3D, rank=rank, world=world, comm=comm, axis=2)
+            ops = ops_cls()
+            bd = {k: dec.scatter(v) for k, v in state.items()}
+            outs = []
+            with torch.no_grad():
+                for _ in range(2):
+                    simulate_distributed(mconf, bd, model, "convnet", dec, ops=ops)
+                    outs.append({k: dec.gather(bd[k]) for k in ("p", "U", "density")})
+            results[rank] = outs
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+            comm.bar.abort()
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    got = results[0]
+    for i in range(2):
+        for k in ("p", "U", "density"):
+            err = float((got[i][k] - ref[i][k]).abs().max() / ref[i][k].abs().max())
+            assert err < 2e-5 * (i + 1), (i, k, err)
+
