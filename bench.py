@@ -575,7 +575,9 @@ def run_distributed(args, name, scaling, guard, transport):
     # pass 1 (value): the public stepper -- the step replayed as CUDA graphs when it is launch-bound;
     # pass 2 below re-issues it kernel by kernel for the roofline
     guard.beat(f"{tag}: stepper set-up / graph capture")
-    use_graph = window_cells <= (1 << 22) and os.environ.get("FLUIDNET_B200_GRAPHS", "1") != "0"
+    # (the 3-D slice-wise CNN step is thousands of small launches: launch-bound at any size)
+    graph_limit = (1 << 25) if (is3d and wl["method"] == "convnet") else (1 << 22)
+    use_graph = window_cells <= graph_limit and os.environ.get("FLUIDNET_B200_GRAPHS", "1") != "0"
     stepper = D.GraphedDistributedStep(mconf, bd, net, wl["method"], decomp, use_graph=use_graph)
     graphed = stepper.graphed
     guard.beat(f"{tag}: graph-vs-direct check")
