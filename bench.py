@@ -795,7 +795,7 @@ def run_distributed_slab(args, name, scaling, guard):
     barrier()
     graphed = step.capture()
     barrier()
-    reach = step.max_reach()
+    reach = step.check_reach()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

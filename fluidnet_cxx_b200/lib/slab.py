@@ -237,8 +237,7 @@ class SlabJacobiStep:
         self.mrows = self.sim._mask_rows(self.lib, self._bd, self.flags, 0)
         nbytes = self.lib.fnx_step_workspace(1, 1, Rh, W, 0)
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        self.ws_j = torch.empty(Rh * W * 4 + 256, dtype=torch.uint8, device=dev)
-        self._descs = []
+        self._descs, self._params = [], []      # ctypes objects the captured launches point at: kept alive here
         self._n_sites = 0
         self._mask_cache = {}
         self._plans = [self._build_plan(par) for par in (0, 1)]
@@ -306,7 +305,7 @@ class SlabJacobiStep:
                 prm.density_const_passes = 2
                 prm.row_begin, prm.row_end = op[1], op[2]
                 prm.held_row_begin, prm.held_row_end = (ya0, ya1) if multi else (0, 0)
-                self._keep_prm = getattr(self, "_keep_prm", []) + [prm]
+                self._params.append(prm)
                 phases.append(lambda prm=prm: N.check(lib.fnx_step_advect_forces_div(
                     ctypes.byref(prm), N.ptr(rho_in), N.ptr(U_in), N.ptr(self.flags), N.ptr(m["UBC"]),
                     N.ptr(m["UBCInvMask"]), N.ptr(m["densityBC"]), N.ptr(m["densityBCInvMask"]), mrows, N.ptr(rho_out),
@@ -394,9 +393,20 @@ class SlabJacobiStep:
     def held(self, name):
         return (self.U if name == "U" else self.rho)[self.parity]
 
+    MAX_REACH = 2.0     # cells per step the ghost width G = 8K + 8 leaves room for (the MacCormack stencil of a cell
+                        # that moves d cells reads about 2 ceil(d) rows beyond the window; tests/test_slab_cpu.py)
+
     def max_reach(self):
-        """max |U| dt over the owned rows (the ghost widths assume <= 1 cell per step)"""
+        """max |U| dt over the owned rows of this rank, in cells per step (a host synchronisation)"""
         return float(self.owned("U").abs().max()) * abs(float(self.mconf["dt"]))
+
+    def check_reach(self):
+        """raise if the velocity outruns the ghost rows (call it every few steps, not every step: it synchronises)"""
+        r = self.max_reach()
+        if not r <= self.MAX_REACH:
+            raise RuntimeError(f"slab step: max|U|*dt = {r:.3f} cells per step exceeds the {self.MAX_REACH} the ghost "
+                               f"rows are sized for; use a smaller dt")
+        return r
 
 
 def run_virtual(steppers, steps):
