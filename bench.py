@@ -472,6 +472,8 @@ def run_single(args, name, guard, local_rank=0, want_cpu_baseline=True):
     e2e_ms = e0.elapsed_time(e1)
 
     roof = build_roofline(wl, steps, cells, total_ms, stage_ms, layer_recs, rec_steps=nstage)
+    # every stage of the per-stage pass (advect+forces[+div] | pressure solve / CNN incl. its wrapper | project), ms per step
+    roof["stages_ms_per_step"] = {k: round(v / steps, 4) for k, v in stage_ms.items()}
     out = make_record(args, name, wl, 1, cells, cells, steps, warmup, total_ms, e2e_ms, e2e_steps, roof, h2d, d2h,
                       int(launches), clocks, t_wall, flush, graphed, "1 GPU", [D, H, W], args.scaling)
     del bd, host, out_host, flush_buf, masks

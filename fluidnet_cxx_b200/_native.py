@@ -118,6 +118,7 @@ SIGNATURES = {
     "fnx_tc_unpack_split": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "fnx_conv_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _I, _I, _P]),
     "fnx_msnet_workspace": (_S, [ctypes.POINTER(MsnetPlan), _I, _I]),
+    "fnx_msnet_workspace_n": (_S, [ctypes.POINTER(MsnetPlan), _I, _I, _I]),
     "fnx_msnet_workspace_init": (_I, [_P, _S, _P]),
     "fnx_msnet_forward": (_I, [ctypes.POINTER(MsnetPlan), _P, _P, _I, _I, _I, _P, _S, _P]),
     "fnx_profile_enable": (_I, [_I]),

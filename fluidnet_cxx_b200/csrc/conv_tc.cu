@@ -95,6 +95,11 @@ struct ConvArgs {
   // b % w_nrep, which spreads the (identical, simultaneous) weight fills of all SMs over more L2 lines
   int w_nrep;
   size_t w_rep_stride;
+  // A BATCH of images as one tall image: image n occupies rows [n*slice_pitch, n*slice_pitch + slice_h) of the H rows
+  // (slice_pitch = slice_h + 2*PAD: between two images lie the zero pad rows of both, which no kernel writes, so every
+  // image keeps its own zero padding).  One launch per layer for the whole batch; rows in the gaps are computed and
+  // dropped.  A single image is the case slice_h = H.
+  int slice_h, slice_pitch;
 };
 
 constexpr int NEPI = 8;                      // epilogue warps (two per TMEM lane quadrant)
@@ -365,7 +370,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
 #pragma unroll 1
       for (int r = 0; r < Rrt; r++) {
         const int y = y0 + r;
-        const bool ok = live && (y < a.H) && (px < a.W);
+        const int img = y / a.slice_pitch, yy = y - img * a.slice_pitch;   // image of the batch, row inside it
+        const bool ok = live && (y < a.H) && (px < a.W) && (yy < a.slice_h);
         mbar_wait(ACC_FULL(r), it & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
 #pragma unroll
               for (int i = 0; i < 16; i++)
                 if (c0 + i < a.Cout) {
-                  yf[((size_t)(a.y_coff + c0 + i) * a.H + y) * a.W + px] = f[i];
+                  yf[((size_t)(img * a.y_ctotal + a.y_coff + c0 + i) * a.slice_h + yy) * a.W + px] = f[i];   // (N, C, h, W)
                   amax = fmaxf(amax, fabsf(f[i]));
                 }
             } else {  // fused 1x1 head over the (<= 16) channels of this single column group
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvArgs a) {
               for (int i = 0; i < 16; i++)
                 if (i < a.Cout) hsum = fmaf(__ldg(a.head_w + i), f[i], hsum);
               hsum += __ldg(a.head_b);
-              reinterpret_cast<float*>(a.y)[(size_t)y * a.W + px] = hsum;
+              reinterpret_cast<float*>(a.y)[((size_t)img * a.slice_h + yy) * a.W + px] = hsum;                  // (N, 1, h, W)
               amax = fmaxf(amax, fabsf(hsum));
             }
           }
@@ -498,14 +504,18 @@ __device__ __forceinline__ float bilinear_at(const float* __restrict__ p, int H,
 __global__ void __launch_bounds__(256)
     k_pyramid_input(const float* __restrict__ x, int C, int H, int W, const ActMeta* __restrict__ x_meta,
                     const float* __restrict__ o, int hc, int wc, const ActMeta* __restrict__ o_meta, int h, int w,
-                    __half* __restrict__ y, size_t y_plane, ActMeta* __restrict__ out_meta) {
-  const int Hp = h + 2 * PAD, Wp = w + 2 * PAD;
+                    __half* __restrict__ y, size_t y_plane, ActMeta* __restrict__ out_meta, int nimg) {
+  // blockIdx.y = image of the batch: its rows start at img * (h + 2 PAD) of the tall split image
+  const int img = blockIdx.y;
+  x += (size_t)img * C * H * W;
+  if (o) o += (size_t)img * hc * wc;
+  const int Hp = nimg * (h + 2 * PAD), Wp = w + 2 * PAD;
   const size_t npix = (size_t)h * w;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   float bound = __uint_as_float(x_meta->amax_bits);
   if (o) bound = fmaxf(bound, __uint_as_float(o_meta->amax_bits));
   const float s = pow2_scale_for(bound);
-  if (e == 0) {
+  if (e == 0 && img == 0) {
     out_meta->scale = s;
     out_meta->amax_bits = __float_as_uint(bound);
   }
@@ -526,7 +536,7 @@ __global__ void __launch_bounds__(256)
     hi[i] = __halves2half2(h0, h1);
     lo[i] = __halves2half2(__float2half_rn(u0 - __half2float(h0)), __float2half_rn(u1 - __half2float(h1)));
   }
-  const size_t off = (((size_t)0 * Hp + (py + PAD)) * Wp + (px + PAD)) * 8;   // chunk 0; chunk 1 stays zero
+  const size_t off = (((size_t)0 * Hp + (img * (h + 2 * PAD) + py + PAD)) * Wp + (px + PAD)) * 8;   // chunk 0; chunk 1 stays zero
   *reinterpret_cast<uint4*>(y + off) = *reinterpret_cast<const uint4*>(hi);
   *reinterpret_cast<uint4*>(y + y_plane + off) = *reinterpret_cast<const uint4*>(lo);
 }
@@ -755,7 +765,7 @@ int fnx_tc_unpack_split(const void* x, const fnx_act_meta* meta, int C, int H, i
 static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin,
                           int Cout, int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max,
                           int out_mode, void* y, fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset,
-                          const float* head_w, const float* head_b, int w_nrep, void* stream);
+                          const float* head_w, const float* head_b, int w_nrep, void* stream, int nimg = 1);
 
 int fnx_conv_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin, int Cout,
                 int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max, int out_mode, void* y,
@@ -768,7 +778,10 @@ int fnx_conv_tc(const void* x, const fnx_act_meta* in_meta, const void* w_packed
 static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void* w_packed, const float* bias, int Cin,
                           int Cout, int ksize, int H, int W, int relu, float w_scale, float w_norm, float b_max,
                           int out_mode, void* y, fnx_act_meta* out_meta, int y_channels_total, int y_channel_offset,
-                          const float* head_w, const float* head_b, int w_nrep, void* stream) {
+                          const float* head_w, const float* head_b, int w_nrep, void* stream, int nimg) {
+  // nimg images of H rows each, stacked as one tall image of nimg * (H + 2 PAD) - 2 PAD rows (see ConvArgs)
+  const int slice_h = H;
+  H = nimg * (H + 2 * PAD) - 2 * PAD;
   if (!tc_eligible(Cin, Cout, ksize))
     return fnx_set_error(FNX_ERR_ARG, "conv_tc: unsupported layer %d->%d k%d", Cin, Cout, ksize);
   if (H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "conv_tc: bad shape");
@@ -795,6 +808,7 @@ static int conv_tc_launch(const void* x, const fnx_act_meta* in_meta, const void
   a.relu = relu; a.out_mode = out_mode; a.y_ctotal = y_channels_total; a.y_coff = y_channel_offset;
   a.w_scale = w_scale; a.w_norm = w_norm; a.b_max = b_max;
   a.tiles_x = 0; a.nblocks = 0; a.R = 1; a.iters = 0; a.dbg = nullptr;
+  a.slice_h = slice_h; a.slice_pitch = slice_h + 2 * PAD;
   cudaStream_t st = (cudaStream_t)stream;
   const int cp = cout_pad(Cout);
   if (ksize == 3) {
@@ -882,6 +896,8 @@ struct Runner {
   Bump ws;
   bool dry;
   cudaStream_t st;
+  int nimg = 1;   // images per forward (tensor-core plan: the whole batch in one launch per layer, as a tall image)
+  int tall(int h) const { return nimg * (h + 2 * PAD) - 2 * PAD; }
   int nmeta = 0;
   ActMeta* metas;
   ActMeta* new_meta() { return metas ? metas + (nmeta++ % MAX_META) : (nmeta++, nullptr); }
@@ -910,38 +926,40 @@ struct Runner {
             cur_meta = new_meta();
             if (!dry) { int rc = fnx_tc_amax(cur_f32, (size_t)l.cin * h * w, (fnx_act_meta*)cur_meta, st); if (rc) return rc; }
           }
+          if (nimg != 1) return fnx_set_error(FNX_ERR_ARG, "msnet: a batched forward needs the all-tensor-core plan");
           void* sp = ws.take(fnx_tc_act_bytes(l.cin, h, w));
           ActMeta* m = new_meta();
           if (!dry) { int rc = fnx_tc_pack_split(cur_f32, l.cin, h, w, (fnx_act_meta*)cur_meta, sp, (fnx_act_meta*)m, st); if (rc) return rc; }
           cur_split = sp; cur_meta = m; is_split = true;
         }
         if (tc_next) {
-          void* sp = ws.take(fnx_tc_act_bytes(l.cout, h, w));
+          void* sp = ws.take(fnx_tc_act_bytes(l.cout, tall(h), w));
           ActMeta* m = new_meta();
           if (!dry) {
-            LayerTimer lt(l, h, w, 1, st);
+            LayerTimer lt(l, h * nimg, w, 1, st);   // (a batched launch: the rows of all its images)
             int rc = conv_tc_launch(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu,
                                     l.w_scale, l.w_norm, l.b_max, 0, sp, (fnx_act_meta*)m, 0, 0, nullptr, nullptr,
-                                    l.w_replicas, st);
+                                    l.w_replicas, st, nimg);
             if (rc) return rc;
           }
           cur_split = sp; cur_meta = m; cur_f32 = nullptr; is_split = true;
         } else {
           const bool fuse_head = last && head != nullptr;
-          float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
+          float* o = last ? out : (float*)ws.take((size_t)nimg * l.cout * h * w * 4);
           if (!dry) {
-            LayerTimer lt(l, h, w, 1, st);
+            LayerTimer lt(l, h * nimg, w, 1, st);
             int rc = conv_tc_launch(cur_split, (fnx_act_meta*)cur_meta, l.w_tc, l.bias, l.cin, l.cout, l.ksize, h, w, l.relu,
                                     l.w_scale, l.w_norm, l.b_max, fuse_head ? 2 : 1, o,
                                     (fnx_act_meta*)(last ? last_meta : nullptr), last ? out_ctotal : l.cout,
                                     last ? out_coff : 0, fuse_head ? head->weight : nullptr,
-                                    fuse_head ? head->bias : nullptr, l.w_replicas, st);
+                                    fuse_head ? head->bias : nullptr, l.w_replicas, st, nimg);
             if (rc) return rc;
           }
           cur_f32 = o; cur_split = nullptr; cur_meta = nullptr; is_split = false;
         }
       } else {
         if (is_split) return fnx_set_error(FNX_ERR_ARG, "msnet: internal layout mismatch");
+        if (nimg != 1) return fnx_set_error(FNX_ERR_ARG, "msnet: a batched forward needs the all-tensor-core plan");
         float* o = last ? out : (float*)ws.take((size_t)l.cout * h * w * 4);
         ActMeta* m = tc_next ? new_meta() : (last ? last_meta : nullptr);
         if (!dry) {
@@ -959,12 +977,12 @@ struct Runner {
   // input of one pyramid level in the split chunked layout (k_pyramid_input)
   int pyramid_input(const float* x, int c, int H, int W, ActMeta* x_meta, const float* o, int hc, int wc, ActMeta* o_meta,
                     int h, int w, void** split_out, ActMeta** meta_out) {
-    void* sp = ws.take(fnx_tc_act_bytes(16, h, w));
+    void* sp = ws.take(fnx_tc_act_bytes(16, tall(h), w));
     ActMeta* m = new_meta();
     if (!dry) {
       const size_t npix = (size_t)h * w;
-      k_pyramid_input<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(x, c, H, W, x_meta, o, hc, wc, o_meta, h, w, (__half*)sp,
-                                                                     act_plane_halves(16, h, w), m);
+      k_pyramid_input<<<dim3((unsigned)((npix + 255) / 256), (unsigned)nimg), 256, 0, st>>>(
+          x, c, H, W, x_meta, o, hc, wc, o_meta, h, w, (__half*)sp, act_plane_halves(16, tall(h), w), m, nimg);
       fnx_count_launches(1);
       FNX_CUDA_TRY("msnet", cudaGetLastError());
     }
@@ -985,23 +1003,25 @@ struct Runner {
     const fnx_conv_layer& fin = plan->final_conv;
     const bool fuse_head = is_tc(lastf) && lastf.cout <= 16 && fin.ksize == 1 && fin.cin == lastf.cout && fin.cout == 1 &&
                            !fin.relu;
-    float* o4 = (float*)ws.take((size_t)h4 * w4 * 4);
-    float* o2 = (float*)ws.take((size_t)h2 * w2 * 4);
-    float* o1 = fuse_head ? nullptr : (float*)ws.take((size_t)lastf.cout * H * W * 4);
+    float* o4 = (float*)ws.take((size_t)nimg * h4 * w4 * 4);
+    float* o2 = (float*)ws.take((size_t)nimg * h2 * w2 * 4);
+    float* o1 = fuse_head ? nullptr : (float*)ws.take((size_t)nimg * lastf.cout * H * W * 4);
     if (is_tc(plan->quarter[0]) && is_tc(plan->half[0]) && is_tc(plan->full[0]) && c + 1 <= 8) {
       // tensor-core plan: every level's input goes straight into the split layout
       ActMeta *mx = new_meta(), *mo4 = new_meta(), *mo2 = new_meta(), *m;
       void* sp;
-      if (!dry && (rc = fnx_tc_amax(x, (size_t)c * H * W, (fnx_act_meta*)mx, st))) return rc;
+      if (!dry && (rc = fnx_tc_amax(x, (size_t)nimg * c * H * W, (fnx_act_meta*)mx, st))) return rc;
       if ((rc = pyramid_input(x, c, H, W, mx, nullptr, 0, 0, nullptr, h4, w4, &sp, &m))) return rc;
       if ((rc = block(plan->quarter, 4, nullptr, sp, m, true, h4, w4, o4, 1, 0, mo4))) return rc;
       if ((rc = pyramid_input(x, c, H, W, mx, o4, h4, w4, mo4, h2, w2, &sp, &m))) return rc;
       if ((rc = block(plan->half, 6, nullptr, sp, m, true, h2, w2, o2, 1, 0, mo2))) return rc;
       if ((rc = pyramid_input(x, c, H, W, mx, o2, h2, w2, mo2, H, W, &sp, &m))) return rc;
       if (fuse_head) return block(plan->full, 6, nullptr, sp, m, true, H, W, y, 1, 0, nullptr, &fin);
+      if (nimg != 1) return fnx_set_error(FNX_ERR_ARG, "msnet: a batched forward needs the fused 1x1 head");
       if ((rc = block(plan->full, 6, nullptr, sp, m, true, H, W, o1, lastf.cout, 0))) return rc;
       return block(&fin, 1, o1, nullptr, nullptr, false, H, W, y, 1, 0);
     }
+    if (nimg != 1) return fnx_set_error(FNX_ERR_ARG, "msnet: a batched forward needs the all-tensor-core plan");
     float* x4 = (float*)ws.take((size_t)c * h4 * w4 * 4);
     float* in2 = (float*)ws.take((size_t)(c + 1) * h2 * w2 * 4);
     float* in1 = (float*)ws.take((size_t)(c + 1) * H * W * 4);
@@ -1021,8 +1041,37 @@ struct Runner {
 };
 }  // namespace
 
-size_t fnx_msnet_workspace(const fnx_msnet_plan* plan, int H, int W) {
+// can the whole batch go through one launch per layer?  (the plan a shipped ScaleNet gets: every layer on the
+// tensor cores, pyramid inputs written straight in the split layout, the 1x1 head fused)
+static bool batchable(const fnx_msnet_plan* plan) {
+  const fnx_conv_layer& lastf = plan->full[5];
+  const fnx_conv_layer& fin = plan->final_conv;
+  auto tc = [](const fnx_conv_layer& l) { return l.w_tc && tc_eligible(l.cin, l.cout, l.ksize); };
+  for (int i = 0; i < 4; i++) if (!tc(plan->quarter[i])) return false;
+  for (int i = 0; i < 6; i++) if (!tc(plan->half[i]) || !tc(plan->full[i])) return false;
+  return plan->data_channels + 1 <= 8 && lastf.cout <= 16 && fin.ksize == 1 && fin.cin == lastf.cout && fin.cout == 1 && !fin.relu;
+}
+
+// Images per launch of a batched forward: the largest divisor of N up to FNX_MSNET_GROUP_MAX.  (Every group must
+// have the same size: the chunk stride of the split layout -- hence where the zero pad rows live -- depends on it.
+// 72 images of 256^2 keep the workspace near 8 GB; a group is already one launch per layer for 72 images.)
+#ifndef FNX_MSNET_GROUP_MAX
+#define FNX_MSNET_GROUP_MAX 72
+#endif
+static int batch_group(const fnx_msnet_plan* plan, int N) {
+  if (N <= 1 || !batchable(plan)) return 1;
+  int g = 1;
+  for (int d = 1; d <= N && d <= FNX_MSNET_GROUP_MAX; d++)
+    if (N % d == 0) g = d;
+  return g;
+}
+
+size_t fnx_msnet_workspace(const fnx_msnet_plan* plan, int H, int W) { return fnx_msnet_workspace_n(plan, 1, H, W); }
+
+size_t fnx_msnet_workspace_n(const fnx_msnet_plan* plan, int N, int H, int W) {
+  if (!plan || N < 1) return 0;
   Runner r{plan, Bump{nullptr}, true, nullptr};
+  r.nimg = batch_group(plan, N);
   if (r.forward_one(nullptr, nullptr, H, W) != FNX_OK) return 0;
   return r.ws.off + 4096;
 }
@@ -1035,11 +1084,22 @@ int fnx_msnet_workspace_init(void* workspace, size_t workspace_bytes, void* stre
 int fnx_msnet_forward(const fnx_msnet_plan* plan, const float* x, float* y, int N, int H, int W, void* workspace,
                       size_t workspace_bytes, void* stream) {
   if (!plan || N < 1 || H < 1 || W < 1) return fnx_set_error(FNX_ERR_ARG, "msnet_forward: bad arguments");
-  const size_t need = fnx_msnet_workspace(plan, H, W);
+  const size_t need = fnx_msnet_workspace_n(plan, N, H, W);
   if (need == 0) return FNX_ERR_ARG;
   if (!workspace || workspace_bytes < need)
     return fnx_set_error(FNX_ERR_WORKSPACE, "msnet_forward: workspace %zu < %zu bytes", workspace_bytes, need);
   const int c = plan->data_channels;
+  const int group = batch_group(plan, N);
+  if (group > 1) {
+    // groups of images as one tall image each: one launch per layer and group (activation scales shared by a group)
+    for (int n = 0; n < N; n += group) {
+      Runner r{plan, Bump{(uint8_t*)workspace}, false, (cudaStream_t)stream};
+      r.nimg = group;
+      int rc = r.forward_one(x + (size_t)n * c * H * W, y + (size_t)n * H * W, H, W);
+      if (rc) return rc;
+    }
+    return FNX_OK;
+  }
   for (int n = 0; n < N; n++) {
     Runner r{plan, Bump{(uint8_t*)workspace}, false, (cudaStream_t)stream};
     int rc = r.forward_one(x + (size_t)n * c * H * W, y + (size_t)n * H * W, H, W);

@@ -143,12 +143,12 @@ class MultiScaleNet(nn.Module):
         # one workspace per (resolution, stream): simulations on different streams never share activations.  A
         # CUDA-graph capture (its own stream) re-uses the workspace of the eager warm-up call that precedes it --
         # zero-filling a fresh one would put the memset of the whole workspace into every replay.
-        wkey = (h, w, st)
+        wkey = (n, h, w, st)
         ws = cache["ws"].get(wkey)
         if ws is None and torch.cuda.is_current_stream_capturing():
-            ws = next((v for k, v in cache["ws"].items() if k[:2] == (h, w)), None)
+            ws = next((v for k, v in cache["ws"].items() if k[:3] == (n, h, w)), None)
         if ws is None:
-            nbytes = lib.fnx_msnet_workspace(ctypes.byref(plan), h, w)
+            nbytes = lib.fnx_msnet_workspace_n(ctypes.byref(plan), n, h, w)
             if nbytes == 0:
                 N.check(-1, "MultiScaleNet.workspace")
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)

@@ -285,6 +285,9 @@ typedef struct fnx_msnet_plan {
   fnx_conv_layer quarter[4], half[6], full[6], final_conv;
 } fnx_msnet_plan;
 size_t fnx_msnet_workspace(const fnx_msnet_plan *plan, int H, int W);
+/* workspace of a forward over N images: with the all-tensor-core plan the batch runs as ONE launch per layer (the
+ * images stacked into a tall image, each keeping its own zero padding; activation scales shared by the batch) */
+size_t fnx_msnet_workspace_n(const fnx_msnet_plan *plan, int N, int H, int W);
 int fnx_msnet_workspace_init(void *workspace, size_t workspace_bytes, void *stream);
 int fnx_msnet_forward(const fnx_msnet_plan *plan, const float *x, float *y, int N, int H, int W,
                       void *workspace, size_t workspace_bytes, void *stream);

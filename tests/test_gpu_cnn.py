@@ -491,3 +491,28 @@ def test_slicewise_3d_step_fused_graph_ops_agree(net):
         sim.clear_graph_cache()
         model.mconf = old
         model.scale.mconf = old
+
+
+@pytest.mark.parametrize("n,hw", [(6, (72, 88)), (5, (40, 130)), (80, (32, 32))])
+def test_msnet_batched_forward_equals_per_image(net, n, hw):
+    """A batch goes through ONE launch per layer (the images stacked into a tall image, each with its own zero
+    padding; groups of <= 72 images): same result as image-by-image forwards up to the fp16-expansion scales, which
+    a group shares (1e-5 relative), and the tall layout must not leak one image into the next."""
+    model, _ = net
+    msn = model.multiScale
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn(n, 2, *hw, device="cuda", generator=g)
+    x[:, 1] = (x[:, 1] > 0.8).float()
+    x[1] *= 3.0                                    # different magnitudes inside one batch
+    with torch.no_grad():
+        yb = msn(x)
+        ys = torch.cat([msn(x[i:i + 1].contiguous()) for i in range(n)], 0)
+    assert yb.shape == ys.shape == (n, 1, *hw)
+    for i in range(n):
+        assert rel_err(yb[i].cpu().numpy(), ys[i].cpu().numpy()) < RTOL, i
+    # no leakage: changing image 0 leaves the other images' outputs bit-identical
+    x2 = x.clone()
+    x2[0] = torch.randn(2, *hw, device="cuda", generator=g) * 0.5      # smaller than the batch maximum: same scales
+    with torch.no_grad():
+        yb2 = msn(x2)
+    assert torch.equal(yb2[1:], yb[1:])
