@@ -82,6 +82,7 @@ SIGNATURES = {
     "fnx_jacobi_workspace": (_S, [_I, _I, _I, _I, _I]),
     "fnx_solve_linear_system_jacobi": (_I, [_P, _P, _P, _P] + _GRID + [_F, _I, ctypes.POINTER(_I), _P, _S, _P]),
     "fnx_jacobi_iterate": (_I, [_P, _P, _P, _P] + _GRID + [_I, _I, _I, _P, _S, _P]),
+    "fnx_jacobi_iterate_resid": (_I, [_P, _P, _P, _P] + _GRID + [_I, _I, _I, _I, _I, _P, _P, _S, _P]),
     "fnx_step_project_bcs_rows": (_I, [_P] * 6 + [_I] + _GRID + [_I, _I, _P]),
     "fnx_jacobi_iterate_held": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _S, _P]),
     "fnx_jacobi_tilemask_bytes": (_S, [_I, _I, _I]),

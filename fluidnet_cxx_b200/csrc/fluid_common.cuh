@@ -27,6 +27,7 @@ struct Grid {
   long long n;   // cells per batch item = D*H*W
   int row0, row1;  // rows of the flattened (D*H) row space the one-thread-per-cell kernels process
                    // (whole grid by default; a slab window in the domain-decomposed step)
+  int own0, own1;  // rows that count in a residual sum (whole grid by default; a slab's OWNED rows otherwise)
 };
 
 __host__ __device__ inline Grid make_grid(int B, int D, int H, int W) {
@@ -36,6 +37,7 @@ __host__ __device__ inline Grid make_grid(int B, int D, int H, int W) {
   g.sz = (long long)H * W;
   g.n = (long long)D * H * W;
   g.row0 = 0; g.row1 = D * H;
+  g.own0 = 0; g.own1 = D * H;
   return g;
 }
 

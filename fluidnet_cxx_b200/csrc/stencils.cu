@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(kBX* kBY)
     }
     cur[c.o] = pn;
     const float d = pn - pC;
-    d2 = d * d;
+    const int row = c.k * g.H + c.j;
+    d2 = (row >= g.own0 && row < g.own1) ? d * d : 0.f;
   }
   if (RESID) {
     // block reduction of sum((p - p_prev)^2) in double, one atomic per block
@@ -785,6 +786,41 @@ int fnx_jacobi_iterate(const float* flags, const float* div, const float* p_init
     fnx_count_launches(1);
   }
   FNX_LAUNCH_CHECK("jacobi_iterate", 0);
+  return FNX_OK;
+}
+
+// Residual-terminated Jacobi across slabs (fluids_init.cpp:958-990 evaluates max_b ||p - p_prev||_2 after EVERY
+// iteration): `iters` single-iteration launches continued from p_init, rows [row_begin, row_end) written, and
+// ssq[it * B + b] = sum over the rows [own_begin, own_end) of (p_it - p_{it-1})^2 -- this rank's share of iteration
+// it's squared residual.  The caller all-reduces (sum) the iters x B vector, takes sqrt and the max over b, and finds
+// the iteration the single-GPU solver stops at; nothing here synchronises.
+int fnx_jacobi_iterate_resid(const float* flags, const float* div, const float* p_init, float* p, int B, int D, int H,
+                             int W, int is3d, int iters, int row_begin, int row_end, int own_begin, int own_end,
+                             double* ssq, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "jacobi_iterate_resid")) return e;
+  if (iters < 1) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate_resid: At least 1 iteration of the solver is needed.");
+  if (p_init == p) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate_resid: p_init must not alias p");
+  if (!ssq) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate_resid: ssq is NULL");
+  const size_t n = (size_t)B * D * H * W;
+  if (!workspace || workspace_bytes < n * sizeof(float))
+    return fnx_set_error(FNX_ERR_WORKSPACE, "jacobi_iterate_resid: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = make_grid(B, D, H, W);
+  if (row_end > row_begin) {
+    if (row_begin < 0 || row_end > D * H) return fnx_set_error(FNX_ERR_ARG, "jacobi_iterate_resid: row window out of range");
+    g.row0 = row_begin; g.row1 = row_end;
+  }
+  if (own_end > own_begin) { g.own0 = own_begin; g.own1 = own_end; }
+  cudaError_t ce = cudaMemsetAsync(ssq, 0, (size_t)iters * B * sizeof(double), st);
+  if (ce != cudaSuccess) return fnx_set_error(FNX_ERR_CUDA, "jacobi_iterate_resid: %s", cudaGetErrorString(ce));
+  float* scratch = (float*)workspace;
+  auto wbuf = [&](int it) { return ((iters - 1 - it) % 2 == 0) ? p : scratch; };
+  for (int it = 0; it < iters; it++) {
+    const float* prev = it == 0 ? p_init : wbuf(it - 1);
+    if (is3d) launch_jacobi_iter<true>(g, prev == nullptr, true, flags, div, prev, wbuf(it), ssq + (size_t)it * B, nullptr, st);
+    else launch_jacobi_iter<false>(g, prev == nullptr, true, flags, div, prev, wbuf(it), ssq + (size_t)it * B, nullptr, st);
+  }
+  FNX_LAUNCH_CHECK("jacobi_iterate_resid", iters);
   return FNX_OK;
 }
 

@@ -348,6 +348,19 @@ class CudaLocalOps:
                                        N.stream_of(flags)), "simulate_distributed")
         return p
 
+    def jacobi_resid(self, flags, div, p_init, iters, rows, own):
+        """`iters` iterations, one per launch; returns p and this rank's (iters, B) sums over its OWNED rows of
+        (p_it - p_{it-1})^2 (float64, device)."""
+        N, lib = self.N, self.lib
+        B, D, H, W = N.grid_of(flags)
+        p = self._out("p", flags, (p_init,))
+        ssq = torch.empty((iters, B), dtype=torch.float64, device=flags.device)
+        ws = N.workspaces.get(flags.device, "jacobi", lib.fnx_jacobi_workspace(B, D, H, W, iters))
+        N.check(lib.fnx_jacobi_iterate_resid(N.ptr(flags), N.ptr(div), N.ptr(p_init), N.ptr(p), B, D, H, W, int(D > 1),
+                                             int(iters), rows[0], rows[1], own[0], own[1], ssq.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), N.stream_of(flags)), "simulate_distributed")
+        return p, ssq
+
     def project(self, p, U, bd, rows):
         N, sim, lib = self.N, self.sim, self.lib
         flags = bd['flags']
@@ -369,10 +382,10 @@ class CudaLocalOps:
         from . import fluid
         fluid.setConstVals(x, inv_mask, bc)
 
-    def cnn(self, net, U, flags, scale):
+    def cnn(self, net, U, flags, scale, prewall=False):
         if U.size(1) == 3:
             return net.forward_fields_3d(U, flags, scale=scale)
-        return net.forward_fields(U, flags, scale=scale)
+        return net.forward_fields(U, flags, scale=scale, prewall=prewall)
 
 
 def _std_partial(decomp, U):
@@ -387,6 +400,24 @@ def _std_finish(decomp, part, owned_count, threshold):
     var = (part[1] - part[0] * part[0] / n) / (n - 1.0)
     s = torch.sqrt(torch.clamp(var, min=0.0)).float().clamp(min=float(threshold))
     return s.view(1, 1, 1, 1, 1)
+
+
+def _seam_y(decomp, U, src_row, multi):
+    """U[:, 0, :, 1] = <row H-1 of component 0 of the seam's source field> (the periodic-y seam of the saved model;
+    component 0 as the reference writes it) across slabs: row H-1 is owned by the last rank -- `src_row` is that
+    (B, D, W) line there and ignored elsewhere -- and row 1 is held by every rank whose window starts at row 0 or 1.
+    The line travels as its int32 bit pattern through an all-reduce(sum) in which every other rank contributes
+    zeros, so the copy is exact (-0.0 included).  A generator like step_phases: yields the communication."""
+    H = decomp.H
+    if not multi:
+        U[:, 0, :, 1] = src_row
+        return
+    row = torch.zeros(U[:, 0, :, 0].shape, dtype=torch.int32, device=U.device)
+    if decomp.lo <= H - 1 < decomp.hi:
+        row.copy_(src_row.contiguous().view(torch.int32))
+    yield lambda: decomp.all_reduce(row)
+    if decomp.r0 <= 1 < decomp.r1:
+        U[:, 0, :, 1] = row.view(torch.float32)
 
 
 def check_reach(decomp, U_local, dt):
@@ -413,10 +444,20 @@ def step_phases(mconf, bd, net, sim_method, decomp, ops, bufs):
     if bd['U'].size(0) != 1:
         raise NotImplementedError("the slab-decomposed step handles one simulation per call (B = 1): the ScaleNet "
                                   "normalisation is reduced over the whole batch tensor")
-    for conf in (mconf, getattr(net, 'mconf', None) or {}):
-        if multi and (conf.get('periodic-x') or conf.get('periodic-y')):
-            raise NotImplementedError("periodic seams across slabs are not implemented: the seam row lives on another "
-                                      "rank (simulate.py:120-128); run periodic configurations on one GPU")
+    # periodic seams (Rayleigh-Taylor: periodic-y).  The ScaleNet model copies one line of U before the network and
+    # one line of the pre-setWallBcs result after it (*_saved.py:123-132, 228-237).  periodic-x copies a column: local
+    # to every row.  periodic-y copies row H-1 into row 1: across slabs the source row lives on the LAST rank and
+    # the target on every rank whose window holds row 1 -- `_seam_y` moves it.  The Jacobi step's seam
+    # (simulate.py:120-128, twice per step around setWallBcs inside the fused kernels) stays single-GPU.
+    net_conf = getattr(net, 'mconf', None) or {}
+    per = sim_method == 'convnet' and 'periodic-x' in net_conf and 'periodic-y' in net_conf
+    per_x, per_y = bool(per and net_conf['periodic-x']), bool(per and net_conf['periodic-y'])
+    if sim_method == 'jacobi' and multi and (mconf.get('periodic-x') or mconf.get('periodic-y')):
+        raise NotImplementedError("the Jacobi step's periodic seam across slabs is not implemented (simulate.py:120-128 "
+                                  "copies it around setWallBcs, which the fused kernels apply in place); run it on one "
+                                  "GPU, or use the ScaleNet projection")
+    if (per_x or per_y) and decomp.axis != 3:
+        raise NotImplementedError("periodic seams are defined for the 2-D model only (model.py:93)")
     if multi:
         is3d_cnn = sim_method == 'convnet' and decomp.axis == 2
         need = RA + (CNN3D_PLANES if is3d_cnn else (CNN_REACH if sim_method == 'convnet' else 1))
@@ -439,6 +480,8 @@ def step_phases(mconf, bd, net, sim_method, decomp, ops, bufs):
         k = jacobi_chunk(g) if multi else iters
         p, done = None, 0
         pb = bufs.setdefault('p', {})
+        p_tol = float(mconf.get('pTol', 0.0))
+        own = (decomp.lo * plane, decomp.hi * plane)
         while done < iters:
             n = min(k, iters - done)
             if done > 0:
@@ -448,11 +491,35 @@ def step_phases(mconf, bd, net, sim_method, decomp, ops, bufs):
                 else:
                     yield lambda: decomp.transfer(pb, "p")
                 decomp.unpack([p], pb, "p")
-            p = ops.jacobi(bd['flags'], div, p, n, rows)
+            if p_tol > 0:
+                # residual-terminated (fluids_init.cpp:958-990: max_b ||p - p_prev||_2 < p_tol, tested after every
+                # iteration): every rank sums its owned rows per iteration, one all-reduce(sum) per chunk of n
+                # iterations, and the chunk is redone up to the stopping iteration when that falls inside it --
+                # the iteration count, hence p, is the single-GPU solver's.  Reads the result on the host (as the
+                # reference does every iteration): this path is not graph-captured.
+                p_start = p
+                p, ssq = ops.jacobi_resid(bd['flags'], div, p_start, n, rows, own)
+                if multi:
+                    yield lambda: decomp.all_reduce(ssq)
+                r = ssq.sqrt().to(torch.float32).max(dim=1).values
+                below = (r < torch.tensor(p_tol, dtype=torch.float32)).nonzero()
+                if below.numel():
+                    hit = int(below[0])
+                    if hit < n - 1:
+                        p, _ = ops.jacobi_resid(bd['flags'], div, p_start, hit + 1, rows, own)
+                    bd['jacobi_iterations'], bd['residual'] = done + hit + 1, r[hit]
+                    break
+                bd['jacobi_iterations'], bd['residual'] = done + n, r[-1]
+            else:
+                p = ops.jacobi(bd['flags'], div, p, n, rows)
             done += n
         U = ops.project(p, U, bd, rows)      # radius 1: p is valid from row ghost-1 inwards after any chunk
     else:
         density, U, _ = ops.advect_forces_div(mconf, dt, bd, False, False, rows)
+        if per_x:       # U[:,1,:,:,1] = U[:,1,:,:,W-1] (*_saved.py:123-132), every window row
+            U[:, 1, :, decomp.r0:decomp.r1, 1] = U[:, 1, :, decomp.r0:decomp.r1, U.size(4) - 1]
+        if per_y:       # U[:,0,:,1] = U[:,0,:,H-1]
+            yield from _seam_y(decomp, U, U[:, 0, :, decomp.H - 1].clone(), multi)
         part = _std_partial(decomp, U)
         if multi:
             yield lambda: decomp.all_reduce(part)
@@ -469,9 +536,16 @@ def step_phases(mconf, bd, net, sim_method, decomp, ops, bufs):
             U[sl] = U_w
         else:
             # the CNN runs on a compact copy of the window (translation invariant), results go back in place
-            p_w, U_w = ops.cnn(net, decomp.window(U), decomp.window(bd['flags']), scale)
+            if per_x or per_y:
+                p_w, U_w, Ut_w = ops.cnn(net, decomp.window(U), decomp.window(bd['flags']), scale, prewall=True)
+                if per_x:
+                    U_w[:, 1, :, :, 1] = Ut_w[:, 1, :, :, U_w.size(4) - 1]
+            else:
+                p_w, U_w = ops.cnn(net, decomp.window(U), decomp.window(bd['flags']), scale)
             p = decomp.put_window(ops.p_buffer(bd['flags'], bd.get('p')), p_w)
             U = decomp.put_window(U, U_w)
+            if per_y:   # the seam source is the corrected velocity BEFORE setWallBcs (*_saved.py:228-237)
+                yield from _seam_y(decomp, U, Ut_w[:, 0, :, min(decomp.H - 1 - decomp.r0, Ut_w.size(3) - 1)], multi)
         if 'UBC' in bd and 'UBCInvMask' in bd:
             ops.set_const(U, bd['UBCInvMask'], bd['UBC'])
         if 'densityBC' in bd and 'densityBCInvMask' in bd:
@@ -512,6 +586,8 @@ class GraphedDistributedStep:
         self.bufs = {}
         self.schedule, self.graphed, self.capture_error = None, False, None
         self._win = decomp._sl(decomp.r0, decomp.r1)
+        if sim_method == 'jacobi' and float(mconf.get('pTol', 0.0)) > 0:
+            use_graph = False       # the residual test reads device results on the host every chunk
         if not (use_graph and decomp.comm is None and self.state['flags'].is_cuda):
             return
         # warm-up on a scratch copy: NCCL communicators, workspaces, halo buffers, the CNN plan

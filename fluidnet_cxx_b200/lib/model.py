@@ -96,9 +96,12 @@ class FluidNet(nn.Module):
             self._seam(self.mconf, U, U.clone())
         return self.forward_fields(U, flags, periodic=periodic)
 
-    def forward_fields(self, U, flags, scale=None, periodic=False):
+    def forward_fields(self, U, flags, scale=None, periodic=False, prewall=False):
         """The forward pass on separate contiguous fields.  `scale` (B device floats) overrides the
-        std normalisation factor: the slab-decomposed step passes the globally reduced one."""
+        std normalisation factor: the slab-decomposed step passes the globally reduced one.
+        prewall=True also returns the corrected velocity BEFORE setWallBcs (the field the periodic seam
+        of *_saved.py:228-237 copies from) and applies no seam: the slab-decomposed step copies the seam
+        itself, its source row lives on another rank."""
         lib = N.load()
         B, _, _, H, W = (int(s) for s in U.shape)
         st = N.stream_of(U)
@@ -110,6 +113,11 @@ class FluidNet(nn.Module):
         U_out = torch.empty_like(U)
         N.check(lib.fnx_fluidnet_output(N.ptr(p_net), N.ptr(U), N.ptr(flags), N.ptr(s), N.ptr(p), N.ptr(U_out),
                                         B, H, W, 1, st), "FluidNet")
+        if prewall:
+            U_temp = torch.empty_like(U)
+            N.check(lib.fnx_fluidnet_output(N.ptr(p_net), N.ptr(U), N.ptr(flags), N.ptr(s), N.ptr(p),
+                                            N.ptr(U_temp), B, H, W, 0, st), "FluidNet")
+            return p, U_out, U_temp
         if periodic and (self.mconf['periodic-x'] or self.mconf['periodic-y']):
             # the seam is copied from the field BEFORE setWallBcs (*_saved.py:228-237): same kernel
             # without the wall pass, only its seam line is used
@@ -129,8 +137,13 @@ class FluidNet(nn.Module):
             s  = max(std(U), threshold)                      (all three components)
             x  = [velocityDivergence_3D(U) / s, occupancy]   per slice k: (2, H, W)
             p~ = MultiScaleNet(x[k]) for every k             (D independent 2-D forwards, one batch)
-            U' = setWallBcs(velocityUpdate_3D(p~, U / s) * s) ;  p = p~ * s
-        A z-invariant state with Uz = 0 reproduces the 2-D model slice by slice (tests/test_gpu_cnn.py)."""
+            U' = setWallBcs(velocityUpdate_inplane(p~, U / s) * s) ;  p = p~ * s
+        The update applies the IN-PLANE pressure gradient only (Ux, Uy; Uz keeps its advected value): slice k's
+        network answers "which in-plane correction removes this slice's 3-D divergence", and the slices' pressures
+        are independent solves whose difference along z is not a gradient of anything -- subtracting it (the first
+        definition tried here) multiplied max|U| by ~20 per step on the 256^3 workload.  As defined, the projection
+        removes the 3-D divergence (to the network's accuracy) with in-plane corrections and the simulation stays
+        bounded.  A z-invariant state with Uz = 0 reproduces the 2-D model slice by slice (tests/test_gpu_cnn.py)."""
         from .fluid import ops as F
         B, C, D, H, W = (int(v) for v in U.shape)
         assert C == 3 and D > 1, 'forward_fields_3d expects a (B, 3, D, H, W) MAC velocity'
@@ -141,7 +154,9 @@ class FluidNet(nn.Module):
         x[:, 1] = F.flagsToOccupancy(flags)[:, 0].reshape(B * D, H, W)
         p_net = self.multiScale(x).view(B, 1, D, H, W)                    # one 2-D forward per slice
         v = (U / s).contiguous()
+        vz = v[:, 2].clone()
         F.velocityUpdate(pressure=p_net, U=v, flags=flags)
+        v[:, 2] = vz                                                      # in-plane update only (see above)
         v = F.setWallBcs((v * s).contiguous(), flags)
         return (p_net * s).contiguous(), v
 

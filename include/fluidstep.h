@@ -84,6 +84,16 @@ int fnx_jacobi_iterate(const float *flags, const float *div, const float *p_init
                        int D, int H, int W, int is3d, int iters, int row_begin, int row_end,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* Residual-terminated Jacobi across slabs.  The reference evaluates max_b ||p - p_prev||_2 after every
+ * iteration and stops below p_tol (pytorch/lib/fluid/cpp/fluids_init.cpp:958-990).  `iters` iterations,
+ * one per launch, continued from p_init; ssq[it * B + b] (device, iters*B doubles, zeroed by the call)
+ * = sum over rows [own_begin, own_end) of (p_it - p_{it-1})^2: this rank's share of iteration it's squared
+ * residual, to be summed over ranks by the caller.  workspace: B*D*H*W floats.  Never synchronises. */
+int fnx_jacobi_iterate_resid(const float *flags, const float *div, const float *p_init, float *p, int B,
+                             int D, int H, int W, int is3d, int iters, int row_begin, int row_end,
+                             int own_begin, int own_end, double *ssq, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
 /* 2-D, arrays that hold rows [held_row_begin, held_row_end) of the H x W grid only (a slab): */
 int fnx_jacobi_iterate_held(const float *flags, const float *div, const float *p_init, float *p,
                             int B, int H, int W, int iters, int row_begin, int row_end,

@@ -94,6 +94,16 @@ class OracleOps:
         p = torch.from_numpy(jacobi_numpy(flags.numpy(), div.numpy(), None if p_init is None else p_init.numpy(), iters))
         return self._win(p, rows)
 
+    def jacobi_resid(self, flags, div, p_init, iters, rows, own):
+        ssq = torch.zeros((iters, 1), dtype=torch.float64)
+        p = p_init
+        for it in range(iters):
+            new = self.jacobi(flags, div, p, 1, rows)
+            d = (new - (p if p is not None else torch.zeros_like(new)))[:, :, :, own[0]:own[1]].double()
+            ssq[it, 0] = float((d * d).sum())
+            p = new
+        return p, ssq
+
     def project(self, p, U, bd, rows):
         o = self.o
         f = self._np(bd["flags"])
@@ -130,20 +140,23 @@ def single_domain_steps(H, W, seed, steps):
     return out
 
 
-def _worker(rank, world, port, H, W, ghost, steps, seed, result_path):
+def _worker(rank, world, port, H, W, ghost, steps, seed, result_path, mconf=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
         from fluidnet_cxx_b200.lib.distributed import SlabDecomposition, simulate_distributed
+        mconf = mconf or MCONF
         dec = SlabDecomposition(H, ghost)
         ops = OracleOps()
         bd = {k: dec.scatter(torch.from_numpy(v)) for k, v in global_state(H, W, seed).items()}
         results = []
         for _ in range(steps):
-            simulate_distributed(MCONF, bd, None, "jacobi", dec, ops=ops)
+            simulate_distributed(mconf, bd, None, "jacobi", dec, ops=ops)
             results.append({k: dec.gather(bd[k]).numpy() for k in ("p", "U", "density")})
+            if "jacobi_iterations" in bd:
+                results[-1]["iters"] = np.array([bd["jacobi_iterations"]])
         if rank == 0:
             np.savez(result_path, **{f"{i}/{k}": v for i, r in enumerate(results) for k, v in r.items()})
     finally:
@@ -169,6 +182,39 @@ def test_slab_decomposition_bit_exact(tmp_path, world, H, ghost):
             got, want = z[f"{i}/{k}"], ref[i][k]
             bad = int(np.sum(~((got == want) | (np.isnan(got) & np.isnan(want)))))
             assert bad == 0, f"step {i} field {k}: {bad} cells differ from the single-domain step"
+
+
+def _oracle_iterations(flags, div, p_tol, max_iter):
+    """the iteration the residual-terminated solver stops at: the smallest n whose fixed-count solve the
+    tolerance solve reproduces (the oracle does not report its count)"""
+    import oracle
+    want, _ = oracle.solveLinearSystemJacobi(flags, div, False, p_tol, max_iter)
+    for n in range(1, max_iter + 1):
+        got, _ = oracle.solveLinearSystemJacobi(flags, div, False, 0.0, n)
+        if np.array_equal(got, want):
+            return n, want
+    raise AssertionError("no fixed count reproduces the tolerance solve")
+
+
+@pytest.mark.parametrize("p_tol", [2.7, 1.4])
+def test_slab_residual_terminated_jacobi(tmp_path, p_tol):
+    """pTol > 0 across slabs (fluids_init.cpp:958-990): one all-reduce(sum) of the per-iteration squared residuals
+    per chunk of iterations; the decomposed solve stops at the SAME iteration as the single-domain oracle and gives
+    the same p, U bit for bit (stopping inside a chunk, not on its last iteration, included)."""
+    world, H, W, ghost, seed = 2, 64, 48, 20, 7        # ghost 20 -> chunks of 7 iterations
+    mconf = dict(MCONF, pTol=p_tol, jacobiIter=60)
+    ops = OracleOps()
+    bd = {k: torch.from_numpy(v.copy()) for k, v in global_state(H, W, seed).items()}
+    rho, U, div = ops.advect_forces_div(mconf, mconf["dt"], bd, True, True, (0, H))
+    n_ref, p_ref = _oracle_iterations(bd["flags"].numpy(), div.numpy(), p_tol, mconf["jacobiIter"])
+    assert 1 < n_ref < mconf["jacobiIter"], n_ref        # the tolerance, not the cap, ends the solve
+    U_ref = ops.project(torch.from_numpy(p_ref), U, bd, (0, H)).numpy()
+    out = str(tmp_path / "res.npz")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, H, W, ghost, 1, seed, out, mconf), nprocs=world, join=True)
+    z = np.load(out)
+    assert int(z["0/iters"][0]) == n_ref
+    assert np.array_equal(z["0/p"], p_ref) and np.array_equal(z["0/U"], U_ref)
 
 
 def test_decomposition_geometry():

@@ -454,6 +454,45 @@ def test_slicewise_3d_reduces_to_2d_model(net):
     assert float(V3[0, 2, 2:D - 1].abs().max()) == 0.0
 
 
+def test_slicewise_3d_projection_removes_divergence_and_stays_bounded(net):
+    """What the slice-wise definition can be held to without a reference: on a white-noise 3-D field the projection
+    removes most of the 3-D divergence (measured 1.16 -> 0.16 rms) without inflating the field, and a simulation
+    started from it stays bounded (the first definition, with the z-gradient of the independent slice pressures,
+    multiplied max|U| by ~20 per step)."""
+    model, mconf_net = net
+    from fluidnet_cxx_b200.lib import fluid
+    from fluidnet_cxx_b200.lib.fluid import ops as F
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from test_gpu_parity import plume_mconf
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 64
+    fl = torch.zeros(1, 1, n, n, n, device="cuda")
+    fluid.emptyDomain(fl)
+    U = F.setWallBcs(torch.randn(1, 3, n, n, n, device="cuda", generator=g) * 0.5, fl)
+    with torch.no_grad():
+        p, V = model.forward_fields_3d(U.contiguous(), fl)
+    rms = lambda t: float(t.pow(2).mean().sqrt())
+    assert rms(F.velocityDivergence(V, fl)) < 0.25 * rms(F.velocityDivergence(U, fl))
+    assert rms(V) < 1.2 * rms(U)
+    mconf = dict(mconf_net)
+    mconf.update(plume_mconf(simMethod="convnet"))
+    old = model.mconf
+    try:
+        model.mconf = mconf
+        model.scale.mconf = mconf
+        sim.clear_graph_cache()
+        bd = {"p": torch.zeros_like(fl), "U": U.clone(), "flags": fl, "density": torch.rand(fl.shape, device="cuda", generator=g)}
+        with torch.no_grad():
+            for _ in range(12):
+                sim.simulate(mconf, bd, model, "convnet")
+        assert torch.isfinite(bd["U"]).all()
+        assert float(bd["U"].abs().max()) < 2.0 * float(U.abs().max()) and rms(bd["U"]) < 1.5 * rms(U)
+    finally:
+        sim.clear_graph_cache()
+        model.mconf = old
+        model.scale.mconf = old
+
+
 def test_slicewise_3d_step_fused_graph_ops_agree(net):
     model, mconf_net = net
     from fluidnet_cxx_b200.lib import fluid

@@ -67,7 +67,7 @@ def locked_ops():
                 torch.cuda.synchronize()
                 return out
         return call
-    for name in ("advect_forces_div", "jacobi", "project", "set_const", "cnn"):
+    for name in ("advect_forces_div", "jacobi", "jacobi_resid", "project", "set_const", "cnn"):
         setattr(LockedOps, name, wrap(name))
     return LockedOps      # one instance per virtual rank: each rank owns its pool of output buffers
 
@@ -136,6 +136,41 @@ def test_virtual_ranks_jacobi_bit_exact(world, H, W, ghost, iters):
             assert torch.equal(got[i][k], ref[i][k]), (i, k, int((got[i][k] != ref[i][k]).sum()))
 
 
+@pytest.mark.parametrize("world,ghost,stop_at", [(2, 24, 19), (4, 24, 16)])
+def test_virtual_ranks_jacobi_residual_terminated(world, ghost, stop_at, monkeypatch):
+    """pTol > 0 across slabs: the decomposed solve stops at the iteration the single-GPU solver stops at (chunks of
+    8 iterations here: 19 = inside a chunk, 16 = a chunk's last iteration) and the step is bit-identical."""
+    from fluidnet_cxx_b200.lib import fluid
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from test_gpu_parity import plume_mconf
+    H, W = 256, 160
+    mconf = plume_mconf(simMethod="jacobi")
+    mconf["jacobiIter"] = 60
+    state = make_state(fluid, H, W, mconf)
+    # the divergence the step solves for, then a tolerance between the residuals of iterations stop_at-1 and stop_at
+    seen = {}
+    real = fluid.solveLinearSystemJacobi
+
+    def spy(flags, div, **kw):
+        seen["div"] = div.clone()
+        return real(flags=flags, div=div, **kw)
+    monkeypatch.setattr(fluid, "solveLinearSystemJacobi", spy)
+    probe = {k: v.clone() for k, v in state.items()}
+    sim._simulate_ops(dict(mconf, pTol=0.0, jacobiIter=1), probe, None, "jacobi", float(mconf["dt"]), False)
+    monkeypatch.setattr(fluid, "solveLinearSystemJacobi", real)
+    r = [float(real(flags=state["flags"], div=seen["div"], is_3d=False, p_tol=0.0, max_iter=n)[1])
+         for n in (stop_at - 1, stop_at)]
+    assert r[1] < r[0]
+    mconf["pTol"] = 0.5 * (r[0] + r[1])
+    ref_bd = {k: v.clone() for k, v in state.items()}
+    sim.simulate(mconf, ref_bd, None, "jacobi")
+    p_fixed = real(flags=state["flags"], div=seen["div"], is_3d=False, p_tol=0.0, max_iter=stop_at)[0]
+    assert torch.equal(ref_bd["p"], p_fixed)                 # the single-GPU solver stopped where intended
+    got = run_virtual(world, ghost, mconf, state, None, "jacobi", 1)[0]
+    for k in ("p", "U", "density"):
+        assert torch.equal(got[k], ref_bd[k]), (k, int((got[k] != ref_bd[k]).sum()))
+
+
 def test_virtual_ranks_convnet():
     from fluidnet_cxx_b200.lib import fluid
     from fluidnet_cxx_b200.lib.pretrained import load_scalenet
@@ -160,6 +195,72 @@ def test_virtual_ranks_convnet():
         for k in ("p", "U", "density"):
             err = float((got[i][k] - ref[i][k]).abs().max() / ref[i][k].abs().max())
             assert err < 2e-5 * (i + 1), (i, k, err)
+
+
+@pytest.mark.parametrize("world,per_x", [(2, False), (4, False), (2, True)])
+def test_virtual_ranks_convnet_periodic_seam(world, per_x):
+    """Rayleigh-Taylor's periodic-y seam across slabs (*_saved.py:123-132, 228-237): row H-1 lives on the last rank,
+    row 1 on the first.  Decomposed == single-GPU step within the CNN tolerance; a missing seam is an O(1) error in
+    row 1 of Ux."""
+    from fluidnet_cxx_b200.lib import fluid
+    from fluidnet_cxx_b200.lib.pretrained import load_scalenet
+    sim = importlib.import_module("fluidnet_cxx_b200.lib.simulate")
+    from test_gpu_parity import plume_mconf
+    model, mconf_net = load_scalenet("cuda")
+    mconf = dict(mconf_net)
+    mconf.update(plume_mconf(simMethod="convnet"))
+    mconf["periodic-y"], mconf["periodic-x"] = True, per_x
+    model.mconf = mconf
+    model.scale.mconf = mconf
+    H, W = 256, 128
+    # no inflow masks (as the Rayleigh-Taylor driver): the plume's velocity mask pins rows 0..3 and would hide the seam
+    state = {k: v for k, v in make_state(fluid, H, W, mconf).items() if k in ("p", "U", "flags", "density")}
+    ref_bd = {k: v.clone() for k, v in state.items()}
+    ref = []
+    sim.clear_graph_cache()
+    with torch.no_grad():
+        for _ in range(2):
+            sim.simulate(mconf, ref_bd, model, "convnet")
+            ref.append({k: ref_bd[k].clone() for k in ("p", "U", "density")})
+    # the seam is there in the single-GPU step: without it row 1 of Ux would be setWallBcs' value
+    noseam = dict(mconf)
+    noseam["periodic-y"] = False
+    model.mconf = noseam
+    nb = {k: v.clone() for k, v in state.items()}
+    with torch.no_grad():
+        sim.simulate(noseam, nb, model, "convnet")
+    assert float((nb["U"][:, 0, :, 1] - ref[0]["U"][:, 0, :, 1]).abs().max()) > 1e-2
+    model.mconf = mconf
+    got = run_virtual(world, 64, mconf, state, model, "convnet", 2)
+    for i in range(2):
+        for k in ("p", "U", "density"):
+            err = float((got[i][k] - ref[i][k]).abs().max() / ref[i][k].abs().max())
+            assert err < 2e-5 * (i + 1), (i, k, err)
+        seam = float((got[i]["U"][:, 0, :, 1] - ref[i]["U"][:, 0, :, 1]).abs().max())
+        assert seam < 1e-4 * float(ref[i]["U"].abs().max()), (i, seam)
+
+
+@pytest.mark.parametrize("name,world", [("plume512_scalenet", 2), ("plume512_scalenet", 4), ("rt1024_scalenet", 4)])
+def test_virtual_ranks_convnet_step_vs_reference_cpu(name, world):
+    """The SLAB-DECOMPOSED ScaleNet step of a bench workload at full size against the reference's own lib.simulate
+    on CPU (oracle/_ref): the north star's 1e-5 relative (max norm) on p and U, density bit-exact -- the window-local
+    activation scales of the split-fp16 convolutions and the all-reduced std stay inside the bar (rt1024: through
+    the cross-slab periodic-y seam)."""
+    from test_gpu_cnn import RTOL, _bench_state, n_bad, rel_err
+    from fluidnet_cxx_b200.lib.pretrained import load_scalenet
+    model, _ = load_scalenet("cuda")
+    reflib, ref_net, mconf, bd = _bench_state(name)
+    ref_net.mconf = mconf
+    ref_net.scale.mconf = mconf
+    state = {k: v.cuda() for k, v in bd.items()}
+    with torch.no_grad():
+        reflib.simulate(mconf, bd, ref_net, "convnet")
+    model.mconf = mconf
+    model.scale.mconf = mconf
+    got = run_virtual(world, 64, mconf, state, model, "convnet", 1)[0]
+    assert n_bad(got["density"].cpu().numpy(), bd["density"].numpy()) == 0, name
+    assert rel_err(got["p"].cpu().numpy(), bd["p"].numpy()) < RTOL, name
+    assert rel_err(got["U"].cpu().numpy(), bd["U"].numpy()) < RTOL, name
 
 
 @pytest.mark.parametrize("method", ["jacobi", "convnet"])
