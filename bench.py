@@ -910,7 +910,7 @@ def run_ours(args):
             out["also"] = [run_single(args, w, guard, local_rank, want_cpu_baseline=not args.no_cpu_baseline)
                            for w in ALSO_SINGLE]
         guard.stop()
-        print(json.dumps(out), flush=True)
+        emit(out)
         return
     import torch.distributed as dist
     dev = torch.device("cuda", local_rank)
@@ -929,7 +929,7 @@ def run_ours(args):
             out["also"] = also
     guard.stop()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -1008,7 +1008,7 @@ def run_reference(args):
     wl = WORKLOADS[name]
     res = wl["cpu_sample_res"]
     if res is None:
-        print(json.dumps({"impl": "reference", "unavailable": "the reference has no runnable 3-D path"}))
+        emit({"impl": "reference", "unavailable": "the reference has no runnable 3-D path"})
         return
     import torch
     # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm is the only work on this box while
@@ -1016,7 +1016,7 @@ def run_reference(args):
     _all_host_threads()
     step = reference_step_runner(wl, res)
     if step is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"})
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
     for _ in range(warm):
@@ -1042,7 +1042,27 @@ def run_reference(args):
                             "sample": sample},
            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     assert tuple(out["config"]) == CONFIG_KEYS
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line (the driver parses it).  Libraries write there too -- NCCL prints its version
+    banner on stdout when NCCL_DEBUG is set in the environment -- so file descriptor 1 is pointed at stderr for the
+    whole run and the record goes out through a private duplicate of the original stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(record):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(record) + "\n")
+    out.flush()
 
 
 def main():
@@ -1066,6 +1086,7 @@ def main():
     ap.add_argument("--hang-timeout", type=float, default=120.0,
                     help="seconds without progress before the run is ended with a diagnosis (0 = off)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -40,15 +40,38 @@ struct Row4 {
 
 // one Jacobi sweep over the lane's 8x4 patch.  `p` holds the old values and receives the new.
 // up/dn: rows adjacent to the strip (old values).  SLOW applies the Neumann/fixed masks.
-template <bool SLOW, bool RESID>
-__device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const float4* __restrict__ sdv, const Row4& up,
-                                             const Row4& dn, unsigned Lb, unsigned Rb, unsigned Ub,
-                                             unsigned Db, unsigned fixedb, float& acc) {
-  Row4 prev = up;
+// EDGE: the tile's first / last warp strip is all halo, and iteration t of n only needs its rows within
+// n - 1 - t of the tile's inner region: rows outside [r_lo, r_hi) are skipped (their stale values are never read
+// by a row that is still needed).
+template <bool SLOW, bool RESID, bool EDGE>
+__device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const float4* __restrict__ sdv,
+                                             const float4* __restrict__ up_row, const float4* __restrict__ dn_row,
+                                             unsigned Lb, unsigned Rb, unsigned Ub,
+                                             unsigned Db, unsigned fixedb, float& acc, int r_lo, int r_hi) {
+  // up_row / dn_row: the neighbouring strips' adjacent rows in shared memory (NULL at the tile edge: any value
+  // does, the row lies in the discarded halo); the row below is fetched when the last row needs it, not before
+  Row4 prev = p[0];
+  if (up_row) {
+    const float4 u4 = *up_row;
+    prev.v[0] = u4.x; prev.v[1] = u4.y; prev.v[2] = u4.z; prev.v[3] = u4.w;
+  }
 #pragma unroll
   for (int rr = 0; rr < JB_R; rr++) {
     const Row4 cur = p[rr];
-    const Row4 down = rr < JB_R - 1 ? p[rr + 1] : dn;
+    if (EDGE && (rr < r_lo || rr >= r_hi)) {  // warp-uniform
+      prev = cur;
+      continue;
+    }
+    Row4 down;
+    if (rr < JB_R - 1) {
+      down = p[rr + 1];
+    } else {
+      down = cur;
+      if (dn_row) {
+        const float4 d4 = *dn_row;
+        down.v[0] = d4.x; down.v[1] = d4.y; down.v[2] = d4.z; down.v[3] = d4.w;
+      }
+    }
     const float4 d4 = sdv[rr * (JB_TW / 4)];  // this lane's 4 divergence values of row rr (shared memory)
     const float dvr[JB_C] = {d4.x, d4.y, d4.z, d4.w};
     const float left = __shfl_up_sync(0xffffffffu, cur.v[JB_C - 1], 1);
@@ -177,6 +200,26 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
   Row4 p[JB_R];
   float4* const sdv = reinterpret_cast<float4*>(sdv_all) + (w * JB_R) * (JB_TW / 4) + lane;
   const bool xvec = vec_ok && gx0 >= 0 && gx0 + JB_C <= W;
+  // the whole 8 x 128 strip of this warp inside the held rows and the grid (all but the tiles on the rim):
+  // 16 unconditional 128-bit loads through two row pointers
+  const bool strip_in = __all_sync(0xffffffffu, xvec && gy0 >= ya0 && gy0 + JB_R <= ya1);
+  if (strip_in) {
+    const long long o = (long long)gy0 * W + gx0;
+    const float4* dp = reinterpret_cast<const float4*>(div + o);
+    const float4* pp = FIRST ? nullptr : reinterpret_cast<const float4*>(prev + o);
+    const int w4 = W >> 2;
+#pragma unroll
+    for (int rr = 0; rr < JB_R; rr++) {
+      sdv[rr * (JB_TW / 4)] = __ldg(dp + rr * w4);
+      if (!FIRST) {
+        const float4 p4 = __ldg(pp + rr * w4);
+        p[rr].v[0] = p4.x; p[rr].v[1] = p4.y; p[rr].v[2] = p4.z; p[rr].v[3] = p4.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < JB_C; c++) p[rr].v[c] = 0.f;
+      }
+    }
+  } else {
 #pragma unroll
   for (int rr = 0; rr < JB_R; rr++) {
     const int gy = gy0 + rr;
@@ -205,6 +248,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
       for (int c = 0; c < JB_C; c++) p[rr].v[c] = 0.f;
     }
   }
+  }
   unsigned Lb, Rb, Ub, Db, fixedb;
   if (PRE) {
     const size_t t = ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (NW * 32) + threadIdx.x;
@@ -224,23 +268,30 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
     *reinterpret_cast<float4*>(mine + JB_TW) =
         make_float4(p[JB_R - 1].v[0], p[JB_R - 1].v[1], p[JB_R - 1].v[2], p[JB_R - 1].v[3]);
     __syncthreads();
-    Row4 up = p[0], dn = p[JB_R - 1];  // tile edge: any value (inside the discarded halo)
-    if (w > 0) {
-      const float4 u4 = *reinterpret_cast<const float4*>(&xch[t & 1][w - 1][1][lane * JB_C]);
-      up.v[0] = u4.x; up.v[1] = u4.y; up.v[2] = u4.z; up.v[3] = u4.w;
-    }
-    if (w < NW - 1) {
-      const float4 d4 = *reinterpret_cast<const float4*>(&xch[t & 1][w + 1][0][lane * JB_C]);
-      dn.v[0] = d4.x; dn.v[1] = d4.y; dn.v[2] = d4.z; dn.v[3] = d4.w;
-    }
+    const float4* up_row = w > 0 ? reinterpret_cast<const float4*>(&xch[t & 1][w - 1][1][lane * JB_C]) : nullptr;
+    const float4* dn_row = w < NW - 1 ? reinterpret_cast<const float4*>(&xch[t & 1][w + 1][0][lane * JB_C]) : nullptr;
     if (RESID) acc = 0.f;  // only the last iteration's |p - p_prev|^2 survives
-    if (slow) jacobi_sweep<true, RESID>(p, sdv, up, dn, Lb, Rb, Ub, Db, fixedb, acc);
-    else jacobi_sweep<false, RESID>(p, sdv, up, dn, Lb, Rb, Ub, Db, fixedb, acc);
+    if (slow) {
+      jacobi_sweep<true, RESID, false>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, 0, JB_R);
+    } else if (w == 0 || w == NW - 1) {
+      // halo strips: iteration t (0-based) of `iters` is needed JB_HALO - (iters - 1 - t) rows into the tile only
+      int skip = JB_HALO + 1 - iters + t;
+      skip = skip < 0 ? 0 : (skip > JB_R ? JB_R : skip);
+      const int r_lo = w == 0 ? skip : 0, r_hi = w == 0 ? JB_R : JB_R - skip;
+      jacobi_sweep<false, RESID, true>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, r_lo, r_hi);
+    } else {
+      jacobi_sweep<false, RESID, false>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, 0, JB_R);
+    }
   }
 
   // write back the cells whose dependency cone stayed inside the tile: warps 1..NW-2, lanes 2..29
   const bool owner = w >= 1 && w <= NW - 2 && lane >= 2 && lane <= 29;
-  if (owner) {
+  if (owner && vec_ok && gx0 + JB_C <= W && gy0 + JB_R <= row1) {
+    float4* op = reinterpret_cast<float4*>(cur + (long long)gy0 * W + gx0);
+    const int w4 = W >> 2;
+#pragma unroll
+    for (int rr = 0; rr < JB_R; rr++) op[rr * w4] = make_float4(p[rr].v[0], p[rr].v[1], p[rr].v[2], p[rr].v[3]);
+  } else if (owner) {
 #pragma unroll
     for (int rr = 0; rr < JB_R; rr++) {
       const int gy = gy0 + rr;
