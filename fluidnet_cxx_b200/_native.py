@@ -90,6 +90,7 @@ SIGNATURES = {
     "fnx_jacobi_iterate_held_masked": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _S, _P]),
     "fnx_halo_exchange": (_I, [ctypes.POINTER(HaloDesc), _P]),
     "fnx_step_project_bcs_held": (_I, [_P] * 6 + [_I] + _GRID + [_I, _I, _I, _I, _P]),
+    "fnx_output_fields": (_I, [_P, _P, _P, _P, _P] + _GRID + [_I, _P]),
     "fnx_velocity_divergence": (_I, [_P, _P, _P] + _GRID + [_P]),
     "fnx_velocity_update": (_I, [_P, _P, _P] + _GRID + [_P]),
     "fnx_set_wall_bcs": (_I, [_P, _P] + _GRID + [_P]),

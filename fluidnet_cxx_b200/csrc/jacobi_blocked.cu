@@ -267,6 +267,9 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
     *reinterpret_cast<float4*>(mine) = make_float4(p[0].v[0], p[0].v[1], p[0].v[2], p[0].v[3]);
     *reinterpret_cast<float4*>(mine + JB_TW) =
         make_float4(p[JB_R - 1].v[0], p[JB_R - 1].v[1], p[JB_R - 1].v[2], p[JB_R - 1].v[3]);
+    // (one __syncthreads per iteration: neighbour-pair named barriers -- bar.sync id, 64, even boundaries first --
+    // were measured and lost, 138 vs 100 us per launch at 4096^2: two barrier instructions per iteration and all 16
+    // hardware barriers reserved per CTA cost more than the looser coupling saves)
     __syncthreads();
     const float4* up_row = w > 0 ? reinterpret_cast<const float4*>(&xch[t & 1][w - 1][1][lane * JB_C]) : nullptr;
     const float4* dn_row = w < NW - 1 ? reinterpret_cast<const float4*>(&xch[t & 1][w + 1][0][lane * JB_C]) : nullptr;

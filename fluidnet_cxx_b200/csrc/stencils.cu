@@ -217,6 +217,61 @@ __global__ void k_set_const_vals(float* __restrict__ x, const float* __restrict_
   if (q < count) x[q] = const_vals_apply(x[q], __ldg(inv_mask + q), __ldg(bc + q));
 }
 
+// The output step of the drivers (plume.py:238-263 plots, :330-423 VTK dump) as ONE pass: divergence
+// (velocity_divergence.py:4-74), cell-centred velocity (grid.py:7-30) and its norm, the centred density and
+// pressure gradients of the VTK block (plume.py:343-359, 2-D as there), pressure; Obstacle cells of the velocity,
+// norm and pressure planes filled with NaN when `mask` (the drivers' numpy masked_array .filled(nan)).
+// out: (B, FNX_OUTPUT_PLANES, D, H, W).  The reference forms these with ~60 tensor ops and 9 device->host copies;
+// here one kernel writes one buffer that goes to the host in one copy.
+template <bool Z>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_output_fields(Grid g, const float* __restrict__ U, const float* __restrict__ flags, const float* __restrict__ rho,
+                    const float* __restrict__ p, float* __restrict__ out, int mask) {
+  constexpr int NC = Z ? 3 : 2;
+  CellIdx c;
+  if (!cell_of(g, c)) return;
+  U += (long long)c.b * NC * g.n; flags += c.b * g.n; out += (long long)c.b * FNX_OUTPUT_PLANES * g.n;
+  if (rho) rho += c.b * g.n;
+  if (p) p += c.b * g.n;
+  const float f = __ldg(flags + c.o);
+  const float ux = __ldg(U + c.o), uy = __ldg(U + g.n + c.o), uz = Z ? __ldg(U + 2 * g.n + c.o) : 0.f;
+  const float ux1 = c.i < g.W - 1 ? __ldg(U + c.o + 1) : 0.f;
+  const float uy1 = c.j < g.H - 1 ? __ldg(U + g.n + c.o + g.sy) : 0.f;
+  const float uz1 = (Z && c.k < g.D - 1) ? __ldg(U + 2 * g.n + c.o + g.sz) : 0.f;
+  float dv = 0.f;
+  if (!is_border<Z>(g, c.k, c.j, c.i)) {
+    dv = ux - ux1 + uy - uy1;
+    if (Z) dv = dv + (uz - uz1);
+  }
+  if (f == kObstacle) dv = 0.f;
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+  if (c.i < g.W - 1) cx = 0.5f * (ux + ux1);
+  if (c.j < g.H - 1) cy = 0.5f * (uy + uy1);
+  if (Z && c.k < g.D - 1) cz = 0.5f * (uz + uz1);
+  float nrm = sqrtf(cx * cx + cy * cy + cz * cz);
+  // centred gradients: getCentered of the face differences of the (H-2) x (W-2) interior, placed at [1, H-1) x [1, W-1)
+  float grx = 0.f, gry = 0.f, gpx = 0.f, gpy = 0.f;
+  if (!Z && c.j >= 1 && c.j <= g.H - 2 && c.i >= 1 && c.i <= g.W - 2) {
+    if (c.i < g.W - 2) {
+      if (rho) grx = 0.5f * ((__ldg(rho + c.o) - __ldg(rho + c.o - 1)) + (__ldg(rho + c.o + 1) - __ldg(rho + c.o)));
+      if (p) gpx = 0.5f * ((__ldg(p + c.o) - __ldg(p + c.o - 1)) + (__ldg(p + c.o + 1) - __ldg(p + c.o)));
+    }
+    if (c.j < g.H - 2) {
+      if (rho) gry = 0.5f * ((__ldg(rho + c.o) - __ldg(rho + c.o - g.sy)) + (__ldg(rho + c.o + g.sy) - __ldg(rho + c.o)));
+      if (p) gpy = 0.5f * ((__ldg(p + c.o) - __ldg(p + c.o - g.sy)) + (__ldg(p + c.o + g.sy) - __ldg(p + c.o)));
+    }
+  }
+  float pm = p ? __ldg(p + c.o) : 0.f;
+  if (mask && f == kObstacle) {
+    const float qnan = __int_as_float(0x7fc00000);
+    cx = cy = cz = nrm = pm = qnan;
+  }
+  out[c.o] = dv;
+  out[1 * g.n + c.o] = cx; out[2 * g.n + c.o] = cy; out[3 * g.n + c.o] = cz; out[4 * g.n + c.o] = nrm;
+  out[5 * g.n + c.o] = grx; out[6 * g.n + c.o] = gry; out[7 * g.n + c.o] = gpx; out[8 * g.n + c.o] = gpy;
+  out[9 * g.n + c.o] = pm;
+}
+
 template <bool Z>
 __global__ void __launch_bounds__(kBX* kBY) k_empty_domain(Grid g, float* __restrict__ flags, int bnd) {
   CellIdx c;
@@ -578,6 +633,16 @@ int fnx_velocity_divergence(const float* U, const float* flags, float* div, int 
   Grid g = make_grid(B, D, H, W);
   FNX_DISPATCH_3D(is3d, k_velocity_divergence, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, U, flags, div));
   FNX_LAUNCH_CHECK("velocity_divergence", 1);
+  return FNX_OK;
+}
+
+int fnx_output_fields(const float* U, const float* flags, const float* density, const float* pressure, float* out,
+                      int B, int D, int H, int W, int is3d, int mask_obstacles, void* stream) {
+  if (int e = check_grid(B, D, H, W, is3d, "output_fields")) return e;
+  if (!U || !flags || !out) return fnx_set_error(FNX_ERR_ARG, "output_fields: U, flags and out are required");
+  Grid g = make_grid(B, D, H, W);
+  FNX_DISPATCH_3D(is3d, k_output_fields, <<<cell_grid(g), cell_block(), 0, (cudaStream_t)stream>>>(g, U, flags, density, pressure, out, mask_obstacles));
+  FNX_LAUNCH_CHECK("output_fields", 1);
   return FNX_OK;
 }
 

@@ -2,6 +2,7 @@
 from .cell_type import CellType
 from .ops import (getDx, getCentered, setWallBcs, flagsToOccupancy, velocityDivergence, velocityUpdate,
                   addBuoyancy, addGravity, addViscosity, emptyDomain, correctScalar, advectScalar, advectVelocity,
-                  solveLinearSystemJacobi, setConstVals)
+                  solveLinearSystemJacobi, setConstVals, outputFields, outputFieldsToHost,
+                  OUTPUT_PLANES)
 from .extras import setWallBcsStick, createCylinder, createBox2D
 from .init_conditions import createPlumeBCs, createRayleighTaylorBCs

@@ -67,6 +67,43 @@ def getCentered(self):
     return out
 
 
+OUTPUT_PLANES = ("div", "velx", "vely", "velz", "vel_norm", "gradRhox", "gradRhoy", "gradPx", "gradPy", "pressure")
+
+
+def outputFields(batch_dict, mask_obstacles=True, out=None):
+    """The drivers' output step in one kernel (plume.py:238-263, 330-423): divergence, centred velocity and its
+    norm, centred density / pressure gradients (2-D) and pressure, Obstacle cells of the velocity / norm /
+    pressure planes NaN-filled.  Returns (out, views): out (B, 10, D, H, W) on the device and a dict
+    name -> (B, D, H, W) view of it (names: OUTPUT_PLANES).  Not part of the reference's lib.fluid (which forms
+    these with ~60 tensor ops and 9 host copies); `outputFieldsToHost` adds the single device-to-host copy."""
+    U, flags = batch_dict['U'], batch_dict['flags']
+    _check_vel_flags(U, flags)
+    B, D, H, W = N.grid_of(flags)
+    is3d = int(U.size(1) == 3)
+    rho, p = batch_dict.get('density'), batch_dict.get('p')
+    if out is None:
+        out = torch.empty((B, len(OUTPUT_PLANES), D, H, W), dtype=torch.float32, device=U.device)
+    assert out.is_contiguous() and tuple(out.shape) == (B, len(OUTPUT_PLANES), D, H, W) and out.device == U.device
+    N.check(N.load().fnx_output_fields(N.ptr(U.contiguous()), N.ptr(flags.contiguous()),
+                                       N.ptr(rho.contiguous()) if rho is not None else None,
+                                       N.ptr(p.contiguous()) if p is not None else None, N.ptr(out), B, D, H, W, is3d,
+                                       int(bool(mask_obstacles)), N.stream_of(U)), "outputFields")
+    return out, {name: out[:, i] for i, name in enumerate(OUTPUT_PLANES)}
+
+
+def outputFieldsToHost(batch_dict, mask_obstacles=True, pinned=None, device_out=None):
+    """outputFields + ONE asynchronous copy into a pinned host buffer (allocated on first use: pass the returned
+    `pinned` / `device_out` back in on the next output step).  Returns (arrays, pinned, device_out); `arrays` maps
+    the plane names to numpy views of the pinned buffer, valid after the stream has been synchronised (done here)."""
+    out, _ = outputFields(batch_dict, mask_obstacles, device_out)
+    if pinned is None:
+        pinned = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    pinned.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(out.device).synchronize()
+    host = pinned.numpy()
+    return {name: host[:, i] for i, name in enumerate(OUTPUT_PLANES)}, pinned, out
+
+
 def emptyDomain(flags, boundary_width=1):
     assert boundary_width > 0, 'Boundary width must be greater than zero!'
     assert flags.dim() == 5, 'Flags tensor should be 5D'

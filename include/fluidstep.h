@@ -163,6 +163,20 @@ int fnx_empty_domain(float *flags, int B, int D, int H, int W, int is3d, int bnd
 int fnx_get_centered(const float *U, float *out, int B, int D, int H, int W, int is3d,
                      void *stream);
 
+/* The drivers' output step (pytorch/plume.py:238-263 and :330-423; rayleighTaylor.py has the same block) in
+ * one pass: out (B, FNX_OUTPUT_PLANES, D, H, W) =
+ *   0 velocityDivergence(U, flags)          (velocity_divergence.py:4-74)
+ *   1,2,3 getCentered(U) x, y, z            (grid.py:7-30)         4 its norm over the components
+ *   5,6 centred density gradient x, y       (plume.py:343-350, 2-D; 0 in 3-D)
+ *   7,8 centred pressure gradient x, y      (plume.py:352-359)
+ *   9 pressure
+ * mask_obstacles: planes 1-4 and 9 hold NaN in Obstacle cells (the drivers' masked_array .filled(nan)).
+ * density / pressure may be NULL (their planes are 0).  One buffer -> one device-to-host copy. */
+#define FNX_OUTPUT_PLANES 10
+int fnx_output_fields(const float *U, const float *flags, const float *density, const float *pressure,
+                      float *out, int B, int D, int H, int W, int is3d, int mask_obstacles,
+                      void *stream);
+
 /* ---- fused fast path behind lib.simulate (simulate.py:28-171) --------------- */
 /* The standard inviscid sequence of both reference drivers
  *   advectScalar -> advectVelocity -> setConstVals -> addBuoyancy/addGravity ->

@@ -383,6 +383,77 @@ def test_get_centered_vs_reference(fluid, shape):
     assert n_mismatch(got, want) == 0
 
 
+def _plume_output_block(reffluid, bd):
+    """plume.py:240-256 and :330-359 on CPU tensors, statement for statement (the drivers' output step):
+    divergence, centred velocity, norm, NaN-filled obstacle cells, centred density / pressure gradients."""
+    import numpy.ma as ma
+    U, flags, density, pressure = bd["U"], bd["flags"], bd["density"], bd["p"]
+    div = reffluid.velocityDivergence(U.clone(), flags.clone())
+    vel = reffluid.getCentered(U.clone())
+    mask = flags.eq(2)[:, 0].numpy().astype(float)
+    out = {"div": div[:, 0].numpy()}
+    for name, t in (("velx", vel[:, 0]), ("vely", vel[:, 1]), ("vel_norm", torch.norm(vel, dim=1)),
+                    ("pressure", pressure[:, 0])):
+        m = ma.array(t.numpy(), mask=mask)
+        ma.set_fill_value(m, np.nan)
+        out[name] = m.filled()
+    b, _, d, h, w = pressure.shape
+    for name, fld in (("gradRho", density), ("gradP", pressure)):
+        c = fld.narrow(4, 1, w - 2).narrow(3, 1, h - 2)
+        c = c.clone().expand(b, 2, d, h - 2, w - 2)
+        m = c.clone()
+        m[:, 0] = fld.narrow(4, 0, w - 2).narrow(3, 1, h - 2).squeeze(1)
+        m[:, 1] = fld.narrow(4, 1, w - 2).narrow(3, 0, h - 2).squeeze(1)
+        center = torch.zeros_like(vel)[:, 0:2].contiguous()
+        center[:, 0:2, 0, 1:(h - 1), 1:(w - 1)] = reffluid.getCentered((c - m).contiguous())[:, 0:2, 0]
+        out[name + "x"], out[name + "y"] = center[:, 0].numpy(), center[:, 1].numpy()
+    return out
+
+
+@pytest.mark.parametrize("hw", [(48, 64), (257, 131)])
+def test_output_fields_vs_driver_output_block(fluid, hw):
+    """fnx_output_fields (one kernel, one buffer, one device-to-host copy) against the drivers' own output block
+    restated with the reference's velocityDivergence / getCentered (oracle/_ref when present, else this
+    package's parity-pinned ops on the same tensors): every plane bit-exact, the norm to 1 ulp."""
+    H, W = hw
+    g = torch.Generator().manual_seed(H)
+    bd = {"U": torch.randn(2, 2, 1, H, W, generator=g), "density": torch.rand(2, 1, 1, H, W, generator=g),
+          "p": torch.randn(2, 1, 1, H, W, generator=g), "flags": torch.ones(2, 1, 1, H, W)}
+    f = bd["flags"]
+    f[..., 0, :] = 2; f[..., -1, :] = 2; f[..., :, 0] = 2; f[..., :, -1] = 2
+    f[0, ..., H // 3:H // 3 + 7, W // 2:W // 2 + 9] = 2
+    f[1, ..., 5:9, 3:30] = 2
+
+    class _Ours:      # the same block driven by this package's (parity-pinned) ops, results moved to the CPU
+        velocityDivergence = staticmethod(lambda U, fl: fluid.velocityDivergence(U.cuda(), fl.cuda()).cpu())
+        getCentered = staticmethod(lambda U: fluid.getCentered(U.cuda()).cpu())
+    reffluid = _Ours
+    try:
+        import ref_loader
+        if ref_loader.available():
+            reffluid = ref_loader.load().fluid
+    except Exception:      # noqa: BLE001
+        pass
+    want = _plume_output_block(reffluid, bd)
+    dev = {k: v.cuda() for k, v in bd.items()}
+    arrays, pinned, dev_out = fluid.outputFieldsToHost(dev)
+    assert set(arrays) == set(fluid.OUTPUT_PLANES)
+    for name, ref in want.items():
+        got = arrays[name][:, 0]
+        ref = ref[:, 0] if ref.ndim == 4 else ref
+        if name == "vel_norm":
+            ok = np.isclose(got, ref, rtol=3e-7, atol=0, equal_nan=True)
+            assert ok.all(), (name, int((~ok).sum()))
+        else:
+            assert n_mismatch(got, ref) == 0, name
+    assert np.isnan(arrays["velx"][0, 0, 0, 0]) and not np.isnan(arrays["div"]).any()
+    assert float(np.abs(arrays["velz"][~np.isnan(arrays["velz"])]).max()) == 0.0
+    # unmasked variant, buffers reused
+    arrays2, _, _ = fluid.outputFieldsToHost(dev, mask_obstacles=False, pinned=pinned, device_out=dev_out)
+    assert not np.isnan(arrays2["velx"]).any()
+    assert n_mismatch(arrays2["pressure"][:, 0], bd["p"][:, 0, 0].numpy()) == 0
+
+
 # ---------------------------------------------------------------------------------------------
 # (4) the fused 2-D step kernels (csrc/step2d.cu: forward pass staged in shared memory, tiled
 # forces / divergence) against the op-by-op sequence AND the generic one-thread-per-cell kernels
