@@ -38,44 +38,102 @@ struct Row4 {
   float v[JB_C];
 };
 
+// sm_100a packed fp32: add.rn.f32x2 / mul.rn.f32x2 (SASS FADD2 / FMUL2) do two IEEE round-to-nearest operations on
+// a 64-bit register pair in ONE issue slot.  The fp32 pipe rate is unchanged (tools/f32x2_probe.cu: 36.9 vs 36.2
+// TFLOP/s, 0 rounding mismatches in 2 M random pairs incl. denormals / infinities / NaNs), but this kernel is bound
+// by issue slots and latency, not by the pipe (36 % busy): pairing the cells halves its arithmetic instructions.
+typedef unsigned long long pair_t;  // two fp32 values: lo = first, hi = second
+__device__ __forceinline__ pair_t pk(float lo, float hi) {
+  pair_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(pair_t r, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+__device__ __forceinline__ pair_t add2(pair_t a, pair_t b) {
+  pair_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ pair_t mul2(pair_t a, pair_t b) {
+  pair_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// A lane's 4 consecutive cells of one row, held as the pairs a = (c0, c2), b = (c1, c3): the left neighbours of
+// (c1, c3) are then exactly a, the right neighbours of (c0, c2) exactly b, and only (left, c1) / (c2, right) have to
+// be assembled around the two shuffled halo values.  The divergence tile and the exchanged rows in shared memory
+// use the same (c0, c2, c1, c3) order, so a 128-bit LDS delivers two ready pairs.
+struct RowP {
+  pair_t a, b;
+};
+__device__ __forceinline__ Row4 unpack_row(const RowP& r) {
+  Row4 o;
+  upk(r.a, o.v[0], o.v[2]);
+  upk(r.b, o.v[1], o.v[3]);
+  return o;
+}
+__device__ __forceinline__ RowP pack_row(const Row4& r) {
+  RowP o;
+  o.a = pk(r.v[0], r.v[2]);
+  o.b = pk(r.v[1], r.v[3]);
+  return o;
+}
+__device__ __forceinline__ RowP load_rowp(const ulonglong2* q) {
+  const ulonglong2 t = *q;
+  RowP o;
+  o.a = t.x; o.b = t.y;
+  return o;
+}
+
 // one Jacobi sweep over the lane's 8x4 patch.  `p` holds the old values and receives the new.
-// up/dn: rows adjacent to the strip (old values).  SLOW applies the Neumann/fixed masks.
+// up_row / dn_row: the neighbouring strips' adjacent rows in shared memory (NULL at the tile edge: any value does,
+// the row lies in the discarded halo); the row below is fetched when the last row needs it, not before.
+// SLOW applies the Neumann/fixed masks, RESID accumulates |p - p_prev|^2: both run cell by cell; the plain sweep
+// runs on pairs.  The per-cell operation order is the one-iteration kernel's either way:
+// ((((pL + pR) + pU) + pD) + div) * 0.25.
 // EDGE: the tile's first / last warp strip is all halo, and iteration t of n only needs its rows within
 // n - 1 - t of the tile's inner region: rows outside [r_lo, r_hi) are skipped (their stale values are never read
 // by a row that is still needed).
 template <bool SLOW, bool RESID, bool EDGE>
-__device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const float4* __restrict__ sdv,
-                                             const float4* __restrict__ up_row, const float4* __restrict__ dn_row,
+__device__ __forceinline__ void jacobi_sweep(RowP (&p)[JB_R], const ulonglong2* __restrict__ sdv,
+                                             const ulonglong2* __restrict__ up_row, const ulonglong2* __restrict__ dn_row,
                                              unsigned Lb, unsigned Rb, unsigned Ub,
                                              unsigned Db, unsigned fixedb, float& acc, int r_lo, int r_hi) {
-  // up_row / dn_row: the neighbouring strips' adjacent rows in shared memory (NULL at the tile edge: any value
-  // does, the row lies in the discarded halo); the row below is fetched when the last row needs it, not before
-  Row4 prev = p[0];
-  if (up_row) {
-    const float4 u4 = *up_row;
-    prev.v[0] = u4.x; prev.v[1] = u4.y; prev.v[2] = u4.z; prev.v[3] = u4.w;
-  }
+  RowP prevp = p[0];
+  if (up_row) prevp = load_rowp(up_row);
+  const pair_t quarter = pk(0.25f, 0.25f);
 #pragma unroll
   for (int rr = 0; rr < JB_R; rr++) {
-    const Row4 cur = p[rr];
+    const RowP curp = p[rr];
     if (EDGE && (rr < r_lo || rr >= r_hi)) {  // warp-uniform
-      prev = cur;
+      prevp = curp;
       continue;
     }
-    Row4 down;
+    RowP downp;
     if (rr < JB_R - 1) {
-      down = p[rr + 1];
+      downp = p[rr + 1];
     } else {
-      down = cur;
-      if (dn_row) {
-        const float4 d4 = *dn_row;
-        down.v[0] = d4.x; down.v[1] = d4.y; down.v[2] = d4.z; down.v[3] = d4.w;
-      }
+      downp = curp;
+      if (dn_row) downp = load_rowp(dn_row);
     }
-    const float4 d4 = sdv[rr * (JB_TW / 4)];  // this lane's 4 divergence values of row rr (shared memory)
-    const float dvr[JB_C] = {d4.x, d4.y, d4.z, d4.w};
+    const ulonglong2 dvp = sdv[rr * (JB_TW / 4)];  // this lane's 4 divergence values of row rr: (d0, d2), (d1, d3)
+    const Row4 cur = unpack_row(curp);
     const float left = __shfl_up_sync(0xffffffffu, cur.v[JB_C - 1], 1);
     const float right = __shfl_down_sync(0xffffffffu, cur.v[0], 1);
+    if (!SLOW && !RESID) {
+      const pair_t la = pk(left, cur.v[1]), rb = pk(cur.v[2], right);
+      const pair_t sa = add2(add2(add2(add2(la, curp.b), prevp.a), downp.a), dvp.x);
+      const pair_t sb = add2(add2(add2(add2(curp.a, rb), prevp.b), downp.b), dvp.y);
+      prevp = curp;
+      p[rr].a = mul2(sa, quarter);
+      p[rr].b = mul2(sb, quarter);
+      continue;
+    }
+    const Row4 prev = unpack_row(prevp), down = unpack_row(downp);
+    float dvr[JB_C];
+    upk(dvp.x, dvr[0], dvr[2]);
+    upk(dvp.y, dvr[1], dvr[3]);
     Row4 nw;
 #pragma unroll
     for (int c = 0; c < JB_C; c++) {
@@ -100,8 +158,8 @@ __device__ __forceinline__ void jacobi_sweep(Row4 (&p)[JB_R], const float4* __re
       }
       nw.v[c] = pn;
     }
-    prev = cur;
-    p[rr] = nw;
+    prevp = curp;
+    p[rr] = pack_row(nw);
   }
 }
 
@@ -197,8 +255,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
   flags += boff; div += boff; cur += boff;
   if (!FIRST) prev += boff;
 
-  Row4 p[JB_R];
-  float4* const sdv = reinterpret_cast<float4*>(sdv_all) + (w * JB_R) * (JB_TW / 4) + lane;
+  RowP p[JB_R];
+  // this lane's slot of the divergence tile: one 16-byte entry per row holding (d0, d2), (d1, d3)
+  ulonglong2* const sdv = reinterpret_cast<ulonglong2*>(sdv_all) + (w * JB_R) * (JB_TW / 4) + lane;
+  const RowP zero_row = {pk(0.f, 0.f), pk(0.f, 0.f)};
   const bool xvec = vec_ok && gx0 >= 0 && gx0 + JB_C <= W;
   // the whole 8 x 128 strip of this warp inside the held rows and the grid (all but the tiles on the rim):
   // 16 unconditional 128-bit loads through two row pointers
@@ -210,13 +270,13 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
     const int w4 = W >> 2;
 #pragma unroll
     for (int rr = 0; rr < JB_R; rr++) {
-      sdv[rr * (JB_TW / 4)] = __ldg(dp + rr * w4);
+      const float4 d4 = __ldg(dp + rr * w4);
+      sdv[rr * (JB_TW / 4)] = make_ulonglong2(pk(d4.x, d4.z), pk(d4.y, d4.w));
       if (!FIRST) {
         const float4 p4 = __ldg(pp + rr * w4);
-        p[rr].v[0] = p4.x; p[rr].v[1] = p4.y; p[rr].v[2] = p4.z; p[rr].v[3] = p4.w;
+        p[rr].a = pk(p4.x, p4.z); p[rr].b = pk(p4.y, p4.w);
       } else {
-#pragma unroll
-        for (int c = 0; c < JB_C; c++) p[rr].v[c] = 0.f;
+        p[rr] = zero_row;
       }
     }
   } else {
@@ -226,27 +286,27 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
     const bool yin = gy >= ya0 && gy < ya1;
     if (xvec && yin) {
       const long long o = (long long)gy * W + gx0;
-      sdv[rr * (JB_TW / 4)] = __ldg(reinterpret_cast<const float4*>(div + o));
+      const float4 d4 = __ldg(reinterpret_cast<const float4*>(div + o));
+      sdv[rr * (JB_TW / 4)] = make_ulonglong2(pk(d4.x, d4.z), pk(d4.y, d4.w));
       if (!FIRST) {
         const float4 p4 = __ldg(reinterpret_cast<const float4*>(prev + o));
-        p[rr].v[0] = p4.x; p[rr].v[1] = p4.y; p[rr].v[2] = p4.z; p[rr].v[3] = p4.w;
+        p[rr].a = pk(p4.x, p4.z); p[rr].b = pk(p4.y, p4.w);
       }
     } else {
       float dvv[JB_C];
+      Row4 pv;
 #pragma unroll
       for (int c = 0; c < JB_C; c++) {
         const int gx = gx0 + c;
         const bool inb = yin && gx >= 0 && gx < W;
         const long long o = (long long)gy * W + gx;
         dvv[c] = inb ? __ldg(div + o) : 0.f;
-        if (!FIRST) p[rr].v[c] = inb ? __ldg(prev + o) : 0.f;
+        pv.v[c] = (!FIRST && inb) ? __ldg(prev + o) : 0.f;
       }
-      sdv[rr * (JB_TW / 4)] = make_float4(dvv[0], dvv[1], dvv[2], dvv[3]);
+      sdv[rr * (JB_TW / 4)] = make_ulonglong2(pk(dvv[0], dvv[2]), pk(dvv[1], dvv[3]));
+      if (!FIRST) p[rr] = pack_row(pv);
     }
-    if (FIRST) {
-#pragma unroll
-      for (int c = 0; c < JB_C; c++) p[rr].v[c] = 0.f;
-    }
+    if (FIRST) p[rr] = zero_row;
   }
   }
   unsigned Lb, Rb, Ub, Db, fixedb;
@@ -264,15 +324,14 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
   for (int t = 0; t < iters; t++) {
     // publish the strip's first and last row (old values), fetch the neighbours'
     float* mine = &xch[t & 1][w][0][lane * JB_C];
-    *reinterpret_cast<float4*>(mine) = make_float4(p[0].v[0], p[0].v[1], p[0].v[2], p[0].v[3]);
-    *reinterpret_cast<float4*>(mine + JB_TW) =
-        make_float4(p[JB_R - 1].v[0], p[JB_R - 1].v[1], p[JB_R - 1].v[2], p[JB_R - 1].v[3]);
+    *reinterpret_cast<ulonglong2*>(mine) = make_ulonglong2(p[0].a, p[0].b);
+    *reinterpret_cast<ulonglong2*>(mine + JB_TW) = make_ulonglong2(p[JB_R - 1].a, p[JB_R - 1].b);
     // (one __syncthreads per iteration: neighbour-pair named barriers -- bar.sync id, 64, even boundaries first --
     // were measured and lost, 138 vs 100 us per launch at 4096^2: two barrier instructions per iteration and all 16
     // hardware barriers reserved per CTA cost more than the looser coupling saves)
     __syncthreads();
-    const float4* up_row = w > 0 ? reinterpret_cast<const float4*>(&xch[t & 1][w - 1][1][lane * JB_C]) : nullptr;
-    const float4* dn_row = w < NW - 1 ? reinterpret_cast<const float4*>(&xch[t & 1][w + 1][0][lane * JB_C]) : nullptr;
+    const ulonglong2* up_row = w > 0 ? reinterpret_cast<const ulonglong2*>(&xch[t & 1][w - 1][1][lane * JB_C]) : nullptr;
+    const ulonglong2* dn_row = w < NW - 1 ? reinterpret_cast<const ulonglong2*>(&xch[t & 1][w + 1][0][lane * JB_C]) : nullptr;
     if (RESID) acc = 0.f;  // only the last iteration's |p - p_prev|^2 survives
     if (slow) {
       jacobi_sweep<true, RESID, false>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, 0, JB_R);
@@ -293,19 +352,23 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
     float4* op = reinterpret_cast<float4*>(cur + (long long)gy0 * W + gx0);
     const int w4 = W >> 2;
 #pragma unroll
-    for (int rr = 0; rr < JB_R; rr++) op[rr * w4] = make_float4(p[rr].v[0], p[rr].v[1], p[rr].v[2], p[rr].v[3]);
+    for (int rr = 0; rr < JB_R; rr++) {
+      const Row4 o4 = unpack_row(p[rr]);
+      op[rr * w4] = make_float4(o4.v[0], o4.v[1], o4.v[2], o4.v[3]);
+    }
   } else if (owner) {
 #pragma unroll
     for (int rr = 0; rr < JB_R; rr++) {
       const int gy = gy0 + rr;
       if (gy >= row1) break;
       const long long o = (long long)gy * W + gx0;
+      const Row4 o4 = unpack_row(p[rr]);
       if (vec_ok && gx0 + JB_C <= W) {
-        *reinterpret_cast<float4*>(cur + o) = make_float4(p[rr].v[0], p[rr].v[1], p[rr].v[2], p[rr].v[3]);
+        *reinterpret_cast<float4*>(cur + o) = make_float4(o4.v[0], o4.v[1], o4.v[2], o4.v[3]);
       } else {
 #pragma unroll
         for (int c = 0; c < JB_C; c++)
-          if (gx0 + c < W) cur[o + c] = p[rr].v[c];
+          if (gx0 + c < W) cur[o + c] = o4.v[c];
       }
     }
   }

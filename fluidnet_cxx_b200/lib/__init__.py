@@ -9,3 +9,4 @@ from .multi_scale_net import MultiScaleNet
 from .model import FluidNet
 from .plot_field import plotField
 from .argument_parser import SmartFormatter
+from .host_pipeline import HostStepPipeline      # not in the reference: host-resident states, copies overlapped
