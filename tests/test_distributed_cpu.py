@@ -104,6 +104,22 @@ class OracleOps:
             p = new
         return p, ssq
 
+    def set_const(self, x, inv_mask, bc):
+        x.mul_(inv_mask).add_(bc)
+
+    def cnn(self, net, U, flags, scale, prewall=False):
+        """a stand-in "network" with the wrapper's structure (*_saved.py:135-232): normalise, divergence, a 3-iteration
+        Jacobi as the pressure model (dependency radius 3, translation invariant like the CNN), velocity update,
+        un-normalise, setWallBcs; prewall also returns the field before setWallBcs (the periodic seam's source)"""
+        o = self.o
+        f = flags.numpy()
+        u = (U / scale).numpy()
+        pn = jacobi_numpy(f, o.velocityDivergence(u, f), None, 3)
+        ut = torch.from_numpy(o.velocityUpdate(pn, u, f)) * scale
+        uo = torch.from_numpy(o.setWallBcs(ut.numpy(), f))
+        p = torch.from_numpy(pn) * scale
+        return (p, uo, ut) if prewall else (p, uo)
+
     def project(self, p, U, bd, rows):
         o = self.o
         f = self._np(bd["flags"])
@@ -215,6 +231,69 @@ def test_slab_residual_terminated_jacobi(tmp_path, p_tol):
     z = np.load(out)
     assert int(z["0/iters"][0]) == n_ref
     assert np.array_equal(z["0/p"], p_ref) and np.array_equal(z["0/U"], U_ref)
+
+
+def _seam_worker(rank, world, port, H, W, ghost, seed, mconf, netconf, result_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+        import types
+        from fluidnet_cxx_b200.lib.distributed import SlabDecomposition, simulate_distributed
+        dec = SlabDecomposition(H, ghost)
+        bd = {k: dec.scatter(torch.from_numpy(v)) for k, v in global_state(H, W, seed).items()}
+        simulate_distributed(mconf, bd, types.SimpleNamespace(mconf=netconf), "convnet", dec, ops=OracleOps())
+        got = {k: dec.gather(bd[k]).numpy() for k in ("p", "U", "density")}
+        if rank == 0:
+            np.savez(result_path, **got)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("per_x", [False, True])
+def test_slab_periodic_seam_over_gloo(tmp_path, per_x):
+    """The periodic-y seam of the ScaleNet step (*_saved.py:123-132, 228-237) across two slabs over gloo: row H-1 of
+    Ux lives on the last rank, row 1 on the first; the line travels as int32 bits through an all-reduce.  A stand-in
+    pressure model (OracleOps.cnn) keeps the step's structure; the decomposed step equals the single-domain one (to
+    the rounding of the all-reduced std), and the seam line itself is checked against a run without it."""
+    import types
+    from fluidnet_cxx_b200.lib import distributed as D
+    world, H, W, ghost, seed = 2, 128, 40, 64, 5
+    netconf = {"normalizeInputThreshold": 1e-5, "periodic-y": True, "periodic-x": per_x}
+    ops = OracleOps()
+
+    def single(conf):
+        bd = {k: torch.from_numpy(v.copy()) for k, v in global_state(H, W, seed).items()}
+        rho, U, _ = ops.advect_forces_div(MCONF, MCONF["dt"], bd, False, False, (0, H))
+        if conf["periodic-x"]:
+            U[:, 1, :, :, 1] = U[:, 1, :, :, W - 1]
+        if conf["periodic-y"]:
+            U[:, 0, :, 1] = U[:, 0, :, H - 1].clone()
+        one = types.SimpleNamespace(world=1, owned=lambda t: t)
+        scale = D._std_finish(one, D._std_partial(one, U), U.numel(), conf["normalizeInputThreshold"])
+        p, Uo, Ut = ops.cnn(None, U, bd["flags"], scale, prewall=True)
+        if conf["periodic-x"]:
+            Uo[:, 1, :, :, 1] = Ut[:, 1, :, :, W - 1]
+        if conf["periodic-y"]:
+            Uo[:, 0, :, 1] = Ut[:, 0, :, H - 1]
+        ops.set_const(Uo, bd["UBCInvMask"], bd["UBC"])
+        ops.set_const(rho, bd["densityBCInvMask"], bd["densityBC"])
+        return {"p": p.numpy(), "U": Uo.numpy(), "density": rho.numpy()}
+
+    want = single(netconf)
+    noseam = single(dict(netconf, **{"periodic-y": False}))
+    # (the inflow mask of this state pins rows 0..3 on a band of columns only: the seam shows on the rest of row 1)
+    assert np.abs(want["U"][:, 0, :, 1] - noseam["U"][:, 0, :, 1]).max() > 1e-3
+    out = str(tmp_path / "seam.npz")
+    port = 33500 + (os.getpid() % 2000) + int(per_x)
+    mp.spawn(_seam_worker, args=(world, port, H, W, ghost, seed, MCONF, netconf, out), nprocs=world, join=True)
+    z = np.load(out)
+    assert np.array_equal(z["density"], want["density"])
+    for k in ("p", "U"):
+        err = np.abs(z[k] - want[k]).max() / np.abs(want[k]).max()
+        assert err < 1e-6, (k, err)
+    assert np.abs(z["U"][:, 0, :, 1] - want["U"][:, 0, :, 1]).max() < 1e-6
 
 
 def test_decomposition_geometry():
