@@ -95,7 +95,7 @@ __device__ __forceinline__ RowP load_rowp(const ulonglong2* q) {
 // EDGE: the tile's first / last warp strip is all halo, and iteration t of n only needs its rows within
 // n - 1 - t of the tile's inner region: rows outside [r_lo, r_hi) are skipped (their stale values are never read
 // by a row that is still needed).
-template <bool SLOW, bool RESID, bool EDGE>
+template <bool SLOW, bool RESID, bool EDGE, bool PACKED>
 __device__ __forceinline__ void jacobi_sweep(RowP (&p)[JB_R], const ulonglong2* __restrict__ sdv,
                                              const ulonglong2* __restrict__ up_row, const ulonglong2* __restrict__ dn_row,
                                              unsigned Lb, unsigned Rb, unsigned Ub,
@@ -121,7 +121,7 @@ __device__ __forceinline__ void jacobi_sweep(RowP (&p)[JB_R], const ulonglong2* 
     const Row4 cur = unpack_row(curp);
     const float left = __shfl_up_sync(0xffffffffu, cur.v[JB_C - 1], 1);
     const float right = __shfl_down_sync(0xffffffffu, cur.v[0], 1);
-    if (!SLOW && !RESID) {
+    if (PACKED && !SLOW && !RESID) {
       const pair_t la = pk(left, cur.v[1]), rb = pk(cur.v[2], right);
       const pair_t sa = add2(add2(add2(add2(la, curp.b), prevp.a), downp.a), dvp.x);
       const pair_t sb = add2(add2(add2(add2(curp.a, rb), prevp.b), downp.b), dvp.y);
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(NW * 32)
   m1[t] = fixedb;
 }
 
-template <int NW, bool FIRST, bool RESID, bool PRE>
+template <int NW, bool FIRST, bool RESID, bool PRE, bool PACKED>
 __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
     k_jacobi2d_blocked(int H, int W, int row0, int row1, int ya0, int ya1, int iters, int vec_ok, const float* __restrict__ flags,
                        const float* __restrict__ div, const float* __restrict__ prev,
@@ -334,15 +334,15 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 3 : 2))
     const ulonglong2* dn_row = w < NW - 1 ? reinterpret_cast<const ulonglong2*>(&xch[t & 1][w + 1][0][lane * JB_C]) : nullptr;
     if (RESID) acc = 0.f;  // only the last iteration's |p - p_prev|^2 survives
     if (slow) {
-      jacobi_sweep<true, RESID, false>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, 0, JB_R);
+      jacobi_sweep<true, RESID, false, PACKED>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, 0, JB_R);
     } else if (w == 0 || w == NW - 1) {
       // halo strips: iteration t (0-based) of `iters` is needed JB_HALO - (iters - 1 - t) rows into the tile only
       int skip = JB_HALO + 1 - iters + t;
       skip = skip < 0 ? 0 : (skip > JB_R ? JB_R : skip);
       const int r_lo = w == 0 ? skip : 0, r_hi = w == 0 ? JB_R : JB_R - skip;
-      jacobi_sweep<false, RESID, true>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, r_lo, r_hi);
+      jacobi_sweep<false, RESID, true, PACKED>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, r_lo, r_hi);
     } else {
-      jacobi_sweep<false, RESID, false>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, 0, JB_R);
+      jacobi_sweep<false, RESID, false, PACKED>(p, sdv, up_row, dn_row, Lb, Rb, Ub, Db, fixedb, acc, 0, JB_R);
     }
   }
 
@@ -404,8 +404,8 @@ static int jacobi_block_iters() {
   return t;
 }
 
-template <int NW, bool PRE>
-static void launch_blocked(bool first, bool resid, dim3 grid, cudaStream_t st, int H, int W, int row0, int row1,
+template <int NW, bool PRE, bool PACKED>
+static void launch_blocked_v(bool first, bool resid, dim3 grid, cudaStream_t st, int H, int W, int row0, int row1,
                            int ya0, int ya1, int iters, int vec_ok,
                            const float* flags, const float* div, const float* prev, float* cur, double* ssq,
                            const uint4* m4, const unsigned* m1) {
@@ -413,16 +413,27 @@ static void launch_blocked(bool first, bool resid, dim3 grid, cudaStream_t st, i
   constexpr size_t dsm = (size_t)NW * JB_R * JB_TW * sizeof(float);   // the divergence tile
   static bool attr_done = false;   // per instantiation; > 48 KB of dynamic shared memory must be opted in
   if (!attr_done) {
-    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, true, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, false, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, true, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, false, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, true, PRE, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, true, false, PRE, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, true, PRE, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(k_jacobi2d_blocked<NW, false, false, PRE, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
     attr_done = true;
   }
-  if (first && resid) k_jacobi2d_blocked<NW, true, true, PRE><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
-  else if (first) k_jacobi2d_blocked<NW, true, false, PRE><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
-  else if (resid) k_jacobi2d_blocked<NW, false, true, PRE><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
-  else k_jacobi2d_blocked<NW, false, false, PRE><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+  if (first && resid) k_jacobi2d_blocked<NW, true, true, PRE, PACKED><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+  else if (first) k_jacobi2d_blocked<NW, true, false, PRE, PACKED><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+  else if (resid) k_jacobi2d_blocked<NW, false, true, PRE, PACKED><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+  else k_jacobi2d_blocked<NW, false, false, PRE, PACKED><<<grid, threads, dsm, st>>>(H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+}
+
+// The sweep on fp32 PAIRS (FADD2 / FMUL2) issues a quarter fewer instructions; FNX_JACOBI_PACKED=0 selects the
+// scalar sweep (same results bit for bit) for A/B measurements.
+template <int NW, bool PRE>
+static void launch_blocked(bool packed, bool first, bool resid, dim3 grid, cudaStream_t st, int H, int W, int row0, int row1,
+                           int ya0, int ya1, int iters, int vec_ok,
+                           const float* flags, const float* div, const float* prev, float* cur, double* ssq,
+                           const uint4* m4, const unsigned* m1) {
+  if (packed) launch_blocked_v<NW, PRE, true>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+  else launch_blocked_v<NW, PRE, false>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
 }
 
 // bytes of tile-mask scratch that make a multi-launch solve on a (B, H, W) grid skip the per-launch flag decode
@@ -496,6 +507,10 @@ static int jacobi_2d_blocked_impl(const float* flags, const float* div, const fl
   if (force) tall = atoi(force) >= 12;
   const int oh = (tall ? 12 : 8) * JB_R - 2 * JB_HALO;
   dim3 grid((W + OW - 1) / OW, (row1 - row0 + oh - 1) / oh, B);
+  // packed (FADD2 / FMUL2) sweep: measured faster or equal at every launch size (tools/jacobi_launch_time.py:
+  // 546 / 1058 / 2082 / 4096 rows x 4096: 49 / 62 / 96 / 162 us against 51 / 65 / 98 / 166 us scalar)
+  static const char* pk_env = getenv("FNX_JACOBI_PACKED");
+  const bool packed = pk_env ? atoi(pk_env) != 0 : true;
   // tile masks once per solve (worth it from the second launch on)
   const size_t nthr = (size_t)grid.x * grid.y * grid.z * (tall ? 384 : 256);
   static const char* nopre = getenv("FNX_JACOBI_NO_TILEMASK");
@@ -525,10 +540,10 @@ static int jacobi_2d_blocked_impl(const float* flags, const float* div, const fl
     const bool first = l == 0 && p_init == nullptr, resid = l == nL - 1 && ssq != nullptr;
     const float* prev = l == 0 ? p_init : wbuf(l - 1);
     float* cur = wbuf(l);
-    if (tall && pre) launch_blocked<12, true>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
-    else if (tall) launch_blocked<12, false>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
-    else if (pre) launch_blocked<8, true>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
-    else launch_blocked<8, false>(first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+    if (tall && pre) launch_blocked<12, true>(packed, first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+    else if (tall) launch_blocked<12, false>(packed, first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+    else if (pre) launch_blocked<8, true>(packed, first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
+    else launch_blocked<8, false>(packed, first, resid, grid, st, H, W, row0, row1, ya0, ya1, iters, vec_ok, flags, div, prev, cur, ssq, m4, m1);
     done += iters;
     fnx_count_launches(1);
   }
