@@ -770,21 +770,26 @@ int fnx_solve_linear_system_jacobi(const float* flags, const float* div, float* 
   if (!tol && !is3d) {
     // fixed iteration count, 2-D: temporally blocked shared-memory kernel
     void* tmask = (char*)ssq + align256((size_t)B * sizeof(double));
-    int e = fnx_jacobi_2d_blocked(flags, div, nullptr, p, scratch, ssq, B, H, W, max_iter, 0, 0, tmask,
+    // residual == NULL (the fused step: simulate.py:150-153 discards it): no residual pass in the last launch
+    int e = fnx_jacobi_2d_blocked(flags, div, nullptr, p, scratch, residual ? ssq : nullptr, B, H, W, max_iter, 0, 0, tmask,
                                   fnx_jacobi_2d_tilemask_bytes(B, H, W), st);
     if (e) return e;
-    k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, max_iter - 1, residual);
-    FNX_LAUNCH_CHECK("solve_linear_system", 1);
+    if (residual) {
+      k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, max_iter - 1, residual);
+      FNX_LAUNCH_CHECK("solve_linear_system", 1);
+    }
     if (iters_run) *iters_run = max_iter;
     return FNX_OK;
   }
   if (!tol && is3d && jacobi3d_vec_ok(g, flags, div, p, scratch)) {
     // fixed iteration count, 3-D: precomputed neighbour masks + 4 cells per thread
     unsigned char* mask = (unsigned char*)((char*)ssq + align256((size_t)B * sizeof(double)));
-    int e = jacobi3d_vec_run(g, flags, div, nullptr, p, scratch, mask, ssq, max_iter, st);
+    int e = jacobi3d_vec_run(g, flags, div, nullptr, p, scratch, mask, residual ? ssq : nullptr, max_iter, st);
     if (e) return e;
-    k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, max_iter - 1, residual);
-    FNX_LAUNCH_CHECK("solve_linear_system", 1);
+    if (residual) {
+      k_jacobi_ctrl<<<1, 1, 0, st>>>(ctrl, ssq, B, p_tol, max_iter - 1, residual);
+      FNX_LAUNCH_CHECK("solve_linear_system", 1);
+    }
     if (iters_run) *iters_run = max_iter;
     return FNX_OK;
   }

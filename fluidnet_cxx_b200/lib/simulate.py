@@ -332,12 +332,12 @@ def _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div):
         return
     prm = _step_params(mconf, dt, mconf['jacobiIter'])
     p = torch.empty_like(flags)
-    residual = torch.empty((), dtype=torch.float32, device=U.device)
+    # (the reference's simulate drops the solver's residual, simulate.py:150-153: not computed here)
     if _stage_hook is None:
         # one C-ABI call for the whole step
         N.check(lib.fnx_step_jacobi(ctypes.byref(prm), N.ptr(rho_in), N.ptr(U_in), N.ptr(flags), N.ptr(UBC),
                                     N.ptr(UBCInv), N.ptr(rBC), N.ptr(rBCInv), rows_ptr, N.ptr(density), N.ptr(U),
-                                    N.ptr(p), residual.data_ptr(), B, D, H, W, is3d, ws.data_ptr(), ws.numel(), st),
+                                    N.ptr(p), None, B, D, H, W, is3d, ws.data_ptr(), ws.numel(), st),
                 "simulate")
     else:
         # same kernels, issued stage by stage so a profiler hook can bracket the pressure solve
@@ -352,7 +352,7 @@ def _simulate_fused(mconf, batch_dict, net, sim_method, dt, output_div):
         _stage_hook("advect_forces", "end")
         wj = N.workspaces.get(U.device, "jacobi", lib.fnx_jacobi_workspace(B, D, H, W, prm.jacobi_iters))
         _stage_hook("pressure", "begin")
-        N.check(lib.fnx_solve_linear_system_jacobi(N.ptr(flags), N.ptr(div), N.ptr(p), residual.data_ptr(), B, D, H,
+        N.check(lib.fnx_solve_linear_system_jacobi(N.ptr(flags), N.ptr(div), N.ptr(p), None, B, D, H,
                                                    W, is3d, 0.0, prm.jacobi_iters, None, wj.data_ptr(), wj.numel(),
                                                    st), "simulate")
         _stage_hook("pressure", "end")

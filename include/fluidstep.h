@@ -65,7 +65,8 @@ int fnx_advect_vel(float dt, const float *orig, const float *U, const float *fla
 
 /* ---- pressure solve: fluidnet_cpp.solve_linear_system ---------------------- */
 /* fluids_init.h:126-142 / fluids_init.cpp:809-1004 (wrapper solve_linear_sys.py:4-40).
- * p (B,1,D,H,W) out (p0 = 0 as in the reference); residual: 1 device float out.
+ * p (B,1,D,H,W) out (p0 = 0 as in the reference); residual: 1 device float out (may be NULL when
+ * p_tol <= 0: the residual pass of the last iteration is skipped).
  * p_tol > 0 makes the call poll a device flag every few iterations (the
  * reference syncs every iteration); p_tol <= 0 never synchronises.
  * `iters_run` (host int, may be NULL) receives the iterations executed
