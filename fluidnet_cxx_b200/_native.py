@@ -127,6 +127,8 @@ SIGNATURES = {
     "fnx_profile_fetch": (_I, [ctypes.POINTER(ProfileRec), _I]),
     "fnx_fluidnet_input": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "fnx_fluidnet_output": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fnx_fluidnet_input_3d": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fnx_fluidnet_output_3d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

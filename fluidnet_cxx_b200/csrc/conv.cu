@@ -207,6 +207,75 @@ __global__ void __launch_bounds__(256)
   p_out[(size_t)b * n + o] = __fmul_rn(P, s);
 }
 
+// ---- 3-D, slice-wise projection (FluidNet.forward_fields_3d: this package's definition, no reference counterpart) ----
+// x[(b*D + k), 0] = velocityDivergence_3D(U, flags) / s ; x[(b*D + k), 1] = flagsToOccupancy(flags): one image per z-slice
+__global__ void __launch_bounds__(256)
+    k_cnn_input_3d(const float* __restrict__ U, const float* __restrict__ flags, const float* __restrict__ scale,
+                   float* __restrict__ x, int B, int D, int H, int W) {
+  const size_t hw = (size_t)H * W, n = (size_t)D * hw;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)B * n) return;
+  const int b = e / n;
+  const size_t o = e % n;
+  const int k = o / hw;
+  const size_t o2 = o % hw;
+  const int j = o2 / W, i = o2 % W;
+  const float* u = U + (size_t)b * 3 * n;
+  const float f = __ldg(flags + (size_t)b * n + o);
+  float d = 0.f;
+  if (!(i < 1 || i > W - 2 || j < 1 || j > H - 2 || k < 1 || k > D - 2)) {
+    // velocity_divergence.py:61-69 order: ((u_i - u_{i+1}) + v_j - v_{j+1}) + (w_k - w_{k+1})
+    d = __fsub_rn(__fadd_rn(__fsub_rn(__ldg(u + o), __ldg(u + o + 1)), __ldg(u + n + o)), __ldg(u + n + o + W));
+    d = __fadd_rn(d, __fsub_rn(__ldg(u + 2 * n + o), __ldg(u + 2 * n + o + hw)));
+  }
+  if (f == kObstacle) d = 0.f;
+  float* xi = x + ((size_t)b * D + k) * 2 * hw;
+  xi[o2] = __fdiv_rn(d, __ldg(scale + b));
+  xi[hw + o2] = occupancy_of(f);
+}
+
+// U/s -> in-plane velocityUpdate(p) on (Ux, Uy), Uz kept -> *s -> setWallBcs_3D ; p_out = p*s
+__global__ void __launch_bounds__(256)
+    k_cnn_output_3d(const float* __restrict__ pnet, const float* __restrict__ U, const float* __restrict__ flags,
+                    const float* __restrict__ scale, float* __restrict__ p_out, float* __restrict__ U_out, int B, int D,
+                    int H, int W) {
+  const size_t hw = (size_t)H * W, n = (size_t)D * hw;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)B * n) return;
+  const int b = e / n;
+  const size_t o = e % n;
+  const int k = o / hw;
+  const size_t o2 = o % hw;
+  const int j = o2 / W, i = o2 % W;
+  const float s = __ldg(scale + b);
+  const float* u = U + (size_t)b * 3 * n;
+  const float* fl = flags + (size_t)b * n;
+  const float* pn = pnet + (size_t)b * n;      // (B*D, 1, H, W) images in slice order == (B, 1, D, H, W)
+  const float fc = __ldg(fl + o), P = __ldg(pn + o);
+  const bool interior = !(i < 1 || i > W - 2 || j < 1 || j > H - 2 || k < 1 || k > D - 2);
+  const int idx[3] = {i, j, k};
+  const size_t nb[3] = {1, (size_t)W, hw};
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float fn = idx[c] > 0 ? __ldg(fl + o - nb[c]) : fc;
+    float v = __fdiv_rn(__ldg(u + c * n + o), s);
+    if (c < 2 && interior) {
+      const float Pn = __ldg(pn + o - nb[c]);
+      const bool cf = fc == kFluid, ce = fc == kEmpty;
+      const float m1 = (cf && fn == kFluid) ? 1.f : 0.f, m2 = (cf && fn == kEmpty) ? 1.f : 0.f;
+      const float m3 = (ce && fn == kFluid) ? 1.f : 0.f;
+      const float t1 = __fmul_rn(m1, __fsub_rn(v, __fsub_rn(P, Pn)));
+      const float t2 = __fmul_rn(m2, __fsub_rn(v, P));
+      const float t3 = __fmul_rn(m3, __fadd_rn(v, Pn));
+      v = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), 0.f);
+    }
+    v = __fmul_rn(v, s);
+    v = wall_bcs_apply(v, fc, fn);
+    U_out[(size_t)b * 3 * n + c * n + o] = v;
+  }
+  p_out[(size_t)b * n + o] = __fmul_rn(P, s);
+}
+
 }  // namespace fnx
 
 using namespace fnx;
@@ -286,6 +355,28 @@ int fnx_fluidnet_output(const float* p_net, const float* U, const float* flags, 
                                                                                  B, H, W, apply_wall_bcs);
   fnx_count_launches(1);
   FNX_CUDA_TRY("fluidnet_output", cudaGetLastError());
+  return FNX_OK;
+}
+
+// the two stencils around the network of the slice-wise 3-D projection (lib/model.py FluidNet.forward_fields_3d)
+int fnx_fluidnet_input_3d(const float* U, const float* flags, const float* scale, float* x, int B, int D, int H, int W,
+                          void* stream) {
+  if (B < 1 || D < 2 || H < 2 || W < 2) return fnx_set_error(FNX_ERR_ARG, "fluidnet_input_3d: bad shape");
+  const size_t total = (size_t)B * D * H * W;
+  k_cnn_input_3d<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(U, flags, scale, x, B, D, H, W);
+  fnx_count_launches(1);
+  FNX_CUDA_TRY("fluidnet_input_3d", cudaGetLastError());
+  return FNX_OK;
+}
+
+int fnx_fluidnet_output_3d(const float* p_net, const float* U, const float* flags, const float* scale, float* p_out,
+                           float* U_out, int B, int D, int H, int W, void* stream) {
+  if (B < 1 || D < 2 || H < 2 || W < 2) return fnx_set_error(FNX_ERR_ARG, "fluidnet_output_3d: bad shape");
+  const size_t total = (size_t)B * D * H * W;
+  k_cnn_output_3d<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p_net, U, flags, scale, p_out, U_out,
+                                                                                    B, D, H, W);
+  fnx_count_launches(1);
+  FNX_CUDA_TRY("fluidnet_output_3d", cudaGetLastError());
   return FNX_OK;
 }
 

@@ -144,19 +144,18 @@ class FluidNet(nn.Module):
         definition tried here) multiplied max|U| by ~20 per step on the 256^3 workload.  As defined, the projection
         removes the 3-D divergence (to the network's accuracy) with in-plane corrections and the simulation stays
         bounded.  A z-invariant state with Uz = 0 reproduces the 2-D model slice by slice (tests/test_gpu_cnn.py)."""
-        from .fluid import ops as F
         B, C, D, H, W = (int(v) for v in U.shape)
         assert C == 3 and D > 1, 'forward_fields_3d expects a (B, 3, D, H, W) MAC velocity'
+        lib = N.load()
+        st = N.stream_of(U)
+        U, flags = U.contiguous(), flags.contiguous()
         s = self.scale(U) if scale is None else scale                     # (B,1,1,1,1)
-        div = F.velocityDivergence(U, flags)                              # (B,1,D,H,W)
         x = torch.empty((B * D, 2, H, W), dtype=torch.float32, device=U.device)
-        x[:, 0] = (div / s)[:, 0].reshape(B * D, H, W)
-        x[:, 1] = F.flagsToOccupancy(flags)[:, 0].reshape(B * D, H, W)
-        p_net = self.multiScale(x).view(B, 1, D, H, W)                    # one 2-D forward per slice
-        v = (U / s).contiguous()
-        vz = v[:, 2].clone()
-        F.velocityUpdate(pressure=p_net, U=v, flags=flags)
-        v[:, 2] = vz                                                      # in-plane update only (see above)
-        v = F.setWallBcs((v * s).contiguous(), flags)
-        return (p_net * s).contiguous(), v
+        N.check(lib.fnx_fluidnet_input_3d(N.ptr(U), N.ptr(flags), N.ptr(s), N.ptr(x), B, D, H, W, st), "FluidNet 3-D")
+        p_net = self.multiScale(x)                                        # (B*D,1,H,W): one 2-D forward per slice
+        p = torch.empty((B, 1, D, H, W), dtype=torch.float32, device=U.device)
+        U_out = torch.empty_like(U)
+        N.check(lib.fnx_fluidnet_output_3d(N.ptr(p_net), N.ptr(U), N.ptr(flags), N.ptr(s), N.ptr(p), N.ptr(U_out),
+                                           B, D, H, W, st), "FluidNet 3-D")
+        return p, U_out
 

@@ -338,6 +338,16 @@ int fnx_fluidnet_output(const float *p_net, const float *U, const float *flags, 
                         float *p_out, float *U_out, int B, int H, int W, int apply_wall_bcs,
                         void *stream);
 
+/* The same two stencils for the SLICE-WISE 3-D projection this package defines for BASELINE configs[4] (no reference
+ * counterpart: the reference model is 2-D only, pytorch/lib/model.py:93).  input: x ((B*D), 2, H, W) = one image
+ * per z-slice: [velocityDivergence_3D(U, flags) / scale[b], flagsToOccupancy(flags)].  output: p_net ((B*D),1,H,W)
+ * -> U_out = setWallBcs_3D((U/s with the IN-PLANE pressure gradient subtracted from Ux, Uy; Uz kept) * s),
+ * p_out = p_net * s. */
+int fnx_fluidnet_input_3d(const float *U, const float *flags, const float *scale, float *x, int B, int D,
+                          int H, int W, void *stream);
+int fnx_fluidnet_output_3d(const float *p_net, const float *U, const float *flags, const float *scale,
+                           float *p_out, float *U_out, int B, int D, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -454,6 +454,36 @@ def test_slicewise_3d_reduces_to_2d_model(net):
     assert float(V3[0, 2, 2:D - 1].abs().max()) == 0.0
 
 
+def test_slicewise_3d_fused_wrapper_equals_op_sequence(net):
+    """fnx_fluidnet_input_3d / _output_3d (two kernels around the batched network) == the same definition spelled out
+    with the per-op kernels and torch arithmetic, bit for bit: divergence_3D / s, occupancy | U / s, velocityUpdate,
+    Uz restored, * s, setWallBcs_3D, p * s."""
+    model, _ = net
+    from fluidnet_cxx_b200.lib.fluid import ops as F
+    g = torch.Generator(device="cuda").manual_seed(12)
+    B, D, H, W = 2, 7, 40, 56
+    U = torch.randn(B, 3, D, H, W, device="cuda", generator=g) * 0.6
+    fl = torch.ones(B, 1, D, H, W, device="cuda")
+    fl[:, :, 0] = 2; fl[:, :, -1] = 2; fl[..., 0, :] = 2; fl[..., -1, :] = 2; fl[..., 0] = 2; fl[..., -1] = 2
+    fl[0, :, 2:5, 10:18, 20:30] = 2
+    fl[1, :, 1:3, 30:35, 5:9] = 4          # Empty cells
+    s = torch.tensor([0.41, 1.7], device="cuda").view(B, 1, 1, 1, 1)
+    with torch.no_grad():
+        p, V = model.forward_fields_3d(U, fl, scale=s)
+        x = torch.empty((B * D, 2, H, W), device="cuda")
+        x[:, 0] = (F.velocityDivergence(U, fl) / s)[:, 0].reshape(B * D, H, W)
+        x[:, 1] = F.flagsToOccupancy(fl)[:, 0].reshape(B * D, H, W)
+        p_net = model.multiScale(x).view(B, 1, D, H, W)
+        v = (U / s).contiguous()
+        vz = v[:, 2].clone()
+        F.velocityUpdate(pressure=p_net, U=v, flags=fl)
+        v[:, 2] = vz
+        v = F.setWallBcs((v * s).contiguous(), fl)
+        p_ref = (p_net * s).contiguous()
+    assert n_bad(p.cpu().numpy(), p_ref.cpu().numpy()) == 0
+    assert n_bad(V.cpu().numpy(), v.cpu().numpy()) == 0
+
+
 def test_slicewise_3d_projection_removes_divergence_and_stays_bounded(net):
     """What the slice-wise definition can be held to without a reference: on a white-noise 3-D field the projection
     removes most of the 3-D divergence (measured 1.16 -> 0.16 rms) without inflating the field, and a simulation
