@@ -558,6 +558,8 @@ def simulate_distributed(mconf, bd, net, sim_method, decomp, ops=None, bufs=None
     Same state transitions as lib.simulate for the fused configuration (inviscid, density-carrying,
     fixed Jacobi count or the ScaleNet model).  Only the owned rows of the returned state are
     meaningful (decomp.owned / decomp.gather); ghost rows are refreshed by the next call.
+    The ghost width assumes max|U| dt <= 1 cell per step: call check_reach() every few steps (GraphedDistributedStep
+    does it by itself) -- a faster flow contaminates owned rows without any other symptom.
     Returns nothing; bd['p'], bd['U'], bd['density'] are rebound -- to buffers of `ops`' output pool,
     which are recycled two steps later: clone what must outlive the next calls (pass the same `ops`
     every step; a fresh one allocates a fresh pool)."""
@@ -579,7 +581,11 @@ class GraphedDistributedStep:
     Falls back to direct launches (same results) when capture is not possible (`graphed` says which).
     """
 
-    def __init__(self, mconf, bd, net, sim_method, decomp, ops=None, use_graph=True, warmup=2):
+    def __init__(self, mconf, bd, net, sim_method, decomp, ops=None, use_graph=True, warmup=2, check_reach_every=64):
+        # The ghost width is sized for a back-trace of at most one cell per step (RA): a faster flow would silently
+        # contaminate owned rows.  The stepper therefore verifies max|U| dt itself every `check_reach_every` steps
+        # (one all-reduce(max) and a host read, amortised; 0 = the caller takes care of it with check_reach()).
+        self.check_reach_every, self._steps = int(check_reach_every), 0
         self.mconf, self.net, self.method, self.decomp = mconf, net, sim_method, decomp
         self.ops = ops or CudaLocalOps()
         self.state = {k: (v.clone() if k in ('p', 'U', 'density') else v) for k, v in bd.items()}
@@ -648,6 +654,9 @@ class GraphedDistributedStep:
         return max(float((self.decomp.owned(ref[k]) - got[k]).abs().max()) for k in got)
 
     def step(self):
+        if self.check_reach_every and self._steps % self.check_reach_every == 0 and self.decomp.world > 1:
+            check_reach(self.decomp, self.state['U'], self.mconf['dt'])
+        self._steps += 1
         if self.graphed:
             for k in ('p', 'U', 'density'):
                 if self.state[k] is not self._inputs[k]:       # someone re-bound an entry: take its rows, keep our buffer

@@ -185,7 +185,10 @@ class SlabJacobiStep:
     (1, C, 1, ya1-ya0, W), or None for an absent mask -- the global grid never has to exist on a GPU.
     """
 
-    def __init__(self, topo, mconf, H, W, held_state, K=1, use_graph=True):
+    def __init__(self, topo, mconf, H, W, held_state, K=1, use_graph=True, check_reach_every=64):
+        # the ghost rows leave room for MAX_REACH cells of back-trace per step: verified every `check_reach_every`
+        # steps by step() itself (a host read, amortised; 0 = the caller calls check_reach())
+        self.check_reach_every, self._steps = int(check_reach_every), 0
         import importlib
         self.sim = importlib.import_module(__package__ + ".simulate")
         self.lib = N.load()
@@ -357,6 +360,9 @@ class SlabJacobiStep:
     def step(self):
         """one time step of this rank (every rank of the group must call it): a replay of the captured
         graph of this parity, or direct launches before capture()"""
+        if self.check_reach_every and self._steps % self.check_reach_every == 0 and self.g["world"] > 1:
+            self.check_reach()
+        self._steps += 1
         gph = self._graphs[self.parity]
         if gph is not None:
             gph.replay()
