@@ -6,8 +6,8 @@
 // The reference runs one whole-grid pass (≈490 ATen ops) per iteration.  Here one launch
 // advances a 128 x (8*NW) tile by up to HALO = 8 iterations:
 //   * a warp owns 8 rows x 128 columns; a lane owns 8 rows x 4 consecutive columns and keeps
-//     p (32 values), div (32 values) and the Neumann/fixed bit masks in REGISTERS for the
-//     whole launch;
+//     p (32 values, as 16 packed fp32 pairs) and the Neumann/fixed bit masks in REGISTERS for
+//     the whole launch; the divergence tile sits in shared memory (one LDS.128 per row and sweep);
 //   * left/right neighbours come from the adjacent lanes by warp shuffle, up/down neighbours
 //     inside the strip are registers; only the strip's first/last row is exchanged with the
 //     neighbouring warps through a small double-buffered shared-memory array (one
@@ -15,8 +15,10 @@
 //   * the tile is loaded with an 8-cell halo and only the inner (128-16) x (8*NW-16) cells,
 //     whose dependency cone stays inside the tile, are written back (halo = exactly 2 lanes
 //     and 1 warp per side, so every store is an aligned float4);
-//   * warps whose cells touch no Obstacle/border cell run a branch-free sweep:
-//     4 FADD + 1 FMUL + 0.5 SHFL per cell-iteration.
+//   * warps whose cells touch no Obstacle/border cell run a branch-free sweep on fp32 PAIRS
+//     (add.rn.f32x2 / mul.rn.f32x2 = SASS FADD2 / FMUL2, same rounding as the scalar ops):
+//     2 FADD2 + 0.5 FMUL2 + 0.5 SHFL per cell-iteration;
+//   * the first and last warp strip of a tile (all halo) skip the rows no later iteration needs.
 // HBM traffic per iteration drops from 16 B/cell to (12*overlap + 4)/8 B/cell.  The per-cell
 // arithmetic and its order are those of the one-iteration kernel (stencils.cu), so results are
 // bit-identical to it (tests/test_gpu_parity.py::test_full_size_properties).  -fmad=false.
