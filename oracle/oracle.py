@@ -160,6 +160,57 @@ def solveLinearSystemJacobi(flags, div, is_3d=False, p_tol=1e-5, max_iter=1000):
     return p, np.float32(res.value)
 
 
+def getCentered(U):
+    """grid.py:7-30: cell-centred velocity (B, 3, D, H, W); the last column / row / plane stay 0."""
+    U = np.asarray(U, np.float32)
+    B, C, D, H, W = U.shape
+    out = np.zeros((B, 3, D, H, W), np.float32)
+    h = np.float32(0.5)
+    out[:, 0, :, :, :-1] = h * (U[:, 0, :, :, :-1] + U[:, 0, :, :, 1:])
+    out[:, 1, :, :-1, :] = h * (U[:, 1, :, :-1, :] + U[:, 1, :, 1:, :])
+    if D > 1:
+        out[:, 2, :-1] = h * (U[:, 2, :-1] + U[:, 2, 1:])
+    return out
+
+
+OUTPUT_PLANES = ("div", "velx", "vely", "velz", "vel_norm", "gradRhox", "gradRhoy", "gradPx", "gradPy", "pressure")
+
+
+def outputFields(U, flags, density, pressure, mask_obstacles=True):
+    """The drivers' output block (pytorch/plume.py:238-263 and :330-423) as one function -> (B, 10, D, H, W):
+    divergence, getCentered(U) x / y / z and its norm, the centred density and pressure gradients of the VTK block
+    (2-D: getCentered of the face differences of the (H-2) x (W-2) interior, placed at [1, H-1) x [1, W-1); 0 in
+    3-D), pressure; Obstacle cells of the velocity / norm / pressure planes NaN-filled when `mask_obstacles`
+    (numpy masked_array .filled(nan) in the drivers).  Restates what fnx_output_fields computes per cell."""
+    U = np.asarray(U, np.float32); flags = np.asarray(flags, np.float32)
+    B, _, D, H, W = flags.shape
+    out = np.zeros((B, len(OUTPUT_PLANES), D, H, W), np.float32)
+    out[:, 0] = velocityDivergence(U, flags)[:, 0]
+    c = getCentered(U)
+    out[:, 1:4] = c
+    out[:, 4] = np.sqrt((c[:, 0] * c[:, 0] + c[:, 1] * c[:, 1]) + c[:, 2] * c[:, 2], dtype=np.float32)
+    h = np.float32(0.5)
+    if D == 1:
+        for first, fld in ((5, density), (7, pressure)):
+            if fld is None:
+                continue
+            f = np.asarray(fld, np.float32)[:, 0]
+            gx = np.zeros_like(f); gy = np.zeros_like(f)
+            # x: cells i in [1, W-3], rows j in [1, H-2]; y: rows j in [1, H-3], cells i in [1, W-2]
+            gx[:, :, 1:H - 1, 1:W - 2] = h * ((f[:, :, 1:H - 1, 1:W - 2] - f[:, :, 1:H - 1, 0:W - 3]) +
+                                              (f[:, :, 1:H - 1, 2:W - 1] - f[:, :, 1:H - 1, 1:W - 2]))
+            gy[:, :, 1:H - 2, 1:W - 1] = h * ((f[:, :, 1:H - 2, 1:W - 1] - f[:, :, 0:H - 3, 1:W - 1]) +
+                                              (f[:, :, 2:H - 1, 1:W - 1] - f[:, :, 1:H - 2, 1:W - 1]))
+            out[:, first], out[:, first + 1] = gx, gy
+    if pressure is not None:
+        out[:, 9] = np.asarray(pressure, np.float32)[:, 0]
+    if mask_obstacles:
+        ob = flags[:, 0] == 2
+        for pl in (1, 2, 3, 4, 9):
+            out[:, pl][ob] = np.nan
+    return out
+
+
 def setConstVals(x, inv_mask, bc):
     x = np.array(x, dtype=np.float32, order="C", copy=True)
     inv_mask, pm = _c(inv_mask); bc, pb = _c(bc)
