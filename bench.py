@@ -1055,8 +1055,18 @@ def cpu_baseline(wl, steps, warmup):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return {"value": round(res * res * steps / dt / 1e6, 4), "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": "reference", "seconds": round(dt, 2), "sample": sample_text(wl, res, steps, warmup)}
+    out = {"value": round(res * res * steps / dt / 1e6, 4), "unit": UNIT, "cores": torch.get_num_threads(),
+           "kind": "reference", "seconds": round(dt, 2), "sample": sample_text(wl, res, steps, warmup)}
+    # SURVEY.md section 8d also asks for the single-thread figure: one more step of the same sample on one thread
+    n_threads = torch.get_num_threads()
+    try:
+        torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        step()
+        out["value_1thread"] = round(res * res / (time.perf_counter() - t0) / 1e6, 4)
+    finally:
+        torch.set_num_threads(n_threads)
+    return out
 
 
 def run_reference(args):
