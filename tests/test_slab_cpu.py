@@ -12,15 +12,16 @@ import torch
 from test_distributed_cpu import MCONF, OracleOps, global_state, jacobi_numpy
 
 
-def single_domain(st, steps):
+def single_domain(st, steps, iters=None):
     """the single-domain oracle step (simulate.py:28-171, jacobi branch) from state `st`"""
+    iters = MCONF["jacobiIter"] if iters is None else iters
     ops = OracleOps()
     H = st["flags"].shape[3]
     bd = {k: torch.from_numpy(v.copy()) for k, v in st.items()}
     out = []
     for _ in range(steps):
         rho, U, div = ops.advect_forces_div(MCONF, MCONF["dt"], bd, True, True, (0, H))
-        p, _ = ops.o.solveLinearSystemJacobi(bd["flags"].numpy(), div.numpy(), False, 0.0, MCONF["jacobiIter"])
+        p, _ = ops.o.solveLinearSystemJacobi(bd["flags"].numpy(), div.numpy(), False, 0.0, iters)
         U = ops.project(torch.from_numpy(p), U, bd, (0, H))
         bd["U"], bd["density"], bd["p"] = U, rho, torch.from_numpy(p)
         out.append({k: bd[k].numpy().copy() for k in ("p", "U", "density")})
@@ -39,19 +40,24 @@ def poison(shape, rng, scale):
 # "ahead" / "behind" let the lowest / highest runnable rank run as far as its exchanges allow before anyone
 # else moves; "random" picks the next rank at random.  A push that lands in rows the receiver still reads
 # (a write-after-read hazard of the schedule) corrupts owned rows under the skewed orders.
-@pytest.mark.parametrize("world,H,K,fast,order", [
-    (2, 64, 1, False, "lockstep"), (3, 96, 1, True, "ahead"), (4, 128, 1, False, "random"), (2, 96, 2, True, "behind"),
-    (3, 144, 2, False, "ahead"), (2, 64, 1, True, "behind"), (3, 144, 3, False, "ahead"), (4, 160, 3, False, "behind"),
-    (3, 120, 3, True, "random"), (4, 128, 2, False, "random")])
-def test_slab_schedule_bit_exact(world, H, K, fast, order):
+# iters: 20 (three 8-iteration launches: one chunk at K = 3) unless given; the longer solves run SEVERAL chunks per
+# step -- 52 iterations = 7 launches = chunks of 3, 3, 1 at K = 3 (the production shape: 100 iterations = 13 launches
+# = 5 chunks), up to the 8 ranks of a full node.
+@pytest.mark.parametrize("world,H,K,fast,order,iters", [
+    (2, 64, 1, False, "lockstep", 20), (3, 96, 1, True, "ahead", 20), (4, 128, 1, False, "random", 20),
+    (2, 96, 2, True, "behind", 20), (3, 144, 2, False, "ahead", 20), (2, 64, 1, True, "behind", 20),
+    (3, 144, 3, False, "ahead", 20), (4, 160, 3, False, "behind", 20), (3, 120, 3, True, "random", 20),
+    (4, 128, 2, False, "random", 20),
+    (4, 192, 3, False, "random", 52), (8, 384, 3, False, "behind", 52), (8, 384, 2, False, "ahead", 44),
+    (2, 96, 3, False, "ahead", 100), (8, 384, 3, True, "random", 100)])
+def test_slab_schedule_bit_exact(world, H, K, fast, order, iters):
     from fluidnet_cxx_b200.lib import slab
     W, steps, seed = 40, (1 if fast else 2), 11
-    iters = MCONF["jacobiIter"]
     ops = OracleOps()
     st = global_state(H, W, seed)
     if fast:
         st["U"] = (st["U"] * np.float32(0.95 / (np.abs(st["U"]).max() * MCONF["dt"]))).astype(np.float32)
-    ref = single_domain(st, steps)
+    ref = single_domain(st, steps, iters)
     rng = np.random.RandomState(99)
     geo = [slab.geometry(H, world, r, K) for r in range(world)]
     scheds = [slab.schedule(H, world, r, iters, K)[1] for r in range(world)]
