@@ -212,12 +212,12 @@ def _oracle_iterations(flags, div, p_tol, max_iter):
     raise AssertionError("no fixed count reproduces the tolerance solve")
 
 
-@pytest.mark.parametrize("p_tol", [2.7, 1.4])
-def test_slab_residual_terminated_jacobi(tmp_path, p_tol):
+@pytest.mark.parametrize("p_tol,world,H", [(2.7, 2, 64), (1.4, 2, 64), (2.2, 4, 128)])
+def test_slab_residual_terminated_jacobi(tmp_path, p_tol, world, H):
     """pTol > 0 across slabs (fluids_init.cpp:958-990): one all-reduce(sum) of the per-iteration squared residuals
     per chunk of iterations; the decomposed solve stops at the SAME iteration as the single-domain oracle and gives
     the same p, U bit for bit (stopping inside a chunk, not on its last iteration, included)."""
-    world, H, W, ghost, seed = 2, 64, 48, 20, 7        # ghost 20 -> chunks of 7 iterations
+    W, ghost, seed = 48, 20, 7                         # ghost 20 -> chunks of 7 iterations
     mconf = dict(MCONF, pTol=p_tol, jacobiIter=60)
     ops = OracleOps()
     bd = {k: torch.from_numpy(v.copy()) for k, v in global_state(H, W, seed).items()}
