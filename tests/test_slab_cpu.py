@@ -168,6 +168,29 @@ def test_slab_schedule_bit_exact(world, H, K, fast, order, iters):
             assert bad == 0, f"world {world} K {K} {order} step {step} field {k}: {bad} owned cells differ"
 
 
+def _random_slab_configs(n, seed):
+    """seeded random (world, H, K, fast, order, iters): slab heights from the minimum the ghost width allows (Hs = G)
+    upwards, iteration counts that end inside / on / right after an 8-iteration launch and a K-launch chunk"""
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        K = int(rng.randint(1, 5))
+        G = 8 * K + 8
+        world = int(rng.randint(2, 7))
+        Hs = G + int(rng.choice([0, 1, 3, 8, 17]))
+        iters = int(rng.choice([1, 5, 8, 9, 16, 8 * K, 8 * K + 1, 8 * K + 7, 16 * K, 16 * K + 3, 40]))
+        out.append((world, world * Hs, K, bool(rng.randint(0, 2)), str(rng.choice(["lockstep", "ahead", "behind", "random"])),
+                    iters))
+    return out
+
+
+@pytest.mark.parametrize("world,H,K,fast,order,iters", _random_slab_configs(24, seed=2024))
+def test_slab_schedule_random_configs(world, H, K, fast, order, iters):
+    """the same replay on seeded random geometries: minimal slab heights (Hs = G), K up to 4, 2-6 ranks, iteration
+    counts around the launch / chunk boundaries"""
+    test_slab_schedule_bit_exact(world, H, K, fast, order, iters)
+
+
 def test_slab_geometry():
     from fluidnet_cxx_b200.lib import slab
     g = slab.geometry(4096, 8, 3)
