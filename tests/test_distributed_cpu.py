@@ -296,6 +296,136 @@ def test_slab_periodic_seam_over_gloo(tmp_path, per_x):
     assert np.abs(z["U"][:, 0, :, 1] - want["U"][:, 0, :, 1]).max() < 1e-6
 
 
+# ---------------------------------------------------------------------------------------------
+# The same decomposition with the ranks as THREADS of this process (barrier-based transport on CPU tensors, the
+# oracle under a lock): no process spawn, so many geometries can be replayed -- seeded random ones below.
+# ---------------------------------------------------------------------------------------------
+class _ThreadComm:
+    def __init__(self, world):
+        import threading
+        self.world, self.bar, self.box = world, threading.Barrier(world), {}
+
+    def exchange_rows(self, dec, sends):
+        for peer, buf in sends.items():
+            self.box[(dec.rank, peer)] = buf.clone()
+        self.bar.wait()
+        out = {peer: self.box[(peer, dec.rank)].clone() for peer in sends}
+        self.bar.wait()
+        return out
+
+    def all_reduce(self, dec, t, op):
+        self.box[("r", dec.rank)] = t.clone()
+        self.bar.wait()
+        parts = torch.stack([self.box[("r", r)] for r in range(self.world)])
+        t.copy_(parts.max(0).values if op == dist.ReduceOp.MAX else parts.sum(0))
+        self.bar.wait()
+
+    def all_gather(self, dec, mine):
+        self.box[("g", dec.rank)] = mine
+        self.bar.wait()
+        parts = [self.box[("g", r)].clone() for r in range(self.world)]
+        self.bar.wait()
+        return parts
+
+
+def run_threads(world, H, W, ghost, mconf, steps, seed, method="jacobi", net=None):
+    """`steps` decomposed steps with `world` thread-ranks; returns the gathered fields of every step (+ the executed
+    Jacobi iterations when the solve is residual-terminated)"""
+    import threading
+    from fluidnet_cxx_b200.lib.distributed import SlabDecomposition, simulate_distributed
+    comm, lock = _ThreadComm(world), threading.Lock()
+    base = OracleOps()
+
+    class Locked:       # the C oracle keeps global counters: one call at a time
+        def __getattr__(self, name):
+            fn = getattr(base, name)
+
+            def call(*a, **kw):
+                with lock:
+                    return fn(*a, **kw)
+            return call
+    results, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            dec = SlabDecomposition(H, ghost, rank=rank, world=world, comm=comm)
+            bd = {k: dec.scatter(torch.from_numpy(v)) for k, v in global_state(H, W, seed).items()}
+            outs = []
+            for _ in range(steps):
+                simulate_distributed(mconf, bd, net, method, dec, ops=Locked())
+                rec = {k: dec.gather(bd[k]).numpy() for k in ("p", "U", "density")}
+                if "jacobi_iterations" in bd:
+                    rec["iters"] = int(bd["jacobi_iterations"])
+                outs.append(rec)
+            results[rank] = outs
+        except Exception as e:      # noqa: BLE001 - surfaced in the main thread
+            errors.append(e)
+            comm.bar.abort()
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results[0]
+
+
+def _random_decompositions(n, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        world = int(rng.randint(2, 6))
+        ghost = int(rng.choice([16, 20, 24, 32]))                 # RA = 12: 3 / 7 / 8 / 16 iterations per exchange
+        Hs = ghost + 4 * int(rng.randint(0, 4))
+        iters = int(rng.choice([1, 3, 7, 8, 9, 16, 21, 30]))
+        out.append((world, world * Hs, ghost, iters))
+    return out
+
+
+@pytest.mark.parametrize("world,H,ghost,iters", _random_decompositions(12, seed=4711))
+def test_slab_decomposition_random_geometries(world, H, ghost, iters):
+    """fixed-count Jacobi step, seeded random geometries (slab height from the ghost width upwards, iteration counts
+    around the exchange interval): decomposed == single-domain, bit for bit, two steps"""
+    W, steps, seed = 36, 2, 3
+    mconf = dict(MCONF, jacobiIter=iters)
+    ops = OracleOps()
+    bd = {k: torch.from_numpy(v.copy()) for k, v in global_state(H, W, seed).items()}
+    got = run_threads(world, H, W, ghost, mconf, steps, seed)
+    for i in range(steps):
+        rho, U, div = ops.advect_forces_div(mconf, mconf["dt"], bd, True, True, (0, H))
+        p, _ = ops.o.solveLinearSystemJacobi(bd["flags"].numpy(), div.numpy(), False, 0.0, iters)
+        U = ops.project(torch.from_numpy(p), U, bd, (0, H))
+        bd["U"], bd["density"], bd["p"] = U, rho, torch.from_numpy(p)
+        for k in ("p", "U", "density"):
+            want = bd[k].numpy()
+            bad = int(np.sum(~((got[i][k] == want) | (np.isnan(got[i][k]) & np.isnan(want)))))
+            assert bad == 0, f"step {i} field {k}: {bad} cells differ"
+
+
+@pytest.mark.parametrize("world,H,ghost,frac", [(3, 96, 20, 0.35), (5, 160, 24, 0.6), (2, 48, 16, 0.2), (4, 144, 32, 0.8)])
+def test_slab_residual_terminated_random_stops(world, H, ghost, frac):
+    """residual-terminated solve: the tolerance is placed between the residuals of two consecutive iterations chosen
+    by `frac` of a 40-iteration run, so that the stop falls at various positions of a chunk"""
+    W, seed, cap = 36, 9, 40
+    ops = OracleOps()
+    bd = {k: torch.from_numpy(v.copy()) for k, v in global_state(H, W, seed).items()}
+    rho, U, div = ops.advect_forces_div(MCONF, MCONF["dt"], bd, True, True, (0, H))
+    f, dv = bd["flags"].numpy(), div.numpy()
+    res, p = [], None
+    for it in range(cap):
+        new = jacobi_numpy(f, dv, p, 1)
+        res.append(float(np.sqrt(((new - (p if p is not None else 0)).astype(np.float64) ** 2).sum())))
+        p = new
+    stop = max(2, int(frac * cap))                  # 1-based iteration the solver should stop at
+    assert res[stop - 1] < res[stop - 2]
+    p_tol = 0.5 * (res[stop - 1] + res[stop - 2])
+    mconf = dict(MCONF, pTol=p_tol, jacobiIter=cap)
+    got = run_threads(world, H, W, ghost, mconf, 1, seed)[0]
+    assert got["iters"] == stop
+    assert np.array_equal(got["p"], jacobi_numpy(f, dv, None, stop))
+
+
 def test_decomposition_geometry():
     from fluidnet_cxx_b200.lib.distributed import SlabDecomposition, jacobi_chunk, RA
     d = SlabDecomposition(256, 48, rank=1, world=4)
