@@ -426,6 +426,37 @@ def test_slab_residual_terminated_random_stops(world, H, ghost, frac):
     assert np.array_equal(got["p"], jacobi_numpy(f, dv, None, stop))
 
 
+@pytest.mark.parametrize("world,per_x", [(3, False), (4, True), (5, False)])
+def test_slab_periodic_seam_thread_ranks(world, per_x):
+    """the cross-slab periodic seam (see test_slab_periodic_seam_over_gloo) with 3-5 thread-ranks: the source row
+    H-1 and the target row 1 are several ranks apart, and interior ranks neither send nor receive it"""
+    import types
+    from fluidnet_cxx_b200.lib import distributed as D
+    H, W, ghost, seed = world * 64, 40, 64, 5
+    netconf = {"normalizeInputThreshold": 1e-5, "periodic-y": True, "periodic-x": per_x}
+    ops = OracleOps()
+    bd = {k: torch.from_numpy(v.copy()) for k, v in global_state(H, W, seed).items()}
+    rho, U, _ = ops.advect_forces_div(MCONF, MCONF["dt"], bd, False, False, (0, H))
+    if per_x:
+        U[:, 1, :, :, 1] = U[:, 1, :, :, W - 1]
+    U[:, 0, :, 1] = U[:, 0, :, H - 1].clone()
+    one = types.SimpleNamespace(world=1, owned=lambda t: t)
+    scale = D._std_finish(one, D._std_partial(one, U), U.numel(), netconf["normalizeInputThreshold"])
+    p, Uo, Ut = ops.cnn(None, U, bd["flags"], scale, prewall=True)
+    if per_x:
+        Uo[:, 1, :, :, 1] = Ut[:, 1, :, :, W - 1]
+    Uo[:, 0, :, 1] = Ut[:, 0, :, H - 1]
+    ops.set_const(Uo, bd["UBCInvMask"], bd["UBC"])
+    ops.set_const(rho, bd["densityBCInvMask"], bd["densityBC"])
+    want = {"p": p.numpy(), "U": Uo.numpy(), "density": rho.numpy()}
+    got = run_threads(world, H, W, ghost, MCONF, 1, seed, method="convnet", net=types.SimpleNamespace(mconf=netconf))[0]
+    assert np.array_equal(got["density"], want["density"])
+    for k in ("p", "U"):
+        err = np.abs(got[k] - want[k]).max() / np.abs(want[k]).max()
+        assert err < 1e-6, (k, err)
+    assert np.abs(got["U"][:, 0, :, 1] - want["U"][:, 0, :, 1]).max() < 1e-6
+
+
 def test_decomposition_geometry():
     from fluidnet_cxx_b200.lib.distributed import SlabDecomposition, jacobi_chunk, RA
     d = SlabDecomposition(256, 48, rank=1, world=4)
